@@ -1,0 +1,130 @@
+/* mzb200.h - C ABI of libmzb200.so: the B200 (sm_100a) self-play hot path of muzero-hypermodel.
+ *
+ * The reference has no FFI: its hot path is a set of duck-typed Python call sites
+ * (SURVEY.md §8b).  Each entry point below names the reference call site it replaces
+ * (file:line under /root/reference).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every function returns int: 0 = MZB_OK, <0 = MZB_E*; message via mzb_last_error() (thread-local).
+ *  - no C++ exceptions, no torch types; plain pointers and sizes.
+ *  - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensors' data_ptr());
+ *    h_* are HOST pointers.  Handles own no data buffers except where stated.
+ *  - every launch takes the cudaStream_t (as void*) to run on and is asynchronous; no hidden syncs
+ *    unless the function name ends in _sync or it takes h_* output pointers.
+ *  - handles are not thread-safe (one owner thread), one handle set per GPU.
+ */
+#ifndef MZB200_H
+#define MZB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZB_VERSION 100           /* 0.1.0 */
+
+#define MZB_OK 0
+#define MZB_EINVAL (-1)           /* bad argument (shape, range, NULL)                      */
+#define MZB_ECUDA (-2)            /* CUDA runtime error, text in mzb_last_error()           */
+#define MZB_EUNSUPPORTED (-3)     /* e.g. more than two players (self_play.py:431)          */
+#define MZB_ESTATE (-4)           /* call out of order (e.g. expand before select)          */
+
+int mzb_version(void);
+const char* mzb_last_error(void);
+/* Number of this library's kernels launched since load / last reset (bench.py "gpu_launches"). */
+uint64_t mzb_launch_count(void);
+void mzb_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Counter-based RNG (Philox4x32-10), see oracle/rng.py.  Replaces numpy's global generator
+ * (self_play.py:22-23) with a pure function of (seed, slot, step, stream, sim, index).
+ * ------------------------------------------------------------------------------------------- */
+#define MZB_STREAM_TIE 0
+#define MZB_STREAM_NOISE 1
+#define MZB_STREAM_ACTION 2
+#define MZB_STREAM_RESET 3
+#define MZB_STREAM_PAD 4
+/* Host-side evaluation (tests): out[4]. */
+void mzb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tree store: structure-of-arrays MCTS trees for G independent games in HBM.
+ * Replaces the Python Node graph + MinMaxStats (self_play.py:434-477, 551-568).
+ * Node k (k>=1) is the node created by simulation k; node 0 is the root.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mzb_tree mzb_tree;
+
+typedef struct {
+  int32_t n_games;          /* G                                                             */
+  int32_t n_actions;        /* A = len(config.action_space), 1..65535                        */
+  int32_t num_simulations;  /* config.num_simulations, 1..65534                              */
+  int32_t n_players;        /* len(config.players): 1 or 2                                   */
+  double discount;          /* config.discount                                               */
+  double pb_c_base;         /* config.pb_c_base                                              */
+  double pb_c_init;         /* config.pb_c_init                                              */
+  int32_t hidden_floats;    /* fp32 elements of one hidden-state slot (0: no slots)          */
+  int32_t reserved;
+  uint64_t seed;            /* Philox key                                                    */
+} mzb_tree_config;
+
+/* Bytes of device workspace a tree of this config needs. */
+size_t mzb_tree_workspace_bytes(const mzb_tree_config* cfg);
+/* d_workspace: caller-owned device memory (>= workspace_bytes, 256-byte aligned), kept alive until destroy.
+ * h_log_lut: optional host array [num_simulations+1] with log((N+base+1)/base)+init per parent visit
+ * count N as the caller's math.log computes it (self_play.py:385-390); NULL = computed with libm log(). */
+int mzb_tree_create(mzb_tree** out, const mzb_tree_config* cfg, void* d_workspace, size_t workspace_bytes,
+                    const double* h_log_lut);
+int mzb_tree_destroy(mzb_tree* t);
+/* Device pointer to hidden-state slots, fp32 [G][num_simulations+1][hidden_floats]. */
+float* mzb_tree_hidden_ptr(mzb_tree* t);
+
+/* Root expansion (+ exploration noise).  Replaces Node.expand at the root and
+ * Node.add_exploration_noise (self_play.py:303-314, 452-477) and resets MinMaxStats (:317).
+ *  d_reward   [G] f32  support_to_scalar(reward logits) of initial_inference
+ *  d_policy   [G,A] f32 policy logits (policy_is_logits=1: softmax over LEGAL actions computed here)
+ *             or priors over the legal actions (0: taken as given, float32 widened like .tolist())
+ *  d_legal    [G,A] u8 or NULL (all legal).  A game with no legal action fails the call with MZB_EINVAL
+ *             only in the *_sync checker mzb_tree_check_legal; kernels treat it as all-illegal.
+ *  d_to_play  [G] i8 or NULL (0)
+ *  d_noise    [G,A] f64 Dirichlet sample laid out by ACTION (entries of illegal actions ignored) or NULL;
+ *             NULL with frac>0 -> generated on device: Gamma(alpha) by Marsaglia-Tsang from Philox.
+ *  frac       root_exploration_fraction, 0 disables noise (add_exploration_noise=False)
+ *  d_slot,d_step [G] u32 RNG counters c0,c1 per game or NULL (slot=g, step=0)                      */
+int mzb_tree_root_init(mzb_tree* t, const float* d_reward, const float* d_policy, int policy_is_logits,
+                       const uint8_t* d_legal, const int8_t* d_to_play, const double* d_noise, double alpha,
+                       double frac, const uint32_t* d_slot, const uint32_t* d_step, void* stream);
+
+/* One select walk per game: pUCT argmax from the root to an unexpanded edge.
+ * Replaces the `while node.expanded()` loop, select_child and ucb_score (self_play.py:326-335, 364-405).
+ * Outputs (any may be NULL): d_parent_slot [G] i32 node whose hidden state feeds recurrent_inference,
+ * d_action [G] i32 last action, d_depth [G] i32 search-path length (= current_tree_depth). */
+int mzb_tree_select(mzb_tree* t, int32_t* d_parent_slot, int32_t* d_action, int32_t* d_depth, void* stream);
+
+/* Expand the selected leaf with the network outputs and back the value up the search path.
+ * Replaces node.expand + backpropagate (self_play.py:346-354, 407-431).
+ *  d_value, d_reward [G] f32 (support_to_scalar outputs), d_policy [G,A] f32 logits or priors. */
+int mzb_tree_expand_backup(mzb_tree* t, const float* d_value, const float* d_reward, const float* d_policy,
+                           int policy_is_logits, void* stream);
+
+/* Root statistics after (or during) a search; any output may be NULL.
+ *  d_visits [G,A] i32 (0 for illegal), d_root_value [G] f64 = value_sum/visit_count (Node.value),
+ *  d_max_depth [G] i32, d_child_value_sum [G,A] f64, d_child_reward [G,A] f32, d_child_prior [G,A] f64,
+ *  d_minmax [G,2] f64. Feeds select_action / store_search_statistics (self_play.py:223-246, 497-512). */
+int mzb_tree_root_stats(mzb_tree* t, int32_t* d_visits, double* d_root_value, int32_t* d_max_depth,
+                        double* d_child_value_sum, float* d_child_reward, double* d_child_prior,
+                        double* d_minmax, void* stream);
+
+/* Copy one game's complete tree to the host (synchronises `stream`): used to materialise the
+ * reference's Node graph for callers that walk it (diagnose_model.py:161-252).
+ * Arrays are [num_simulations+1][A] unless noted; h_root_prior [A] f64; h_scalars[4] =
+ * {root_visit, root_value_sum, root_reward, nodes_used}. */
+int mzb_tree_export_game_sync(mzb_tree* t, int32_t game, double* h_value_sum, float* h_prior, int32_t* h_visit,
+                              float* h_reward, int32_t* h_child, double* h_root_prior, double* h_scalars,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MZB200_H */
