@@ -85,8 +85,7 @@ float* mzb_tree_hidden_ptr(mzb_tree* t);
  *  d_reward   [G] f32  support_to_scalar(reward logits) of initial_inference
  *  d_policy   [G,A] f32 policy logits (policy_is_logits=1: softmax over LEGAL actions computed here)
  *             or priors over the legal actions (0: taken as given, float32 widened like .tolist())
- *  d_legal    [G,A] u8 or NULL (all legal).  A game with no legal action fails the call with MZB_EINVAL
- *             only in the *_sync checker mzb_tree_check_legal; kernels treat it as all-illegal.
+ *  d_legal    [G,A] u8 or NULL (all legal).  The caller asserts non-empty legal sets (self_play.py:297-302).
  *  d_to_play  [G] i8 or NULL (0)
  *  d_noise    [G,A] f64 Dirichlet sample laid out by ACTION (entries of illegal actions ignored) or NULL;
  *             NULL with frac>0 -> generated on device: Gamma(alpha) by Marsaglia-Tsang from Philox.
@@ -123,6 +122,55 @@ int mzb_tree_root_stats(mzb_tree* t, int32_t* d_visits, double* d_root_value, in
 int mzb_tree_export_game_sync(mzb_tree* t, int32_t game, double* h_value_sum, float* h_prior, int32_t* h_visit,
                               float* h_reward, int32_t* h_child, double* h_root_prior, double* h_scalars,
                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fully-connected MuZero network (models.py:80-195): cartpole, tictactoe-FC.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mzb_fc_model mzb_fc_model;
+
+typedef struct {
+  int32_t obs_dim;          /* C*H*W*(stacked+1) + stacked*H*W  (models.py:100-107)              */
+  int32_t encoding_size;    /* config.encoding_size                                              */
+  int32_t n_actions;        /* len(config.action_space)                                          */
+  int32_t support_size;     /* config.support_size; logits are 2*support_size+1 wide             */
+  int32_t n_rep; int32_t rep[3];   /* config.fc_representation_layers (hidden widths, <= 3)     */
+  int32_t n_dyn; int32_t dyn[3];   /* config.fc_dynamics_layers                                  */
+  int32_t n_rew; int32_t rew[3];   /* config.fc_reward_layers                                    */
+  int32_t n_val; int32_t val[3];   /* config.fc_value_layers                                     */
+  int32_t n_pol; int32_t pol[3];   /* config.fc_policy_layers                                    */
+} mzb_fc_config;
+
+int mzb_fc_create(mzb_fc_model** out, const mzb_fc_config* cfg);
+int mzb_fc_destroy(mzb_fc_model* m);
+int mzb_fc_num_tensors(const mzb_fc_model* m);
+/* Replaces AbstractNetwork.set_weights (models.py:72-73).  h_tensors: HOST float32 pointers in
+ * state_dict() order (representation, dynamics_encoded_state, dynamics_reward, prediction_policy,
+ * prediction_value; per Linear: weight [out][in] row-major, then bias [out]).  The weights are copied
+ * into a library-owned packed device blob; the call synchronises `stream`. */
+int mzb_fc_set_weights(mzb_fc_model* m, const float* const* h_tensors, int n_tensors, void* stream);
+
+/* initial_inference (models.py:172-190) for B rows, fused with support_to_scalar (self_play.py:293-296)
+ * and the root softmax of Node.expand (:459-461).  Outputs may be NULL.
+ *  d_obs [B, obs_dim] f32; d_legal [B,A] u8 or NULL (softmax over all actions)
+ *  d_state_out: row r is written at d_state_out + r*out_row_stride + out_offset (floats), encoding_size wide
+ *  d_value_logits/d_reward_logits [B, 2S+1], d_policy_logits [B,A]  (the reference's return values)
+ *  d_value/d_reward [B] scalars, d_priors [B,A] (0 for illegal) */
+int mzb_fc_initial(mzb_fc_model* m, int64_t B, const float* d_obs, const uint8_t* d_legal, float* d_state_out,
+                   int64_t out_row_stride, int64_t out_offset, float* d_value_logits, float* d_reward_logits,
+                   float* d_policy_logits, float* d_value, float* d_reward, float* d_priors, void* stream);
+
+/* recurrent_inference (models.py:192-195) for B rows.  Row r reads its state at
+ * d_state_in + r*in_row_stride + (d_in_slot ? d_in_slot[r] : 0)*slot_stride, so the hidden-state slots of a
+ * tree store can be consumed in place (d_in_slot = parent slots from mzb_tree_select). */
+int mzb_fc_recurrent(mzb_fc_model* m, int64_t B, const float* d_state_in, int64_t in_row_stride,
+                     const int32_t* d_in_slot, int64_t slot_stride, const int32_t* d_action, float* d_state_out,
+                     int64_t out_row_stride, int64_t out_offset, float* d_value_logits, float* d_reward_logits,
+                     float* d_policy_logits, float* d_value, float* d_reward, float* d_priors, void* stream);
+
+/* models.support_to_scalar (models.py:641-662): d_logits [B, 2S+1] -> d_out [B]. */
+int mzb_support_to_scalar(const float* d_logits, int64_t B, int support_size, float* d_out, void* stream);
+/* models.scalar_to_support (models.py:665-685): d_x [n] -> d_out [n, 2S+1]. */
+int mzb_scalar_to_support(const float* d_x, int64_t n, int support_size, float* d_out, void* stream);
 
 #ifdef __cplusplus
 }
