@@ -172,6 +172,24 @@ int mzb_support_to_scalar(const float* d_logits, int64_t B, int support_size, fl
 /* models.scalar_to_support (models.py:665-685): d_x [n] -> d_out [n, 2S+1]. */
 int mzb_scalar_to_support(const float* d_x, int64_t n, int support_size, float* d_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Batched MCTS.run for fully-connected networks (self_play.py:261-362): G searches in one call.
+ *  d_obs [G, obs_dim] f32 (the stacked observation MCTS.run receives), d_legal [G,A] u8 | NULL,
+ *  d_to_play [G] i8 | NULL; noise/alpha/frac/slot/step as in mzb_tree_root_init (frac=0 <=>
+ *  add_exploration_noise=False).  num_simulations <= the tree's capacity.
+ *  allow_fused=1: shapes with a compiled whole-search kernel (cartpole, tictactoe-FC; see
+ *  mzb_search_fc_is_fused) run as ONE launch, one thread per game; otherwise - and always with
+ *  allow_fused=0 - the modular kernels run: fc_initial, root_init, then select / fc_recurrent /
+ *  expand_backup per simulation.  Both paths leave the identical tree in `t` (bit-for-bit), so
+ *  mzb_tree_root_stats / mzb_tree_export_game_sync work after either.
+ *  Outputs (NULL to skip): d_visits [G,A] i32, d_root_value [G] f64 (root.value()),
+ *  d_root_predicted_value [G] f32 (extra_info["root_predicted_value"]), d_max_depth [G] i32.      */
+int mzb_search_fc(mzb_tree* t, mzb_fc_model* m, const float* d_obs, const uint8_t* d_legal, const int8_t* d_to_play,
+                  const double* d_noise, double alpha, double frac, const uint32_t* d_slot, const uint32_t* d_step,
+                  int32_t num_simulations, int allow_fused, int32_t* d_visits, double* d_root_value,
+                  float* d_root_predicted_value, int32_t* d_max_depth, void* stream);
+int mzb_search_fc_is_fused(const mzb_fc_model* m);
+
 #ifdef __cplusplus
 }
 #endif

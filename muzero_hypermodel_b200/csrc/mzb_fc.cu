@@ -7,15 +7,6 @@
 
 #include "mzb_fc.cuh"
 
-struct mzb_fc_model {
-  mzb_fc_config cfg;
-  FcDesc d;
-  float* d_pack;
-  int n_tensors;
-  int rows_per_block;
-  size_t smem_bytes;
-};
-
 namespace {
 
 struct RowIO {

@@ -23,6 +23,15 @@ struct FcDesc {
   FcNet rep, dyn, rew, pol, val;
 };
 
+struct mzb_fc_model {
+  mzb_fc_config cfg;
+  FcDesc d;
+  float* d_pack;
+  int n_tensors;
+  int rows_per_block;
+  size_t smem_bytes;
+};
+
 __device__ __forceinline__ float elu_f32(float x) {
   // ATen's ELU evaluates exp(x) - 1 for x <= 0 (alpha = 1)
   return x > 0.0f ? x : __fsub_rn(expf(x), 1.0f);

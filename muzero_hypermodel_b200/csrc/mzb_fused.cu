@@ -1,0 +1,407 @@
+// K12: whole-search kernel for fully-connected MuZero configs - one launch runs MCTS.run
+// (self_play.py:261-362) for every game: initial inference, root expansion + exploration noise,
+// num_simulations x {pUCT select walk, recurrent inference, expand, value backup}.
+//
+// One THREAD owns one game.  The network weights (6-16 KB) live in shared memory and every lane of a
+// warp reads the same weight, so a broadcast LDS.128 feeds four FMAs; activations stay in registers
+// (layer widths are template constants, loops fully unrolled).  The tree is the same HBM store the
+// modular kernels use (mzb_tree.cuh): a thread reads one node's edges as one contiguous record.
+// The float32/float64 arithmetic is shared with the batched kernels (mzb_fc.cuh, mzb_common.cuh), so
+// this path and the modular path (K5, K0, K1+K4+K3 per simulation) give bit-identical trees.
+#include "mzb_fc.cuh"
+#include "mzb_tree.cuh"
+
+namespace {
+
+__host__ __device__ constexpr int pad4(int x) { return (x + 3) / 4 * 4; }
+
+// ---- one Linear layer, compile-time shape.  w: Wt [*][OUTP] in shared memory, b: [OUTP].
+template <int NIN, int OUT, int OUTP>
+__device__ __forceinline__ void lin(const float* __restrict__ w, const float* __restrict__ b, const float (&x)[NIN],
+                                    int hot, float (&y)[OUT], bool elu) {
+#pragma unroll
+  for (int o = 0; o < OUT; ++o) y[o] = b[o];
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) {
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) y[o] = fmaf(x[i], w[i * OUTP + o], y[o]);
+  }
+  if (hot >= 0) {
+    const float* wr = w + (NIN + hot) * OUTP;
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) y[o] = __fadd_rn(y[o], wr[o]);
+  }
+  if (elu) {
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) y[o] = elu_f32(y[o]);
+  }
+}
+
+// ---- mlp(): IN inputs (NDIRECT dense + optional one-hot tail), one optional hidden layer H, OUT outputs.
+template <int NDIRECT, int IN, int H, int OUT>
+struct Mlp {
+  static constexpr int OUT0 = H > 0 ? H : OUT;
+  static constexpr int SIZE0 = IN * pad4(OUT0) + pad4(OUT0);
+  static constexpr int SIZE = SIZE0 + (H > 0 ? H * pad4(OUT) + pad4(OUT) : 0);
+  __device__ __forceinline__ static void run(const float* __restrict__ p, const float (&x)[NDIRECT], int hot,
+                                             float (&y)[OUT]) {
+    if constexpr (H > 0) {
+      float h[H];
+      lin<NDIRECT, H, pad4(H)>(p, p + IN * pad4(H), x, hot, h, true);
+      lin<H, OUT, pad4(OUT)>(p + SIZE0, p + SIZE0 + H * pad4(OUT), h, -1, y, false);
+    } else {
+      lin<NDIRECT, OUT, pad4(OUT)>(p, p + IN * pad4(OUT), x, hot, y, false);
+    }
+  }
+};
+
+template <int OBS_, int ENC_, int A_, int SUP_, int REP_H, int DYN_H, int REW_H, int VAL_H, int POL_H>
+struct Shape {
+  static constexpr int OBS = OBS_, ENC = ENC_, A = A_, SUP = SUP_, FULL = 2 * SUP_ + 1;
+  using Rep = Mlp<OBS, OBS, REP_H, ENC>;
+  using Dyn = Mlp<ENC, ENC + A, DYN_H, ENC>;
+  using Rew = Mlp<ENC, ENC, REW_H, FULL>;
+  using Pol = Mlp<ENC, ENC, POL_H, A>;
+  using Val = Mlp<ENC, ENC, VAL_H, FULL>;
+  // pack order = add_net order in mzb_fc.cu: rep, dyn, rew, pol, val
+  static constexpr int OFF_REP = 0;
+  static constexpr int OFF_DYN = OFF_REP + Rep::SIZE;
+  static constexpr int OFF_REW = OFF_DYN + Dyn::SIZE;
+  static constexpr int OFF_POL = OFF_REW + Rew::SIZE;
+  static constexpr int OFF_VAL = OFF_POL + Pol::SIZE;
+  static constexpr int PACK = OFF_VAL + Val::SIZE;
+  static bool matches(const FcDesc& d) {
+    auto one = [](const FcNet& n, int h) { return h > 0 ? (n.n == 2 && n.l[0].out == h) : n.n == 1; };
+    return d.obs_dim == OBS && d.enc == ENC && d.A == A && d.S == SUP && d.pack_floats == PACK && one(d.rep, REP_H) &&
+           one(d.dyn, DYN_H) && one(d.rew, REW_H) && one(d.val, VAL_H) && one(d.pol, POL_H);
+  }
+};
+
+template <int N>
+__device__ __forceinline__ void minmax_regs(float (&s)[N]) {
+  float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { lo = fminf(lo, s[i]); hi = fmaxf(hi, s[i]); }
+  float scale = __fsub_rn(hi, lo);
+  if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = __fdiv_rn(__fsub_rn(s[i], lo), scale);
+}
+
+template <int SUP>
+__device__ __forceinline__ float s2s_regs(const float (&l)[2 * SUP + 1]) {
+  constexpr int FULL = 2 * SUP + 1;
+  float e[FULL];
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int i = 0; i < FULL; ++i) m = fmaxf(m, l[i]);
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < FULL; ++i) { e[i] = softmax_exp(l[i], m); sum = __fadd_rn(sum, e[i]); }
+  float x = 0.0f;
+#pragma unroll
+  for (int i = 0; i < FULL; ++i) x = __fadd_rn(x, __fmul_rn((float)(i - SUP), __fdiv_rn(e[i], sum)));
+  return inverse_value_transform(x);
+}
+
+// softmax over the legal actions (all when legal == NULL), summed in action order; 0 elsewhere
+template <int A>
+__device__ __forceinline__ void priors_regs(const float (&logit)[A], const uint8_t* legal, float (&p)[A]) {
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int a = 0; a < A; ++a) if (!legal || legal[a]) m = fmaxf(m, logit[a]);
+  float sum = 0.0f;
+#pragma unroll
+  for (int a = 0; a < A; ++a) { p[a] = (!legal || legal[a]) ? softmax_exp(logit[a], m) : 0.0f; sum = __fadd_rn(sum, p[a]); }
+#pragma unroll
+  for (int a = 0; a < A; ++a) p[a] = __fdiv_rn(p[a], sum);
+}
+
+struct SearchIO {
+  const float* obs; const uint8_t* legal; const int8_t* to_play; const double* noise;
+  double alpha, frac;
+  const uint32_t* slot; const uint32_t* step;
+  int num_sims;
+  int* visits; double* root_value; float* root_pred_value; int* max_depth;
+};
+
+constexpr int kFusedThreads = 128;
+
+template <class SH>
+__global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, const float* __restrict__ gpack, SearchIO io) {
+  constexpr int A = SH::A, ENC = SH::ENC, FULL = SH::FULL;
+  extern __shared__ float4 smem4[];
+  float* pack = reinterpret_cast<float*>(smem4);
+  double* lut = reinterpret_cast<double*>(pack + SH::PACK);
+  for (int i = threadIdx.x; i < SH::PACK / 4; i += kFusedThreads) smem4[i] = reinterpret_cast<const float4*>(gpack)[i];
+  for (int i = threadIdx.x; i <= io.num_sims; i += kFusedThreads) lut[i] = t.log_lut[i];
+  __syncthreads();
+  const int g = blockIdx.x * kFusedThreads + threadIdx.x;
+  if (g >= t.G) return;
+  const bool two = t.P == 2;
+  const size_t G = (size_t)t.G;
+  const uint32_t my_slot = io.slot ? io.slot[g] : (uint32_t)g;
+  const uint32_t my_step = io.step ? io.step[g] : 0u;
+  const uint8_t* legal = io.legal ? io.legal + (size_t)g * A : nullptr;
+  float* hid = t.hidden + (size_t)g * (t.S + 1) * ENC;
+
+  // ---------------- initial inference (models.py:172-190) + root expansion (self_play.py:292-314)
+  double rp[A];                       // root priors, float64 after the noise mix
+  float root_reward;
+  {
+    float ob[SH::OBS];
+#pragma unroll
+    for (int i = 0; i < SH::OBS; ++i) ob[i] = io.obs[(size_t)g * SH::OBS + i];
+    float st[ENC];
+    SH::Rep::run(pack + SH::OFF_REP, ob, -1, st);
+    minmax_regs(st);
+#pragma unroll
+    for (int i = 0; i < ENC; ++i) hid[i] = st[i];
+    float pl[A], pri[A];
+    SH::Pol::run(pack + SH::OFF_POL, st, -1, pl);
+    priors_regs<A>(pl, legal, pri);
+    if (io.root_pred_value) {
+      float vl[FULL];
+      SH::Val::run(pack + SH::OFF_VAL, st, -1, vl);
+      io.root_pred_value[g] = s2s_regs<SH::SUP>(vl);
+    }
+    float zl[FULL];
+#pragma unroll
+    for (int i = 0; i < FULL; ++i) zl[i] = (i == SH::SUP) ? 0.0f : -CUDART_INF_F;
+    root_reward = s2s_regs<SH::SUP>(zl);
+    // root record
+    uint8_t* r = t.rec(g, 0);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      const bool ok = !legal || legal[a];
+      t.value_sum(r)[a] = 0.0;
+      t.prior(r)[a] = ok ? pri[a] : 0.0f;
+      t.visit(r)[a] = 0;
+      t.reward(r)[a] = 0.0f;
+      t.child(r)[a] = ok ? MZB_CHILD_NONE : MZB_CHILD_ILLEGAL;
+    }
+    if (io.frac > 0.0) {
+      const double keep = __dsub_rn(1.0, io.frac);
+      double nz[A];
+      if (io.noise) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) nz[a] = io.noise[(size_t)g * A + a];
+      } else {
+        double sum = 0.0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          nz[a] = (!legal || legal[a]) ? gamma_sample(t.key, my_slot, my_step, (uint32_t)a, io.alpha) : 0.0;
+          sum = __dadd_rn(sum, nz[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a) nz[a] = __ddiv_rn(nz[a], sum);
+      }
+#pragma unroll
+      for (int a = 0; a < A; ++a)
+        rp[a] = (!legal || legal[a]) ? __dadd_rn(__dmul_rn((double)pri[a], keep), __dmul_rn(nz[a], io.frac)) : 0.0;
+    } else {
+#pragma unroll
+      for (int a = 0; a < A; ++a) rp[a] = (!legal || legal[a]) ? (double)pri[a] : 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) t.root_prior[(size_t)g * A + a] = rp[a];
+  }
+
+  int root_visit = 0, max_depth = 0;
+  double root_vs = 0.0, vmin = CUDART_INF, vmax = -CUDART_INF;
+  uint32_t* path = t.path + g;                       // transposed use of the path buffer: path[depth * G]
+
+  for (int sim = 0; sim < io.num_sims; ++sim) {
+    // ---------------- select walk (self_play.py:326-335, 364-405)
+    int node = 0, N = root_visit, depth = 0, action = 0;
+    while (true) {
+      uint8_t* r = t.rec(g, node);
+      double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        vs[a] = t.value_sum(r)[a]; pr[a] = t.prior(r)[a]; vi[a] = t.visit(r)[a]; rw[a] = t.reward(r)[a]; ch[a] = t.child(r)[a];
+      }
+      const double pbc0 = lut[N];
+      const double sqrtN = __dsqrt_rn((double)N);
+      double sc[A];
+      double best = -CUDART_INF;
+      int n_best = 0;
+      action = -1;
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        if (ch[a] == MZB_CHILD_ILLEGAL) { sc[a] = -CUDART_INF; continue; }
+        const double p = node == 0 ? rp[a] : (double)pr[a];
+        sc[a] = ucb_score(pbc0, sqrtN, vi[a], p, vs[a], (double)rw[a], t.discount, two, vmin, vmax);
+        if (sc[a] > best || action < 0) { best = sc[a]; n_best = 1; action = a; }
+        else if (sc[a] == best) ++n_best;
+      }
+      if (n_best > 1) {
+        int pick = (int)rng_tie_index(t.key, my_slot, my_step, (uint32_t)sim, (uint32_t)depth, (uint32_t)n_best);
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          if (ch[a] != MZB_CHILD_ILLEGAL && sc[a] == best) {
+            if (pick == 0) action = a;
+            --pick;
+          }
+        }
+      }
+      path[(size_t)depth * G] = ((uint32_t)node << 16) | (uint32_t)action;
+      ++depth;
+      int next = MZB_CHILD_NONE, nv = 0;
+#pragma unroll
+      for (int a = 0; a < A; ++a) if (a == action) { next = ch[a]; nv = vi[a]; }
+      if (next < 0) break;
+      N = nv;
+      node = next;
+    }
+    const int L = depth, fresh = sim + 1;
+
+    // ---------------- recurrent inference on the parent's hidden state (models.py:192-195)
+    float value, reward, pri[A];
+    {
+      float st[ENC];
+      const float* hp = hid + (size_t)node * ENC;
+#pragma unroll
+      for (int i = 0; i < ENC; ++i) st[i] = hp[i];
+      float nx[ENC];
+      SH::Dyn::run(pack + SH::OFF_DYN, st, action, nx);
+      {
+        float rl[FULL];
+        SH::Rew::run(pack + SH::OFF_REW, nx, -1, rl);
+        reward = s2s_regs<SH::SUP>(rl);
+      }
+      minmax_regs(nx);
+      float* ho = hid + (size_t)fresh * ENC;
+#pragma unroll
+      for (int i = 0; i < ENC; ++i) ho[i] = nx[i];
+      {
+        float pl[A];
+        SH::Pol::run(pack + SH::OFF_POL, nx, -1, pl);
+        priors_regs<A>(pl, nullptr, pri);
+      }
+      {
+        float vl[FULL];
+        SH::Val::run(pack + SH::OFF_VAL, nx, -1, vl);
+        value = s2s_regs<SH::SUP>(vl);
+      }
+    }
+
+    // ---------------- expand (self_play.py:346-352)
+    {
+      uint8_t* r = t.rec(g, fresh);
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        t.value_sum(r)[a] = 0.0; t.prior(r)[a] = pri[a]; t.visit(r)[a] = 0; t.reward(r)[a] = 0.0f;
+        t.child(r)[a] = MZB_CHILD_NONE;
+      }
+      uint8_t* pr_ = t.rec(g, node);
+      t.reward(pr_)[action] = reward;
+      t.child(pr_)[action] = fresh;
+    }
+
+    // ---------------- backup (self_play.py:407-431), leaf first
+    double val = (double)value;
+    for (int k = L - 1; k >= 0; --k) {
+      const uint32_t pe = path[(size_t)k * G];
+      uint8_t* er = t.rec(g, (int)(pe >> 16));
+      const int pa = (int)(pe & 0xFFFFu);
+      double e_vs = t.value_sum(er)[pa];
+      int e_vi = t.visit(er)[pa];
+      const double e_rw = (k == L - 1) ? (double)reward : (double)t.reward(er)[pa];
+      backup_step(e_vs, e_vi, e_rw, val, t.discount, two, ((L - (k + 1)) & 1) == 0, vmin, vmax);
+      t.value_sum(er)[pa] = e_vs;
+      t.visit(er)[pa] = e_vi;
+    }
+    backup_step(root_vs, root_visit, (double)root_reward, val, t.discount, two, (L & 1) == 0, vmin, vmax);
+    max_depth = L > max_depth ? L : max_depth;
+  }
+
+  // ---------------- publish the per-game scalars (same fields the modular kernels keep)
+  t.root_value_sum[g] = root_vs;
+  t.vmin[g] = vmin;
+  t.vmax[g] = vmax;
+  t.root_reward[g] = root_reward;
+  t.root_visit[g] = root_visit;
+  t.path_len[g] = 0;
+  t.max_depth[g] = max_depth;
+  t.sims_done[g] = io.num_sims;
+  t.slot[g] = my_slot;
+  t.step[g] = my_step;
+  t.to_play[g] = io.to_play ? io.to_play[g] : (int8_t)0;
+  if (io.visits) {
+    uint8_t* r = t.rec(g, 0);
+#pragma unroll
+    for (int a = 0; a < A; ++a) io.visits[(size_t)g * A + a] = t.child(r)[a] == MZB_CHILD_ILLEGAL ? 0 : t.visit(r)[a];
+  }
+  if (io.root_value) io.root_value[g] = root_visit > 0 ? __ddiv_rn(root_vs, (double)root_visit) : 0.0;
+  if (io.max_depth) io.max_depth[g] = max_depth;
+}
+
+using CartpoleShape = Shape<4, 8, 2, 10, 0, 16, 16, 16, 16>;       // games/cartpole.py:21-71
+using TicTacToeFcShape = Shape<27, 32, 9, 10, 0, 16, 16, 0, 0>;    // games/tictactoe.py:20-70, network="fullyconnected"
+
+template <class SH>
+int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
+  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(io.num_sims + 1);
+  static bool configured = false;
+  if (!configured) {
+    MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  MZB_CHECK_ARG(smem <= 64 * 1024, "fused search: shared memory %zu > 64 KiB", smem);
+  const int grid = (t->v.G + kFusedThreads - 1) / kFusedThreads;
+  k_search_fc<SH><<<grid, kFusedThreads, smem, s>>>(t->v, m->d_pack, io);
+  MZB_LAUNCH_CHECK();
+  return MZB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mzb_search_fc_is_fused(const mzb_fc_model* m) {
+  if (!m) return 0;
+  return (CartpoleShape::matches(m->d) || TicTacToeFcShape::matches(m->d)) ? 1 : 0;
+}
+
+int mzb_search_fc(mzb_tree* t, mzb_fc_model* m, const float* d_obs, const uint8_t* d_legal, const int8_t* d_to_play,
+                  const double* d_noise, double alpha, double frac, const uint32_t* d_slot, const uint32_t* d_step,
+                  int32_t num_simulations, int allow_fused, int32_t* d_visits, double* d_root_value,
+                  float* d_root_predicted_value, int32_t* d_max_depth, void* stream) {
+  MZB_CHECK_ARG(t && m && d_obs, "NULL argument");
+  MZB_CHECK_ARG(t->v.A == m->d.A, "tree has %d actions, network %d", t->v.A, m->d.A);
+  MZB_CHECK_ARG(t->v.H == m->d.enc, "tree hidden slots hold %d floats, network encoding_size is %d", t->v.H, m->d.enc);
+  MZB_CHECK_ARG(num_simulations > 0 && num_simulations <= t->v.S, "num_simulations %d outside 1..%d", num_simulations,
+                t->v.S);
+  MZB_CHECK_ARG(frac >= 0.0 && frac <= 1.0, "exploration fraction out of [0,1]: %f", frac);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int G = t->v.G;
+  if (allow_fused) {
+    SearchIO io{d_obs, d_legal, d_to_play, d_noise, alpha, frac, d_slot, d_step, num_simulations,
+                d_visits, d_root_value, d_root_predicted_value, d_max_depth};
+    if (CartpoleShape::matches(m->d)) return launch_fused<CartpoleShape>(t, m, io, s);
+    if (TicTacToeFcShape::matches(m->d)) return launch_fused<TicTacToeFcShape>(t, m, io, s);
+  }
+  // modular path: K5, K0, then (K1, K4, K3) per simulation - any FC shape
+  const int64_t hs = (int64_t)(t->v.S + 1) * t->v.H;
+  int rc = mzb_fc_initial(m, G, d_obs, d_legal, t->v.hidden, hs, 0, nullptr, nullptr, nullptr, d_root_predicted_value,
+                          t->tmp_reward, t->tmp_priors, s);
+  if (rc) return rc;
+  rc = mzb_tree_root_init(t, t->tmp_reward, t->tmp_priors, 0, d_legal, d_to_play, d_noise, alpha, frac, d_slot, d_step, s);
+  if (rc) return rc;
+  for (int sim = 0; sim < num_simulations; ++sim) {
+    rc = mzb_tree_select(t, t->tmp_parent, t->tmp_action, nullptr, s);
+    if (rc) return rc;
+    rc = mzb_fc_recurrent(m, G, t->v.hidden, hs, t->tmp_parent, t->v.H, t->tmp_action, t->v.hidden, hs,
+                          (int64_t)(sim + 1) * t->v.H, nullptr, nullptr, nullptr, t->tmp_value, t->tmp_reward,
+                          t->tmp_priors, s);
+    if (rc) return rc;
+    rc = mzb_tree_expand_backup(t, t->tmp_value, t->tmp_reward, t->tmp_priors, 0, s);
+    if (rc) return rc;
+  }
+  if (d_visits || d_root_value || d_max_depth)
+    return mzb_tree_root_stats(t, d_visits, d_root_value, d_max_depth, nullptr, nullptr, nullptr, nullptr, s);
+  return MZB_OK;
+}
+
+}  // extern "C"

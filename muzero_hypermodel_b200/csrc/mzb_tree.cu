@@ -10,14 +10,6 @@
 
 #include "mzb_tree.cuh"
 
-struct mzb_tree {
-  mzb_tree_config cfg;
-  TreeView v;
-  int lpg;
-  double* d_log_lut;
-  size_t bytes;
-};
-
 namespace {
 
 constexpr int kThreads = 128;
@@ -349,7 +341,8 @@ int pick_lpg(int A) {
 }
 
 struct Offsets {
-  size_t nodes, root_prior, path, rvs, vmin, vmax, rrew, rvis, plen, mdep, sdone, slot, step, toplay, hidden, total;
+  size_t nodes, root_prior, path, rvs, vmin, vmax, rrew, rvis, plen, mdep, sdone, slot, step, toplay, hidden;
+  size_t tmp_parent, tmp_action, tmp_value, tmp_reward, tmp_priors, total;
 };
 
 Offsets layout(const mzb_tree_config& c) {
@@ -364,6 +357,8 @@ Offsets layout(const mzb_tree_config& c) {
   o.rrew = take(G * 4); o.rvis = take(G * 4); o.plen = take(G * 4); o.mdep = take(G * 4); o.sdone = take(G * 4);
   o.slot = take(G * 4); o.step = take(G * 4); o.toplay = take(G);
   o.hidden = take(G * S1 * (size_t)c.hidden_floats * 4);
+  o.tmp_parent = take(G * 4); o.tmp_action = take(G * 4); o.tmp_value = take(G * 4); o.tmp_reward = take(G * 4);
+  o.tmp_priors = take(G * A * 4);
   o.total = off;
   return o;
 }
@@ -447,6 +442,9 @@ int mzb_tree_create(mzb_tree** out, const mzb_tree_config* cfg, void* d_workspac
   v.to_play = (int8_t*)(w + o.toplay);
   v.hidden = cfg->hidden_floats ? (float*)(w + o.hidden) : nullptr;
   v.log_lut = t->d_log_lut;
+  t->tmp_parent = (int*)(w + o.tmp_parent); t->tmp_action = (int*)(w + o.tmp_action);
+  t->tmp_value = (float*)(w + o.tmp_value); t->tmp_reward = (float*)(w + o.tmp_reward);
+  t->tmp_priors = (float*)(w + o.tmp_priors);
   v.key = rng_key(cfg->seed);
   *out = t;
   return MZB_OK;

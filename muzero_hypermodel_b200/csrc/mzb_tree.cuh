@@ -47,6 +47,20 @@ struct TreeView {
   __device__ __forceinline__ int* child(uint8_t* r) const { return (int*)(r + 20 * (size_t)A); }
 };
 
+struct mzb_tree {
+  mzb_tree_config cfg;
+  TreeView v;
+  int lpg;
+  double* d_log_lut;
+  size_t bytes;
+  // scratch for the modular search driven from C (mzb_search_fc): one entry per game
+  int* tmp_parent;
+  int* tmp_action;
+  float* tmp_value;
+  float* tmp_reward;
+  float* tmp_priors;
+};
+
 // Gamma(alpha, 1) by Marsaglia & Tsang (2000) driven by Philox; alpha < 1 handled by the
 // Gamma(alpha+1) * U^(1/alpha) boost.  Device-generated exploration noise only (parity mode injects).
 __device__ inline double gamma_sample(RngKey key, uint32_t slot, uint32_t step, uint32_t action, double alpha) {

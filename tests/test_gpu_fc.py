@@ -88,7 +88,10 @@ def test_codec_kernels():
     z = T.load("codec")
     s = models.support_to_scalar(torch.tensor(z["logits"], device=DEV), 10).cpu().numpy()
     np.testing.assert_allclose(s, z["scalars"], rtol=3e-4, atol=2e-4)
-    np.testing.assert_array_equal(s[256:277], z["scalars"][256:277])       # exact expectation -> bit-exact transform
+    # one-hot rows have an exact expectation -> the float32 transform is bit-exact; the centre row is excluded:
+    # its expectation is a rounding residue of +-1e-20 whose SIGN (summation order) picks +-2.6e-5.
+    rows = [r for r in range(256, 277) if r != 266]
+    np.testing.assert_array_equal(s[rows], z["scalars"][rows])
     assert s[-2, 0] == 0
     sup = models.scalar_to_support(torch.tensor(z["x"], device=DEV), 10).cpu().numpy()
     np.testing.assert_allclose(sup, z["support"], rtol=0, atol=2e-6)
