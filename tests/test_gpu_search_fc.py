@@ -1,0 +1,143 @@
+"""Whole-search kernel (K12) vs the modular kernels (bit-exact) and vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import _tables as T
+from _configs import product_config
+from oracle import mcts as omcts
+from oracle import networks as onet
+from oracle import rng
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _net(tag):
+    from muzero_hypermodel_b200 import models
+    cfg = product_config({"cartpole_shipped": "cartpole"}.get(tag, tag))
+    z = T.load("net")
+    pre = tag + "/w/"
+    net = models.MuZeroNetwork(cfg)
+    net.set_weights({k[len(pre):]: torch.tensor(z[k]) for k in z.files if k.startswith(pre)})
+    return net.to(DEV).eval(), cfg
+
+
+def _inputs(cfg, G, seed, legal_p=1.0):
+    rs = np.random.RandomState(seed)
+    A = len(cfg.action_space)
+    if cfg.observation_shape == (1, 1, 4):
+        obs = rs.uniform(-0.2, 0.2, (G, 1, 1, 4)).astype(np.float32)
+    else:
+        stones = rs.randint(-1, 2, (G, 3, 3))
+        tp = rs.choice([-1, 1], size=(G, 1, 1))
+        obs = np.stack([(stones == 1), (stones == -1), np.broadcast_to(tp, stones.shape)], axis=1).astype(np.float32)
+    legal = rs.uniform(size=(G, A)) < legal_p
+    legal[np.arange(G), rs.randint(A, size=G)] = True
+    to_play = rs.randint(len(cfg.players), size=G).astype(np.int8)
+    noise = np.zeros((G, A))
+    for g in range(G):
+        k = int(legal[g].sum())
+        noise[g, legal[g]] = rs.dirichlet([cfg.root_dirichlet_alpha] * k)
+    slot = (rs.randint(1 << 20, size=G)).astype(np.int32)
+    step = rs.randint(500, size=G).astype(np.int32)
+    return obs, legal, to_play, noise, slot, step
+
+
+def _run(cfg, net, G, inp, fused, noise_mode, seed=11):
+    from muzero_hypermodel_b200.search import BatchedMCTS
+    obs, legal, to_play, noise, slot, step = inp
+    m = BatchedMCTS(cfg, G, device=DEV, seed=seed)
+    out = m.run(net, torch.tensor(obs, device=DEV), torch.tensor(legal, device=DEV), torch.tensor(to_play, device=DEV),
+                add_exploration_noise=noise_mode != "off",
+                noise=torch.tensor(noise, device=DEV) if noise_mode == "injected" else None,
+                slot=torch.tensor(slot, device=DEV), step=torch.tensor(step, device=DEV), allow_fused=fused)
+    torch.cuda.synchronize()
+    return m, {k: v.cpu().numpy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("tag,legal_p", [("cartpole_shipped", 1.0), ("cartpole", 1.0), ("tictactoe_fc", 0.6)])
+@pytest.mark.parametrize("noise_mode", ["injected", "device", "off"])
+def test_fused_equals_modular(tag, legal_p, noise_mode):
+    from muzero_hypermodel_b200 import _lib
+    net, cfg = _net(tag)
+    assert _lib.lib.mzb_search_fc_is_fused(net.handle()) == 1
+    G = 1500
+    inp = _inputs(cfg, G, 3, legal_p)
+    mf, of = _run(cfg, net, G, inp, True, noise_mode)
+    mm, om = _run(cfg, net, G, inp, False, noise_mode)
+    for k in ("visits", "root_value", "root_predicted_value", "max_depth"):
+        assert of[k].tobytes() == om[k].tobytes(), k
+    assert (of["visits"].sum(1) == cfg.num_simulations).all()
+    assert (of["visits"][~inp[1]] == 0).all()
+    sf = {k: v.cpu().numpy() for k, v in mf.tree.root_stats(full=True).items()}
+    sm = {k: v.cpu().numpy() for k, v in mm.tree.root_stats(full=True).items()}
+    for k in sf:
+        assert sf[k].tobytes() == sm[k].tobytes(), k
+    for g in (0, 7, G - 1):
+        ef, em = mf.tree.export_game(g), mm.tree.export_game(g)
+        for k in ("value_sum", "prior", "visit", "reward", "child", "root_prior"):
+            assert ef[k].tobytes() == em[k].tobytes(), (g, k)
+
+
+@pytest.mark.parametrize("tag,legal_p", [("cartpole_shipped", 1.0), ("tictactoe_fc", 0.6)])
+def test_fused_search_equals_oracle_given_kernel_network_outputs(tag, legal_p):
+    """The oracle's MCTS (pinned to the reference) fed by the batched FC kernels, one row at a time,
+    must rebuild exactly the tree the whole-search kernel built: visit counts, float64 sums, depth."""
+    net, cfg = _net(tag)
+    G = 6
+    inp = _inputs(cfg, G, 5, legal_p)
+    obs, legal, to_play, noise, slot, step = inp
+    m, out = _run(cfg, net, G, inp, True, "injected", seed=T.SEED)
+    A = len(cfg.action_space)
+    for g in range(G):
+        legal_actions = np.nonzero(legal[g])[0].tolist()
+        o = net.initial_inference_fused(torch.tensor(obs[g:g + 1], device=DEV), legal=torch.tensor(legal[g:g + 1], device=DEV))
+        root = (float(o["value"][0]), float(o["reward"][0]), [float(o["priors"][0, a]) for a in legal_actions], o["state"])
+
+        def rec(hidden, action):
+            r = net.recurrent_inference_fused(hidden, torch.tensor([[action]], device=DEV))
+            return float(r["value"][0]), float(r["reward"][0]), [float(x) for x in r["priors"][0]], r["state"]
+
+        res = omcts.search(rec, root, legal_actions, int(to_play[g]), n_actions=A, n_players=len(cfg.players),
+                           num_simulations=cfg.num_simulations, discount=cfg.discount, pb_c_base=cfg.pb_c_base,
+                           pb_c_init=cfg.pb_c_init, noise=[float(noise[g, a]) for a in legal_actions],
+                           exploration_fraction=cfg.root_exploration_fraction,
+                           tie=lambda n, sim, depth: rng.tie_index(T.SEED, int(slot[g]), int(step[g]), sim, depth, n))
+        np.testing.assert_array_equal(out["visits"][g][legal_actions], res.visits)
+        assert np.float64(out["root_value"][g]).tobytes() == np.float64(res.root_value()).tobytes()
+        assert out["max_depth"][g] == res.max_tree_depth
+        assert np.float32(out["root_predicted_value"][g]) == np.float32(root[0])
+        ex = m.tree.export_game(g)
+        assert np.float64(ex["root_value_sum"]).tobytes() == np.float64(res.root_value_sum).tobytes()
+        assert np.array(res.value_sums).tobytes() == ex["value_sum"][0][legal_actions].tobytes()
+
+
+def test_search_vs_reference_network_agreement():
+    """Network in the loop (L-e2e): oracle MCTS driven by the numpy restatement of models.py vs the kernel.
+    Network outputs agree to 1e-5 (logits) / 3e-4 (decoded scalars), so most searches coincide exactly;
+    the rest diverge at a near-tie.  Root values must stay close, visit counts mostly identical."""
+    net, cfg = _net("cartpole_shipped")
+    G = 48
+    inp = _inputs(cfg, G, 9)
+    obs, legal, to_play, noise, slot, step = inp
+    m, out = _run(cfg, net, G, inp, True, "injected", seed=T.SEED)
+    onn = onet.FullyConnected({k: v.numpy() for k, v in net.get_weights().items()}, 2, cfg.support_size)
+    same, dv = 0, []
+    for g in range(G):
+        v, r, p, s = onn.initial_inference(obs[g:g + 1])
+        root = (float(onet.support_to_scalar(v, 10)[0, 0]), float(onet.support_to_scalar(r, 10)[0, 0]),
+                [float(x) for x in omcts.softmax_f32(p[0])], s)
+
+        def rec(hidden, action):
+            v, r, p, s = onn.recurrent_inference(hidden, np.array([action]))
+            return (float(onet.support_to_scalar(v, 10)[0, 0]), float(onet.support_to_scalar(r, 10)[0, 0]),
+                    [float(x) for x in omcts.softmax_f32(p[0])], s)
+
+        res = omcts.search(rec, root, [0, 1], 0, n_actions=2, n_players=1, num_simulations=50, discount=cfg.discount,
+                           pb_c_base=cfg.pb_c_base, pb_c_init=cfg.pb_c_init, noise=[float(x) for x in noise[g]],
+                           tie=lambda n, sim, depth: rng.tie_index(T.SEED, int(slot[g]), int(step[g]), sim, depth, n))
+        same += int(list(out["visits"][g]) == res.visits)
+        dv.append(abs(out["root_value"][g] - res.root_value()) / max(1.0, abs(res.root_value())))
+    assert same >= 0.8 * G, f"only {same}/{G} searches have identical visit counts"
+    assert np.median(dv) < 1e-4 and max(dv) < 5e-2
