@@ -190,6 +190,61 @@ int mzb_search_fc(mzb_tree* t, mzb_fc_model* m, const float* d_obs, const uint8_
                   float* d_root_predicted_value, int32_t* d_max_depth, void* stream);
 int mzb_search_fc_is_fused(const mzb_fc_model* m);
 
+/* ---------------------------------------------------------------------------------------------
+ * Vectorised environments + the play_game bookkeeping around each search.
+ * Replaces Game.step/legal_actions/to_play/reset (games/*.py), SelfPlay.select_action
+ * (self_play.py:223-246), GameHistory appends (:176-182) and the hand-over of finished games
+ * (:52) for G games per GPU.  Game g has the global id first_slot + g (RNG counter c0).
+ * ------------------------------------------------------------------------------------------- */
+#define MZB_ENV_CARTPOLE 0   /* games/cartpole.py (gym CartPole-v1 physics)  */
+#define MZB_ENV_TICTACTOE 1  /* games/tictactoe.py                           */
+#define MZB_ENV_CONNECT4 2   /* games/connect4.py                            */
+#define MZB_ENV_GOMOKU 3     /* games/gomoku.py                              */
+
+typedef struct mzb_env mzb_env;
+typedef struct {
+  int32_t kind;             /* MZB_ENV_*                                                        */
+  int32_t n_games;          /* G                                                                */
+  int32_t max_moves;        /* config.max_moves                                                 */
+  int32_t export_entries;   /* capacity of the finished-game ring, in history entries (moves+1) */
+  int32_t export_games;     /* capacity of the ring's game index                                */
+  uint32_t first_slot;      /* global id of game 0 (= rank * G when games are sharded)          */
+  uint64_t seed;            /* Philox key (config.seed)                                         */
+} mzb_env_config;
+
+size_t mzb_env_workspace_bytes(const mzb_env_config* cfg);
+/* Creates the environments in caller-owned device memory and resets every game (Game.reset). */
+int mzb_env_create(mzb_env** out, const mzb_env_config* cfg, void* d_workspace, size_t workspace_bytes, void* stream);
+int mzb_env_destroy(mzb_env* e);
+int mzb_env_info(const mzb_env* e, int32_t* n_actions, int32_t* obs_dim, int32_t* rec_floats);
+int mzb_env_reset(mzb_env* e, void* stream);
+/* What play_game passes to MCTS.run (self_play.py:138-150): d_obs [G, obs_dim] f32 (C*H*W planes,
+ * to-play plane +1/-1), d_legal [G,A] u8, d_to_play [G] i8, plus the RNG counters of this move:
+ * d_slot [G] u32 (global game id), d_step [G] u32 (env steps the slot has taken).  NULL = skip. */
+int mzb_env_observe(mzb_env* e, float* d_obs, uint8_t* d_legal, int8_t* d_to_play, uint32_t* d_slot, uint32_t* d_step,
+                    void* stream);
+/* One move for every running game: select_action from the root visit counts at `temperature`
+ * (0 past temperature_threshold, <=0 disables the threshold), Game.step, GameHistory appends.
+ *  d_uniforms [G] f64 injects the random draw (NULL = Philox(slot, step, STREAM_ACTION));
+ *  d_forced_action [G] i32 overrides the choice (parity tests / opponents).
+ *  Outputs (NULL = skip): d_action [G] i32, d_reward [G] f32, d_done [G] u8 (episode finished). */
+int mzb_env_act_step(mzb_env* e, const int32_t* d_visits, const double* d_root_value, const uint8_t* d_legal,
+                     double temperature, int32_t temperature_threshold, const double* d_uniforms,
+                     const int32_t* d_forced_action, int32_t* d_action, float* d_reward, uint8_t* d_done, void* stream);
+/* Finished games are appended to the export ring (do_export=1) and restarted (auto-reset). */
+int mzb_env_harvest(mzb_env* e, int do_export, void* stream);
+/* h_counters4: {games finished, moves of finished games, env steps, games dropped by a full ring}. */
+int mzb_env_counters_sync(mzb_env* e, uint64_t* h_counters4, void* stream);
+int mzb_env_state_ptrs(mzb_env* e, double** d_cartpole_state, int8_t** d_board, int8_t** d_player, int32_t** d_hist_len,
+                       uint8_t** d_finished);
+/* Copy the ring to host arrays sized for the configured capacities and empty it.  Entry arrays:
+ * h_obs [E, rec_floats] f32 (cartpole: 4 floats; boards: cells+1 int8 packed), h_action/h_reward/h_to_play [E],
+ * h_visits [E, A] u16 (root child visit counts; child_visits = count / sum), h_root_value [E] f64;
+ * game g occupies entries [h_game_start[g], h_game_start[g] + h_game_len[g]] (len moves, len+1 entries). */
+int mzb_env_export_drain_sync(mzb_env* e, int32_t* h_n_entries, int32_t* h_n_games, float* h_obs, int32_t* h_action,
+                              float* h_reward, int8_t* h_to_play, uint16_t* h_visits, double* h_root_value,
+                              int32_t* h_game_start, int32_t* h_game_len, uint32_t* h_game_slot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

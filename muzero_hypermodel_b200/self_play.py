@@ -1,0 +1,330 @@
+"""Self-play + search with the reference's names (self_play.py), on the batched device path.
+
+  MCTS(config).run(model, observation, legal_actions, to_play, add_exploration_noise, override_root_with=None)
+      -> (root Node, {"max_tree_depth", "root_predicted_value"})                       self_play.py:261-362
+  Node / MinMaxStats / GameHistory                                                     :434-568
+  SelfPlay(initial_checkpoint, Game, config, seed)  .play_game(...) -> GameHistory     :11-246
+  SelfPlay.play_games(...)                          G games in lock-step per GPU (the B200 path)
+
+`MCTS.run` is the G=1 compatibility wrapper: it runs the same kernels as the batched path and
+rebuilds the Python Node graph from the device tree, so callers that walk `root.children`
+(select_action, store_search_statistics, diagnose_model.py) keep working unchanged.
+"""
+import math
+
+import numpy
+import torch
+
+from . import models
+from .envs import VectorEnv, game_kind
+from .search import BatchedMCTS
+
+
+class MinMaxStats:
+    """Min-max of the Q values seen in one search (self_play.py:551-568); the device keeps these per game."""
+
+    def __init__(self):
+        self.maximum = -float("inf")
+        self.minimum = float("inf")
+
+    def update(self, value):
+        self.maximum = max(self.maximum, value)
+        self.minimum = min(self.minimum, value)
+
+    def normalize(self, value):
+        if self.maximum > self.minimum:
+            return (value - self.minimum) / (self.maximum - self.minimum)
+        return value
+
+
+class Node:
+    """Host view of one tree node with the reference's read API (self_play.py:434-450)."""
+
+    def __init__(self, prior):
+        self.visit_count = 0
+        self.to_play = -1
+        self.prior = prior
+        self.value_sum = 0
+        self.children = {}
+        self.hidden_state = None
+        self.reward = 0
+
+    def expanded(self):
+        return len(self.children) > 0
+
+    def value(self):
+        if self.visit_count == 0:
+            return 0
+        return self.value_sum / self.visit_count
+
+    def expand(self, actions, to_play, reward, policy_logits, hidden_state):
+        """Node.expand (self_play.py:452-466) for callers that pre-build a root (diagnose_model.py:57-69)."""
+        self.to_play = to_play
+        self.reward = reward
+        self.hidden_state = hidden_state
+        logits = torch.as_tensor(policy_logits).detach().float().cpu().reshape(-1)
+        values = torch.softmax(torch.tensor([logits[a] for a in actions]), dim=0).tolist()
+        for a, p in zip(actions, values):
+            self.children[a] = Node(p)
+
+
+class GameHistory:
+    """Trajectory of one self-played game, field for field the reference's (self_play.py:480-548)."""
+
+    def __init__(self):
+        self.observation_history = []
+        self.action_history = []
+        self.reward_history = []
+        self.to_play_history = []
+        self.child_visits = []
+        self.root_values = []
+        self.reanalysed_predicted_root_values = None
+        self.priorities = None
+        self.game_priority = None
+
+    def store_search_statistics(self, root, action_space):
+        if root is not None:
+            sum_visits = sum(child.visit_count for child in root.children.values())
+            self.child_visits.append([root.children[a].visit_count / sum_visits if a in root.children else 0
+                                      for a in action_space])
+            self.root_values.append(root.value())
+        else:
+            self.root_values.append(None)
+
+    def get_stacked_observations(self, index, num_stacked_observations):
+        index = index % len(self.observation_history)
+        stacked = self.observation_history[index].copy()
+        for past in reversed(range(index - num_stacked_observations, index)):
+            if 0 <= past:
+                previous = numpy.concatenate((self.observation_history[past],
+                                              [numpy.ones_like(stacked[0]) * self.action_history[past + 1]]))
+            else:
+                previous = numpy.concatenate((numpy.zeros_like(self.observation_history[index]),
+                                              [numpy.zeros_like(stacked[0])]))
+            stacked = numpy.concatenate((stacked, previous))
+        return stacked
+
+
+def _model_device(model):
+    return next(model.parameters()).device
+
+
+class MCTS:
+    """`MCTS(config).run(...)`: one search, executed by the batched kernels with G = 1."""
+
+    _cache = {}
+
+    def __init__(self, config):
+        self.config = config
+
+    def _engine(self, device):
+        cfg = self.config
+        key = (id(cfg), str(device), cfg.num_simulations, len(cfg.action_space))
+        eng = MCTS._cache.get(key)
+        if eng is None:
+            eng = MCTS._cache[key] = BatchedMCTS(cfg, 1, device=device)
+        return eng
+
+    def run(self, model, observation, legal_actions, to_play, add_exploration_noise, override_root_with=None,
+            noise=None, slot=None, step=None):
+        cfg = self.config
+        device = _model_device(model)
+        if device.type != "cuda":
+            raise RuntimeError("MCTS.run: the B200 hot path has no CPU fallback - move the model to a CUDA device")
+        if len(cfg.players) > 2:
+            raise NotImplementedError("More than two player mode not implemented.")
+        A = len(cfg.action_space)
+        eng = self._engine(device)
+        if override_root_with:
+            return self._run_from_root(model, eng, override_root_with, to_play, add_exploration_noise, noise)
+        assert legal_actions, f"Legal actions should not be an empty array. Got {legal_actions}."
+        assert set(legal_actions).issubset(set(cfg.action_space)), "Legal actions should be a subset of the action space."
+        obs = torch.as_tensor(numpy.array(observation)).float().unsqueeze(0).to(device)
+        legal = torch.zeros((1, A), dtype=torch.uint8, device=device)
+        legal[0, list(legal_actions)] = 1
+        nz = None
+        if noise is not None:
+            nz = torch.zeros((1, A), dtype=torch.float64, device=device)
+            nz[0, list(legal_actions)] = torch.as_tensor(numpy.asarray(noise, dtype=numpy.float64), device=device)
+        out = eng.run(model, obs, legal, torch.tensor([to_play], dtype=torch.int8, device=device), add_exploration_noise,
+                      noise=nz, slot=None if slot is None else torch.tensor([slot], dtype=torch.int32, device=device),
+                      step=None if step is None else torch.tensor([step], dtype=torch.int32, device=device))
+        root = self._materialise(eng, 0, list(legal_actions), to_play)
+        info = {"max_tree_depth": int(out["max_depth"][0]), "root_predicted_value": float(out["root_predicted_value"][0])}
+        return root, info
+
+    def _run_from_root(self, model, eng, root, to_play, add_exploration_noise, noise):
+        """override_root_with (self_play.py:276-278): the caller expanded the root itself."""
+        cfg = self.config
+        device = eng.device
+        A = len(cfg.action_space)
+        tree = eng.tree
+        actions = list(root.children.keys())
+        pri = torch.zeros((1, A), dtype=torch.float32, device=device)
+        legal = torch.zeros((1, A), dtype=torch.uint8, device=device)
+        for a in actions:
+            pri[0, a] = float(root.children[a].prior)
+            legal[0, a] = 1
+        nz = None
+        if noise is not None:
+            nz = torch.zeros((1, A), dtype=torch.float64, device=device)
+            nz[0, actions] = torch.as_tensor(numpy.asarray(noise, dtype=numpy.float64), device=device)
+        frac = float(cfg.root_exploration_fraction) if add_exploration_noise else 0.0
+        tree.root_init(torch.tensor([float(root.reward)], device=device), pri, False, legal,
+                       torch.tensor([to_play], dtype=torch.int8, device=device), nz, cfg.root_dirichlet_alpha, frac)
+        hidden = tree.hidden()
+        hs = root.hidden_state.to(device).float()
+        hidden[0, 0] = hs.reshape(-1)
+        parent = torch.empty(1, dtype=torch.int32, device=device)
+        action = torch.empty(1, dtype=torch.int32, device=device)
+        for sim in range(cfg.num_simulations):
+            tree.select(parent, action)
+            state = hidden[0, int(parent[0])].reshape(hs.shape)
+            v, r, pl, ns = model.recurrent_inference(state, action.reshape(1, 1))
+            hidden[0, sim + 1] = ns.reshape(-1)
+            tree.expand_backup(models.support_to_scalar(v, cfg.support_size).reshape(1).contiguous(),
+                               models.support_to_scalar(r, cfg.support_size).reshape(1).contiguous(), pl.contiguous(), True)
+        stats = tree.root_stats()
+        new_root = self._materialise(eng, 0, actions, to_play, hidden_shape=tuple(hs.shape))
+        return new_root, {"max_tree_depth": int(stats["max_depth"][0]), "root_predicted_value": None}
+
+    def _materialise(self, eng, game, legal_actions, to_play, hidden_shape=None):
+        """Device tree of one game -> the reference's Node graph (children dict in action order)."""
+        cfg = self.config
+        ex = eng.tree.export_game(game)
+        hidden = eng.tree.hidden()
+        players = cfg.players
+        A = len(cfg.action_space)
+
+        def build(slot, node, depth, tp):
+            node.to_play = tp
+            h = hidden[game, slot]
+            node.hidden_state = (h.reshape(hidden_shape) if hidden_shape else h.reshape(1, -1)).clone()
+            nxt = players[(players.index(tp) + 1) % len(players)]
+            for a in (legal_actions if slot == 0 else range(A)):
+                prior = float(ex["root_prior"][a]) if slot == 0 else float(ex["prior"][slot][a])
+                ch = Node(prior)
+                ch.visit_count = int(ex["visit"][slot][a])
+                ch.value_sum = float(ex["value_sum"][slot][a]) if ch.visit_count else 0
+                ch.reward = float(ex["reward"][slot][a]) if int(ex["child"][slot][a]) >= 0 else 0
+                node.children[a] = ch
+                cs = int(ex["child"][slot][a])
+                if cs >= 0:
+                    build(cs, ch, depth + 1, nxt)
+
+        root = Node(0)
+        root.visit_count = ex["root_visit"]
+        root.value_sum = ex["root_value_sum"]
+        root.reward = ex["root_reward"]
+        build(0, root, 0, to_play)
+        return root
+
+
+class SelfPlay:
+    """Self-play worker.  `play_games` advances G games in lock-step on one GPU; `play_game` keeps the
+    reference's one-game signature (self_play.py:110-184) on top of it."""
+
+    def __init__(self, initial_checkpoint, Game, config, seed, n_games=None, device=None, first_slot=0):
+        self.config = config
+        self.Game = Game
+        self.seed = seed
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("SelfPlay: the B200 hot path has no CPU fallback")
+        numpy.random.seed(seed)
+        torch.manual_seed(seed)
+        self.model = models.MuZeroNetwork(config)
+        if initial_checkpoint is not None and initial_checkpoint.get("weights") is not None:
+            self.model.set_weights(initial_checkpoint["weights"])
+        self.model.to(self.device)
+        self.model.eval()
+        self.G = int(n_games if n_games is not None else getattr(config, "num_parallel_games", 1))
+        self.first_slot = first_slot
+        self._env = None
+        self._mcts = None
+        self.num_played_games = 0
+        self.num_played_steps = 0
+
+    # -- batched device loop
+    def _setup(self):
+        if self._env is None:
+            cfg = self.config
+            self._env = VectorEnv(game_kind(cfg), self.G, cfg.max_moves, seed=self.seed, first_slot=self.first_slot,
+                                  device=self.device)
+            self._mcts = BatchedMCTS(cfg, self.G, device=self.device, seed=self.seed)
+        return self._env, self._mcts
+
+    def step(self, temperature=1.0, temperature_threshold=None, add_exploration_noise=True, export=True,
+             allow_fused=True):
+        """One move of every game: observe -> search -> select_action + Game.step + record -> harvest."""
+        env, mcts = self._setup()
+        obs, legal, to_play = env.observe()
+        out = mcts.run(self.model, obs, legal, to_play, add_exploration_noise, slot=env.slot, step=env.step_count,
+                       allow_fused=allow_fused, out=getattr(self, "_out", None))
+        self._out = out
+        env.act_step(out["visits"], out["root_value"], legal, temperature, temperature_threshold)
+        env.harvest(export)
+
+    def play_games(self, n_moves, temperature=1.0, temperature_threshold=None, drain=True):
+        """Advance every game by n_moves moves; returns the GameHistory objects of games that finished."""
+        done = []
+        for _ in range(n_moves):
+            self.step(temperature, temperature_threshold)
+        if drain:
+            done = self.drain()
+        return done
+
+    def drain(self):
+        env, _ = self._setup()
+        ne, ng, h = env.drain_raw()
+        games = []
+        A = env.A
+        for k in range(ng):
+            s, n = int(h["start"][k]), int(h["len"][k])
+            gh = GameHistory()
+            gh.observation_history = [env.decode_observation(h["obs"][s + i]) for i in range(n + 1)]
+            gh.action_history = h["action"][s:s + n + 1].tolist()
+            gh.reward_history = [float(x) for x in h["reward"][s:s + n + 1]]
+            gh.reward_history[0] = 0
+            gh.to_play_history = h["to_play"][s:s + n + 1].astype(int).tolist()
+            v = h["visits"][s:s + n].astype(numpy.int64)
+            tot = v.sum(axis=1)
+            gh.child_visits = [[int(v[i, a]) / int(tot[i]) if v[i, a] else 0 for a in range(A)] for i in range(n)]
+            gh.root_values = h["root_value"][s:s + n].tolist()
+            gh.slot = int(h["slot"][k])
+            games.append(gh)
+        self.num_played_games += ng
+        self.num_played_steps += sum(len(g.root_values) for g in games)
+        return games
+
+    # -- reference-compatible single game
+    def play_game(self, temperature, temperature_threshold, render, opponent, muzero_player):
+        """One complete game with G = 1 (self_play.py:110-184); `opponent` other than "self" is not on the
+        device path."""
+        if opponent != "self" and len(self.config.players) > 1:
+            raise NotImplementedError('device self-play implements opponent="self"')
+        solo = SelfPlay({"weights": self.model.get_weights()}, self.Game, self.config, self.seed, n_games=1,
+                        device=self.device, first_slot=self.first_slot)
+        for _ in range(self.config.max_moves + 1):
+            solo.step(float(temperature), temperature_threshold)
+            games = solo.drain()
+            if games:
+                return games[0]
+        raise RuntimeError("game did not finish within max_moves")
+
+    def close_game(self):
+        self._env = None
+        self._mcts = None
+
+    @staticmethod
+    def select_action(node, temperature):
+        """Host-side select_action on a Node (self_play.py:223-246); the batched path does this on the device."""
+        visit_counts = numpy.array([child.visit_count for child in node.children.values()], dtype="int32")
+        actions = [action for action in node.children.keys()]
+        if temperature == 0:
+            return actions[numpy.argmax(visit_counts)]
+        if temperature == float("inf"):
+            return numpy.random.choice(actions)
+        dist = visit_counts ** (1 / temperature)
+        dist = dist / sum(dist)
+        return numpy.random.choice(actions, p=dist)
