@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py - self-play hot path throughput: MCTS simulations/s (and env steps/s) per BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cartpole|tictactoe]
+                    [--games G]
+
+One "step" = one self-play move of every game on every GPU: observe -> MCTS.run (num_simulations
+simulations, network in the loop) -> select_action -> Game.step -> GameHistory append -> harvest/auto-reset.
+Workload (config.workload): BASELINE.json configs[0], "cartpole FC MuZero (games/cartpole.py defaults,
+num_simulations=50)" - the configuration the headline target (>=1e8 simulations/s on 8xB200) is quoted on.
+Weights: the reference's shipped cartpole checkpoint (tests/golden/net.npz "cartpole_shipped", 1,532
+parameters); observations come from the device CartPole-v1 environments (synthetic games, no dataset).
+
+JSON line keys: see the task contract; `value` = simulations/s over all GPUs with state resident in HBM,
+`e2e` = the same searches driven through the batched MCTS.run entry point with HOST observation /
+legal-action / to-play buffers (pinned H2D before, D2H of visit counts + root values after, every step),
+`roofline` = the whole-search kernel against the measured HBM copy peak, `cpu_baseline` = the oracle
+port of SelfPlay.play_game on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (golden weight tag, config module, games per GPU)
+    "cartpole": ("cartpole_shipped", "cartpole", 262144),
+    "tictactoe": ("tictactoe_fc", "tictactoe", 4096 * 16),
+}
+
+
+def load_weights(tag):
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "net.npz"))
+    pre = tag + "/w/"
+    return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+
+
+def make_config(workload):
+    import importlib
+    mod = importlib.import_module(f"muzero_hypermodel_b200.games.{WORKLOADS[workload][1]}")
+    cfg = mod.MuZeroConfig()
+    if workload == "tictactoe":
+        cfg.network = "fullyconnected"
+    return cfg
+
+
+def oracle_cfg(cfg):
+    return dict(action_space=list(cfg.action_space), support_size=cfg.support_size, seed=cfg.seed, slot=0,
+                max_moves=cfg.max_moves, n_players=len(cfg.players), num_simulations=cfg.num_simulations,
+                discount=cfg.discount, pb_c_base=cfg.pb_c_base, pb_c_init=cfg.pb_c_init,
+                root_dirichlet_alpha=cfg.root_dirichlet_alpha, root_exploration_fraction=cfg.root_exploration_fraction)
+
+
+def cpu_leg(workload, cfg, seconds):
+    """Oracle port of play_game on every host core for ~`seconds` (the bench's only use of oracle/)."""
+    from oracle import cpu_baseline
+    cores = os.cpu_count() or 1
+    w = load_weights(WORKLOADS[workload][0])
+    sims, steps, wall = cpu_baseline.run_parallel(WORKLOADS[workload][1], w, oracle_cfg(cfg), cores, max_seconds=seconds)
+    return {"value": sims / wall, "unit": "simulations/s", "cores": cores, "kind": "port",
+            "env_steps_per_s": steps / wall,
+            "sample": f"{cores} processes x {seconds:.0f} s of oracle play_game ({steps} searches of "
+                      f"{cfg.num_simulations} simulations, batch-1 numpy network, same weights/config)"}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import cpu_baseline
+    cfg = make_config(args.workload)
+    cores = os.cpu_count() or 1
+    w = load_weights(WORKLOADS[args.workload][0])
+    ocfg = oracle_cfg(cfg)
+    searches = 24                                   # searches per process per step (bounded sample)
+    pool = mp.get_context("fork").Pool(cores)
+    times, sims_total = [], 0
+    for i in range(args.warmup + args.steps):
+        sims, steps, wall = cpu_baseline.run_parallel(WORKLOADS[args.workload][1], w, dict(ocfg, seed=ocfg["seed"] + i),
+                                                      cores, max_searches=searches, pool=pool)
+        if i >= args.warmup:
+            times.append(wall)
+            sims_total += sims
+    pool.close()
+    pool.join()
+    total = sum(times)
+    value = sims_total / total
+    sample = (f"each step = {cores} processes x {searches} searches x {cfg.num_simulations} simulations of the oracle "
+              f"port of SelfPlay.play_game (batch-1 numpy network)")
+    line = {"impl": "reference", "metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, cfg), "games_per_gpu": cores,
+                       "num_simulations": cfg.num_simulations},
+            "cpu_baseline": {"value": value, "unit": "simulations/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(workload, cfg):
+    return {"cartpole": "cartpole FC MuZero (games/cartpole.py defaults, num_simulations=50)",
+            "tictactoe": "tictactoe FC MuZero, two-player, network=fullyconnected, num_simulations=25"}[workload]
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cartpole", choices=list(WORKLOADS))
+    ap.add_argument("--games", type=int, default=0, help="games per GPU (default: workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--modular", action="store_true", help="force the modular kernels instead of the whole-search kernel")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = make_config(args.workload)
+
+    # CPU baseline first (rank 0, N=1 only): forked workers must not inherit a CUDA context
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_leg(args.workload, cfg, args.cpu_seconds)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from muzero_hypermodel_b200 import _lib
+    from muzero_hypermodel_b200.self_play import SelfPlay
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    G = args.games or WORKLOADS[args.workload][2]
+    S = cfg.num_simulations
+    weights = {k: torch.tensor(v) for k, v in load_weights(WORKLOADS[args.workload][0]).items()}
+    sp = SelfPlay({"weights": weights}, None, cfg, cfg.seed, n_games=G, device=dev, first_slot=rank * G)
+    env, mcts = sp._setup()
+    fused = bool(_lib.lib.mzb_search_fc_is_fused(sp.model.handle())) and not args.modular
+
+    def step():
+        sp.step(temperature=1.0, temperature_threshold=None, add_exploration_noise=True, export=True,
+                allow_fused=not args.modular)
+
+    for _ in range(args.warmup):
+        step()
+    sp.drain()
+    mcts.tree.counters(reset=True)
+    barrier()
+
+    # ---------------- timed region: K whole self-play steps, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    c0 = env.counters()
+    _lib.lib.mzb_reset_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        step()
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    launches = int(_lib.lib.mzb_launch_count())
+    clocks = sampler.stop() if sampler else None
+    c1 = env.counters()
+    tc = mcts.tree.counters()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    sims_total = args.steps * G * S * world
+    value = sims_total / (ms * 1e-3)
+    env_steps = args.steps * G * world / (ms * 1e-3)
+    mean_path = tc["path_length_sum"] / max(1, tc["simulations"])
+    finished = sp.drain()
+
+    # ---------------- the dominant kernel alone: search launches timed with events (same inputs every launch;
+    # the tree store it streams through is G*(S+1)*(24A + 4H) bytes >> L2, no L2 flush needed)
+    obs, legal, to_play = env.observe()
+    kt = []
+    for i in range(3 + 5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        mcts.run(sp.model, obs, legal, to_play, True, slot=env.slot, step=env.step_count, allow_fused=not args.modular,
+                 out=sp._out)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            kt.append(a.elapsed_time(b))
+    k_ms = sum(kt) / len(kt)
+    A, H = len(cfg.action_space), cfg.encoding_size
+    L = mean_path + 1.0                              # nodes on the path incl. root (SURVEY.md §8d counts nodes)
+    bytes_per_sim = (L - 1) * A * 20 + L * 24 + 8 * A + 8 + 2 * H * 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_per_sim * G * S / (k_ms * 1e-3) / 1e9
+    flops = {"cartpole": (1312, 2752), "tictactoe": (3648, 5952)}[args.workload]
+    roofline = {"bound": "hbm", "kernel": "k_search_fc (whole-search, fused)" if fused else "modular: k_select+k_fc_recurrent+k_expand_backup",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "kernel_ms": k_ms, "bytes_per_sim": bytes_per_sim, "mean_path_nodes": L,
+                "fp32_tflops": (flops[1] * S + flops[0]) * G / (k_ms * 1e-3) / 1e12,
+                "kernel_share_of_step": k_ms * args.steps / ms if world == 1 else None}
+
+    # ---------------- e2e: batched MCTS.run entry point with HOST buffers, copies inside the timed region
+    h_obs = torch.empty((G, env.obs_dim), dtype=torch.float32).pin_memory()
+    h_legal = torch.empty((G, A), dtype=torch.uint8).pin_memory()
+    h_tp = torch.empty(G, dtype=torch.int8).pin_memory()
+    h_obs.copy_(obs.cpu()); h_legal.copy_(legal.cpu()); h_tp.copy_(to_play.cpu())
+    h_vis = torch.empty((G, A), dtype=torch.int32).pin_memory()
+    h_rv = torch.empty(G, dtype=torch.float64).pin_memory()
+    d_obs, d_legal, d_tp = torch.empty_like(obs), torch.empty_like(legal), torch.empty_like(to_play)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        d_obs.copy_(h_obs, non_blocking=True); d_legal.copy_(h_legal, non_blocking=True); d_tp.copy_(h_tp, non_blocking=True)
+        o = mcts.run(sp.model, d_obs, d_legal, d_tp, True, slot=env.slot, step=env.step_count,
+                     allow_fused=not args.modular, out=sp._out)
+        h_vis.copy_(o["visits"], non_blocking=True); h_rv.copy_(o["root_value"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the visit counts before the next move
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    barrier()
+    t2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    assert int(h_vis.sum(1).min()) == S and int(h_vis.sum(1).max()) == S
+    e2e = {"value": e2e_steps * G * S * world / (float(t2[0]) * 1e-3), "unit": "simulations/s",
+           "h2d_bytes_per_step": (h_obs.numel() * 4 + h_legal.numel() + h_tp.numel()) * world,
+           "d2h_bytes_per_step": (h_vis.numel() * 4 + h_rv.numel() * 8) * world,
+           "api": "BatchedMCTS.run == mzb_search_fc (G x MCTS.run) with pinned host buffers"}
+
+    if rank == 0:
+        line = {"metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 network / f64 tree statistics", "data": "synthetic",
+                "config": {"workload": workload_name(args.workload, cfg), "games_per_gpu": G,
+                           "num_simulations": S, "weights": WORKLOADS[args.workload][0],
+                           "l2_policy": f"working set {mcts.tree.nbytes / 2**30:.1f} GiB tree store per GPU >> 126 MB L2",
+                           "path": "fused whole-search kernel" if fused else "modular kernels", "parallelism": f"games sharded x{world}, no collective"},
+                "env_steps_per_sec": env_steps, "e2e": e2e, "roofline": roofline, "gpu_launches": launches,
+                "clocks": clocks, "mean_search_path_nodes": L,
+                "games_finished_in_timed_region": c1["games"] - c0["games"],
+                "games_dropped": c1["dropped_games"] - c0["dropped_games"], "games_exported_after": len(finished)}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -115,6 +115,9 @@ int mzb_tree_root_stats(mzb_tree* t, int32_t* d_visits, double* d_root_value, in
                         double* d_child_value_sum, float* d_child_reward, double* d_child_prior,
                         double* d_minmax, void* stream);
 
+/* h_counters2 = {sum of search-path lengths (nodes below the root), simulations} since creation / last reset. */
+int mzb_tree_counters_sync(mzb_tree* t, uint64_t* h_counters2, int reset, void* stream);
+
 /* Copy one game's complete tree to the host (synchronises `stream`): used to materialise the
  * reference's Node graph for callers that walk it (diagnose_model.py:161-252).
  * Arrays are [num_simulations+1][A] unless noted; h_root_prior [A] f64; h_scalars[4] =

@@ -42,6 +42,7 @@ def _load():
         "mzb_tree_select": (C.c_int, [vp, vp, vp, vp, vp]),
         "mzb_tree_expand_backup": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
         "mzb_tree_root_stats": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "mzb_tree_counters_sync": (C.c_int, [vp, C.POINTER(u64), C.c_int, vp]),
         "mzb_tree_export_game_sync": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():

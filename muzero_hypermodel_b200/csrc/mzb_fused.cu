@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
   }
 
   int root_visit = 0, max_depth = 0;
+  unsigned int depth_sum = 0;
   double root_vs = 0.0, vmin = CUDART_INF, vmax = -CUDART_INF;
   uint32_t* path = t.path + g;                       // transposed use of the path buffer: path[depth * G]
 
@@ -314,7 +315,10 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
     }
     backup_step(root_vs, root_visit, (double)root_reward, val, t.discount, two, (L & 1) == 0, vmin, vmax);
     max_depth = L > max_depth ? L : max_depth;
+    depth_sum += (unsigned int)L;
   }
+  atomicAdd(t.counters, (unsigned long long)depth_sum);
+  atomicAdd(t.counters + 1, (unsigned long long)io.num_sims);
 
   // ---------------- publish the per-game scalars (same fields the modular kernels keep)
   t.root_value_sum[g] = root_vs;

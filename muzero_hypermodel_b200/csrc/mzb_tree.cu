@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(kThreads) k_select(TreeView t, int* __restrict
     node = next;
   }
   if (lane == 0) {
+    atomicAdd(t.counters, (unsigned long long)depth);
+    atomicAdd(t.counters + 1, 1ull);
     t.path_len[g] = depth;
     if (out_parent) out_parent[g] = node;
     if (out_action) out_action[g] = action;
@@ -342,7 +344,7 @@ int pick_lpg(int A) {
 
 struct Offsets {
   size_t nodes, root_prior, path, rvs, vmin, vmax, rrew, rvis, plen, mdep, sdone, slot, step, toplay, hidden;
-  size_t tmp_parent, tmp_action, tmp_value, tmp_reward, tmp_priors, total;
+  size_t tmp_parent, tmp_action, tmp_value, tmp_reward, tmp_priors, counters, total;
 };
 
 Offsets layout(const mzb_tree_config& c) {
@@ -359,6 +361,7 @@ Offsets layout(const mzb_tree_config& c) {
   o.hidden = take(G * S1 * (size_t)c.hidden_floats * 4);
   o.tmp_parent = take(G * 4); o.tmp_action = take(G * 4); o.tmp_value = take(G * 4); o.tmp_reward = take(G * 4);
   o.tmp_priors = take(G * A * 4);
+  o.counters = take(64);
   o.total = off;
   return o;
 }
@@ -446,6 +449,8 @@ int mzb_tree_create(mzb_tree** out, const mzb_tree_config* cfg, void* d_workspac
   t->tmp_value = (float*)(w + o.tmp_value); t->tmp_reward = (float*)(w + o.tmp_reward);
   t->tmp_priors = (float*)(w + o.tmp_priors);
   v.key = rng_key(cfg->seed);
+  v.counters = (unsigned long long*)(w + o.counters);
+  cudaMemset(v.counters, 0, 64);
   *out = t;
   return MZB_OK;
 }
@@ -505,6 +510,15 @@ int mzb_tree_root_stats(mzb_tree* t, int32_t* d_visits, double* d_root_value, in
   k_root_stats<<<grid, threads, 0, (cudaStream_t)stream>>>(t->v, d_visits, d_root_value, d_max_depth,
                                                            d_child_value_sum, d_child_reward, d_child_prior, d_minmax);
   MZB_LAUNCH_CHECK();
+  return MZB_OK;
+}
+
+int mzb_tree_counters_sync(mzb_tree* t, uint64_t* h_counters2, int reset, void* stream) {
+  MZB_CHECK_ARG(t && h_counters2, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  MZB_CUDA(cudaMemcpyAsync(h_counters2, t->v.counters, 16, cudaMemcpyDeviceToHost, s));
+  if (reset) MZB_CUDA(cudaMemsetAsync(t->v.counters, 0, 16, s));
+  MZB_CUDA(cudaStreamSynchronize(s));
   return MZB_OK;
 }
 

@@ -37,6 +37,7 @@ struct TreeView {
   int8_t* to_play;
   float* hidden;
   const double* log_lut;
+  unsigned long long* counters;   // [0] sum of search-path lengths, [1] simulations (bench: mean path length)
   RngKey key;
 
   __device__ __forceinline__ uint8_t* rec(int g, int n) const { return nodes + (size_t)g * game_stride + (size_t)n * rec_bytes; }

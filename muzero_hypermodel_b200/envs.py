@@ -55,9 +55,9 @@ class VectorEnv:
         self.max_moves = int(max_moves)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if export_games is None:
-            export_games = max(1024, self.G // 2)
+            export_games = max(1024, self.G)
         if export_entries is None:
-            export_entries = int(min(2 ** 31 - 1, max(export_games * 32, 4 * (self.max_moves + 1))))
+            export_entries = int(min(2 ** 30, max(4 * (self.max_moves + 1), self.G * min(self.max_moves + 1, 32))))
         self.cfg = EnvConfig(KINDS[kind], self.G, self.max_moves, int(export_entries), int(export_games),
                              int(first_slot), int(seed) & 0xFFFFFFFFFFFFFFFF)
         nbytes = _lib.lib.mzb_env_workspace_bytes(C.byref(self.cfg))

@@ -265,13 +265,16 @@ class SelfPlay:
         env.act_step(out["visits"], out["root_value"], legal, temperature, temperature_threshold)
         env.harvest(export)
 
-    def play_games(self, n_moves, temperature=1.0, temperature_threshold=None, drain=True):
-        """Advance every game by n_moves moves; returns the GameHistory objects of games that finished."""
+    def play_games(self, n_moves, temperature=1.0, temperature_threshold=None, drain_every=4):
+        """Advance every game by n_moves moves; returns the GameHistory objects of games that finished.
+        The export ring is drained to the host every `drain_every` moves (0: never - the caller drains)."""
         done = []
-        for _ in range(n_moves):
+        for i in range(n_moves):
             self.step(temperature, temperature_threshold)
-        if drain:
-            done = self.drain()
+            if drain_every and (i + 1) % drain_every == 0:
+                done += self.drain()
+        if drain_every:
+            done += self.drain()
         return done
 
     def drain(self):

@@ -74,6 +74,11 @@ class BatchedTree:
                                            ptr(cpr), ptr(mm), _lib.current_stream()))
         return out
 
+    def counters(self, reset=False):
+        c = (C.c_uint64 * 2)()
+        check(_lib.lib.mzb_tree_counters_sync(self._h, c, int(reset), _lib.current_stream()))
+        return {"path_length_sum": int(c[0]), "simulations": int(c[1])}
+
     def hidden(self):
         """fp32 view [G, S+1, H] of the hidden-state slots (inside the workspace)."""
         p = _lib.lib.mzb_tree_hidden_ptr(self._h)

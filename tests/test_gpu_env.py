@@ -203,7 +203,7 @@ def test_auto_reset_and_counters():
     net, cfg, sd = _fc_net("tictactoe_fc")
     G = 512
     sp = SelfPlay({"weights": sd}, None, cfg, 1, n_games=G, device=DEV)
-    games = sp.play_games(30)
+    games = sp.play_games(30, drain_every=3)
     c = sp._env.counters()
     assert c["env_steps"] == 30 * G                      # every game moves every step (auto-reset keeps the batch full)
     assert c["games"] == len(games) and c["dropped_games"] == 0
