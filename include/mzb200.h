@@ -248,6 +248,24 @@ int mzb_env_export_drain_sync(mzb_env* e, int32_t* h_n_entries, int32_t* h_n_gam
                               float* h_reward, int8_t* h_to_play, uint16_t* h_visits, double* h_root_value,
                               int32_t* h_game_start, int32_t* h_game_len, uint32_t* h_game_slot, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * n-step targets (ReplayBuffer.make_target / compute_target_value, replay_buffer.py:222-295) for a
+ * batch of (game, position) pairs.  Games are given in the export layout of mzb_env: entry arrays
+ * d_reward/d_to_play/d_action [E], d_root_value [E] f64, d_visits [E,A] u16, game g occupying
+ * entries d_game_start[g] .. d_game_start[g] + d_game_len[g] (len = number of moves).
+ * d_reanalysed_root_value [E] f64 or NULL (GameHistory.reanalysed_predicted_root_values).
+ * d_discount_pow [td_steps+1] f64 = discount ** i as the caller's pow rounds it.
+ * d_batch_slot/d_batch_step [B] u32 (or NULL): counters of the random padding action (:291).
+ * Outputs, one row per unroll step: d_target_value, d_target_reward [B, K+1] f64,
+ * d_target_policy [B, K+1, A] f64, d_actions [B, K+1] i32. */
+int mzb_make_target(const float* d_reward, const int8_t* d_to_play, const double* d_root_value,
+                    const double* d_reanalysed_root_value, const uint16_t* d_visits, const int32_t* d_action,
+                    const int32_t* d_game_start, const int32_t* d_game_len, int32_t n_actions,
+                    const int32_t* d_batch_game, const int32_t* d_batch_index, const uint32_t* d_batch_slot,
+                    const uint32_t* d_batch_step, int32_t batch, int32_t num_unroll_steps, int32_t td_steps,
+                    const double* d_discount_pow, uint64_t seed, double* d_target_value, double* d_target_reward,
+                    double* d_target_policy, int32_t* d_actions, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,3 +43,12 @@ class MuZeroConfig(ConfigBase):
     )
     TEMPERATURE = ((500e3, 1.0), (750e3, 0.5))
     TEMPERATURE_FINAL = 0.25
+
+
+class Game:
+    """The reference wraps the ALE emulator (games/breakout.py:135-185), which is third-party, absent and
+    excluded by BASELINE.json ("synthetic 96x96 frames"): the device path feeds the residual network with
+    synthetic frames instead (bench.py --workload breakout)."""
+
+    def __init__(self, seed=None):
+        raise NotImplementedError("Breakout needs the ALE emulator; the B200 path benchmarks it on synthetic frames")

@@ -38,3 +38,8 @@ class MuZeroConfig(ConfigBase):
         n_actions=7,
         n_players=2,
     )
+
+
+from ._device_game import make_game_class  # noqa: E402
+
+Game = make_game_class("connect4", 42)

@@ -44,3 +44,8 @@ class MuZeroConfig(ConfigBase):
     )
     TEMPERATURE = ((0.5, 1.0), (0.75, 0.5))
     TEMPERATURE_FINAL = 0.25
+
+
+from ._device_game import make_game_class  # noqa: E402
+
+Game = make_game_class("gomoku", 121)

@@ -221,3 +221,21 @@ def test_auto_reset_and_counters():
             obs, r, d = env.step(np.array([gh.action_history[i + 1]]))
             assert float(r[0]) == gh.reward_history[i + 1] and int(env.to_play()[0]) == gh.to_play_history[i + 1]
         assert bool(d[0])
+
+
+def test_game_plugin_contract():
+    """AbstractGame contract: reset / legal_actions / to_play / step return what the reference wrappers return."""
+    from muzero_hypermodel_b200.games import connect4, tictactoe
+    z = T.load("env")
+    for mod, name in ((tictactoe, "tictactoe"), (connect4, "connect4")):
+        game = mod.Game(seed=0)
+        obs = game.reset()
+        pre = f"{name}/0/"
+        acts = z[pre + "actions"]
+        for t, a in enumerate(acts):
+            np.testing.assert_array_equal(np.asarray(obs, dtype=np.float32), z[pre + "obs"][t])
+            assert game.legal_actions() == np.nonzero(z[pre + "legal"][t])[0].tolist()
+            assert game.to_play() == z[pre + "to_play"][t]
+            obs, reward, done = game.step(int(a))
+            assert reward == z[pre + "rewards"][t] and done == bool(z[pre + "dones"][t])
+        assert obs.dtype == (np.int32 if name == "tictactoe" else np.float64)
