@@ -266,6 +266,50 @@ int mzb_make_target(const float* d_reward, const int8_t* d_to_play, const double
                     const double* d_discount_pow, uint64_t seed, double* d_target_value, double* d_target_reward,
                     double* d_target_policy, int32_t* d_actions, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Residual MuZero network (models.py:206-619): tictactoe (default), connect4, gomoku, breakout.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mzb_resnet_model mzb_resnet_model;
+
+typedef struct {
+  int32_t obs_channels;              /* observation_shape[0]*(stacked+1)+stacked                        */
+  int32_t height, width;             /* observation_shape[1:], latent = same, or ceil(/16) when downsampling */
+  int32_t n_actions;
+  int32_t blocks, channels;          /* config.blocks, config.channels                                  */
+  int32_t reduced_channels_reward, reduced_channels_value, reduced_channels_policy;
+  int32_t n_fc_reward; int32_t fc_reward[3];     /* config.resnet_fc_reward_layers                       */
+  int32_t n_fc_value; int32_t fc_value[3];       /* config.resnet_fc_value_layers                        */
+  int32_t n_fc_policy; int32_t fc_policy[3];     /* config.resnet_fc_policy_layers                       */
+  int32_t support_size;
+  int32_t downsample;                /* 0: False, 1: "resnet" (models.py:233-275); "CNN" unsupported     */
+  int32_t precision;                 /* 0: fp32 CUDA-core path, 1: bf16 tcgen05 path (fp32 accumulate)   */
+} mzb_resnet_config;
+
+int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* cfg);
+int mzb_resnet_destroy(mzb_resnet_model* m);
+int mzb_resnet_num_tensors(const mzb_resnet_model* m);
+int mzb_resnet_latent_dims(const mzb_resnet_model* m, int32_t* C, int32_t* H, int32_t* W);
+/* set_weights (models.py:72-73): HOST fp32 tensors in state_dict() order with the integer
+ * `num_batches_tracked` entries skipped; h_numel gives each tensor's element count (validated).
+ * Eval-mode batch-norm is folded to per-channel scale/shift here.  Synchronises the device. */
+int mzb_resnet_set_weights(mzb_resnet_model* m, const float* const* h_tensors, const int64_t* h_numel, int n_tensors,
+                           void* stream);
+size_t mzb_resnet_workspace_bytes(const mzb_resnet_model* m, int64_t max_batch);
+/* State layouts: 0 = NCHW fp32 (the reference's tensors), 1 = NHWC fp32, 2 = NHWC bf16 (internal pools;
+ * must match the model precision).  Row r of a state lives at base + r*row_stride (+ slot*slot_stride on
+ * input, + offset on output), in elements of the layout's type.
+ * initial_inference (models.py:597-614): d_obs [B, obs_channels, H, W] fp32; outputs as mzb_fc_initial. */
+int mzb_resnet_initial(mzb_resnet_model* m, int64_t B, const float* d_obs, const uint8_t* d_legal, void* d_workspace,
+                       size_t workspace_bytes, void* d_state_out, int state_layout, int64_t out_row_stride,
+                       int64_t out_offset, float* d_value_logits, float* d_reward_logits, float* d_policy_logits,
+                       float* d_value, float* d_reward, float* d_priors, void* stream);
+/* recurrent_inference (models.py:616-619). */
+int mzb_resnet_recurrent(mzb_resnet_model* m, int64_t B, const void* d_state_in, int in_layout, int64_t in_row_stride,
+                         const int32_t* d_in_slot, int64_t slot_stride, const int32_t* d_action, void* d_workspace,
+                         size_t workspace_bytes, void* d_state_out, int out_layout, int64_t out_row_stride,
+                         int64_t out_offset, float* d_value_logits, float* d_reward_logits, float* d_policy_logits,
+                         float* d_value, float* d_reward, float* d_priors, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,600 @@
+// Residual MuZero network: model handle, weight packing, layer program, fp32 kernels (K6-K8 exact path).
+// Reference: models.py:206-619.  See mzb_resnet.cuh for the data layout.
+#include <math.h>
+#include <string.h>
+
+#include "mzb_fc.cuh"
+#include "mzb_resnet.cuh"
+#include "mzb_resnet_model.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ helpers
+template <class T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <class T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// NCHW fp32 rows (optionally slot addressed) -> NHWC T, channels padded with zeros up to cpad
+template <class T>
+__global__ void k_nchw_to_nhwc(const float* __restrict__ in, long long in_row_stride, const int* __restrict__ in_slot,
+                               long long slot_stride, int B, int C, int HW, int cpad, T* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW * cpad) return;
+  const int c = (int)(i % cpad);
+  const int p = (int)((i / cpad) % HW);
+  const int b = (int)(i / ((long long)cpad * HW));
+  const float* src = in + b * in_row_stride + (in_slot ? (long long)in_slot[b] * slot_stride : 0);
+  stf(out + i, c < C ? src[(long long)c * HW + p] : 0.0f);
+}
+
+// NHWC T rows (slot addressed) -> dense NHWC T
+template <class T>
+__global__ void k_gather_nhwc(const T* __restrict__ in, long long in_row_stride, const int* __restrict__ in_slot,
+                              long long slot_stride, int B, int n, T* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * n) return;
+  const int b = (int)(i / n), k = (int)(i % n);
+  out[i] = in[b * in_row_stride + (in_slot ? (long long)in_slot[b] * slot_stride : 0) + k];
+}
+
+// dense NHWC T -> state rows in the requested layout: 0 NCHW fp32, 1 NHWC fp32, 2 NHWC bf16
+template <class T>
+__global__ void k_store_state(const T* __restrict__ in, int B, int C, int HW, int layout, void* __restrict__ out,
+                              long long out_row_stride, long long out_off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW * C) return;
+  const int c = (int)(i % C);
+  const int p = (int)((i / C) % HW);
+  const int b = (int)(i / ((long long)C * HW));
+  const float v = ldf(in + i);
+  if (layout == 0) ((float*)out)[b * out_row_stride + out_off + (long long)c * HW + p] = v;
+  else if (layout == 1) ((float*)out)[b * out_row_stride + out_off + (long long)p * C + c] = v;
+  else ((__nv_bfloat16*)out)[b * out_row_stride + out_off + (long long)p * C + c] = __float2bfloat16_rn(v);
+}
+
+// 3x3 convolution, padding 1, stride s, + folded batch-norm + residual + ReLU.  Direct fp32 form:
+// one thread per (position, output channel); x reads broadcast across the warp, weight reads coalesced.
+template <class T>
+__global__ void k_conv3x3_direct(const T* __restrict__ x, int B, int H, int W, int cin_stride, ConvParams cp,
+                                 const float* __restrict__ plane, const T* __restrict__ residual, int relu,
+                                 T* __restrict__ y) {
+  const int Ho = (H + 2 - 3) / cp.stride + 1, Wo = (W + 2 - 3) / cp.stride + 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Ho * Wo * cp.cout) return;
+  const int co = (int)(i % cp.cout);
+  const int ox = (int)((i / cp.cout) % Wo);
+  const int oy = (int)((i / ((long long)cp.cout * Wo)) % Ho);
+  const int b = (int)(i / ((long long)cp.cout * Wo * Ho));
+  const int cw = cp.cin + cp.extra_plane;
+  float acc = 0.0f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * cp.stride + ky - 1;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * cp.stride + kx - 1;
+      if (ix < 0 || ix >= W) continue;
+      const T* xp = x + (((long long)b * H + iy) * W + ix) * cin_stride;
+      const float* wp = cp.w + (size_t)(ky * 3 + kx) * cw * cp.cout + co;
+      for (int c = 0; c < cp.cin; ++c) acc = fmaf(ldf(xp + c), wp[(size_t)c * cp.cout], acc);
+      if (cp.extra_plane) acc = fmaf(plane[b], wp[(size_t)cp.cin * cp.cout], acc);
+    }
+  }
+  float v = fmaf(acc, cp.scale[co], cp.shift[co]);
+  if (residual) v += ldf(residual + i);
+  if (relu) v = fmaxf(v, 0.0f);
+  stf(y + i, v);
+}
+
+// AvgPool2d(kernel 3, stride 2, padding 1), count_include_pad (models.py:257-262)
+template <class T>
+__global__ void k_avgpool(const T* __restrict__ x, int B, int H, int W, int C, T* __restrict__ y) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Ho * Wo * C) return;
+  const int c = (int)(i % C);
+  const int ox = (int)((i / C) % Wo);
+  const int oy = (int)((i / ((long long)C * Wo)) % Ho);
+  const int b = (int)(i / ((long long)C * Wo * Ho));
+  float s = 0.0f;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int iy = oy * 2 + ky - 1, ix = ox * 2 + kx - 1;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) s += ldf(x + (((long long)b * H + iy) * W + ix) * C + c);
+    }
+  stf(y + i, s / 9.0f);
+}
+
+// per-(image, channel) min-max scaling over H*W with the +1e-5 guard (models.py:525-549, 571-595)
+template <class Tin, class Tout>
+__global__ void k_minmax(const Tin* __restrict__ x, int B, int HW, int C, Tout* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  const Tin* p = x + (long long)b * HW * C + c;
+  float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+  for (int k = 0; k < HW; ++k) { const float v = ldf(p + (long long)k * C); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+  float scale = __fsub_rn(hi, lo);
+  if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+  Tout* q = y + (long long)b * HW * C + c;
+  for (int k = 0; k < HW; ++k) stf(q + (long long)k * C, __fdiv_rn(__fsub_rn(ldf(p + (long long)k * C), lo), scale));
+}
+
+// Head: conv1x1(+bias) -> flatten (channel-major, like .view on NCHW) -> mlp -> logits -> decode.
+// One block per image.  mode 0: support_to_scalar -> scalar_out; mode 1: softmax over legal -> priors_out.
+template <class T>
+__global__ void k_head(const T* __restrict__ x, int B, HeadParams hp, int S, int mode, const uint8_t* __restrict__ legal,
+                       float* __restrict__ logits_out, float* __restrict__ scalar_out, float* __restrict__ priors_out) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+  float* flat = sm;                                   // [r*hw]
+  float* bufA = flat + hp.r * hp.hw;                  // mlp ping-pong, width <= 128
+  float* bufB = bufA + 128;
+  const T* xb = x + (long long)b * hp.hw * hp.cin;
+  for (int i = tid; i < hp.r * hp.hw; i += NT) {
+    const int r = i / hp.hw, p = i % hp.hw;
+    float acc = hp.b1x1[r];
+    const float* w = hp.w1x1 + (size_t)r * hp.cin;
+    const T* xp = xb + (long long)p * hp.cin;
+    for (int c = 0; c < hp.cin; ++c) acc = fmaf(ldf(xp + c), w[c], acc);
+    flat[i] = acc;
+  }
+  __syncthreads();
+  const float* in = flat;
+  float* out = bufA;
+  for (int l = 0; l < hp.n_fc; ++l) {
+    for (int o = tid; o < hp.fc_out[l]; o += NT) {
+      float acc = hp.fc_b[l][o];
+      const float* w = hp.fc_w[l] + (size_t)o * hp.fc_in[l];
+      for (int k = 0; k < hp.fc_in[l]; ++k) acc = fmaf(in[k], w[k], acc);
+      out[o] = l < hp.n_fc - 1 ? elu_f32(acc) : acc;
+    }
+    __syncthreads();
+    in = out;
+    out = (out == bufA) ? bufB : bufA;
+  }
+  const int n = hp.out;
+  if (logits_out) for (int o = tid; o < n; o += NT) logits_out[(long long)b * n + o] = in[o];
+  if (tid == 0) {
+    if (mode == 0 && scalar_out) {
+      float* e = out;
+      scalar_out[b] = support_to_scalar_dev([=](int i) { return in[i]; }, [=](int i) -> float& { return e[i]; }, S);
+    } else if (mode == 1 && priors_out) {
+      const uint8_t* lg = legal ? legal + (long long)b * n : nullptr;
+      float m = -CUDART_INF_F;
+      for (int a = 0; a < n; ++a) if (!lg || lg[a]) m = fmaxf(m, in[a]);
+      float sum = 0.0f;
+      for (int a = 0; a < n; ++a) { const float ev = (!lg || lg[a]) ? softmax_exp(in[a], m) : 0.0f; out[a] = ev; sum = __fadd_rn(sum, ev); }
+      for (int a = 0; a < n; ++a) priors_out[(long long)b * n + a] = __fdiv_rn(out[a], sum);
+    }
+  }
+}
+
+__global__ void k_zero_reward(int B, int S, float* __restrict__ logits, float* __restrict__ scalar) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int full = 2 * S + 1;
+  if (logits) for (int i = 0; i < full; ++i) logits[(long long)b * full + i] = (i == S) ? 0.0f : -CUDART_INF_F;
+  if (scalar) {
+    float e[64];
+    scalar[b] = support_to_scalar_dev([=](int i) { return i == S ? 0.0f : -CUDART_INF_F; },
+                                      [&](int i) -> float& { return e[i < 64 ? i : 63]; }, S);
+  }
+}
+
+__global__ void k_action_plane(const int* __restrict__ action, int B, int A, float* __restrict__ plane) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) plane[b] = __fdiv_rn((float)action[b], (float)A);          // action * ones / action_space_size (:553-568)
+}
+
+inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ model build
+static void* dev_alloc(mzb_resnet_model* m, size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, bytes ? bytes : 4);
+  m->allocs.push_back(p);
+  return p;
+}
+
+static bool init_conv(mzb_resnet_model* m, ConvParams& c, int cin, int cout, int stride, int extra, int hw) {
+  c.cin = cin; c.cout = cout; c.stride = stride; c.extra_plane = extra;
+  c.w = (float*)dev_alloc(m, sizeof(float) * 9 * (size_t)(cin + extra) * cout);
+  c.scale = (float*)dev_alloc(m, sizeof(float) * cout);
+  c.shift = (float*)dev_alloc(m, sizeof(float) * cout);
+  c.w_bf16 = (__nv_bfloat16*)dev_alloc(m, sizeof(__nv_bfloat16) * 9 * (size_t)cin * cout);
+  c.plane_table = extra ? (float*)dev_alloc(m, sizeof(float) * (size_t)hw * cout) : nullptr;
+  return c.w && c.scale && c.shift && c.w_bf16 && (!extra || c.plane_table);
+}
+
+static bool init_head(mzb_resnet_model* m, HeadParams& h, int cin, int r, int hw, const int32_t* hidden, int n_hidden, int out) {
+  h.cin = cin; h.r = r; h.hw = hw; h.out = out; h.n_fc = n_hidden + 1;
+  h.w1x1 = (float*)dev_alloc(m, sizeof(float) * (size_t)r * cin);
+  h.b1x1 = (float*)dev_alloc(m, sizeof(float) * r);
+  int cur = r * hw;
+  for (int l = 0; l < h.n_fc; ++l) {
+    const int o = l < n_hidden ? hidden[l] : out;
+    if (o <= 0 || o > 128) return false;
+    h.fc_in[l] = cur; h.fc_out[l] = o;
+    h.fc_w[l] = (float*)dev_alloc(m, sizeof(float) * (size_t)cur * o);
+    h.fc_b[l] = (float*)dev_alloc(m, sizeof(float) * o);
+    if (!h.fc_w[l] || !h.fc_b[l]) return false;
+    cur = o;
+  }
+  return h.w1x1 && h.b1x1;
+}
+
+static int count_tensors(const mzb_resnet_model* m) {
+  const int blk = 2 * 5;                                  // conv + 4 bn tensors, twice
+  int n = 0;
+  if (m->downsample) n += 1 + 2 * blk + 1 + 3 * blk + 3 * blk;
+  n += 5 + m->blocks * blk;                               // representation conv+bn (present even when unused), resblocks
+  n += 5 + m->blocks * blk + 2 + 2 * m->reward.n_fc;      // dynamics
+  n += m->blocks * blk + 2 + 2 + 2 * m->value.n_fc + 2 * m->policy.n_fc;
+  return n;
+}
+
+extern "C" {
+
+int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* c) {
+  MZB_CHECK_ARG(out && c, "NULL argument");
+  *out = nullptr;
+  MZB_CHECK_ARG(c->obs_channels > 0 && c->height > 0 && c->width > 0 && c->n_actions > 0 && c->blocks >= 0 &&
+                c->channels > 0 && c->support_size > 0 && c->support_size <= 31, "resnet config out of range");
+  MZB_CHECK_ARG(c->downsample == 0 || c->downsample == 1, "downsample must be 0 (False) or 1 (\"resnet\")");
+  MZB_CHECK_ARG(c->n_fc_reward >= 0 && c->n_fc_reward <= 3 && c->n_fc_value >= 0 && c->n_fc_value <= 3 &&
+                c->n_fc_policy >= 0 && c->n_fc_policy <= 3, "at most 3 hidden layers per head mlp");
+  mzb_resnet_model* m = new mzb_resnet_model();
+  m->cfg = *c;
+  m->Cobs = c->obs_channels; m->H = c->height; m->W = c->width; m->A = c->n_actions; m->S = c->support_size;
+  m->full = 2 * c->support_size + 1; m->blocks = c->blocks; m->C = c->channels; m->downsample = c->downsample;
+  m->precision = c->precision;
+  m->Hl = c->downsample ? (c->height + 15) / 16 : c->height;
+  m->Wl = c->downsample ? (c->width + 15) / 16 : c->width;
+  const int hw = m->Hl * m->Wl, C = m->C;
+  bool ok = true;
+  if (m->downsample) {
+    ok = ok && init_conv(m, m->ds_conv1, m->Cobs, C / 2, 2, 0, 0) && init_conv(m, m->ds_conv2, C / 2, C, 2, 0, 0);
+    m->ds1.resize(2); m->ds2.resize(3); m->ds3.resize(3);
+    for (auto& b : m->ds1) ok = ok && init_conv(m, b.c1, C / 2, C / 2, 1, 0, 0) && init_conv(m, b.c2, C / 2, C / 2, 1, 0, 0);
+    for (auto& b : m->ds2) ok = ok && init_conv(m, b.c1, C, C, 1, 0, 0) && init_conv(m, b.c2, C, C, 1, 0, 0);
+    for (auto& b : m->ds3) ok = ok && init_conv(m, b.c1, C, C, 1, 0, 0) && init_conv(m, b.c2, C, C, 1, 0, 0);
+  }
+  ok = ok && init_conv(m, m->rep_conv, m->Cobs, C, 1, 0, 0) && init_conv(m, m->dyn_conv, C, C, 1, 1, hw);
+  m->rep_blocks.resize(m->blocks); m->dyn_blocks.resize(m->blocks); m->pred_blocks.resize(m->blocks);
+  for (auto* v : {&m->rep_blocks, &m->dyn_blocks, &m->pred_blocks})
+    for (auto& b : *v) ok = ok && init_conv(m, b.c1, C, C, 1, 0, 0) && init_conv(m, b.c2, C, C, 1, 0, 0);
+  ok = ok && init_head(m, m->reward, C, c->reduced_channels_reward, hw, c->fc_reward, c->n_fc_reward, m->full) &&
+       init_head(m, m->value, C, c->reduced_channels_value, hw, c->fc_value, c->n_fc_value, m->full) &&
+       init_head(m, m->policy, C, c->reduced_channels_policy, hw, c->fc_policy, c->n_fc_policy, m->A);
+  if (!ok) {
+    mzb_resnet_destroy(m);
+    mzb_set_error("resnet create: allocation failed or head mlp wider than 128");
+    return MZB_ECUDA;
+  }
+  m->n_tensors = count_tensors(m);
+  *out = m;
+  return MZB_OK;
+}
+
+int mzb_resnet_destroy(mzb_resnet_model* m) {
+  if (!m) return MZB_OK;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return MZB_OK;
+}
+
+int mzb_resnet_num_tensors(const mzb_resnet_model* m) { return m ? m->n_tensors : 0; }
+
+int mzb_resnet_latent_dims(const mzb_resnet_model* m, int32_t* C, int32_t* H, int32_t* W) {
+  MZB_CHECK_ARG(m, "model is NULL");
+  if (C) *C = m->C;
+  if (H) *H = m->Hl;
+  if (W) *W = m->Wl;
+  return MZB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------ weights
+namespace {
+
+struct Cursor {
+  const float* const* t; const int64_t* numel; int n; int i; bool bad;
+  const float* take(int64_t expect) {
+    if (i >= n || numel[i] != expect || !t[i]) { bad = true; ++i; return nullptr; }
+    return t[i++];
+  }
+};
+
+bool upload(void* dst, const void* src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess; }
+
+// conv weight [cout][cin(+extra)][3][3] -> fp32 [tap][cin+extra][cout], bf16 [cout][tap][cin]; plane table
+bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl) {
+  const int cw = c.cin + c.extra_plane;
+  const float* w = cur.take((int64_t)c.cout * cw * 9);
+  std::vector<float> scale(c.cout, 1.0f), shift(c.cout, 0.0f);
+  if (with_bn) {
+    const float* g = cur.take(c.cout); const float* b = cur.take(c.cout);
+    const float* mu = cur.take(c.cout); const float* var = cur.take(c.cout);
+    if (cur.bad) return false;
+    for (int o = 0; o < c.cout; ++o) {
+      scale[o] = g[o] / sqrtf(var[o] + 1e-5f);
+      shift[o] = b[o] - mu[o] * scale[o];
+    }
+  }
+  if (cur.bad) return false;
+  std::vector<float> wp((size_t)9 * cw * c.cout);
+  std::vector<__nv_bfloat16> wb((size_t)9 * c.cin * c.cout);
+  for (int o = 0; o < c.cout; ++o)
+    for (int ci = 0; ci < cw; ++ci)
+      for (int tap = 0; tap < 9; ++tap) {
+        const float v = w[((size_t)o * cw + ci) * 9 + tap];
+        wp[((size_t)tap * cw + ci) * c.cout + o] = v;
+        if (ci < c.cin) wb[((size_t)o * 9 + tap) * c.cin + ci] = __float2bfloat16(v);
+      }
+  bool ok = upload(c.w, wp.data(), wp.size() * 4) && upload(c.w_bf16, wb.data(), wb.size() * 2) &&
+            upload(c.scale, scale.data(), scale.size() * 4) && upload(c.shift, shift.data(), shift.size() * 4);
+  if (c.extra_plane) {
+    std::vector<float> tab((size_t)Hl * Wl * c.cout, 0.0f);
+    for (int y = 0; y < Hl; ++y)
+      for (int x = 0; x < Wl; ++x)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const int iy = y + ky - 1, ix = x + kx - 1;
+            if (iy < 0 || iy >= Hl || ix < 0 || ix >= Wl) continue;
+            for (int o = 0; o < c.cout; ++o) tab[((size_t)y * Wl + x) * c.cout + o] += w[((size_t)o * cw + c.cin) * 9 + ky * 3 + kx];
+          }
+    ok = ok && upload(c.plane_table, tab.data(), tab.size() * 4);
+  }
+  return ok;
+}
+
+bool load_block(Cursor& cur, Block& b) { return load_conv(cur, b.c1, true, 0, 0) && load_conv(cur, b.c2, true, 0, 0); }
+
+bool load_1x1(Cursor& cur, HeadParams& h) {
+  const float* w = cur.take((int64_t)h.r * h.cin); const float* b = cur.take(h.r);
+  if (cur.bad) return false;
+  return upload(h.w1x1, w, sizeof(float) * h.r * h.cin) && upload(h.b1x1, b, sizeof(float) * h.r);
+}
+bool load_fc(Cursor& cur, HeadParams& h) {
+  for (int l = 0; l < h.n_fc; ++l) {
+    const float* w = cur.take((int64_t)h.fc_in[l] * h.fc_out[l]); const float* b = cur.take(h.fc_out[l]);
+    if (cur.bad) return false;
+    if (!upload(h.fc_w[l], w, sizeof(float) * h.fc_in[l] * h.fc_out[l]) || !upload(h.fc_b[l], b, sizeof(float) * h.fc_out[l])) return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" int mzb_resnet_set_weights(mzb_resnet_model* m, const float* const* h_tensors, const int64_t* h_numel,
+                                      int n_tensors, void* stream) {
+  MZB_CHECK_ARG(m && h_tensors && h_numel, "NULL argument");
+  MZB_CHECK_ARG(n_tensors == m->n_tensors, "expected %d weight tensors (state_dict order, num_batches_tracked skipped), got %d",
+                m->n_tensors, n_tensors);
+  MZB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  Cursor cur{h_tensors, h_numel, n_tensors, 0, false};
+  bool ok = true;
+  // state_dict order = module registration order (models.py:300-429)
+  if (m->downsample) {
+    ok = ok && load_conv(cur, m->ds_conv1, false, 0, 0);
+    for (auto& b : m->ds1) ok = ok && load_block(cur, b);
+    ok = ok && load_conv(cur, m->ds_conv2, false, 0, 0);
+    for (auto& b : m->ds2) ok = ok && load_block(cur, b);
+    for (auto& b : m->ds3) ok = ok && load_block(cur, b);
+  }
+  ok = ok && load_conv(cur, m->rep_conv, true, 0, 0);
+  for (auto& b : m->rep_blocks) ok = ok && load_block(cur, b);
+  ok = ok && load_conv(cur, m->dyn_conv, true, m->Hl, m->Wl);
+  for (auto& b : m->dyn_blocks) ok = ok && load_block(cur, b);
+  ok = ok && load_1x1(cur, m->reward) && load_fc(cur, m->reward);
+  for (auto& b : m->pred_blocks) ok = ok && load_block(cur, b);
+  ok = ok && load_1x1(cur, m->value) && load_1x1(cur, m->policy) && load_fc(cur, m->value) && load_fc(cur, m->policy);
+  if (!ok || cur.bad || cur.i != n_tensors) {
+    mzb_set_error("resnet set_weights: tensor %d has an unexpected size (or upload failed)", cur.i - 1);
+    return MZB_EINVAL;
+  }
+  MZB_CUDA(cudaDeviceSynchronize());
+  return MZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+namespace {
+
+struct Runner {
+  mzb_resnet_model* m; int B; cudaStream_t s; uint8_t* ws; size_t ws_bytes; size_t act_bytes;
+  int rc = MZB_OK;
+  template <class T> T* buf(int i) { return reinterpret_cast<T*>(ws + (size_t)i * act_bytes); }
+  float* plane() { return reinterpret_cast<float*>(ws + 4 * act_bytes); }
+};
+
+template <class T>
+void conv(Runner& r, const T* x, int H, int W, int cin_stride, const ConvParams& cp, const float* plane, const T* res,
+          int relu, T* y) {
+  if (r.rc) return;
+  if (sizeof(T) == 2 && mzb_conv_tc_supported(cp, H, W, cin_stride)) {
+    r.rc = mzb_conv_tc_launch(r.B, H, W, cp, (const __nv_bfloat16*)x, plane, (const __nv_bfloat16*)res, relu,
+                              (__nv_bfloat16*)y, r.s);
+    return;
+  }
+  const int Ho = (H - 1) / cp.stride + 1, Wo = (W - 1) / cp.stride + 1;
+  const long long n = (long long)r.B * Ho * Wo * cp.cout;
+  k_conv3x3_direct<T><<<nblk(n, 128), 128, 0, r.s>>>(x, r.B, H, W, cin_stride, cp, plane, res, relu, y);
+  mzb_count_launch();
+}
+
+// residual tower: x -> blocks; uses the three rotating buffers, returns the buffer index holding the result
+template <class T>
+int tower(Runner& r, std::vector<Block>& blocks, int H, int W, int C, int cur) {
+  for (auto& b : blocks) {
+    const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+    conv<T>(r, r.buf<T>(cur), H, W, C, b.c1, nullptr, nullptr, 1, r.buf<T>(t));
+    conv<T>(r, r.buf<T>(t), H, W, C, b.c2, nullptr, r.buf<T>(cur), 1, r.buf<T>(o));
+    cur = o;
+  }
+  return cur;
+}
+
+template <class T>
+void head(Runner& r, const T* x, const HeadParams& hp, int mode, const uint8_t* legal, float* logits, float* scalar,
+          float* priors) {
+  if (r.rc || (!logits && !scalar && !priors)) return;
+  const size_t smem = sizeof(float) * ((size_t)hp.r * hp.hw + 256);
+  k_head<T><<<r.B, 128, smem, r.s>>>(x, r.B, hp, r.m->S, mode, legal, logits, scalar, priors);
+  mzb_count_launch();
+}
+
+struct Outputs {
+  void* state; int layout; long long row_stride, off;
+  float* value_logits; float* reward_logits; float* policy_logits; float* value; float* reward; float* priors;
+};
+
+template <class T>
+void prediction_and_state(Runner& r, int cur, const Outputs& o, const uint8_t* legal) {
+  mzb_resnet_model* m = r.m;
+  const int HW = m->Hl * m->Wl, C = m->C;
+  if (o.state) {
+    const long long n = (long long)r.B * HW * C;
+    k_store_state<T><<<nblk(n, 256), 256, 0, r.s>>>(r.buf<T>(cur), r.B, C, HW, o.layout, o.state, o.row_stride, o.off);
+    mzb_count_launch();
+  }
+  if (o.value_logits || o.policy_logits || o.value || o.priors) {
+    const int p = tower<T>(r, m->pred_blocks, m->Hl, m->Wl, C, cur);
+    head<T>(r, r.buf<T>(p), m->value, 0, nullptr, o.value_logits, o.value, nullptr);
+    head<T>(r, r.buf<T>(p), m->policy, 1, legal, o.policy_logits, nullptr, o.priors);
+  }
+}
+
+template <class T>
+int run_initial(Runner& r, const float* obs, const uint8_t* legal, const Outputs& o) {
+  mzb_resnet_model* m = r.m;
+  const int B = r.B, C = m->C;
+  int H = m->H, W = m->W;
+  // observation planes NCHW fp32 -> NHWC
+  {
+    const long long n = (long long)B * H * W * m->Cobs;
+    k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>(obs, (long long)m->Cobs * H * W, nullptr, 0, B, m->Cobs, H * W, m->Cobs, r.buf<T>(0));
+    mzb_count_launch();
+  }
+  int cur = 0;
+  if (m->downsample) {                                               // DownSample.forward (models.py:264-275)
+    conv<T>(r, r.buf<T>(0), H, W, m->Cobs, m->ds_conv1, nullptr, nullptr, 0, r.buf<T>(1));
+    H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1; cur = 1;
+    cur = tower<T>(r, m->ds1, H, W, C / 2, cur);
+    { const int nx = (cur + 1) % 3; conv<T>(r, r.buf<T>(cur), H, W, C / 2, m->ds_conv2, nullptr, nullptr, 0, r.buf<T>(nx)); cur = nx; }
+    H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1;
+    cur = tower<T>(r, m->ds2, H, W, C, cur);
+    for (int stage = 0; stage < 2; ++stage) {
+      const int nx = (cur + 1) % 3;
+      const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+      k_avgpool<T><<<nblk((long long)B * Ho * Wo * C, 256), 256, 0, r.s>>>(r.buf<T>(cur), B, H, W, C, r.buf<T>(nx));
+      mzb_count_launch();
+      cur = nx; H = Ho; W = Wo;
+      if (stage == 0) cur = tower<T>(r, m->ds3, H, W, C, cur);
+    }
+  } else {
+    conv<T>(r, r.buf<T>(0), H, W, m->Cobs, m->rep_conv, nullptr, nullptr, 1, r.buf<T>(1));
+    cur = 1;
+  }
+  if (H != m->Hl || W != m->Wl) { mzb_set_error("latent size mismatch %dx%d vs %dx%d", H, W, m->Hl, m->Wl); return MZB_EINVAL; }
+  cur = tower<T>(r, m->rep_blocks, H, W, C, cur);
+  const int nx = (cur + 1) % 3;
+  k_minmax<T, T><<<nblk(B * C, 128), 128, 0, r.s>>>(r.buf<T>(cur), B, H * W, C, r.buf<T>(nx));
+  mzb_count_launch();
+  if (o.reward_logits || o.reward) { k_zero_reward<<<nblk(B, 128), 128, 0, r.s>>>(B, m->S, o.reward_logits, o.reward); mzb_count_launch(); }
+  prediction_and_state<T>(r, nx, o, legal);
+  return r.rc;
+}
+
+template <class T>
+int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_row_stride, const int* in_slot,
+                  long long slot_stride, const int* action, const Outputs& o) {
+  mzb_resnet_model* m = r.m;
+  const int B = r.B, C = m->C, H = m->Hl, W = m->Wl, HW = H * W;
+  const long long n = (long long)B * HW * C;
+  if (in_layout == 0) {
+    k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const float*)state_in, in_row_stride, in_slot, slot_stride, B, C, HW, C, r.buf<T>(0));
+  } else if ((in_layout == 1 && sizeof(T) == 4) || (in_layout == 2 && sizeof(T) == 2)) {
+    k_gather_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const T*)state_in, in_row_stride, in_slot, slot_stride, B, HW * C, r.buf<T>(0));
+  } else {
+    mzb_set_error("state layout %d does not match the model precision", in_layout);
+    return MZB_EINVAL;
+  }
+  mzb_count_launch();
+  k_action_plane<<<nblk(B, 128), 128, 0, r.s>>>(action, B, m->A, r.plane());
+  mzb_count_launch();
+  conv<T>(r, r.buf<T>(0), H, W, C, m->dyn_conv, r.plane(), nullptr, 1, r.buf<T>(1));          // DynamicsNetwork.forward :377-387
+  int cur = tower<T>(r, m->dyn_blocks, H, W, C, 1);
+  head<T>(r, r.buf<T>(cur), m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr);       // reward on the un-normalised state
+  const int nx = (cur + 1) % 3;
+  k_minmax<T, T><<<nblk(B * C, 128), 128, 0, r.s>>>(r.buf<T>(cur), B, HW, C, r.buf<T>(nx));
+  mzb_count_launch();
+  prediction_and_state<T>(r, nx, o, nullptr);
+  return r.rc;
+}
+
+size_t act_bytes_for(const mzb_resnet_model* m, long long B) {
+  long long per = (long long)m->H * m->W * m->Cobs;
+  if (m->downsample) {
+    const long long h1 = (m->H - 1) / 2 + 1, w1 = (m->W - 1) / 2 + 1;
+    per = std::max(per, h1 * w1 * (long long)(m->C / 2));
+    const long long h2 = (h1 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1;
+    per = std::max(per, h2 * w2 * (long long)m->C);
+  }
+  per = std::max(per, (long long)m->Hl * m->Wl * m->C);
+  return mzb_align_up((size_t)(per * B * 4 + 1024), 1024);        // sized for fp32; bf16 uses half
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mzb_resnet_workspace_bytes(const mzb_resnet_model* m, int64_t max_batch) {
+  if (!m || max_batch <= 0) return 0;
+  return 4 * act_bytes_for(m, max_batch) + mzb_align_up((size_t)max_batch * 4, 256) + 1024;
+}
+
+int mzb_resnet_initial(mzb_resnet_model* m, int64_t B, const float* d_obs, const uint8_t* d_legal, void* d_workspace,
+                       size_t workspace_bytes, void* d_state_out, int state_layout, int64_t out_row_stride,
+                       int64_t out_offset, float* d_value_logits, float* d_reward_logits, float* d_policy_logits,
+                       float* d_value, float* d_reward, float* d_priors, void* stream) {
+  MZB_CHECK_ARG(m && d_obs && d_workspace, "NULL argument");
+  MZB_CHECK_ARG(B > 0 && B < (1ll << 24), "batch out of range");
+  MZB_CHECK_ARG(workspace_bytes >= mzb_resnet_workspace_bytes(m, B), "workspace too small");
+  MZB_CHECK_ARG(state_layout >= 0 && state_layout <= 2, "bad state layout");
+  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes_for(m, B)};
+  Outputs o{d_state_out, state_layout, out_row_stride, out_offset, d_value_logits, d_reward_logits, d_policy_logits,
+            d_value, d_reward, d_priors};
+  int rc = m->precision == 1 ? run_initial<__nv_bfloat16>(r, d_obs, d_legal, o) : run_initial<float>(r, d_obs, d_legal, o);
+  if (rc) return rc;
+  MZB_CUDA(cudaGetLastError());
+  return MZB_OK;
+}
+
+int mzb_resnet_recurrent(mzb_resnet_model* m, int64_t B, const void* d_state_in, int in_layout, int64_t in_row_stride,
+                         const int32_t* d_in_slot, int64_t slot_stride, const int32_t* d_action, void* d_workspace,
+                         size_t workspace_bytes, void* d_state_out, int out_layout, int64_t out_row_stride,
+                         int64_t out_offset, float* d_value_logits, float* d_reward_logits, float* d_policy_logits,
+                         float* d_value, float* d_reward, float* d_priors, void* stream) {
+  MZB_CHECK_ARG(m && d_state_in && d_action && d_workspace, "NULL argument");
+  MZB_CHECK_ARG(B > 0 && B < (1ll << 24), "batch out of range");
+  MZB_CHECK_ARG(workspace_bytes >= mzb_resnet_workspace_bytes(m, B), "workspace too small");
+  MZB_CHECK_ARG(in_layout >= 0 && in_layout <= 2 && out_layout >= 0 && out_layout <= 2, "bad state layout");
+  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes_for(m, B)};
+  Outputs o{d_state_out, out_layout, out_row_stride, out_offset, d_value_logits, d_reward_logits, d_policy_logits,
+            d_value, d_reward, d_priors};
+  int rc = m->precision == 1
+               ? run_recurrent<__nv_bfloat16>(r, d_state_in, in_layout, in_row_stride, d_in_slot, slot_stride, d_action, o)
+               : run_recurrent<float>(r, d_state_in, in_layout, in_row_stride, d_in_slot, slot_stride, d_action, o);
+  if (rc) return rc;
+  MZB_CUDA(cudaGetLastError());
+  return MZB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// Residual MuZero network (models.py:206-619) on device: layer program + parameters.
+//
+// Activations are NHWC ([B][H][W][C], channel fastest): a 3x3 convolution is an implicit GEMM with
+// M = B*H*W output positions, N = C_out, K = 9*C_in (tap-major).  Two arithmetic paths share the layer
+// program, the head / min-max / pooling kernels and the weights:
+//   * fp32  (precision 0): CUDA-core direct convolution, float32 activations - the exact path parity is
+//           pinned on (1e-4 vs torch's conv).
+//   * bf16  (precision 1): tcgen05 implicit GEMM, bf16 operands staged by TMA, fp32 accumulation in TMEM,
+//           folded batch-norm + residual + ReLU in the epilogue (mzb_conv_tc.cu).  Stated bf16 bound.
+// Eval-mode batch-norm (self_play.py:29) is folded to per-channel scale/shift at set_weights time.
+#pragma once
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "mzb_common.cuh"
+
+struct ConvParams {
+  int cin, cout, stride;          // 3x3, padding 1, no bias (models.py:206-209)
+  int extra_plane;                // 1: one more input channel, constant per image (the action plane :553-568)
+  float* w;                       // fp32 [9][cin + extra_plane][cout]
+  __nv_bfloat16* w_bf16;          // bf16 [cout][9][cin]   (K-major B operand of the implicit GEMM), or NULL
+  float* plane_table;             // fp32 [H*W][cout]: sum over in-bounds taps of the extra-plane weights
+  float* scale;                   // folded batch-norm: y = conv * scale + shift   (identity when no bn)
+  float* shift;
+};
+
+struct HeadParams {
+  int cin, r, hw;                 // conv1x1 cin -> r channels (with bias), flattened r*hw (channel-major like .view)
+  int n_fc;                       // Linear layers of the mlp (hidden ... out)
+  int fc_in[4], fc_out[4];
+  float* w1x1;                    // [r][cin]
+  float* b1x1;                    // [r]
+  float* fc_w[4];                 // [out][in]
+  float* fc_b[4];
+  int out;                        // logits width
+};
+
+struct Block { ConvParams c1, c2; };

@@ -1,0 +1,22 @@
+// Residual model handle + the tensor-core convolution hooks shared by mzb_resnet.cu / mzb_conv_tc.cu.
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "mzb_resnet.cuh"
+
+struct mzb_resnet_model {
+  mzb_resnet_config cfg;
+  int Cobs, H, W, A, S, full, blocks, C, downsample, precision;
+  int Hl, Wl;                      // latent (hidden-state) height / width
+  int n_tensors;
+  ConvParams rep_conv, dyn_conv, ds_conv1, ds_conv2;
+  std::vector<Block> rep_blocks, dyn_blocks, pred_blocks, ds1, ds2, ds3;
+  HeadParams reward, value, policy;
+  std::vector<void*> allocs;
+};
+
+// tcgen05 implicit-GEMM 3x3 convolution on NHWC bf16 (mzb_conv_tc.cu)
+bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride);
+int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
+                       const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream);

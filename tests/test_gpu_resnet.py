@@ -1,0 +1,50 @@
+"""Residual network kernels (through the C ABI) vs the reference model outputs."""
+import numpy as np
+import pytest
+import torch
+
+import _tables as T
+from _configs import product_config
+from _weights import seeded_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(tag, precision="fp32"):
+    from muzero_hypermodel_b200 import models
+    cfg = product_config(tag)
+    net = models.MuZeroNetwork(cfg)
+    z = T.load("net")
+    if tag == "gomoku":
+        keys = str(z["gomoku/keys"]).split("\n")
+        shapes = [[int(d) for d in s.split("x")] if s else [] for s in z["gomoku/shapes"]]
+        sd = {k: torch.tensor(v) for k, v in seeded_state_dict(keys, shapes).items()}
+    else:
+        pre = tag + "/w/"
+        sd = {k[len(pre):]: torch.tensor(z[k]) for k in z.files if k.startswith(pre)}
+    assert list(net.state_dict().keys()) == list(sd.keys())            # reference checkpoint keys, same order
+    for k, v in net.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    net.set_weights(sd)
+    net.set_precision(precision)
+    return net.to(DEV).eval(), cfg, z
+
+
+@pytest.mark.parametrize("tag", ["tictactoe", "connect4", "gomoku", "breakout"])
+def test_resnet_fp32_matches_reference(tag):
+    from muzero_hypermodel_b200 import models
+    net, cfg, z = _model(tag)
+    obs = torch.tensor(z[tag + "/obs"], device=DEV)
+    v0, r0, p0, s0 = net.initial_inference(obs)
+    v1, r1, p1, s1 = net.recurrent_inference(s0, torch.tensor(z[tag + "/act"], device=DEV))
+    v2, r2, p2, s2 = net.recurrent_inference(s1, torch.tensor(z[tag + "/act2"], device=DEV))
+    tol = dict(rtol=2e-4, atol=2e-5)
+    for got, name in ((v0, "v0"), (p0, "p0"), (s0, "s0"), (v1, "v1"), (r1, "r1"), (p1, "p1"), (s1, "s1"),
+                      (v2, "v2"), (r2, "r2"), (p2, "p2"), (s2, "s2")):
+        np.testing.assert_allclose(got.cpu().numpy(), z[f"{tag}/{name}"], err_msg=name, **tol)
+    np.testing.assert_array_equal(r0.cpu().numpy(), z[tag + "/r0"])
+    assert s0.shape == tuple(z[tag + "/s0"].shape)
+    o = net.recurrent_inference_fused(s0, torch.tensor(z[tag + "/act"], device=DEV))
+    np.testing.assert_allclose(o["value"].cpu().numpy(), z[tag + "/sv1"][:, 0], rtol=3e-3, atol=1e-3)
+    np.testing.assert_allclose(o["priors"].cpu().numpy(), torch.softmax(torch.tensor(z[tag + "/p1"]), 1).numpy(), rtol=1e-3, atol=1e-5)
