@@ -295,6 +295,9 @@ int mzb_resnet_latent_dims(const mzb_resnet_model* m, int32_t* C, int32_t* H, in
 int mzb_resnet_set_weights(mzb_resnet_model* m, const float* const* h_tensors, const int64_t* h_numel, int n_tensors,
                            void* stream);
 size_t mzb_resnet_workspace_bytes(const mzb_resnet_model* m, int64_t max_batch);
+/* Must be called once on a freshly allocated workspace (zeroes it: the padded activation layout of the
+ * tensor-core path relies on zero pad rows that no kernel ever writes). */
+int mzb_resnet_workspace_init(const mzb_resnet_model* m, void* d_workspace, size_t workspace_bytes, void* stream);
 /* State layouts: 0 = NCHW fp32 (the reference's tensors), 1 = NHWC fp32, 2 = NHWC bf16 (internal pools;
  * must match the model precision).  Row r of a state lives at base + r*row_stride (+ slot*slot_stride on
  * input, + offset on output), in elements of the layout's type.

@@ -17,127 +17,137 @@ template <class T> __device__ __forceinline__ void stf(T* p, float v);
 template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// NCHW fp32 rows (optionally slot addressed) -> NHWC T, channels padded with zeros up to cpad
+// NCHW fp32 rows (optionally slot addressed) -> NHWC T in geometry g
 template <class T>
 __global__ void k_nchw_to_nhwc(const float* __restrict__ in, long long in_row_stride, const int* __restrict__ in_slot,
-                               long long slot_stride, int B, int C, int HW, int cpad, T* __restrict__ out) {
+                               long long slot_stride, int B, Geo g, T* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * HW * cpad) return;
-  const int c = (int)(i % cpad);
-  const int p = (int)((i / cpad) % HW);
-  const int b = (int)(i / ((long long)cpad * HW));
+  const int HW = g.H * g.W;
+  if (i >= (long long)B * HW * g.C) return;
+  const int c = (int)(i % g.C);
+  const int p = (int)((i / g.C) % HW);
+  const int b = (int)(i / ((long long)g.C * HW));
   const float* src = in + b * in_row_stride + (in_slot ? (long long)in_slot[b] * slot_stride : 0);
-  stf(out + i, c < C ? src[(long long)c * HW + p] : 0.0f);
+  stf(out + geo_row(g, b, p / g.W, p % g.W) * g.C + c, src[(long long)c * HW + p]);
 }
 
-// NHWC T rows (slot addressed) -> dense NHWC T
+// dense NHWC T rows (slot addressed pool) -> NHWC T in geometry g
 template <class T>
 __global__ void k_gather_nhwc(const T* __restrict__ in, long long in_row_stride, const int* __restrict__ in_slot,
-                              long long slot_stride, int B, int n, T* __restrict__ out) {
+                              long long slot_stride, int B, Geo g, T* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * n) return;
-  const int b = (int)(i / n), k = (int)(i % n);
-  out[i] = in[b * in_row_stride + (in_slot ? (long long)in_slot[b] * slot_stride : 0) + k];
+  const int HW = g.H * g.W;
+  if (i >= (long long)B * HW * g.C) return;
+  const int c = (int)(i % g.C);
+  const int p = (int)((i / g.C) % HW);
+  const int b = (int)(i / ((long long)g.C * HW));
+  out[geo_row(g, b, p / g.W, p % g.W) * g.C + c] =
+      in[b * in_row_stride + (in_slot ? (long long)in_slot[b] * slot_stride : 0) + (long long)p * g.C + c];
 }
 
-// dense NHWC T -> state rows in the requested layout: 0 NCHW fp32, 1 NHWC fp32, 2 NHWC bf16
+// NHWC T in geometry g -> state rows in the requested layout: 0 NCHW fp32, 1 dense NHWC fp32, 2 dense NHWC bf16
 template <class T>
-__global__ void k_store_state(const T* __restrict__ in, int B, int C, int HW, int layout, void* __restrict__ out,
+__global__ void k_store_state(const T* __restrict__ in, int B, Geo g, int layout, void* __restrict__ out,
                               long long out_row_stride, long long out_off) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = g.H * g.W, C = g.C;
   if (i >= (long long)B * HW * C) return;
   const int c = (int)(i % C);
   const int p = (int)((i / C) % HW);
   const int b = (int)(i / ((long long)C * HW));
-  const float v = ldf(in + i);
+  const float v = ldf(in + geo_row(g, b, p / g.W, p % g.W) * C + c);
   if (layout == 0) ((float*)out)[b * out_row_stride + out_off + (long long)c * HW + p] = v;
   else if (layout == 1) ((float*)out)[b * out_row_stride + out_off + (long long)p * C + c] = v;
   else ((__nv_bfloat16*)out)[b * out_row_stride + out_off + (long long)p * C + c] = __float2bfloat16_rn(v);
 }
 
-// 3x3 convolution, padding 1, stride s, + folded batch-norm + residual + ReLU.  Direct fp32 form:
+// 3x3 convolution, padding 1, stride s, + folded batch-norm + residual + ReLU.  Direct fp32-accumulate form:
 // one thread per (position, output channel); x reads broadcast across the warp, weight reads coalesced.
 template <class T>
-__global__ void k_conv3x3_direct(const T* __restrict__ x, int B, int H, int W, int cin_stride, ConvParams cp,
-                                 const float* __restrict__ plane, const T* __restrict__ residual, int relu,
-                                 T* __restrict__ y) {
-  const int Ho = (H + 2 - 3) / cp.stride + 1, Wo = (W + 2 - 3) / cp.stride + 1;
+__global__ void k_conv3x3_direct(const T* __restrict__ x, int B, Geo gi, ConvParams cp, const float* __restrict__ plane,
+                                 const T* __restrict__ residual, int relu, Geo go, T* __restrict__ y) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * Ho * Wo * cp.cout) return;
+  if (i >= (long long)B * go.H * go.W * cp.cout) return;
   const int co = (int)(i % cp.cout);
-  const int ox = (int)((i / cp.cout) % Wo);
-  const int oy = (int)((i / ((long long)cp.cout * Wo)) % Ho);
-  const int b = (int)(i / ((long long)cp.cout * Wo * Ho));
+  const int ox = (int)((i / cp.cout) % go.W);
+  const int oy = (int)((i / ((long long)cp.cout * go.W)) % go.H);
+  const int b = (int)(i / ((long long)cp.cout * go.W * go.H));
   const int cw = cp.cin + cp.extra_plane;
   float acc = 0.0f;
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy * cp.stride + ky - 1;
-    if (iy < 0 || iy >= H) continue;
+    if (iy < 0 || iy >= gi.H) continue;
     for (int kx = 0; kx < 3; ++kx) {
       const int ix = ox * cp.stride + kx - 1;
-      if (ix < 0 || ix >= W) continue;
-      const T* xp = x + (((long long)b * H + iy) * W + ix) * cin_stride;
+      if (ix < 0 || ix >= gi.W) continue;
+      const T* xp = x + geo_row(gi, b, iy, ix) * gi.C;
       const float* wp = cp.w + (size_t)(ky * 3 + kx) * cw * cp.cout + co;
       for (int c = 0; c < cp.cin; ++c) acc = fmaf(ldf(xp + c), wp[(size_t)c * cp.cout], acc);
       if (cp.extra_plane) acc = fmaf(plane[b], wp[(size_t)cp.cin * cp.cout], acc);
     }
   }
   float v = fmaf(acc, cp.scale[co], cp.shift[co]);
-  if (residual) v += ldf(residual + i);
+  const long long o = geo_row(go, b, oy, ox) * go.C + co;
+  if (residual) v += ldf(residual + o);
   if (relu) v = fmaxf(v, 0.0f);
-  stf(y + i, v);
+  stf(y + o, v);
 }
 
 // AvgPool2d(kernel 3, stride 2, padding 1), count_include_pad (models.py:257-262)
 template <class T>
-__global__ void k_avgpool(const T* __restrict__ x, int B, int H, int W, int C, T* __restrict__ y) {
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+__global__ void k_avgpool(const T* __restrict__ x, int B, Geo gi, Geo go, T* __restrict__ y) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * Ho * Wo * C) return;
+  const int C = go.C;
+  if (i >= (long long)B * go.H * go.W * C) return;
   const int c = (int)(i % C);
-  const int ox = (int)((i / C) % Wo);
-  const int oy = (int)((i / ((long long)C * Wo)) % Ho);
-  const int b = (int)(i / ((long long)C * Wo * Ho));
+  const int ox = (int)((i / C) % go.W);
+  const int oy = (int)((i / ((long long)C * go.W)) % go.H);
+  const int b = (int)(i / ((long long)C * go.W * go.H));
   float s = 0.0f;
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) {
       const int iy = oy * 2 + ky - 1, ix = ox * 2 + kx - 1;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) s += ldf(x + (((long long)b * H + iy) * W + ix) * C + c);
+      if (iy >= 0 && iy < gi.H && ix >= 0 && ix < gi.W) s += ldf(x + geo_row(gi, b, iy, ix) * C + c);
     }
-  stf(y + i, s / 9.0f);
+  stf(y + geo_row(go, b, oy, ox) * C + c, s / 9.0f);
 }
 
 // per-(image, channel) min-max scaling over H*W with the +1e-5 guard (models.py:525-549, 571-595)
-template <class Tin, class Tout>
-__global__ void k_minmax(const Tin* __restrict__ x, int B, int HW, int C, Tout* __restrict__ y) {
+template <class T>
+__global__ void k_minmax(const T* __restrict__ x, int B, Geo g, T* __restrict__ y) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = g.C, HW = g.H * g.W;
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
-  const Tin* p = x + (long long)b * HW * C + c;
   float lo = CUDART_INF_F, hi = -CUDART_INF_F;
-  for (int k = 0; k < HW; ++k) { const float v = ldf(p + (long long)k * C); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+  for (int k = 0; k < HW; ++k) {
+    const float v = ldf(x + geo_row(g, b, k / g.W, k % g.W) * C + c);
+    lo = fminf(lo, v); hi = fmaxf(hi, v);
+  }
   float scale = __fsub_rn(hi, lo);
   if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
-  Tout* q = y + (long long)b * HW * C + c;
-  for (int k = 0; k < HW; ++k) stf(q + (long long)k * C, __fdiv_rn(__fsub_rn(ldf(p + (long long)k * C), lo), scale));
+  for (int k = 0; k < HW; ++k) {
+    const long long o = geo_row(g, b, k / g.W, k % g.W) * C + c;
+    stf(y + o, __fdiv_rn(__fsub_rn(ldf(x + o), lo), scale));
+  }
 }
 
 // Head: conv1x1(+bias) -> flatten (channel-major, like .view on NCHW) -> mlp -> logits -> decode.
 // One block per image.  mode 0: support_to_scalar -> scalar_out; mode 1: softmax over legal -> priors_out.
 template <class T>
-__global__ void k_head(const T* __restrict__ x, int B, HeadParams hp, int S, int mode, const uint8_t* __restrict__ legal,
-                       float* __restrict__ logits_out, float* __restrict__ scalar_out, float* __restrict__ priors_out) {
+__global__ void k_head(const T* __restrict__ x, int B, Geo g, HeadParams hp, int S, int mode,
+                       const uint8_t* __restrict__ legal, float* __restrict__ logits_out, float* __restrict__ scalar_out,
+                       float* __restrict__ priors_out) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
   float* flat = sm;                                   // [r*hw]
   float* bufA = flat + hp.r * hp.hw;                  // mlp ping-pong, width <= 128
   float* bufB = bufA + 128;
-  const T* xb = x + (long long)b * hp.hw * hp.cin;
   for (int i = tid; i < hp.r * hp.hw; i += NT) {
     const int r = i / hp.hw, p = i % hp.hw;
     float acc = hp.b1x1[r];
     const float* w = hp.w1x1 + (size_t)r * hp.cin;
-    const T* xp = xb + (long long)p * hp.cin;
+    const T* xp = x + geo_row(g, b, p / g.W, p % g.W) * hp.cin;
     for (int c = 0; c < hp.cin; ++c) acc = fmaf(ldf(xp + c), w[c], acc);
     flat[i] = acc;
   }
@@ -411,42 +421,40 @@ struct Runner {
   mzb_resnet_model* m; int B; cudaStream_t s; uint8_t* ws; size_t ws_bytes; size_t act_bytes;
   int rc = MZB_OK;
   template <class T> T* buf(int i) { return reinterpret_cast<T*>(ws + (size_t)i * act_bytes); }
-  float* plane() { return reinterpret_cast<float*>(ws + 4 * act_bytes); }
+  float* plane() { return reinterpret_cast<float*>(ws + 3 * act_bytes); }
 };
 
 template <class T>
-void conv(Runner& r, const T* x, int H, int W, int cin_stride, const ConvParams& cp, const float* plane, const T* res,
-          int relu, T* y) {
+void conv(Runner& r, const T* x, Geo gi, const ConvParams& cp, const float* plane, const T* res, int relu, Geo go, T* y) {
   if (r.rc) return;
-  if (sizeof(T) == 2 && mzb_conv_tc_supported(cp, H, W, cin_stride)) {
-    r.rc = mzb_conv_tc_launch(r.B, H, W, cp, (const __nv_bfloat16*)x, plane, (const __nv_bfloat16*)res, relu,
+  if (sizeof(T) == 2 && gi.pad && go.pad && mzb_conv_tc_supported(cp, gi.H, gi.W, gi.C)) {
+    r.rc = mzb_conv_tc_launch(r.B, gi.H, gi.W, cp, (const __nv_bfloat16*)x, plane, (const __nv_bfloat16*)res, relu,
                               (__nv_bfloat16*)y, r.s);
     return;
   }
-  const int Ho = (H - 1) / cp.stride + 1, Wo = (W - 1) / cp.stride + 1;
-  const long long n = (long long)r.B * Ho * Wo * cp.cout;
-  k_conv3x3_direct<T><<<nblk(n, 128), 128, 0, r.s>>>(x, r.B, H, W, cin_stride, cp, plane, res, relu, y);
+  const long long n = (long long)r.B * go.H * go.W * cp.cout;
+  k_conv3x3_direct<T><<<nblk(n, 128), 128, 0, r.s>>>(x, r.B, gi, cp, plane, res, relu, go, y);
   mzb_count_launch();
 }
 
 // residual tower: x -> blocks; uses the three rotating buffers, returns the buffer index holding the result
 template <class T>
-int tower(Runner& r, std::vector<Block>& blocks, int H, int W, int C, int cur) {
+int tower(Runner& r, std::vector<Block>& blocks, Geo g, int cur) {
   for (auto& b : blocks) {
     const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-    conv<T>(r, r.buf<T>(cur), H, W, C, b.c1, nullptr, nullptr, 1, r.buf<T>(t));
-    conv<T>(r, r.buf<T>(t), H, W, C, b.c2, nullptr, r.buf<T>(cur), 1, r.buf<T>(o));
+    conv<T>(r, r.buf<T>(cur), g, b.c1, nullptr, nullptr, 1, g, r.buf<T>(t));
+    conv<T>(r, r.buf<T>(t), g, b.c2, nullptr, r.buf<T>(cur), 1, g, r.buf<T>(o));
     cur = o;
   }
   return cur;
 }
 
 template <class T>
-void head(Runner& r, const T* x, const HeadParams& hp, int mode, const uint8_t* legal, float* logits, float* scalar,
-          float* priors) {
+void head(Runner& r, const T* x, Geo g, const HeadParams& hp, int mode, const uint8_t* legal, float* logits,
+          float* scalar, float* priors) {
   if (r.rc || (!logits && !scalar && !priors)) return;
   const size_t smem = sizeof(float) * ((size_t)hp.r * hp.hw + 256);
-  k_head<T><<<r.B, 128, smem, r.s>>>(x, r.B, hp, r.m->S, mode, legal, logits, scalar, priors);
+  k_head<T><<<r.B, 128, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors);
   mzb_count_launch();
 }
 
@@ -456,59 +464,83 @@ struct Outputs {
 };
 
 template <class T>
-void prediction_and_state(Runner& r, int cur, const Outputs& o, const uint8_t* legal) {
+void prediction_and_state(Runner& r, int cur, Geo g, const Outputs& o, const uint8_t* legal) {
   mzb_resnet_model* m = r.m;
-  const int HW = m->Hl * m->Wl, C = m->C;
   if (o.state) {
-    const long long n = (long long)r.B * HW * C;
-    k_store_state<T><<<nblk(n, 256), 256, 0, r.s>>>(r.buf<T>(cur), r.B, C, HW, o.layout, o.state, o.row_stride, o.off);
+    const long long n = (long long)r.B * g.H * g.W * g.C;
+    k_store_state<T><<<nblk(n, 256), 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, o.layout, o.state, o.row_stride, o.off);
     mzb_count_launch();
   }
   if (o.value_logits || o.policy_logits || o.value || o.priors) {
-    const int p = tower<T>(r, m->pred_blocks, m->Hl, m->Wl, C, cur);
-    head<T>(r, r.buf<T>(p), m->value, 0, nullptr, o.value_logits, o.value, nullptr);
-    head<T>(r, r.buf<T>(p), m->policy, 1, legal, o.policy_logits, nullptr, o.priors);
+    const int p = tower<T>(r, m->pred_blocks, g, cur);
+    head<T>(r, r.buf<T>(p), g, m->value, 0, nullptr, o.value_logits, o.value, nullptr);
+    head<T>(r, r.buf<T>(p), g, m->policy, 1, legal, o.policy_logits, nullptr, o.priors);
   }
 }
+
+// the latent-resolution geometry: padded on the tensor-core path
+template <class T> Geo latent_geo(const mzb_resnet_model* m) { return Geo{m->Hl, m->Wl, m->C, sizeof(T) == 2 ? 1 : 0}; }
 
 template <class T>
 int run_initial(Runner& r, const float* obs, const uint8_t* legal, const Outputs& o) {
   mzb_resnet_model* m = r.m;
   const int B = r.B, C = m->C;
-  int H = m->H, W = m->W;
-  // observation planes NCHW fp32 -> NHWC
-  {
-    const long long n = (long long)B * H * W * m->Cobs;
-    k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>(obs, (long long)m->Cobs * H * W, nullptr, 0, B, m->Cobs, H * W, m->Cobs, r.buf<T>(0));
-    mzb_count_launch();
-  }
+  const Geo gl = latent_geo<T>(m);
   int cur = 0;
   if (m->downsample) {                                               // DownSample.forward (models.py:264-275)
-    conv<T>(r, r.buf<T>(0), H, W, m->Cobs, m->ds_conv1, nullptr, nullptr, 0, r.buf<T>(1));
-    H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1; cur = 1;
-    cur = tower<T>(r, m->ds1, H, W, C / 2, cur);
-    { const int nx = (cur + 1) % 3; conv<T>(r, r.buf<T>(cur), H, W, C / 2, m->ds_conv2, nullptr, nullptr, 0, r.buf<T>(nx)); cur = nx; }
-    H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1;
-    cur = tower<T>(r, m->ds2, H, W, C, cur);
-    for (int stage = 0; stage < 2; ++stage) {
-      const int nx = (cur + 1) % 3;
-      const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-      k_avgpool<T><<<nblk((long long)B * Ho * Wo * C, 256), 256, 0, r.s>>>(r.buf<T>(cur), B, H, W, C, r.buf<T>(nx));
+    Geo g0{m->H, m->W, m->Cobs, 0};
+    {
+      const long long n = (long long)B * g0.H * g0.W * g0.C;
+      k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>(obs, (long long)m->Cobs * g0.H * g0.W, nullptr, 0, B, g0, r.buf<T>(0));
       mzb_count_launch();
-      cur = nx; H = Ho; W = Wo;
-      if (stage == 0) cur = tower<T>(r, m->ds3, H, W, C, cur);
+    }
+    Geo g1{(g0.H - 1) / 2 + 1, (g0.W - 1) / 2 + 1, C / 2, 0};
+    conv<T>(r, r.buf<T>(0), g0, m->ds_conv1, nullptr, nullptr, 0, g1, r.buf<T>(1));
+    cur = tower<T>(r, m->ds1, g1, 1);
+    Geo g2{(g1.H - 1) / 2 + 1, (g1.W - 1) / 2 + 1, C, 0};
+    { const int nx = (cur + 1) % 3; conv<T>(r, r.buf<T>(cur), g1, m->ds_conv2, nullptr, nullptr, 0, g2, r.buf<T>(nx)); cur = nx; }
+    cur = tower<T>(r, m->ds2, g2, cur);
+    Geo g3{(g2.H - 1) / 2 + 1, (g2.W - 1) / 2 + 1, C, 0};
+    { const int nx = (cur + 1) % 3;
+      k_avgpool<T><<<nblk((long long)B * g3.H * g3.W * C, 256), 256, 0, r.s>>>(r.buf<T>(cur), B, g2, g3, r.buf<T>(nx));
+      mzb_count_launch(); cur = nx; }
+    cur = tower<T>(r, m->ds3, g3, cur);
+    if ((g3.H - 1) / 2 + 1 != m->Hl || (g3.W - 1) / 2 + 1 != m->Wl) { mzb_set_error("latent size mismatch"); return MZB_EINVAL; }
+    // the last pooling writes the latent tensor densely; the padded path then restores the zero pads the stem
+    // overwrote (the buffers were used at other resolutions) and scatters the latent into the padded layout
+    Geo gd{m->Hl, m->Wl, C, 0};
+    { const int nx = (cur + 1) % 3;
+      k_avgpool<T><<<nblk((long long)B * gd.H * gd.W * C, 256), 256, 0, r.s>>>(r.buf<T>(cur), B, g3, gd, r.buf<T>(nx));
+      mzb_count_launch(); cur = nx; }
+    if (gl.pad) {
+      T* dense = r.buf<T>(cur);
+      const int a = (cur + 1) % 3, b2 = (cur + 2) % 3;
+      cudaMemsetAsync(r.buf<T>(a), 0, r.act_bytes, r.s);
+      cudaMemsetAsync(r.buf<T>(b2), 0, r.act_bytes, r.s);
+      const long long n = (long long)B * gd.H * gd.W * C;
+      k_gather_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>(dense, (long long)gd.H * gd.W * C, nullptr, 0, B, gl, r.buf<T>(a));
+      mzb_count_launch();
+      cudaMemsetAsync(dense, 0, r.act_bytes, r.s);
+      cur = a;
     }
   } else {
-    conv<T>(r, r.buf<T>(0), H, W, m->Cobs, m->rep_conv, nullptr, nullptr, 1, r.buf<T>(1));
+    // observation planes NCHW fp32 -> NHWC staged in buffer 0 (Cobs channels); on the padded path the staging area
+    // is zeroed again afterwards because buffer 0 is reused with C channels and must keep zero pad rows
+    Geo g0{m->H, m->W, m->Cobs, gl.pad};
+    const long long n = (long long)B * g0.H * g0.W * g0.C;
+    if (gl.pad) cudaMemsetAsync(r.buf<T>(0), 0, (size_t)geo_rows_total(g0, B) * g0.C * sizeof(T), r.s);
+    k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>(obs, (long long)m->Cobs * g0.H * g0.W, nullptr, 0, B, g0, r.buf<T>(0));
+    mzb_count_launch();
+    conv<T>(r, r.buf<T>(0), g0, m->rep_conv, nullptr, nullptr, 1, gl, r.buf<T>(1));
+    if (gl.pad) cudaMemsetAsync(r.buf<T>(0), 0, (size_t)geo_rows_total(g0, B) * g0.C * sizeof(T), r.s);
     cur = 1;
   }
-  if (H != m->Hl || W != m->Wl) { mzb_set_error("latent size mismatch %dx%d vs %dx%d", H, W, m->Hl, m->Wl); return MZB_EINVAL; }
-  cur = tower<T>(r, m->rep_blocks, H, W, C, cur);
+  cur = tower<T>(r, m->rep_blocks, gl, cur);
   const int nx = (cur + 1) % 3;
-  k_minmax<T, T><<<nblk(B * C, 128), 128, 0, r.s>>>(r.buf<T>(cur), B, H * W, C, r.buf<T>(nx));
+  k_minmax<T><<<nblk(B * C, 128), 128, 0, r.s>>>(r.buf<T>(cur), B, gl, r.buf<T>(nx));
   mzb_count_launch();
   if (o.reward_logits || o.reward) { k_zero_reward<<<nblk(B, 128), 128, 0, r.s>>>(B, m->S, o.reward_logits, o.reward); mzb_count_launch(); }
-  prediction_and_state<T>(r, nx, o, legal);
+  prediction_and_state<T>(r, nx, gl, o, legal);
   return r.rc;
 }
 
@@ -516,12 +548,13 @@ template <class T>
 int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_row_stride, const int* in_slot,
                   long long slot_stride, const int* action, const Outputs& o) {
   mzb_resnet_model* m = r.m;
-  const int B = r.B, C = m->C, H = m->Hl, W = m->Wl, HW = H * W;
-  const long long n = (long long)B * HW * C;
+  const int B = r.B, C = m->C;
+  const Geo gl = latent_geo<T>(m);
+  const long long n = (long long)B * gl.H * gl.W * C;
   if (in_layout == 0) {
-    k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const float*)state_in, in_row_stride, in_slot, slot_stride, B, C, HW, C, r.buf<T>(0));
+    k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const float*)state_in, in_row_stride, in_slot, slot_stride, B, gl, r.buf<T>(0));
   } else if ((in_layout == 1 && sizeof(T) == 4) || (in_layout == 2 && sizeof(T) == 2)) {
-    k_gather_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const T*)state_in, in_row_stride, in_slot, slot_stride, B, HW * C, r.buf<T>(0));
+    k_gather_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const T*)state_in, in_row_stride, in_slot, slot_stride, B, gl, r.buf<T>(0));
   } else {
     mzb_set_error("state layout %d does not match the model precision", in_layout);
     return MZB_EINVAL;
@@ -529,13 +562,13 @@ int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_r
   mzb_count_launch();
   k_action_plane<<<nblk(B, 128), 128, 0, r.s>>>(action, B, m->A, r.plane());
   mzb_count_launch();
-  conv<T>(r, r.buf<T>(0), H, W, C, m->dyn_conv, r.plane(), nullptr, 1, r.buf<T>(1));          // DynamicsNetwork.forward :377-387
-  int cur = tower<T>(r, m->dyn_blocks, H, W, C, 1);
-  head<T>(r, r.buf<T>(cur), m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr);       // reward on the un-normalised state
+  conv<T>(r, r.buf<T>(0), gl, m->dyn_conv, r.plane(), nullptr, 1, gl, r.buf<T>(1));           // DynamicsNetwork.forward :377-387
+  int cur = tower<T>(r, m->dyn_blocks, gl, 1);
+  head<T>(r, r.buf<T>(cur), gl, m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr);   // reward on the un-normalised state
   const int nx = (cur + 1) % 3;
-  k_minmax<T, T><<<nblk(B * C, 128), 128, 0, r.s>>>(r.buf<T>(cur), B, HW, C, r.buf<T>(nx));
+  k_minmax<T><<<nblk(B * C, 128), 128, 0, r.s>>>(r.buf<T>(cur), B, gl, r.buf<T>(nx));
   mzb_count_launch();
-  prediction_and_state<T>(r, nx, o, nullptr);
+  prediction_and_state<T>(r, nx, gl, o, nullptr);
   return r.rc;
 }
 
@@ -546,9 +579,12 @@ size_t act_bytes_for(const mzb_resnet_model* m, long long B) {
     per = std::max(per, h1 * w1 * (long long)(m->C / 2));
     const long long h2 = (h1 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1;
     per = std::max(per, h2 * w2 * (long long)m->C);
+  } else {
+    per = std::max(per, (long long)(m->H + 1) * (m->W + 2) * m->Cobs);
   }
-  per = std::max(per, (long long)m->Hl * m->Wl * m->C);
-  return mzb_align_up((size_t)(per * B * 4 + 1024), 1024);        // sized for fp32; bf16 uses half
+  per = std::max(per, (long long)(m->Hl + 1) * (m->Wl + 2) * m->C);
+  const long long halo = 2ll * (m->Wl + 3) * std::max(m->C, m->Cobs) + 2ll * (m->W + 3) * m->Cobs;
+  return mzb_align_up((size_t)((per * B + halo) * 4 + 4096), 1024);      // sized for fp32; bf16 uses half
 }
 
 }  // namespace
@@ -557,7 +593,14 @@ extern "C" {
 
 size_t mzb_resnet_workspace_bytes(const mzb_resnet_model* m, int64_t max_batch) {
   if (!m || max_batch <= 0) return 0;
-  return 4 * act_bytes_for(m, max_batch) + mzb_align_up((size_t)max_batch * 4, 256) + 1024;
+  return 3 * act_bytes_for(m, max_batch) + mzb_align_up((size_t)max_batch * 4, 256) + 1024;
+}
+
+/* Zero a freshly allocated workspace: the padded activation layout relies on zero pad rows that no kernel writes. */
+int mzb_resnet_workspace_init(const mzb_resnet_model* m, void* d_workspace, size_t workspace_bytes, void* stream) {
+  MZB_CHECK_ARG(m && d_workspace, "NULL argument");
+  MZB_CUDA(cudaMemsetAsync(d_workspace, 0, workspace_bytes, (cudaStream_t)stream));
+  return MZB_OK;
 }
 
 int mzb_resnet_initial(mzb_resnet_model* m, int64_t B, const float* d_obs, const uint8_t* d_legal, void* d_workspace,

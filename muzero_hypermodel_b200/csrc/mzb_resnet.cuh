@@ -15,6 +15,22 @@
 
 #include "mzb_common.cuh"
 
+// Activation geometry.  pad = 0: dense NHWC, row (b,y,x) = (b*H + y)*W + x.
+// pad = 1 (tensor-core path): every image is stored as (H+1) x (W+2) rows - one zero row above it and a
+// zero column on each side - after a leading halo of W+3 zero rows, so the 3x3 neighbour (dy,dx) of ANY
+// row is the row at flat offset dy*(W+2)+dx and out-of-image taps read zeros.  The pad rows are written
+// once (workspace init) and never again.
+struct Geo {
+  int H, W, C, pad;
+};
+__host__ __device__ __forceinline__ long long geo_row(const Geo& g, int b, int y, int x) {
+  return g.pad ? (long long)(g.W + 3) + (long long)b * (g.H + 1) * (g.W + 2) + (long long)(y + 1) * (g.W + 2) + (x + 1)
+               : ((long long)b * g.H + y) * g.W + x;
+}
+__host__ __device__ __forceinline__ long long geo_rows_total(const Geo& g, long long B) {
+  return g.pad ? 2ll * (g.W + 3) + B * (g.H + 1) * (g.W + 2) : B * g.H * g.W;
+}
+
 struct ConvParams {
   int cin, cout, stride;          // 3x3, padding 1, no bias (models.py:206-209)
   int extra_plane;                // 1: one more input channel, constant per image (the action plane :553-568)

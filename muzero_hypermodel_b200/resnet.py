@@ -28,6 +28,7 @@ _lib.bind("mzb_resnet_destroy", C.c_int, [_vp])
 _lib.bind("mzb_resnet_num_tensors", C.c_int, [_vp])
 _lib.bind("mzb_resnet_set_weights", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), C.c_int, _vp])
 _lib.bind("mzb_resnet_workspace_bytes", C.c_size_t, [_vp, _i64])
+_lib.bind("mzb_resnet_workspace_init", C.c_int, [_vp, _vp, C.c_size_t, _vp])
 _lib.bind("mzb_resnet_initial", C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_size_t, _vp, C.c_int, _i64, _i64] + [_vp] * 7)
 _lib.bind("mzb_resnet_recurrent", C.c_int, [_vp, _i64, _vp, C.c_int, _i64, _vp, _i64, _vp, _vp, C.c_size_t, _vp, C.c_int,
                                             _i64, _i64] + [_vp] * 7)
@@ -180,6 +181,7 @@ class MuZeroResidualNetwork(AbstractNetwork):
         need = _lib.lib.mzb_resnet_workspace_bytes(self._h, B)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            check(_lib.lib.mzb_resnet_workspace_init(self._h, ptr(self._ws), need, _lib.current_stream()))
         return self._ws
 
     # ---- reference API
