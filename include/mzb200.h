@@ -286,6 +286,8 @@ typedef struct {
 } mzb_resnet_config;
 
 int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* cfg);
+/* Test hook: 0 makes the bf16 path run the CUDA-core direct convolution instead of the tcgen05 kernel. */
+void mzb_conv_tc_enable(int on);
 int mzb_resnet_destroy(mzb_resnet_model* m);
 int mzb_resnet_num_tensors(const mzb_resnet_model* m);
 int mzb_resnet_latent_dims(const mzb_resnet_model* m, int32_t* C, int32_t* H, int32_t* W);

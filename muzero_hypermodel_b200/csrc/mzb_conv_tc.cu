@@ -1,10 +1,318 @@
-// tcgen05 implicit-GEMM 3x3 convolution (placeholder until the kernel lands: reports "unsupported" so the
-// direct kernel runs).
+// K6: 3x3 convolution as an implicit GEMM on the 5th-generation tensor cores (tcgen05 / UMMA),
+// bf16 operands, fp32 accumulators in TMEM, folded batch-norm + action-plane term + residual + ReLU fused
+// into the epilogue.  Reference: conv3x3 + BatchNorm2d + relu / ResidualBlock (models.py:206-229),
+// DynamicsNetwork's first convolution with the action plane (:363, :551-568).
+//
+// Formulation.  Activations live in the PADDED NHWC layout of mzb_resnet.cuh: flat rows of C channels,
+// (H+1)*(W+2) rows per image with zero pad rows, so the 3x3 neighbour (dy,dx) of EVERY row is the row at
+// flat offset dy*(W+2)+dx.  One CTA owns MT tiles of 128 consecutive rows (M = 128 per UMMA):
+//   * TMA loads the rows [m0 - halo, m0 + MT*128 + halo) ONCE into shared memory (SWIZZLE_128B/64B/32B by
+//     channel-chunk width) - the input is read from L2/HBM once, not once per tap;
+//   * the A operand of tap (dy,dx) is the SAME shared-memory tile addressed through a UMMA descriptor whose
+//     start address is shifted by (halo + dy*(W+2) + dx) rows.  The swizzle XOR is a function of the absolute
+//     shared-memory address bits (measured: every row shift is exact with descriptor base_offset = 0 for
+//     SWIZZLE_128B/64B/32B, tests/debug_conv_tc.py), so the im2col matrix is never materialised;
+//   * the B operand (weights [C_out][9*C_in], K-major) streams through a 4-stage TMA/mbarrier ring, each
+//     k-block feeding all MT accumulators (MT*C_out TMEM columns);
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2-5 = epilogue
+//     (tcgen05.ld 32x32b, scale/shift/plane/residual/ReLU, bf16 pack, 16-byte stores).
+// Rows that are pad positions compute garbage that is simply not stored (pads stay zero for the next layer).
+#include <cuda.h>
+
 #include "mzb_resnet_model.h"
 
-bool mzb_conv_tc_supported(const ConvParams&, int, int, int) { return false; }
-int mzb_conv_tc_launch(int, int, int, const ConvParams&, const __nv_bfloat16*, const float*, const __nv_bfloat16*, int,
-                       __nv_bfloat16*, cudaStream_t) {
-  mzb_set_error("tensor-core convolution not available");
-  return MZB_EUNSUPPORTED;
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+
+struct TcArgs {
+  int B, H, W, Cin, Cout, R_img, mt, n_chunks, relu, ncols;
+  long long rows_valid;                 // B * R_img
+  const float* scale; const float* shift; const float* plane; const float* plane_table;
+  const __nv_bfloat16* residual; __nv_bfloat16* y;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // bounded spin: a protocol bug traps (launch error) instead of hanging the GPU
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO>>4 | version 1 |
+// base_offset 0 | layout type.  The start address may sit at ANY row of a TMA-written swizzled tile.
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
+  constexpr uint64_t layout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);         // SWIZZLE_128B / 64B / 32B
+  constexpr uint64_t sbo = (8 * KC * 2) >> 4;                            // 8 rows of KC bf16
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  constexpr int ROWB = KC * 2;                                           // bytes per shared-memory row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int MT = a.mt, N = a.Cout, halo = a.W + 3;
+  const int a_rows = (MT + 1) * 128;
+  const uint32_t a_chunk_bytes = (uint32_t)a_rows * ROWB;
+  const uint32_t b_stage_bytes = (uint32_t)N * ROWB;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)a.n_chunks * a_chunk_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kStages * b_stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;
+  uint64_t* b_empty = bars + 1 + kStages;
+  uint64_t* acc_full = bars + 1 + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kStages);
+  const long long m0 = (long long)blockIdx.x * MT * 128;                 // first row of this CTA (image-row space)
+  const int NKB = 9 * a.n_chunks;
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: the activation rows once, then the weight k-blocks through the ring
+      mbar_expect_tx(a_full, (uint32_t)a.n_chunks * a_chunk_bytes);
+      for (int j = 0; j < a.n_chunks; ++j)
+        for (int box = 0; box <= MT; ++box)
+          tma_load_2d(smem_u32(sA + (size_t)j * a_chunk_bytes + (size_t)box * 128 * ROWB), &tmA, j * KC,
+                      (int)(m0 + (long long)box * 128), a_full);
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) mbar_wait(b_empty + s, ((kb / kStages) - 1) & 1);
+        mbar_expect_tx(b_full + s, b_stage_bytes);
+        const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
+        tma_load_2d(smem_u32(sB + (size_t)s * b_stage_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer: D[tile t] += A(shifted rows of tap) * B(tap, chunk)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      mbar_wait(a_full, 0);
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(b_full + s, (kb / kStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
+        const int shift = (tap / 3 - 1) * (a.W + 2) + (tap % 3 - 1);
+        const uint32_t b_addr = smem_u32(sB + (size_t)s * b_stage_bytes);
+        for (int t = 0; t < MT; ++t) {
+          const uint32_t a_addr = smem_u32(sA + (size_t)j * a_chunk_bytes) + (uint32_t)(halo + t * 128 + shift) * ROWB;
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)
+            umma_bf16(tmem_base + (uint32_t)(t * N), make_desc<KC>(a_addr + k * 32), make_desc<KC>(b_addr + k * 32), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(b_empty + s);               // frees this weight stage when the MMAs above retire
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ---- epilogue warps: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int t = 0; t < MT; ++t) {
+      const long long m = m0 + (long long)t * 128 + q * 32 + lane;
+      const int b = (int)(m / a.R_img);
+      const int rem = (int)(m % a.R_img);
+      const int yy = rem / (a.W + 2), xx = rem % (a.W + 2);
+      const bool valid = m < a.rows_valid && yy >= 1 && xx >= 1 && xx <= a.W;
+      const long long row_off = (m + halo) * (long long)N;
+      const float pl = (valid && a.plane) ? a.plane[b] : 0.0f;
+      const float* ptab = (valid && a.plane) ? a.plane_table + (size_t)((yy - 1) * a.W + (xx - 1)) * N : nullptr;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * N + c0), v);
+        if (!valid) continue;
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float acc = __uint_as_float(v[i]);
+          if (ptab) acc = fmaf(pl, ptab[c0 + i], acc);
+          f[i] = fmaf(acc, a.scale[c0 + i], a.shift[c0 + i]);
+        }
+        if (a.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + row_off + c0);
+          const uint4 r0 = rp[0], r1 = rp[1];
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f[2 * i] += __uint_as_float(rw[i] << 16);
+            f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
+          }
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float lo = f[2 * i], hi = f[2 * i + 1];
+          if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+          o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+        uint4* op = reinterpret_cast<uint4*>(a.y + row_off + c0);
+        op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.ncols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes, uint32_t box_inner,
+                 uint32_t box_outer, int kc) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {row_bytes};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
+
+int pick_mt(int cout, int n_chunks, int kc, int max_smem) {
+  for (int mt = 4; mt >= 1; mt >>= 1) {
+    if (mt * cout > 512) continue;
+    const size_t smem = (size_t)n_chunks * (mt + 1) * 128 * kc * 2 + (size_t)kStages * cout * kc * 2 + 1024 + 256;
+    if (smem <= (size_t)max_smem) return mt;
+  }
+  return 0;
+}
+
+}  // namespace
+
+static bool g_tc_enabled = true;
+extern "C" void mzb_conv_tc_enable(int on) { g_tc_enabled = on != 0; }
+
+bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
+  return g_tc_enabled && cp.stride == 1 && cp.cin == cin_stride && cp.cin % 16 == 0 && cp.cout % 16 == 0 && cp.cout >= 16 &&
+         cp.cout <= 256 && W <= 61 && cp.w_bf16 != nullptr && encode_fn() != nullptr &&
+         pick_mt(cp.cout, cp.cin / pick_kc(cp.cin), pick_kc(cp.cin), 227 * 1024) > 0;
+}
+
+int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
+                       const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream) {
+  const int kc = pick_kc(cp.cin), n_chunks = cp.cin / kc;
+  const int mt = pick_mt(cp.cout, n_chunks, kc, 227 * 1024);
+  MZB_CHECK_ARG(mt > 0, "tensor-core convolution: no tile configuration fits");
+  const Geo g{H, W, cp.cin, 1};
+  const long long rows_total = geo_rows_total(g, B);
+  CUtensorMap tmA, tmB;
+  if (!make_map_2d(&tmA, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)kc, 128, kc) ||
+      !make_map_2d(&tmB, cp.w_bf16, (uint64_t)9 * cp.cin, (uint64_t)cp.cout, (uint64_t)9 * cp.cin * 2, (uint32_t)kc,
+                   (uint32_t)cp.cout, kc)) {
+    mzb_set_error("cuTensorMapEncodeTiled failed (C_in=%d C_out=%d rows=%lld)", cp.cin, cp.cout, rows_total);
+    return MZB_ECUDA;
+  }
+  TcArgs a{};
+  a.B = B; a.H = H; a.W = W; a.Cin = cp.cin; a.Cout = cp.cout; a.R_img = (H + 1) * (W + 2); a.mt = mt; a.n_chunks = n_chunks;
+  a.relu = relu;
+  int ncols = 32;
+  while (ncols < mt * cp.cout) ncols <<= 1;
+  a.ncols = ncols;
+  a.rows_valid = (long long)B * a.R_img;
+  a.scale = cp.scale; a.shift = cp.shift; a.plane = cp.extra_plane ? plane : nullptr; a.plane_table = cp.plane_table;
+  a.residual = residual; a.y = y;
+  const size_t smem = (size_t)n_chunks * (mt + 1) * 128 * kc * 2 + (size_t)kStages * cp.cout * kc * 2 + 1024 + 256;
+  const long long tiles = (a.rows_valid + 127) / 128;
+  const unsigned grid = (unsigned)((tiles + mt - 1) / mt);
+#define LAUNCH_KC(KCV)                                                                                              \
+  {                                                                                                                 \
+    static bool configured = false;                                                                                 \
+    if (!configured) {                                                                                              \
+      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));      \
+      configured = true;                                                                                            \
+    }                                                                                                               \
+    k_conv_tc<KCV><<<grid, kThreads, smem, stream>>>(tmA, tmB, a);                                                  \
+  }
+  if (kc == 64) LAUNCH_KC(64) else if (kc == 32) LAUNCH_KC(32) else LAUNCH_KC(16)
+#undef LAUNCH_KC
+  MZB_LAUNCH_CHECK();
+  return MZB_OK;
 }

@@ -641,3 +641,54 @@ int mzb_resnet_recurrent(mzb_resnet_model* m, int64_t B, const void* d_state_in,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ debug / self-test
+// One 3x3 convolution (no batch-norm, no ReLU) through both bf16 kernels on host data: dense NHWC float input
+// [B,H,W,Cin], torch-layout weights [Cout][Cin][3][3]; outputs dense NHWC float.  Used by tests to localise
+// descriptor / swizzle errors of the tensor-core kernel.
+extern "C" int mzb_debug_conv3x3(int B, int H, int W, int Cin, int Cout, const float* h_x, const float* h_w,
+                                 float* h_y_direct, float* h_y_tc) {
+  mzb_resnet_model m{};
+  ConvParams cp{};
+  if (!init_conv(&m, cp, Cin, Cout, 1, 0, 0)) return MZB_ECUDA;
+  std::vector<float> ones(Cout, 1.0f), zeros(Cout, 0.0f);
+  const float* tensors[5] = {h_w, ones.data(), zeros.data(), zeros.data(), ones.data()};
+  const int64_t numel[5] = {(int64_t)Cout * Cin * 9, Cout, Cout, Cout, Cout};
+  Cursor cur{tensors, numel, 1, 0, false};
+  if (!load_conv(cur, cp, false, 0, 0)) return MZB_EINVAL;
+  const Geo g{H, W, Cin, 1}, go{H, W, Cout, 1};
+  const size_t in_elems = (size_t)geo_rows_total(g, B) * Cin, out_elems = (size_t)geo_rows_total(go, B) * Cout;
+  __nv_bfloat16 *dx = nullptr, *dy = nullptr;
+  cudaMalloc(&dx, in_elems * 2); cudaMalloc(&dy, out_elems * 2);
+  cudaMemset(dx, 0, in_elems * 2);
+  std::vector<__nv_bfloat16> hx(in_elems, __float2bfloat16(0.0f));
+  for (int b = 0; b < B; ++b)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        for (int c = 0; c < Cin; ++c)
+          hx[(size_t)geo_row(g, b, y, x) * Cin + c] = __float2bfloat16(h_x[(((size_t)b * H + y) * W + x) * Cin + c]);
+  cudaMemcpy(dx, hx.data(), in_elems * 2, cudaMemcpyHostToDevice);
+  std::vector<__nv_bfloat16> hy(out_elems);
+  int rc = MZB_OK;
+  for (int pass = 0; pass < 2 && rc == MZB_OK; ++pass) {
+    cudaMemset(dy, 0, out_elems * 2);
+    float* dst = pass == 0 ? h_y_direct : h_y_tc;
+    if (pass == 0) {
+      const long long n = (long long)B * H * W * Cout;
+      k_conv3x3_direct<__nv_bfloat16><<<nblk(n, 128), 128>>>(dx, B, g, cp, nullptr, nullptr, 0, go, dy);
+    } else {
+      if (!mzb_conv_tc_supported(cp, H, W, Cin)) { mzb_set_error("shape not supported by the tensor-core kernel"); rc = MZB_EUNSUPPORTED; break; }
+      rc = mzb_conv_tc_launch(B, H, W, cp, dx, nullptr, nullptr, 0, dy, 0);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) { mzb_set_error("debug conv: %s", cudaGetErrorString(cudaGetLastError())); rc = MZB_ECUDA; break; }
+    cudaMemcpy(hy.data(), dy, out_elems * 2, cudaMemcpyDeviceToHost);
+    for (int b = 0; b < B; ++b)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+          for (int c = 0; c < Cout; ++c)
+            dst[(((size_t)b * H + y) * W + x) * Cout + c] = __bfloat162float(hy[(size_t)geo_row(go, b, y, x) * Cout + c]);
+  }
+  cudaFree(dx); cudaFree(dy);
+  for (void* p : m.allocs) cudaFree(p);
+  return rc;
+}
