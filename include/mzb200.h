@@ -315,6 +315,16 @@ int mzb_resnet_recurrent(mzb_resnet_model* m, int64_t B, const void* d_state_in,
                          int64_t out_offset, float* d_value_logits, float* d_reward_logits, float* d_policy_logits,
                          float* d_value, float* d_reward, float* d_priors, void* stream);
 
+/* Batched MCTS.run for residual networks (self_play.py:261-362): as mzb_search_fc, with the tree kernels and
+ * the resnet layer program launched per simulation.  d_hidden_pool: caller-owned hidden-state slots
+ * [G][tree capacity + 1][H*W*C] dense NHWC, bf16 (precision 1) or fp32 (precision 0);
+ * d_workspace as for mzb_resnet_recurrent with batch G. */
+int mzb_search_resnet(mzb_tree* t, mzb_resnet_model* m, const float* d_obs, const uint8_t* d_legal,
+                      const int8_t* d_to_play, const double* d_noise, double alpha, double frac, const uint32_t* d_slot,
+                      const uint32_t* d_step, int32_t num_simulations, void* d_hidden_pool, void* d_workspace,
+                      size_t workspace_bytes, int32_t* d_visits, double* d_root_value, float* d_root_predicted_value,
+                      int32_t* d_max_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,8 @@ _vp = C.c_void_p
 _lib.bind("mzb_search_fc", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, C.c_int32, C.c_int,
                                      _vp, _vp, _vp, _vp, _vp])
 _lib.bind("mzb_search_fc_is_fused", C.c_int, [_vp])
+_lib.bind("mzb_search_resnet", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, C.c_int32, _vp, _vp,
+                                         C.c_size_t, _vp, _vp, _vp, _vp, _vp])
 
 
 class BatchedMCTS:
@@ -29,13 +31,8 @@ class BatchedMCTS:
         if len(config.players) > 2:
             raise NotImplementedError("More than two player mode not implemented.")
         if hidden_floats is None:
-            if config.network == "fullyconnected":
-                hidden_floats = config.encoding_size
-            else:
-                c, h, w = config.observation_shape
-                if config.downsample:
-                    h, w = -(-h // 16), -(-w // 16)
-                hidden_floats = config.channels * h * w
+            # fully-connected: slots inside the tree store; residual: a separate NHWC pool (see run)
+            hidden_floats = config.encoding_size if config.network == "fullyconnected" else 0
         self.tree = BatchedTree(self.G, self.A, config.num_simulations, len(config.players), config.discount,
                                 config.pb_c_base, config.pb_c_init, hidden_floats=hidden_floats,
                                 seed=config.seed if seed is None else seed, device=self.device)
@@ -69,6 +66,22 @@ class BatchedMCTS:
                                              ptr(out["root_predicted_value"]), ptr(out["max_depth"]),
                                              _lib.current_stream()))
             return out
+        if hasattr(model, "handle") and cfg.network == "resnet":
+            h = model.handle()
+            state = int(model.latent_shape[0] * model.latent_shape[1] * model.latent_shape[2])
+            dt = torch.bfloat16 if model.precision == "bf16" else torch.float32
+            pool = getattr(self, "_pool", None)
+            if pool is None or pool.dtype != dt:
+                pool = self._pool = torch.empty((G, cfg.num_simulations + 1, state), dtype=dt, device=dev)
+            obs4 = observations.to(device=dev, dtype=torch.float32).reshape((G,) + tuple(model.observation_shape)).contiguous()
+            with torch.cuda.device(dev):
+                ws = model._workspace(G, dev)
+                check(_lib.lib.mzb_search_resnet(self.tree._h, h, ptr(obs4), ptr(lg), ptr(tp), ptr(nz),
+                                                 float(cfg.root_dirichlet_alpha), frac, ptr(sl), ptr(st), int(S), ptr(pool),
+                                                 ptr(ws), ws.numel(), ptr(out["visits"]), ptr(out["root_value"]),
+                                                 ptr(out["root_predicted_value"]), ptr(out["max_depth"]),
+                                                 _lib.current_stream()))
+            return out
         return self._run_generic(model, observations, lg, tp, nz, frac, sl, st, S, out)
 
     def _run_generic(self, model, observations, lg, tp, nz, frac, sl, st, S, out):
@@ -80,7 +93,9 @@ class BatchedMCTS:
         v, r, pl, hs = model.initial_inference(obs)
         out["root_predicted_value"].copy_(models.support_to_scalar(v, cfg.support_size).reshape(G))
         reward = models.support_to_scalar(r, cfg.support_size).reshape(G).contiguous()
-        hidden = tree.hidden()
+        hidden = getattr(self, "_generic_hidden", None)
+        if hidden is None or hidden.shape[2] != hs[0].numel():
+            hidden = self._generic_hidden = torch.empty((G, cfg.num_simulations + 1, hs[0].numel()), device=dev)
         hidden[:, 0] = hs.reshape(G, -1)
         tree.root_init(reward, pl.contiguous(), True, lg, tp, nz, cfg.root_dirichlet_alpha, frac, sl, st)
         parent = torch.empty(G, dtype=torch.int32, device=dev)

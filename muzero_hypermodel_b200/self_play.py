@@ -172,8 +172,8 @@ class MCTS:
         frac = float(cfg.root_exploration_fraction) if add_exploration_noise else 0.0
         tree.root_init(torch.tensor([float(root.reward)], device=device), pri, False, legal,
                        torch.tensor([to_play], dtype=torch.int8, device=device), nz, cfg.root_dirichlet_alpha, frac)
-        hidden = tree.hidden()
         hs = root.hidden_state.to(device).float()
+        hidden = torch.empty((1, cfg.num_simulations + 1, hs.numel()), device=device)
         hidden[0, 0] = hs.reshape(-1)
         parent = torch.empty(1, dtype=torch.int32, device=device)
         action = torch.empty(1, dtype=torch.int32, device=device)
@@ -185,21 +185,31 @@ class MCTS:
             tree.expand_backup(models.support_to_scalar(v, cfg.support_size).reshape(1).contiguous(),
                                models.support_to_scalar(r, cfg.support_size).reshape(1).contiguous(), pl.contiguous(), True)
         stats = tree.root_stats()
-        new_root = self._materialise(eng, 0, actions, to_play, hidden_shape=tuple(hs.shape))
+        new_root = self._materialise(eng, 0, actions, to_play, hidden_shape=tuple(hs.shape), hidden=hidden)
         return new_root, {"max_tree_depth": int(stats["max_depth"][0]), "root_predicted_value": None}
 
-    def _materialise(self, eng, game, legal_actions, to_play, hidden_shape=None):
+    def _materialise(self, eng, game, legal_actions, to_play, hidden_shape=None, hidden=None):
         """Device tree of one game -> the reference's Node graph (children dict in action order)."""
         cfg = self.config
         ex = eng.tree.export_game(game)
-        hidden = eng.tree.hidden()
+        nhwc = None
+        if hidden is None:
+            hidden = eng.tree.hidden()
+            if hidden is None:                         # residual networks: dense NHWC pool of the search driver
+                hidden = eng._pool
+                c, hh, ww = (cfg.channels, ) + ((-(-cfg.observation_shape[1] // 16), -(-cfg.observation_shape[2] // 16))
+                                                if cfg.downsample else tuple(cfg.observation_shape[1:]))
+                nhwc = (hh, ww, c)
         players = cfg.players
         A = len(cfg.action_space)
 
         def build(slot, node, depth, tp):
             node.to_play = tp
-            h = hidden[game, slot]
-            node.hidden_state = (h.reshape(hidden_shape) if hidden_shape else h.reshape(1, -1)).clone()
+            h = hidden[game, slot].float()
+            if nhwc is not None:
+                node.hidden_state = h.reshape(nhwc).permute(2, 0, 1).unsqueeze(0).contiguous()
+            else:
+                node.hidden_state = (h.reshape(hidden_shape) if hidden_shape else h.reshape(1, -1)).clone()
             nxt = players[(players.index(tp) + 1) % len(players)]
             for a in (legal_actions if slot == 0 else range(A)):
                 prior = float(ex["root_prior"][a]) if slot == 0 else float(ex["prior"][slot][a])
