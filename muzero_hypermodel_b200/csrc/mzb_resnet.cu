@@ -587,13 +587,28 @@ size_t act_bytes_for(const mzb_resnet_model* m, long long B) {
   return mzb_align_up((size_t)((per * B + halo) * 4 + 4096), 1024);      // sized for fp32; bf16 uses half
 }
 
+size_t ws_bytes_for(const mzb_resnet_model* m, long long B) {
+  return 3 * act_bytes_for(m, B) + mzb_align_up((size_t)B * 4, 256) + 1024;
+}
+
+// The buffer offsets inside a workspace must not depend on the batch of the call (the zero pad rows of the padded
+// layout sit at fixed places): derive them from the workspace CAPACITY = the largest batch it was sized for.
+size_t act_bytes_of_workspace(const mzb_resnet_model* m, size_t workspace_bytes) {
+  long long lo = 1, hi = 1ll << 24;
+  while (lo < hi) {
+    const long long mid = (lo + hi + 1) / 2;
+    if (ws_bytes_for(m, mid) <= workspace_bytes) lo = mid; else hi = mid - 1;
+  }
+  return act_bytes_for(m, lo);
+}
+
 }  // namespace
 
 extern "C" {
 
 size_t mzb_resnet_workspace_bytes(const mzb_resnet_model* m, int64_t max_batch) {
   if (!m || max_batch <= 0) return 0;
-  return 3 * act_bytes_for(m, max_batch) + mzb_align_up((size_t)max_batch * 4, 256) + 1024;
+  return ws_bytes_for(m, max_batch);
 }
 
 /* Zero a freshly allocated workspace: the padded activation layout relies on zero pad rows that no kernel writes. */
@@ -611,7 +626,7 @@ int mzb_resnet_initial(mzb_resnet_model* m, int64_t B, const float* d_obs, const
   MZB_CHECK_ARG(B > 0 && B < (1ll << 24), "batch out of range");
   MZB_CHECK_ARG(workspace_bytes >= mzb_resnet_workspace_bytes(m, B), "workspace too small");
   MZB_CHECK_ARG(state_layout >= 0 && state_layout <= 2, "bad state layout");
-  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes_for(m, B)};
+  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes_of_workspace(m, workspace_bytes)};
   Outputs o{d_state_out, state_layout, out_row_stride, out_offset, d_value_logits, d_reward_logits, d_policy_logits,
             d_value, d_reward, d_priors};
   int rc = m->precision == 1 ? run_initial<__nv_bfloat16>(r, d_obs, d_legal, o) : run_initial<float>(r, d_obs, d_legal, o);
@@ -629,7 +644,7 @@ int mzb_resnet_recurrent(mzb_resnet_model* m, int64_t B, const void* d_state_in,
   MZB_CHECK_ARG(B > 0 && B < (1ll << 24), "batch out of range");
   MZB_CHECK_ARG(workspace_bytes >= mzb_resnet_workspace_bytes(m, B), "workspace too small");
   MZB_CHECK_ARG(in_layout >= 0 && in_layout <= 2 && out_layout >= 0 && out_layout <= 2, "bad state layout");
-  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes_for(m, B)};
+  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes_of_workspace(m, workspace_bytes)};
   Outputs o{d_state_out, out_layout, out_row_stride, out_offset, d_value_logits, d_reward_logits, d_policy_logits,
             d_value, d_reward, d_priors};
   int rc = m->precision == 1
