@@ -30,15 +30,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (golden weight tag, config module, games per GPU)
-    "cartpole": ("cartpole_shipped", "cartpole", 262144),
-    "tictactoe": ("tictactoe_fc", "tictactoe", 4096 * 16),
+    # name: (golden weight tag, config module, games per GPU, (initial FLOP, recurrent FLOP) per BASELINE.md §3)
+    "cartpole": ("cartpole_shipped", "cartpole", 262144, (1312, 2752)),
+    "tictactoe": ("tictactoe_fc", "tictactoe", 4096 * 16, (3648, 5952)),
+    "connect4": ("connect4", "connect4", 16384, (37372160, 40396160)),
+    "gomoku": ("gomoku", "gomoku", 1024, (857557760, 892780160)),
 }
 
 
 def load_weights(tag):
     import numpy as np
     z = np.load(os.path.join(ROOT, "tests", "golden", "net.npz"))
+    if tag == "gomoku":                       # 22 MB of fp32: seeded values, regenerated (tests/_weights.py)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from _weights import seeded_state_dict
+        keys = str(z["gomoku/keys"]).split("\n")
+        shapes = [[int(d) for d in s.split("x")] if s else [] for s in z["gomoku/shapes"]]
+        return seeded_state_dict(keys, shapes)
     pre = tag + "/w/"
     return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
 
@@ -49,6 +57,8 @@ def make_config(workload):
     cfg = mod.MuZeroConfig()
     if workload == "tictactoe":
         cfg.network = "fullyconnected"
+    if cfg.network == "resnet":
+        cfg.resnet_precision = "bf16"          # tcgen05 path: bf16 operands, fp32 accumulation
     return cfg
 
 
@@ -56,7 +66,9 @@ def oracle_cfg(cfg):
     return dict(action_space=list(cfg.action_space), support_size=cfg.support_size, seed=cfg.seed, slot=0,
                 max_moves=cfg.max_moves, n_players=len(cfg.players), num_simulations=cfg.num_simulations,
                 discount=cfg.discount, pb_c_base=cfg.pb_c_base, pb_c_init=cfg.pb_c_init,
-                root_dirichlet_alpha=cfg.root_dirichlet_alpha, root_exploration_fraction=cfg.root_exploration_fraction)
+                root_dirichlet_alpha=cfg.root_dirichlet_alpha, root_exploration_fraction=cfg.root_exploration_fraction,
+                network=cfg.network, observation_shape=tuple(cfg.observation_shape), blocks=cfg.blocks,
+                downsample=cfg.downsample)
 
 
 def cpu_leg(workload, cfg, seconds):
@@ -82,7 +94,7 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     w = load_weights(WORKLOADS[args.workload][0])
     ocfg = oracle_cfg(cfg)
-    searches = 24                                   # searches per process per step (bounded sample)
+    searches = 24 if cfg.network == "fullyconnected" else 1      # searches per process per step (bounded sample)
     pool = mp.get_context("fork").Pool(cores)
     times, sims_total = [], 0
     for i in range(args.warmup + args.steps):
@@ -110,7 +122,9 @@ def reference_arm(args):
 
 def workload_name(workload, cfg):
     return {"cartpole": "cartpole FC MuZero (games/cartpole.py defaults, num_simulations=50)",
-            "tictactoe": "tictactoe FC MuZero, two-player, network=fullyconnected, num_simulations=25"}[workload]
+            "tictactoe": "tictactoe FC MuZero, two-player, network=fullyconnected, num_simulations=25",
+            "connect4": "connect4 residual-network MuZero (games/connect4.py defaults, 3 blocks x 64 ch, num_simulations=200)",
+            "gomoku": "gomoku residual MuZero (games/gomoku.py defaults, 6 blocks x 128 ch, A=121, num_simulations=400)"}[workload]
 
 
 class ClockSampler:
@@ -122,7 +136,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -160,7 +174,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 50 for FC workloads, 3 for resnets)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cartpole", choices=list(WORKLOADS))
@@ -170,6 +184,10 @@ def main():
     ap.add_argument("--modular", action="store_true", help="force the modular kernels instead of the whole-search kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.steps <= 0:
+        args.steps = 50 if args.workload in ("cartpole", "tictactoe") else 3
+        if args.impl == "reference":
+            args.steps = 10
 
     if args.impl == "reference":
         return reference_arm(args)
@@ -206,7 +224,8 @@ def main():
     weights = {k: torch.tensor(v) for k, v in load_weights(WORKLOADS[args.workload][0]).items()}
     sp = SelfPlay({"weights": weights}, None, cfg, cfg.seed, n_games=G, device=dev, first_slot=rank * G)
     env, mcts = sp._setup()
-    fused = bool(_lib.lib.mzb_search_fc_is_fused(sp.model.handle())) and not args.modular
+    is_fc = cfg.network == "fullyconnected"
+    fused = is_fc and bool(_lib.lib.mzb_search_fc_is_fused(sp.model.handle())) and not args.modular
 
     def step():
         sp.step(temperature=1.0, temperature_threshold=None, add_exploration_noise=True, export=True,
@@ -248,19 +267,21 @@ def main():
     # the tree store it streams through is G*(S+1)*(24A + 4H) bytes >> L2, no L2 flush needed)
     obs, legal, to_play = env.observe()
     kt = []
-    for i in range(3 + 5):
+    for i in range(3 + 5 if is_fc else 1 + 2):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         mcts.run(sp.model, obs, legal, to_play, True, slot=env.slot, step=env.step_count, allow_fused=not args.modular,
                  out=sp._out)
         b.record()
         torch.cuda.synchronize()
-        if i >= 3:
+        if i >= (3 if is_fc else 1):
             kt.append(a.elapsed_time(b))
     k_ms = sum(kt) / len(kt)
-    A, H = len(cfg.action_space), cfg.encoding_size
+    A = len(cfg.action_space)
+    H = cfg.encoding_size if is_fc else int(sp.model.latent_shape[0] * sp.model.latent_shape[1] * sp.model.latent_shape[2])
+    hs = 4 if is_fc else 2                           # bytes per hidden-state element (bf16 pool on the resnet path)
     L = mean_path + 1.0                              # nodes on the path incl. root (SURVEY.md §8d counts nodes)
-    bytes_per_sim = (L - 1) * A * 20 + L * 24 + 8 * A + 8 + 2 * H * 4
+    bytes_per_sim = (L - 1) * A * 20 + L * 24 + 8 * A + 8 + 2 * H * hs
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -268,13 +289,21 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_per_sim * G * S / (k_ms * 1e-3) / 1e9
-    flops = {"cartpole": (1312, 2752), "tictactoe": (3648, 5952)}[args.workload]
-    roofline = {"bound": "hbm", "kernel": "k_search_fc (whole-search, fused)" if fused else "modular: k_select+k_fc_recurrent+k_expand_backup",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                "kernel_ms": k_ms, "bytes_per_sim": bytes_per_sim, "mean_path_nodes": L,
-                "fp32_tflops": (flops[1] * S + flops[0]) * G / (k_ms * 1e-3) / 1e12,
-                "kernel_share_of_step": k_ms * args.steps / ms if world == 1 else None}
+    flops = WORKLOADS[args.workload][3]
+    tflops = (flops[1] * S + flops[0]) * G / (k_ms * 1e-3) / 1e12
+    if is_fc:
+        roofline = {"bound": "hbm", "kernel": "k_search_fc (whole-search, fused)" if fused else "modular: k_select+k_fc_recurrent+k_expand_backup",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                    "kernel_ms": k_ms, "bytes_per_sim": bytes_per_sim, "mean_path_nodes": L, "fp32_tflops": tflops,
+                    "kernel_share_of_step": k_ms * args.steps / ms if world == 1 else None}
+    else:
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        roofline = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM 3x3 conv) inside mzb_search_resnet",
+                    "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1400 TFLOP/s",
+                    "search_ms": k_ms, "flop_per_sim": flops[1], "tree_bytes_per_sim": bytes_per_sim, "mean_path_nodes": L,
+                    "tree_hbm_gbs": achieved, "search_share_of_step": k_ms * args.steps / ms if world == 1 else None}
 
     # ---------------- e2e: batched MCTS.run entry point with HOST buffers, copies inside the timed region
     h_obs = torch.empty((G, env.obs_dim), dtype=torch.float32).pin_memory()
@@ -284,7 +313,7 @@ def main():
     h_vis = torch.empty((G, A), dtype=torch.int32).pin_memory()
     h_rv = torch.empty(G, dtype=torch.float64).pin_memory()
     d_obs, d_legal, d_tp = torch.empty_like(obs), torch.empty_like(legal), torch.empty_like(to_play)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 10)) if is_fc else 2
 
     def e2e_step():
         d_obs.copy_(h_obs, non_blocking=True); d_legal.copy_(h_legal, non_blocking=True); d_tp.copy_(h_tp, non_blocking=True)
@@ -293,7 +322,7 @@ def main():
         h_vis.copy_(o["visits"], non_blocking=True); h_rv.copy_(o["root_value"], non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the caller reads the visit counts before the next move
 
-    for _ in range(2):
+    for _ in range(2 if is_fc else 1):
         e2e_step()
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -314,11 +343,14 @@ def main():
     if rank == 0:
         line = {"metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 network / f64 tree statistics", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 network / f64 tree statistics" if is_fc else "bf16 conv operands, f32 accumulate / f64 tree statistics",
+                "data": "synthetic",
                 "config": {"workload": workload_name(args.workload, cfg), "games_per_gpu": G,
                            "num_simulations": S, "weights": WORKLOADS[args.workload][0],
                            "l2_policy": f"working set {mcts.tree.nbytes / 2**30:.1f} GiB tree store per GPU >> 126 MB L2",
-                           "path": "fused whole-search kernel" if fused else "modular kernels", "parallelism": f"games sharded x{world}, no collective"},
+                           "path": ("fused whole-search kernel" if fused else "modular kernels") if is_fc else "tree kernels + tcgen05 resnet per simulation",
+                           "parallelism": f"games sharded x{world}, no collective"},
                 "env_steps_per_sec": env_steps, "e2e": e2e, "roofline": roofline, "gpu_launches": launches,
                 "clocks": clocks, "mean_search_path_nodes": L,
                 "games_finished_in_timed_region": c1["games"] - c0["games"],

@@ -53,7 +53,8 @@ class MuZeroNetwork:
                 config.observation_shape, config.stacked_observations, len(config.action_space), config.blocks,
                 config.channels, config.reduced_channels_reward, config.reduced_channels_value,
                 config.reduced_channels_policy, config.resnet_fc_reward_layers, config.resnet_fc_value_layers,
-                config.resnet_fc_policy_layers, config.support_size, config.downsample)
+                config.resnet_fc_policy_layers, config.support_size, config.downsample,
+                precision=getattr(config, "resnet_precision", "fp32"))
         raise NotImplementedError('The network parameter should be "fullyconnected" or "resnet".')
 
 

@@ -15,9 +15,16 @@ from . import games, mcts, networks, rng
 
 def _make(kind, weights, cfg):
     A = len(cfg["action_space"])
-    net = networks.FullyConnected(weights, A, cfg["support_size"])
+    if cfg.get("network", "fullyconnected") == "resnet":
+        import torch
+        torch.set_num_threads(1)
+        net = networks.Residual(weights, cfg["observation_shape"], A, cfg["blocks"], cfg["support_size"],
+                                cfg.get("downsample", False))
+    else:
+        net = networks.FullyConnected(weights, A, cfg["support_size"])
     env = {"cartpole": lambda: games.CartPole(1, seed=cfg["seed"], slot0=cfg["slot"]),
-           "tictactoe": lambda: games.TicTacToe(1)}[kind]()
+           "tictactoe": lambda: games.TicTacToe(1), "connect4": lambda: games.Connect4(1),
+           "gomoku": lambda: games.Gomoku(1)}[kind]()
     return net, env, A
 
 
