@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - self-play hot path throughput: MCTS simulations/s (and env steps/s) per BASELINE.json.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cartpole|tictactoe]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cartpole|tictactoe|connect4|gomoku|breakout]
                     [--games G]
 
 One "step" = one self-play move of every game on every GPU: observe -> MCTS.run (num_simulations
@@ -35,6 +35,7 @@ WORKLOADS = {
     "tictactoe": ("tictactoe_fc", "tictactoe", 4096 * 16, (3648, 5952)),
     "connect4": ("connect4", "connect4", 16384, (37372160, 40396160)),
     "gomoku": ("gomoku", "gomoku", 1024, (857557760, 892780160)),
+    "breakout": ("breakout", "breakout", 8192, (34192160, 1532480)),
 }
 
 
@@ -124,7 +125,8 @@ def workload_name(workload, cfg):
     return {"cartpole": "cartpole FC MuZero (games/cartpole.py defaults, num_simulations=50)",
             "tictactoe": "tictactoe FC MuZero, two-player, network=fullyconnected, num_simulations=25",
             "connect4": "connect4 residual-network MuZero (games/connect4.py defaults, 3 blocks x 64 ch, num_simulations=200)",
-            "gomoku": "gomoku residual MuZero (games/gomoku.py defaults, 6 blocks x 128 ch, A=121, num_simulations=400)"}[workload]
+            "gomoku": "gomoku residual MuZero (games/gomoku.py defaults, 6 blocks x 128 ch, A=121, num_simulations=400)",
+            "breakout": "Atari Breakout residual MuZero on synthetic 96x96 frames (games/breakout.py defaults, num_simulations=30)"}[workload]
 
 
 class ClockSampler:
@@ -206,23 +208,18 @@ def main():
     import torch
     import torch.distributed as dist
     from muzero_hypermodel_b200 import _lib
+    from muzero_hypermodel_b200 import dist as mdist
     from muzero_hypermodel_b200.self_play import SelfPlay
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    mdist.init(backend="nccl", device=dev)
+    barrier = mdist.barrier
 
     G = args.games or WORKLOADS[args.workload][2]
     S = cfg.num_simulations
     weights = {k: torch.tensor(v) for k, v in load_weights(WORKLOADS[args.workload][0]).items()}
-    sp = SelfPlay({"weights": weights}, None, cfg, cfg.seed, n_games=G, device=dev, first_slot=rank * G)
+    sp = SelfPlay({"weights": weights}, None, cfg, cfg.seed, n_games=G, device=dev, first_slot=mdist.first_slot(rank, G))
     env, mcts = sp._setup()
     is_fc = cfg.network == "fullyconnected"
     fused = is_fc and bool(_lib.lib.mzb_search_fc_is_fused(sp.model.handle())) and not args.modular
@@ -253,10 +250,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     c1 = env.counters()
     tc = mcts.tree.counters()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
+    ms = mdist.max_over_ranks(ms, dev)
     sims_total = args.steps * G * S * world
     value = sims_total / (ms * 1e-3)
     env_steps = args.steps * G * world / (ms * 1e-3)
@@ -331,11 +325,9 @@ def main():
         e2e_step()
     b.record()
     barrier()
-    t2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = mdist.max_over_ranks(a.elapsed_time(b), dev)
     assert int(h_vis.sum(1).min()) == S and int(h_vis.sum(1).max()) == S
-    e2e = {"value": e2e_steps * G * S * world / (float(t2[0]) * 1e-3), "unit": "simulations/s",
+    e2e = {"value": e2e_steps * G * S * world / (e2e_ms * 1e-3), "unit": "simulations/s",
            "h2d_bytes_per_step": (h_obs.numel() * 4 + h_legal.numel() + h_tp.numel()) * world,
            "d2h_bytes_per_step": (h_vis.numel() * 4 + h_rv.numel() * 8) * world,
            "api": "BatchedMCTS.run == mzb_search_fc (G x MCTS.run) with pinned host buffers"}

@@ -203,6 +203,8 @@ int mzb_search_fc_is_fused(const mzb_fc_model* m);
 #define MZB_ENV_TICTACTOE 1  /* games/tictactoe.py                           */
 #define MZB_ENV_CONNECT4 2   /* games/connect4.py                            */
 #define MZB_ENV_GOMOKU 3     /* games/gomoku.py                              */
+#define MZB_ENV_SYNTHETIC_FRAMES 4 /* breakout stand-in (BASELINE.json): 3x96x96 frames U[0,1) from Philox, A = 4,
+                                      reward 0, never done before max_moves (the ALE emulator is out of scope) */
 
 typedef struct mzb_env mzb_env;
 typedef struct {

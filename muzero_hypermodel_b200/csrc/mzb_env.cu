@@ -75,6 +75,7 @@ __device__ inline bool any_empty(const int8_t* b, int n) {
 }
 
 __device__ inline void env_reset_game(const EnvView& e, int g) {
+  if (e.kind == MZB_ENV_SYNTHETIC_FRAMES) return;
   if (e.kind == MZB_ENV_CARTPOLE) {
     // gym reset: U(-0.05, 0.05)^4, drawn from Philox(slot, steps so far, STREAM_RESET)
     const uint32_t slot = e.slot0 + (uint32_t)g, st = e.steps[g];
@@ -94,12 +95,13 @@ __device__ inline void env_reset_game(const EnvView& e, int g) {
 }
 
 __device__ inline int env_to_play(const EnvView& e, int g) {
-  return e.kind == MZB_ENV_CARTPOLE ? 0 : (e.player[g] == 1 ? 0 : 1);
+  return (e.kind == MZB_ENV_CARTPOLE || e.kind == MZB_ENV_SYNTHETIC_FRAMES) ? 0 : (e.player[g] == 1 ? 0 : 1);
 }
 
 __device__ inline bool env_legal(const EnvView& e, int g, int a) {
   switch (e.kind) {
     case MZB_ENV_CARTPOLE: return true;
+    case MZB_ENV_SYNTHETIC_FRAMES: return true;
     case MZB_ENV_CONNECT4: return board_of(e, g)[5 * 7 + a] == 0;          // connect4.py:249-254
     default: return board_of(e, g)[a] == 0;                                  // tictactoe.py:270-277, gomoku.py:247-253
   }
@@ -107,6 +109,7 @@ __device__ inline bool env_legal(const EnvView& e, int g, int a) {
 
 // Game.step: returns reward (already scaled by the wrapper), sets done
 __device__ inline double env_step_game(const EnvView& e, int g, int a, bool& done) {
+  if (e.kind == MZB_ENV_SYNTHETIC_FRAMES) { done = false; return 0.0; }   // rewards 0, never done before max_moves
   if (e.kind == MZB_ENV_CARTPOLE) {
     double* s = e.cp + (size_t)g * 4;
     double x = s[0], xd = s[1], th = s[2], thd = s[3];
@@ -159,6 +162,7 @@ __device__ inline double env_step_game(const EnvView& e, int g, int a, bool& don
 
 // observation record of the current state into a history slot (compact native form)
 __device__ inline void write_obs_record(const EnvView& e, int g, float* rec) {
+  if (e.kind == MZB_ENV_SYNTHETIC_FRAMES) { rec[0] = (float)e.steps[g]; return; }   // frames are regenerable from (slot, step)
   if (e.kind == MZB_ENV_CARTPOLE) {
     const double* s = e.cp + (size_t)g * 4;
     for (int i = 0; i < 4; ++i) rec[i] = (float)s[i];
@@ -191,7 +195,9 @@ __global__ void k_env_observe(EnvView e, float* __restrict__ obs, uint8_t* __res
   if (g >= e.G) return;
   if (obs) {
     float* o = obs + (size_t)g * e.obs_dim;
-    if (e.kind == MZB_ENV_CARTPOLE) {
+    if (e.kind == MZB_ENV_SYNTHETIC_FRAMES) {
+      // written by k_synthetic_frames
+    } else if (e.kind == MZB_ENV_CARTPOLE) {
       const double* s = e.cp + (size_t)g * 4;
       for (int i = 0; i < 4; ++i) o[i] = (float)s[i];
     } else {
@@ -208,6 +214,18 @@ __global__ void k_env_observe(EnvView e, float* __restrict__ obs, uint8_t* __res
   if (to_play) to_play[g] = (int8_t)env_to_play(e, g);
   if (slot) slot[g] = e.slot0 + (uint32_t)g;
   if (step) step[g] = e.steps[g];
+}
+
+// Synthetic 3x96x96 frames U[0,1) (BASELINE.json: breakout on synthetic frames), a pure function of
+// (seed, slot, step, pixel): four pixels per Philox call, coalesced float4 stores.
+__global__ void k_synthetic_frames(EnvView e, float* __restrict__ obs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4
+  const int per = e.obs_dim / 4;
+  if (i >= (long long)e.G * per) return;
+  const int g = (int)(i / per), q = (int)(i % per);
+  const Philox4 r = rng_draw(e.key, e.slot0 + (uint32_t)g, e.steps[g], MZB_STREAM_RESET, 1, (uint32_t)q);
+  const float k = 1.0f / 16777216.0f;
+  reinterpret_cast<float4*>(obs)[i] = make_float4((r.x >> 8) * k, (r.y >> 8) * k, (r.z >> 8) * k, (r.w >> 8) * k);
 }
 
 // SelfPlay.select_action (self_play.py:223-246): children = legal actions in order, counts = visits.
@@ -355,6 +373,7 @@ int describe(const mzb_env_config& c, EnvView& v) {
     case MZB_ENV_CARTPOLE: v.A = 2; v.H = 1; v.W = 4; v.cells = 0; v.obs_dim = 4; v.reward_scale = 1; v.rec_floats = 4; break;
     case MZB_ENV_TICTACTOE: v.A = 9; v.H = 3; v.W = 3; v.cells = 9; v.obs_dim = 27; v.reward_scale = 20; v.rec_floats = 3; break;
     case MZB_ENV_CONNECT4: v.A = 7; v.H = 6; v.W = 7; v.cells = 42; v.obs_dim = 126; v.reward_scale = 10; v.rec_floats = 11; break;
+    case MZB_ENV_SYNTHETIC_FRAMES: v.A = 4; v.H = 96; v.W = 96; v.cells = 0; v.obs_dim = 3 * 96 * 96; v.reward_scale = 1; v.rec_floats = 1; break;
     case MZB_ENV_GOMOKU: v.A = 121; v.H = 11; v.W = 11; v.cells = 121; v.obs_dim = 363; v.reward_scale = 1; v.rec_floats = 31; break;
     default: mzb_set_error("unknown environment kind %d", c.kind); return MZB_EINVAL;
   }
@@ -458,6 +477,11 @@ int mzb_env_observe(mzb_env* e, float* d_obs, uint8_t* d_legal, int8_t* d_to_pla
   MZB_CHECK_ARG(e, "env is NULL");
   k_env_observe<<<blocks(e->v.G, 256), 256, 0, (cudaStream_t)stream>>>(e->v, d_obs, d_legal, d_to_play, d_slot, d_step);
   MZB_LAUNCH_CHECK();
+  if (e->v.kind == MZB_ENV_SYNTHETIC_FRAMES && d_obs) {
+    const long long n4 = (long long)e->v.G * (e->v.obs_dim / 4);
+    k_synthetic_frames<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->v, d_obs);
+    MZB_LAUNCH_CHECK();
+  }
   return MZB_OK;
 }
 

@@ -15,8 +15,9 @@ from ._lib import check, ptr
 
 _vp, _i32 = C.c_void_p, C.c_int32
 
-KINDS = {"cartpole": 0, "tictactoe": 1, "connect4": 2, "gomoku": 3}
-SHAPES = {"cartpole": (1, 1, 4), "tictactoe": (3, 3, 3), "connect4": (3, 6, 7), "gomoku": (3, 11, 11)}
+KINDS = {"cartpole": 0, "tictactoe": 1, "connect4": 2, "gomoku": 3, "breakout": 4}
+SHAPES = {"cartpole": (1, 1, 4), "tictactoe": (3, 3, 3), "connect4": (3, 6, 7), "gomoku": (3, 11, 11),
+          "breakout": (3, 96, 96)}
 
 
 class EnvConfig(C.Structure):

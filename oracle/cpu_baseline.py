@@ -24,7 +24,8 @@ def _make(kind, weights, cfg):
         net = networks.FullyConnected(weights, A, cfg["support_size"])
     env = {"cartpole": lambda: games.CartPole(1, seed=cfg["seed"], slot0=cfg["slot"]),
            "tictactoe": lambda: games.TicTacToe(1), "connect4": lambda: games.Connect4(1),
-           "gomoku": lambda: games.Gomoku(1)}[kind]()
+           "gomoku": lambda: games.Gomoku(1),
+           "breakout": lambda: games.SyntheticFrames(1, seed=cfg["seed"], slot0=cfg["slot"])}[kind]()
     return net, env, A
 
 

@@ -235,3 +235,38 @@ class CartPole:
         for g, e in enumerate(self.envs):
             _, rew[g], done[g] = e.step(int(actions[g]))
         return self.observation(), rew, done
+
+
+class SyntheticFrames:
+    """Breakout stand-in of BASELINE.json ("synthetic 96x96 frames"): frames are U[0,1) float32 drawn from the
+    shared counter RNG keyed by (seed, slot, step, pixel quad); reward 0; never done before max_moves.
+    (The reference wraps the ALE emulator, games/breakout.py:135-185 - third-party, absent: parity N/A.)"""
+
+    N_ACTIONS = 4
+
+    def __init__(self, n_games, seed=0, slot0=0):
+        self.G, self.seed, self.slot0 = n_games, seed, slot0
+        self.steps = np.zeros(n_games, dtype=np.int64)
+
+    def reset(self, mask=None):
+        return self.observation()
+
+    def observation(self):
+        n4 = 3 * 96 * 96 // 4
+        out = np.empty((self.G, n4, 4), dtype=np.float32)
+        for g in range(self.G):
+            r = rng.philox4x32_np(np.full(n4, self.slot0 + g), np.full(n4, self.steps[g]),
+                                  np.full(n4, (rng.STREAM_RESET << 16) | 1), np.arange(n4), self.seed & rng.MASK,
+                                  (self.seed >> 32) & rng.MASK)
+            out[g] = (np.stack(r, axis=1) >> np.uint64(8)).astype(np.float32) / np.float32(16777216.0)
+        return out.reshape(self.G, 3, 96, 96)
+
+    def to_play(self):
+        return np.zeros(self.G, dtype=np.int32)
+
+    def legal_mask(self):
+        return np.ones((self.G, 4), dtype=bool)
+
+    def step(self, actions):
+        self.steps += 1
+        return self.observation(), np.zeros(self.G), np.zeros(self.G, dtype=bool)

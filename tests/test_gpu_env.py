@@ -239,3 +239,17 @@ def test_game_plugin_contract():
             obs, reward, done = game.step(int(a))
             assert reward == z[pre + "rewards"][t] and done == bool(z[pre + "dones"][t])
         assert obs.dtype == (np.int32 if name == "tictactoe" else np.float64)
+
+
+def test_synthetic_frames_env_matches_oracle():
+    from muzero_hypermodel_b200.envs import VectorEnv
+    env = VectorEnv("breakout", 3, 50, seed=5, first_slot=7, device=DEV)
+    o = ogames.SyntheticFrames(3, seed=5, slot0=7)
+    for t in range(3):
+        obs, legal, tp = env.observe()
+        np.testing.assert_array_equal(obs.cpu().numpy().reshape(3, 3, 96, 96), o.observation())
+        assert legal.all() and not tp.any()
+        _, r, d = env.act_step(None, None, forced_action=torch.zeros(3, dtype=torch.int32, device=DEV), want_outputs=True)
+        o.step(np.zeros(3))
+        assert not r.any() and not d.any()
+    assert 0.45 < float(obs.mean()) < 0.55

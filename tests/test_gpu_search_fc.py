@@ -141,3 +141,23 @@ def test_search_vs_reference_network_agreement():
         dv.append(abs(out["root_value"][g] - res.root_value()) / max(1.0, abs(res.root_value())))
     assert same >= 0.8 * G, f"only {same}/{G} searches have identical visit counts"
     assert np.median(dv) < 1e-4 and max(dv) < 5e-2
+
+
+def test_sharding_invariance_same_slots_same_games():
+    """Games are keyed by their GLOBAL slot: playing slots [0, 2G) on one GPU or as two ranks of G games gives
+    identical episodes (device-generated noise, device action sampling, device env)."""
+    from muzero_hypermodel_b200.self_play import SelfPlay
+    net, cfg = _net("tictactoe_fc")
+    sd = net.get_weights()
+    G = 96
+
+    def play(n, first):
+        sp = SelfPlay({"weights": sd}, None, cfg, 5, n_games=n, device=DEV, first_slot=first)
+        games = sp.play_games(12, drain_every=2)
+        return {(g.slot, tuple(g.action_history)): g for g in games}
+
+    whole = play(2 * G, 0)
+    shards = {**play(G, 0), **play(G, G)}
+    assert len(whole) > G and set(whole) == set(shards)
+    for key in whole:
+        assert np.array(whole[key].root_values).tobytes() == np.array(shards[key].root_values).tobytes()
