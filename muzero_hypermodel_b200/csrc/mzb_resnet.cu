@@ -31,18 +31,20 @@ __global__ void k_nchw_to_nhwc(const float* __restrict__ in, long long in_row_st
   stf(out + geo_row(g, b, p / g.W, p % g.W) * g.C + c, src[(long long)c * HW + p]);
 }
 
-// dense NHWC T rows (slot addressed pool) -> NHWC T in geometry g
+// dense NHWC T rows (slot addressed pool) -> NHWC T in geometry g, 16 bytes per thread (C*sizeof(T) % 16 == 0)
 template <class T>
 __global__ void k_gather_nhwc(const T* __restrict__ in, long long in_row_stride, const int* __restrict__ in_slot,
                               long long slot_stride, int B, Geo g, T* __restrict__ out) {
+  constexpr int V = 16 / sizeof(T);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int HW = g.H * g.W;
-  if (i >= (long long)B * HW * g.C) return;
-  const int c = (int)(i % g.C);
-  const int p = (int)((i / g.C) % HW);
-  const int b = (int)(i / ((long long)g.C * HW));
-  out[geo_row(g, b, p / g.W, p % g.W) * g.C + c] =
-      in[b * in_row_stride + (in_slot ? (long long)in_slot[b] * slot_stride : 0) + (long long)p * g.C + c];
+  const int HW = g.H * g.W, cv = g.C / V;
+  if (i >= (long long)B * HW * cv) return;
+  const int c = (int)(i % cv) * V;
+  const int p = (int)((i / cv) % HW);
+  const int b = (int)(i / ((long long)cv * HW));
+  const uint4 v = *reinterpret_cast<const uint4*>(in + b * in_row_stride + (in_slot ? (long long)in_slot[b] * slot_stride : 0) +
+                                                  (long long)p * g.C + c);
+  *reinterpret_cast<uint4*>(out + geo_row(g, b, p / g.W, p % g.W) * g.C + c) = v;
 }
 
 // NHWC T in geometry g -> state rows in the requested layout: 0 NCHW fp32, 1 dense NHWC fp32, 2 dense NHWC bf16
@@ -133,51 +135,203 @@ __global__ void k_minmax(const T* __restrict__ x, int B, Geo g, T* __restrict__ 
 }
 
 // Head: conv1x1(+bias) -> flatten (channel-major, like .view on NCHW) -> mlp -> logits -> decode.
-// One block per image.  mode 0: support_to_scalar -> scalar_out; mode 1: softmax over legal -> priors_out.
-template <class T>
-__global__ void k_head(const T* __restrict__ x, int B, Geo g, HeadParams hp, int S, int mode,
-                       const uint8_t* __restrict__ legal, float* __restrict__ logits_out, float* __restrict__ scalar_out,
-                       float* __restrict__ priors_out) {
+// One WARP per image (grid-stride), 8 warps per block; the head's weights are staged once per block in shared
+// memory (fc weights transposed [in][out] so lanes = outputs read conflict-free).  mode 0: support_to_scalar ->
+// scalar_out; mode 1: softmax over legal -> priors_out.  Reductions are warp shuffles.
+struct HeadSmem { int w1, b1, fw[4], fb[4], scratch, per_warp, total; };
+
+__host__ __device__ inline HeadSmem head_smem(const HeadParams& hp, int warps) {
+  HeadSmem L{};
+  int off = 0;
+  L.w1 = off; off += 16 * hp.cin;                  // padded to the largest R instantiation, zero filled
+  L.b1 = off; off += hp.r;
+  for (int l = 0; l < hp.n_fc; ++l) { L.fw[l] = off; off += hp.fc_in[l] * hp.fc_out[l]; L.fb[l] = off; off += hp.fc_out[l]; }
+  off = (off + 3) & ~3;
+  L.scratch = off;
+  int widest = hp.r * hp.hw;
+  for (int l = 0; l < hp.n_fc; ++l) widest = widest > hp.fc_out[l] ? widest : hp.fc_out[l];
+  L.per_warp = 2 * ((widest + 3) & ~3);
+  L.total = off + warps * L.per_warp;
+  return L;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+template <class T, int R>
+__global__ void __launch_bounds__(256) k_head(const T* __restrict__ x, int B, Geo g, HeadParams hp, int S, int mode,
+                                              const uint8_t* __restrict__ legal, float* __restrict__ logits_out,
+                                              float* __restrict__ scalar_out, float* __restrict__ priors_out) {
   extern __shared__ float sm[];
-  const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
-  float* flat = sm;                                   // [r*hw]
-  float* bufA = flat + hp.r * hp.hw;                  // mlp ping-pong, width <= 128
-  float* bufB = bufA + 128;
-  for (int i = tid; i < hp.r * hp.hw; i += NT) {
-    const int r = i / hp.hw, p = i % hp.hw;
-    float acc = hp.b1x1[r];
-    const float* w = hp.w1x1 + (size_t)r * hp.cin;
-    const T* xp = x + geo_row(g, b, p / g.W, p % g.W) * hp.cin;
-    for (int c = 0; c < hp.cin; ++c) acc = fmaf(ldf(xp + c), w[c], acc);
-    flat[i] = acc;
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const HeadSmem L = head_smem(hp, warps);
+  for (int i = threadIdx.x; i < R * hp.cin; i += blockDim.x) sm[L.w1 + i] = i < hp.r * hp.cin ? hp.w1x1[i] : 0.0f;
+  for (int i = threadIdx.x; i < hp.r; i += blockDim.x) sm[L.b1 + i] = hp.b1x1[i];
+  for (int l = 0; l < hp.n_fc; ++l) {
+    const int in = hp.fc_in[l], out = hp.fc_out[l];
+    for (int i = threadIdx.x; i < in * out; i += blockDim.x) {        // [out][in] -> [in][out]
+      const int o = i / in, k = i % in;
+      sm[L.fw[l] + k * out + o] = hp.fc_w[l][i];
+    }
+    for (int i = threadIdx.x; i < out; i += blockDim.x) sm[L.fb[l] + i] = hp.fc_b[l][i];
   }
   __syncthreads();
-  const float* in = flat;
-  float* out = bufA;
-  for (int l = 0; l < hp.n_fc; ++l) {
-    for (int o = tid; o < hp.fc_out[l]; o += NT) {
-      float acc = hp.fc_b[l][o];
-      const float* w = hp.fc_w[l] + (size_t)o * hp.fc_in[l];
-      for (int k = 0; k < hp.fc_in[l]; ++k) acc = fmaf(in[k], w[k], acc);
-      out[o] = l < hp.n_fc - 1 ? elu_f32(acc) : acc;
+  float* bufA = sm + L.scratch + warp * L.per_warp;
+  float* bufB = bufA + L.per_warp / 2;
+  const int n_flat = hp.r * hp.hw, n = hp.out;
+  // conv1x1 mapping: a group of LPP lanes shares one position, each lane owns 16-byte channel chunks
+  constexpr int V = 16 / (int)sizeof(T);
+  const int cpr = hp.cin / V;                               // 16-byte chunks per row
+  const int LPP = cpr < 32 ? cpr : 32;                      // lanes per position (power of two)
+  const int PPI = 32 / LPP;                                 // positions per warp iteration
+  const int sub = lane % LPP;
+  for (int b = blockIdx.x * warps + warp; b < B; b += gridDim.x * warps) {
+    for (int p0 = 0; p0 < hp.hw; p0 += PPI) {
+      const int p = p0 + lane / LPP;
+      const bool valid = p < hp.hw;
+      float acc[R];
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) acc[rr] = 0.0f;
+      if (valid) {
+        const T* row = x + geo_row(g, b, p / g.W, p % g.W) * hp.cin;
+        for (int ch = sub; ch < cpr; ch += LPP) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(row + ch * V);
+          float xv[V];
+          if (sizeof(T) == 2) {
+            const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { xv[(2 * j) % V] = __uint_as_float(w4[j] << 16); xv[(2 * j + 1) % V] = __uint_as_float(w4[j] & 0xFFFF0000u); }
+          } else {
+            xv[0] = __uint_as_float(raw.x); xv[1] = __uint_as_float(raw.y); xv[2 % V] = __uint_as_float(raw.z); xv[3 % V] = __uint_as_float(raw.w);
+          }
+          const float* w = sm + L.w1 + ch * V;
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[rr] = fmaf(xv[j], w[rr * hp.cin + j], acc[rr]);
+          }
+        }
+      }
+      for (int o = LPP >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) acc[rr] += __shfl_xor_sync(0xFFFFFFFFu, acc[rr], o);
+      }
+      if (valid && sub == 0) {
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) if (rr < hp.r) bufA[rr * hp.hw + p] = acc[rr] + sm[L.b1 + rr];
+      }
     }
-    __syncthreads();
-    in = out;
-    out = (out == bufA) ? bufB : bufA;
-  }
-  const int n = hp.out;
-  if (logits_out) for (int o = tid; o < n; o += NT) logits_out[(long long)b * n + o] = in[o];
-  if (tid == 0) {
+    __syncwarp();
+    float* in = bufA;
+    float* out = bufB;
+    for (int l = 0; l < hp.n_fc; ++l) {
+      const int ni = hp.fc_in[l], no = hp.fc_out[l];
+      const float* w = sm + L.fw[l];
+      for (int o = lane; o < no; o += 32) {
+        float acc = sm[L.fb[l] + o];
+        for (int k = 0; k < ni; ++k) acc = fmaf(in[k], w[k * no + o], acc);
+        out[o] = l < hp.n_fc - 1 ? elu_f32(acc) : acc;
+      }
+      __syncwarp();
+      float* t = in; in = out; out = t;
+    }
+    if (logits_out) for (int o = lane; o < n; o += 32) logits_out[(long long)b * n + o] = in[o];
     if (mode == 0 && scalar_out) {
-      float* e = out;
-      scalar_out[b] = support_to_scalar_dev([=](int i) { return in[i]; }, [=](int i) -> float& { return e[i]; }, S);
+      // support_to_scalar (models.py:641-662): softmax expectation over [-S..S], inverse transform
+      float m = -CUDART_INF_F;
+      for (int i = lane; i < n; i += 32) m = fmaxf(m, in[i]);
+      m = warp_max(m);
+      float se = 0.0f, sx = 0.0f;
+      for (int i = lane; i < n; i += 32) { const float e = softmax_exp(in[i], m); se += e; sx = fmaf((float)(i - S), e, sx); }
+      se = warp_sum(se); sx = warp_sum(sx);
+      if (lane == 0) scalar_out[b] = inverse_value_transform(__fdiv_rn(sx, se));
     } else if (mode == 1 && priors_out) {
       const uint8_t* lg = legal ? legal + (long long)b * n : nullptr;
       float m = -CUDART_INF_F;
-      for (int a = 0; a < n; ++a) if (!lg || lg[a]) m = fmaxf(m, in[a]);
-      float sum = 0.0f;
-      for (int a = 0; a < n; ++a) { const float ev = (!lg || lg[a]) ? softmax_exp(in[a], m) : 0.0f; out[a] = ev; sum = __fadd_rn(sum, ev); }
-      for (int a = 0; a < n; ++a) priors_out[(long long)b * n + a] = __fdiv_rn(out[a], sum);
+      for (int a = lane; a < n; a += 32) if (!lg || lg[a]) m = fmaxf(m, in[a]);
+      m = warp_max(m);
+      float se = 0.0f;
+      for (int a = lane; a < n; a += 32) { const float e = (!lg || lg[a]) ? softmax_exp(in[a], m) : 0.0f; out[a] = e; se += e; }
+      se = warp_sum(se);
+      for (int a = lane; a < n; a += 32) priors_out[(long long)b * n + a] = __fdiv_rn(out[a], se);
+    }
+    __syncwarp();
+  }
+}
+
+// Fused: per-(image, channel) min-max scaling (models.py:525-549) + normalised state written both to the next
+// layer's input buffer and to the caller's state rows.  One warp per image, lanes = channel pairs, so every
+// position is one coalesced row read; C must be even and <= 512.
+template <class T> struct Pair;
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+  static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+template <> struct Pair<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+};
+
+template <class T, int MAXP>
+__global__ void __launch_bounds__(256) k_minmax_store(const T* __restrict__ x, int B, Geo g, T* __restrict__ y, int layout,
+                                                      void* __restrict__ state, long long row_stride, long long off) {
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = g.C, HW = g.H * g.W, pairs = C / 2;       // MAXP = channel pairs per lane (C <= 64 * MAXP)
+  for (int b = blockIdx.x * warps + warp; b < B; b += gridDim.x * warps) {
+    float lo[2 * MAXP], hi[2 * MAXP];
+#pragma unroll
+    for (int k = 0; k < 2 * MAXP; ++k) { lo[k] = CUDART_INF_F; hi[k] = -CUDART_INF_F; }
+    for (int p = 0; p < HW; ++p) {
+      const T* row = x + geo_row(g, b, p / g.W, p % g.W) * C;
+#pragma unroll
+      for (int k = 0; k < MAXP; ++k) {
+        const int c2 = lane + 32 * k;
+        if (c2 < pairs) {
+          const float2 v = Pair<T>::ld(row + 2 * c2);
+          lo[2 * k] = fminf(lo[2 * k], v.x); hi[2 * k] = fmaxf(hi[2 * k], v.x);
+          lo[2 * k + 1] = fminf(lo[2 * k + 1], v.y); hi[2 * k + 1] = fmaxf(hi[2 * k + 1], v.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * MAXP; ++k) {
+      float scale = __fsub_rn(hi[k], lo[k]);
+      if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+      hi[k] = scale;
+    }
+    for (int p = 0; p < HW; ++p) {
+      const long long ro = geo_row(g, b, p / g.W, p % g.W) * C;
+#pragma unroll
+      for (int k = 0; k < MAXP; ++k) {
+        const int c2 = lane + 32 * k;
+        if (c2 < pairs) {
+          float2 v = Pair<T>::ld(x + ro + 2 * c2);
+          v.x = __fdiv_rn(__fsub_rn(v.x, lo[2 * k]), hi[2 * k]);
+          v.y = __fdiv_rn(__fsub_rn(v.y, lo[2 * k + 1]), hi[2 * k + 1]);
+          Pair<T>::st(y + ro + 2 * c2, v);
+          if (state) {
+            const int c = 2 * c2;
+            if (layout == 0) {
+              float* o = (float*)state + b * row_stride + off;
+              o[(long long)c * HW + p] = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(v.x)) : v.x;
+              o[(long long)(c + 1) * HW + p] = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(v.y)) : v.y;
+            } else if (layout == 1) {
+              *reinterpret_cast<float2*>((float*)state + b * row_stride + off + (long long)p * C + c) = v;
+            } else {
+              *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)state + b * row_stride + off + (long long)p * C + c) =
+                  __floats2bfloat162_rn(v.x, v.y);
+            }
+          }
+        }
+      }
     }
   }
 }
@@ -453,8 +607,26 @@ template <class T>
 void head(Runner& r, const T* x, Geo g, const HeadParams& hp, int mode, const uint8_t* legal, float* logits,
           float* scalar, float* priors) {
   if (r.rc || (!logits && !scalar && !priors)) return;
-  const size_t smem = sizeof(float) * ((size_t)hp.r * hp.hw + 256);
-  k_head<T><<<r.B, 128, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors);
+  const int warps = 8;
+  const size_t smem = sizeof(float) * (size_t)head_smem(hp, warps).total;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_head<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_head<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_head<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  const int V = 16 / (int)sizeof(T), cpr = hp.cin / V;
+  if (smem > 200 * 1024 || hp.r > 16 || hp.cin % V != 0 || (cpr & (cpr - 1)) != 0) {
+    mzb_set_error("head shape unsupported (smem %zu bytes, r=%d, cin=%d)", smem, hp.r, hp.cin);
+    r.rc = MZB_EUNSUPPORTED;
+    return;
+  }
+  int grid = (r.B + warps - 1) / warps;
+  if (grid > 148 * 4) grid = 148 * 4;                 // persistent: weights are staged once per block
+  if (hp.r <= 2) k_head<T, 2><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors);
+  else if (hp.r <= 4) k_head<T, 4><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors);
+  else k_head<T, 16><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors);
   mzb_count_launch();
 }
 
@@ -463,14 +635,22 @@ struct Outputs {
   float* value_logits; float* reward_logits; float* policy_logits; float* value; float* reward; float* priors;
 };
 
+// min-max scaling of buffer `cur` into buffer `nx` + the caller's state rows, one fused launch
+template <class T>
+void minmax_store(Runner& r, int cur, int nx, Geo g, const Outputs& o) {
+  if (r.rc) return;
+  if (g.C % 2 != 0 || g.C > 512) { mzb_set_error("min-max kernel needs an even channel count <= 512"); r.rc = MZB_EUNSUPPORTED; return; }
+  int grid = (r.B + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (g.C <= 64) k_minmax_store<T, 1><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
+  else if (g.C <= 128) k_minmax_store<T, 2><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
+  else k_minmax_store<T, 8><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
+  mzb_count_launch();
+}
+
 template <class T>
 void prediction_and_state(Runner& r, int cur, Geo g, const Outputs& o, const uint8_t* legal) {
   mzb_resnet_model* m = r.m;
-  if (o.state) {
-    const long long n = (long long)r.B * g.H * g.W * g.C;
-    k_store_state<T><<<nblk(n, 256), 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, o.layout, o.state, o.row_stride, o.off);
-    mzb_count_launch();
-  }
   if (o.value_logits || o.policy_logits || o.value || o.priors) {
     const int p = tower<T>(r, m->pred_blocks, g, cur);
     head<T>(r, r.buf<T>(p), g, m->value, 0, nullptr, o.value_logits, o.value, nullptr);
@@ -518,7 +698,7 @@ int run_initial(Runner& r, const float* obs, const uint8_t* legal, const Outputs
       cudaMemsetAsync(r.buf<T>(a), 0, r.act_bytes, r.s);
       cudaMemsetAsync(r.buf<T>(b2), 0, r.act_bytes, r.s);
       const long long n = (long long)B * gd.H * gd.W * C;
-      k_gather_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>(dense, (long long)gd.H * gd.W * C, nullptr, 0, B, gl, r.buf<T>(a));
+      k_gather_nhwc<T><<<nblk(n / (16 / sizeof(T)), 256), 256, 0, r.s>>>(dense, (long long)gd.H * gd.W * C, nullptr, 0, B, gl, r.buf<T>(a));
       mzb_count_launch();
       cudaMemsetAsync(dense, 0, r.act_bytes, r.s);
       cur = a;
@@ -537,8 +717,7 @@ int run_initial(Runner& r, const float* obs, const uint8_t* legal, const Outputs
   }
   cur = tower<T>(r, m->rep_blocks, gl, cur);
   const int nx = (cur + 1) % 3;
-  k_minmax<T><<<nblk(B * C, 128), 128, 0, r.s>>>(r.buf<T>(cur), B, gl, r.buf<T>(nx));
-  mzb_count_launch();
+  minmax_store<T>(r, cur, nx, gl, o);
   if (o.reward_logits || o.reward) { k_zero_reward<<<nblk(B, 128), 128, 0, r.s>>>(B, m->S, o.reward_logits, o.reward); mzb_count_launch(); }
   prediction_and_state<T>(r, nx, gl, o, legal);
   return r.rc;
@@ -554,7 +733,8 @@ int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_r
   if (in_layout == 0) {
     k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const float*)state_in, in_row_stride, in_slot, slot_stride, B, gl, r.buf<T>(0));
   } else if ((in_layout == 1 && sizeof(T) == 4) || (in_layout == 2 && sizeof(T) == 2)) {
-    k_gather_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const T*)state_in, in_row_stride, in_slot, slot_stride, B, gl, r.buf<T>(0));
+    if ((C * sizeof(T)) % 16 != 0) { mzb_set_error("channels * element size must be a multiple of 16 bytes"); return MZB_EUNSUPPORTED; }
+    k_gather_nhwc<T><<<nblk(n / (16 / sizeof(T)), 256), 256, 0, r.s>>>((const T*)state_in, in_row_stride, in_slot, slot_stride, B, gl, r.buf<T>(0));
   } else {
     mzb_set_error("state layout %d does not match the model precision", in_layout);
     return MZB_EINVAL;
@@ -566,8 +746,7 @@ int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_r
   int cur = tower<T>(r, m->dyn_blocks, gl, 1);
   head<T>(r, r.buf<T>(cur), gl, m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr);   // reward on the un-normalised state
   const int nx = (cur + 1) % 3;
-  k_minmax<T><<<nblk(B * C, 128), 128, 0, r.s>>>(r.buf<T>(cur), B, gl, r.buf<T>(nx));
-  mzb_count_launch();
+  minmax_store<T>(r, cur, nx, gl, o);
   prediction_and_state<T>(r, nx, gl, o, nullptr);
   return r.rc;
 }
