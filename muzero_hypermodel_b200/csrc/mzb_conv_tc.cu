@@ -79,6 +79,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO>>4 | version 1 |
 // base_offset 0 | layout type.  The start address may sit at ANY row of a TMA-written swizzled tile.
 template <int KC>
@@ -89,7 +98,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 }
 
 template <int KC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   constexpr int ROWB = KC * 2;                                           // bytes per shared-memory row
   extern __shared__ uint8_t smem_raw[];
@@ -107,6 +116,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* b_empty = bars + 1 + kStages;
   uint64_t* acc_full = bars + 1 + 2 * kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kStages);
+  float* s_scale = reinterpret_cast<float*>(bars + 4 + 2 * kStages);
+  float* s_shift = s_scale + N;
   const long long m0 = (long long)blockIdx.x * MT * 128;                 // first row of this CTA (image-row space)
   const int NKB = 9 * a.n_chunks;
 
@@ -166,8 +177,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       umma_commit(acc_full);
     }
   } else {
-    // ---- epilogue warps: TMEM lane quarter = warp % 4
+    // ---- epilogue warps: TMEM lane quarter = warp % 4.  Per 64-column group: the residual row is requested
+    // first (one exposed global latency per group, not per chunk), then four 16-column TMEM loads are issued
+    // back to back behind a single wait.
     const int q = warp & 3;
+    for (int i = threadIdx.x - 64; i < N; i += kThreads - 64) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+    asm volatile("bar.sync 1, 128;" ::: "memory");             // epilogue warps only
     mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int t = 0; t < MT; ++t) {
@@ -179,38 +194,52 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const long long row_off = (m + halo) * (long long)N;
       const float pl = (valid && a.plane) ? a.plane[b] : 0.0f;
       const float* ptab = (valid && a.plane) ? a.plane_table + (size_t)((yy - 1) * a.W + (xx - 1)) * N : nullptr;
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * N + c0), v);
-        if (!valid) continue;
-        float f[16];
+      for (int g0 = 0; g0 < N; g0 += 64) {
+        const int gw = N - g0 < 64 ? N - g0 : 64;              // columns in this group (multiple of 16)
+        uint4 res[8];
+        if (valid && a.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + row_off + g0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float acc = __uint_as_float(v[i]);
-          if (ptab) acc = fmaf(pl, ptab[c0 + i], acc);
-          f[i] = fmaf(acc, a.scale[c0 + i], a.shift[c0 + i]);
+          for (int i = 0; i < 8; ++i) if (i * 8 < gw) res[i] = rp[i];
         }
-        if (a.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + row_off + c0);
-          const uint4 r0 = rp[0], r1 = rp[1];
-          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        uint32_t v[64];
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * N + g0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (c * 16 < gw) tmem_ld16_nowait(tbase + c * 16, v + c * 16);
+        tmem_wait_ld();
+        if (!valid) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 16 >= gw) break;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = g0 + c * 16 + i;
+            float acc = __uint_as_float(v[c * 16 + i]);
+            if (ptab) acc = fmaf(pl, ptab[col], acc);
+            f[i] = fmaf(acc, s_scale[col], s_shift[col]);
+          }
+          if (a.residual) {
+            const uint32_t rw[8] = {res[2 * c].x, res[2 * c].y, res[2 * c].z, res[2 * c].w,
+                                    res[2 * c + 1].x, res[2 * c + 1].y, res[2 * c + 1].z, res[2 * c + 1].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[2 * i] += __uint_as_float(rw[i] << 16);
+              f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
+            }
+          }
+          uint32_t o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            f[2 * i] += __uint_as_float(rw[i] << 16);
-            f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
+            float lo = f[2 * i], hi = f[2 * i + 1];
+            if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+            o[i] = *reinterpret_cast<const uint32_t*>(&pk);
           }
+          uint4* op = reinterpret_cast<uint4*>(a.y + row_off + g0 + c * 16);
+          op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          op[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
-        uint32_t o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float lo = f[2 * i], hi = f[2 * i + 1];
-          if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
-          const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-          o[i] = *reinterpret_cast<const uint32_t*>(&pk);
-        }
-        uint4* op = reinterpret_cast<uint4*>(a.y + row_off + c0);
-        op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        op[1] = make_uint4(o[4], o[5], o[6], o[7]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -259,10 +288,16 @@ int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
 int pick_mt(int cout, int n_chunks, int kc, int max_smem) {
   for (int mt = 4; mt >= 1; mt >>= 1) {
     if (mt * cout > 512) continue;
-    const size_t smem = (size_t)n_chunks * (mt + 1) * 128 * kc * 2 + (size_t)kStages * cout * kc * 2 + 1024 + 256;
+    const size_t smem = (size_t)n_chunks * (mt + 1) * 128 * kc * 2 + (size_t)kStages * cout * kc * 2 + 1024 + 256 + 8 * (size_t)cout;
     if (smem <= (size_t)max_smem) return mt;
   }
   return 0;
+}
+
+// two CTAs per SM (epilogue of one overlaps the MMAs of the other) when a configuration fits in half the SM
+int pick_mt_auto(int cout, int n_chunks, int kc) {
+  const int two = pick_mt(cout, n_chunks, kc, 113 * 1024);
+  return two > 0 ? two : pick_mt(cout, n_chunks, kc, 227 * 1024);
 }
 
 }  // namespace
@@ -273,13 +308,13 @@ extern "C" void mzb_conv_tc_enable(int on) { g_tc_enabled = on != 0; }
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
   return g_tc_enabled && cp.stride == 1 && cp.cin == cin_stride && cp.cin % 16 == 0 && cp.cout % 16 == 0 && cp.cout >= 16 &&
          cp.cout <= 256 && W <= 61 && cp.w_bf16 != nullptr && encode_fn() != nullptr &&
-         pick_mt(cp.cout, cp.cin / pick_kc(cp.cin), pick_kc(cp.cin), 227 * 1024) > 0;
+         pick_mt_auto(cp.cout, cp.cin / pick_kc(cp.cin), pick_kc(cp.cin)) > 0;
 }
 
 int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
                        const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream) {
   const int kc = pick_kc(cp.cin), n_chunks = cp.cin / kc;
-  const int mt = pick_mt(cp.cout, n_chunks, kc, 227 * 1024);
+  const int mt = pick_mt_auto(cp.cout, n_chunks, kc);
   MZB_CHECK_ARG(mt > 0, "tensor-core convolution: no tile configuration fits");
   const Geo g{H, W, cp.cin, 1};
   const long long rows_total = geo_rows_total(g, B);
@@ -299,7 +334,7 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   a.rows_valid = (long long)B * a.R_img;
   a.scale = cp.scale; a.shift = cp.shift; a.plane = cp.extra_plane ? plane : nullptr; a.plane_table = cp.plane_table;
   a.residual = residual; a.y = y;
-  const size_t smem = (size_t)n_chunks * (mt + 1) * 128 * kc * 2 + (size_t)kStages * cp.cout * kc * 2 + 1024 + 256;
+  const size_t smem = (size_t)n_chunks * (mt + 1) * 128 * kc * 2 + (size_t)kStages * cp.cout * kc * 2 + 1024 + 256 + 8 * (size_t)cp.cout;
   const long long tiles = (a.rows_valid + 127) / 128;
   const unsigned grid = (unsigned)((tiles + mt - 1) / mt);
 #define LAUNCH_KC(KCV)                                                                                              \
