@@ -173,9 +173,9 @@ __global__ void k_support_to_scalar(const float* __restrict__ logits, long long 
   for (int i = 0; i < full; ++i) m = fmaxf(m, l[i]);
   float sum = 0.0f;
   for (int i = 0; i < full; ++i) sum = __fadd_rn(sum, softmax_exp(l[i], m));
-  float x = 0.0f;
-  for (int i = 0; i < full; ++i) x = __fadd_rn(x, __fmul_rn((float)(i - S), __fdiv_rn(softmax_exp(l[i], m), sum)));
-  out[row] = inverse_value_transform(x);
+  float num = 0.0f;
+  for (int i = 0; i < full; ++i) num = fmaf((float)(i - S), softmax_exp(l[i], m), num);
+  out[row] = inverse_value_transform(__fdiv_rn(num, sum));
 }
 
 // scalar_to_support (models.py:665-685): h-transform, clamp, two-hot on floor / floor+1

@@ -69,7 +69,8 @@ __device__ __forceinline__ float support_to_scalar_dev(Logit logit, Scratch e, i
     e(i) = v;
     sum = __fadd_rn(sum, v);
   }
-  float x = 0.0f;
-  for (int i = 0; i < full; ++i) x = __fadd_rn(x, __fmul_rn((float)(i - S), __fdiv_rn(e(i), sum)));
-  return inverse_value_transform(x);
+  // expectation = (sum_i support_i * e_i) / (sum_i e_i): one division instead of one per bin
+  float num = 0.0f;
+  for (int i = 0; i < full; ++i) num = fmaf((float)(i - S), e(i), num);
+  return inverse_value_transform(__fdiv_rn(num, sum));
 }

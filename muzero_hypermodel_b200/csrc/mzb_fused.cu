@@ -8,6 +8,8 @@
 // modular kernels use (mzb_tree.cuh): a thread reads one node's edges as one contiguous record.
 // The float32/float64 arithmetic is shared with the batched kernels (mzb_fc.cuh, mzb_common.cuh), so
 // this path and the modular path (K5, K0, K1+K4+K3 per simulation) give bit-identical trees.
+#include <stdlib.h>
+
 #include "mzb_fc.cuh"
 #include "mzb_tree.cuh"
 
@@ -98,10 +100,10 @@ __device__ __forceinline__ float s2s_regs(const float (&l)[2 * SUP + 1]) {
   float sum = 0.0f;
 #pragma unroll
   for (int i = 0; i < FULL; ++i) { e[i] = softmax_exp(l[i], m); sum = __fadd_rn(sum, e[i]); }
-  float x = 0.0f;
+  float num = 0.0f;
 #pragma unroll
-  for (int i = 0; i < FULL; ++i) x = __fadd_rn(x, __fmul_rn((float)(i - SUP), __fdiv_rn(e[i], sum)));
-  return inverse_value_transform(x);
+  for (int i = 0; i < FULL; ++i) num = fmaf((float)(i - SUP), e[i], num);
+  return inverse_value_transform(__fdiv_rn(num, sum));
 }
 
 // softmax over the legal actions (all when legal == NULL), summed in action order; 0 elsewhere
@@ -125,19 +127,31 @@ struct SearchIO {
   int* visits; double* root_value; float* root_pred_value; int* max_depth;
 };
 
-constexpr int kFusedThreads = 128;
-
-template <class SH>
-__global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, const float* __restrict__ gpack, SearchIO io) {
+// THREADS per block, PHASE_SYNC: a block barrier before the network phase of every simulation re-aligns the
+// block's warps so they fetch the (fully unrolled, ~100 KB) network code together; PB_LUT: the exploration factor
+// pb(N, n) = (log((N+base+1)/base)+init) * (sqrt(N)/(n+1)) comes from a shared-memory table built with the same
+// three float64 operations (bit-identical), removing a double division and square root per child and level.
+template <class SH, int THREADS, bool PHASE_SYNC, bool PB_LUT>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t, const float* __restrict__ gpack, SearchIO io) {
   constexpr int A = SH::A, ENC = SH::ENC, FULL = SH::FULL;
   extern __shared__ float4 smem4[];
   float* pack = reinterpret_cast<float*>(smem4);
   double* lut = reinterpret_cast<double*>(pack + SH::PACK);
-  for (int i = threadIdx.x; i < SH::PACK / 4; i += kFusedThreads) smem4[i] = reinterpret_cast<const float4*>(gpack)[i];
-  for (int i = threadIdx.x; i <= io.num_sims; i += kFusedThreads) lut[i] = t.log_lut[i];
+  const int S1 = io.num_sims + 1;
+  double* pbt = lut + ((S1 + 1) & ~1);                     // [S1][S1] when PB_LUT
+  for (int i = threadIdx.x; i < SH::PACK / 4; i += THREADS) smem4[i] = reinterpret_cast<const float4*>(gpack)[i];
+  for (int i = threadIdx.x; i < S1; i += THREADS) lut[i] = t.log_lut[i];
+  if (PB_LUT) {
+    for (int i = threadIdx.x; i < S1 * S1; i += THREADS) {
+      const int N = i / S1, n = i % S1;
+      pbt[i] = ucb_pb(t.log_lut[N], __dsqrt_rn((double)N), n);
+    }
+  }
   __syncthreads();
-  const int g = blockIdx.x * kFusedThreads + threadIdx.x;
-  if (g >= t.G) return;
+  const int g_raw = blockIdx.x * THREADS + threadIdx.x;
+  const bool active = g_raw < t.G;
+  if (!PHASE_SYNC && !active) return;
+  const int g = active ? g_raw : 0;                        // idle threads of the last block only take part in barriers
   const bool two = t.P == 2;
   const size_t G = (size_t)t.G;
   const uint32_t my_slot = io.slot ? io.slot[g] : (uint32_t)g;
@@ -147,8 +161,8 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
 
   // ---------------- initial inference (models.py:172-190) + root expansion (self_play.py:292-314)
   double rp[A];                       // root priors, float64 after the noise mix
-  float root_reward;
-  {
+  float root_reward = 0.0f;
+  if (active) {
     float ob[SH::OBS];
 #pragma unroll
     for (int i = 0; i < SH::OBS; ++i) ob[i] = io.obs[(size_t)g * SH::OBS + i];
@@ -211,19 +225,24 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
   unsigned int depth_sum = 0;
   double root_vs = 0.0, vmin = CUDART_INF, vmax = -CUDART_INF;
   uint32_t* path = t.path + g;                       // transposed use of the path buffer: path[depth * G]
+  // PB_LUT kernels (num_simulations <= 63) keep the search path AND the statistics of the edges they walked in
+  // per-thread local memory (L1-resident), so the backup issues no dependent global loads.
+  constexpr int LP = PB_LUT ? 64 : 1;
+  uint32_t lp_edge[LP]; double lp_vs[LP]; int lp_vi[LP]; float lp_rw[LP];
 
   for (int sim = 0; sim < io.num_sims; ++sim) {
     // ---------------- select walk (self_play.py:326-335, 364-405)
     int node = 0, N = root_visit, depth = 0, action = 0;
-    while (true) {
+    while (active) {
       uint8_t* r = t.rec(g, node);
       double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
 #pragma unroll
       for (int a = 0; a < A; ++a) {
         vs[a] = t.value_sum(r)[a]; pr[a] = t.prior(r)[a]; vi[a] = t.visit(r)[a]; rw[a] = t.reward(r)[a]; ch[a] = t.child(r)[a];
       }
-      const double pbc0 = lut[N];
-      const double sqrtN = __dsqrt_rn((double)N);
+      const double pbc0 = PB_LUT ? 0.0 : lut[N];
+      const double sqrtN = PB_LUT ? 0.0 : __dsqrt_rn((double)N);
+      const double* pbrow = pbt + N * S1;
       double sc[A];
       double best = -CUDART_INF;
       int n_best = 0;
@@ -232,7 +251,8 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
       for (int a = 0; a < A; ++a) {
         if (ch[a] == MZB_CHILD_ILLEGAL) { sc[a] = -CUDART_INF; continue; }
         const double p = node == 0 ? rp[a] : (double)pr[a];
-        sc[a] = ucb_score(pbc0, sqrtN, vi[a], p, vs[a], (double)rw[a], t.discount, two, vmin, vmax);
+        const double pb = PB_LUT ? pbrow[vi[a]] : ucb_pb(pbc0, sqrtN, vi[a]);
+        sc[a] = ucb_score_pb(pb, vi[a], p, vs[a], (double)rw[a], t.discount, two, vmin, vmax);
         if (sc[a] > best || action < 0) { best = sc[a]; n_best = 1; action = a; }
         else if (sc[a] == best) ++n_best;
       }
@@ -246,16 +266,23 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
           }
         }
       }
-      path[(size_t)depth * G] = ((uint32_t)node << 16) | (uint32_t)action;
-      ++depth;
       int next = MZB_CHILD_NONE, nv = 0;
+      double nvs = 0.0; float nrw = 0.0f;
 #pragma unroll
-      for (int a = 0; a < A; ++a) if (a == action) { next = ch[a]; nv = vi[a]; }
+      for (int a = 0; a < A; ++a) if (a == action) { next = ch[a]; nv = vi[a]; nvs = vs[a]; nrw = rw[a]; }
+      if (PB_LUT) {
+        lp_edge[depth] = ((uint32_t)node << 16) | (uint32_t)action; lp_vs[depth] = nvs; lp_vi[depth] = nv; lp_rw[depth] = nrw;
+      } else {
+        path[(size_t)depth * G] = ((uint32_t)node << 16) | (uint32_t)action;
+      }
+      ++depth;
       if (next < 0) break;
       N = nv;
       node = next;
     }
     const int L = depth, fresh = sim + 1;
+    if (PHASE_SYNC) __syncthreads();          // warps of the block enter the unrolled network code together
+    if (!active) continue;
 
     // ---------------- recurrent inference on the parent's hidden state (models.py:192-195)
     float value, reward, pri[A];
@@ -303,12 +330,12 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
     // ---------------- backup (self_play.py:407-431), leaf first
     double val = (double)value;
     for (int k = L - 1; k >= 0; --k) {
-      const uint32_t pe = path[(size_t)k * G];
+      const uint32_t pe = PB_LUT ? lp_edge[k] : path[(size_t)k * G];
       uint8_t* er = t.rec(g, (int)(pe >> 16));
       const int pa = (int)(pe & 0xFFFFu);
-      double e_vs = t.value_sum(er)[pa];
-      int e_vi = t.visit(er)[pa];
-      const double e_rw = (k == L - 1) ? (double)reward : (double)t.reward(er)[pa];
+      double e_vs = PB_LUT ? lp_vs[k] : t.value_sum(er)[pa];
+      int e_vi = PB_LUT ? lp_vi[k] : t.visit(er)[pa];
+      const double e_rw = (k == L - 1) ? (double)reward : (PB_LUT ? (double)lp_rw[k] : (double)t.reward(er)[pa]);
       backup_step(e_vs, e_vi, e_rw, val, t.discount, two, ((L - (k + 1)) & 1) == 0, vmin, vmax);
       t.value_sum(er)[pa] = e_vs;
       t.visit(er)[pa] = e_vi;
@@ -320,6 +347,7 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
   atomicAdd(t.counters, (unsigned long long)depth_sum);
   atomicAdd(t.counters + 1, (unsigned long long)io.num_sims);
 
+  if (!active) return;
   // ---------------- publish the per-game scalars (same fields the modular kernels keep)
   t.root_value_sum[g] = root_vs;
   t.vmin[g] = vmin;
@@ -344,19 +372,45 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_search_fc(TreeView t, cons
 using CartpoleShape = Shape<4, 8, 2, 10, 0, 16, 16, 16, 16>;       // games/cartpole.py:21-71
 using TicTacToeFcShape = Shape<27, 32, 9, 10, 0, 16, 16, 0, 0>;    // games/tictactoe.py:20-70, network="fullyconnected"
 
-template <class SH>
-int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
-  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(io.num_sims + 1);
+template <class SH, int THREADS, bool PHASE_SYNC, bool PB_LUT>
+int launch_variant(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
+  const int S1 = io.num_sims + 1;
+  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? S1 * S1 : 0));
   static bool configured = false;
   if (!configured) {
-    MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = true;
   }
-  MZB_CHECK_ARG(smem <= 64 * 1024, "fused search: shared memory %zu > 64 KiB", smem);
-  const int grid = (t->v.G + kFusedThreads - 1) / kFusedThreads;
-  k_search_fc<SH><<<grid, kFusedThreads, smem, s>>>(t->v, m->d_pack, io);
+  MZB_CHECK_ARG(smem <= 96 * 1024, "fused search: shared memory %zu > 96 KiB", smem);
+  const int grid = (t->v.G + THREADS - 1) / THREADS;
+  k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT><<<grid, THREADS, smem, s>>>(t->v, m->d_pack, io);
   MZB_LAUNCH_CHECK();
   return MZB_OK;
+}
+
+// Kernel variant: MZB_FUSED_VARIANT = threads(128|256) + 1000*phase_sync + 10000*pb_lut (tuning knob; default below)
+int fused_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MZB_FUSED_VARIANT");
+    v = e ? atoi(e) : 11256;
+  }
+  return v;
+}
+
+template <class SH>
+int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
+  int v = fused_variant();
+  const bool lut_ok = io.num_sims <= 63;                 // (S+1)^2 doubles must fit next to the weights
+  const int threads = v % 1000;
+  const bool sync = (v / 1000) % 10 != 0;
+  const bool lut = (v / 10000) % 10 != 0 && lut_ok;
+  if (threads == 256) {
+    if (sync) return lut ? launch_variant<SH, 256, true, true>(t, m, io, s) : launch_variant<SH, 256, true, false>(t, m, io, s);
+    return lut ? launch_variant<SH, 256, false, true>(t, m, io, s) : launch_variant<SH, 256, false, false>(t, m, io, s);
+  }
+  if (sync) return lut ? launch_variant<SH, 128, true, true>(t, m, io, s) : launch_variant<SH, 128, true, false>(t, m, io, s);
+  return lut ? launch_variant<SH, 128, false, true>(t, m, io, s) : launch_variant<SH, 128, false, false>(t, m, io, s);
 }
 
 }  // namespace

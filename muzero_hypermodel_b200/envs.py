@@ -83,7 +83,10 @@ class VectorEnv:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            _lib.lib.mzb_env_destroy(self._h)
+            try:
+                _lib.lib.mzb_env_destroy(self._h)
+            except (AttributeError, TypeError):      # interpreter shutdown
+                pass
             self._h = None
 
     def reset(self):

@@ -172,7 +172,10 @@ class MuZeroFullyConnectedNetwork(AbstractNetwork):
 
     def _free(self):
         if getattr(self, "_h", None):
-            _lib.lib.mzb_fc_destroy(self._h)
+            try:
+                _lib.lib.mzb_fc_destroy(self._h)
+            except (AttributeError, TypeError):      # interpreter shutdown
+                pass
             self._h = None
 
     def __del__(self):

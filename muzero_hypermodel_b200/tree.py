@@ -40,7 +40,10 @@ class BatchedTree:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            _lib.lib.mzb_tree_destroy(h)
+            try:
+                _lib.lib.mzb_tree_destroy(h)
+            except (AttributeError, TypeError):      # interpreter shutdown
+                pass
             self._h = None
 
     # -- search steps
