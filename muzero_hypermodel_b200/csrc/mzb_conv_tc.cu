@@ -24,10 +24,11 @@
 namespace {
 
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                       // two epilogue warpgroups
+constexpr int kThreads = 64 + kEpiWarps * 32;
 
 struct TcArgs {
-  int B, H, W, Cin, Cout, R_img, mt, n_chunks, relu, ncols;
+  int B, H, W, Cin, Cout, R_img, mt, n_chunks, relu, ncols, tail_rows, b_resident;
   long long rows_valid;                 // B * R_img
   const float* scale; const float* shift; const float* plane; const float* plane_table;
   const __nv_bfloat16* residual; __nv_bfloat16* y;
@@ -97,34 +98,47 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
+// Persistent, warp-specialised kernel.  A CTA loops over super-tiles (MT tiles of 128 rows):
+//   warp 0        TMA producer: activation rows of super-tile i+1 are loaded while i is multiplied (2 A stages);
+//                 weights either stay resident in shared memory (loaded once) or stream through a ring
+//   warp 1        MMA issuer; accumulators are double buffered in TMEM (2 x MT x C_out columns), so the MMAs of
+//                 super-tile i+1 run while the epilogue drains super-tile i
+//   warps 2..9    two epilogue warpgroups (TMEM lane quarter = warp % 4); work items (tile, 64-column group) are
+//                 dealt round-robin to the groups
 template <int KC>
-__global__ void __launch_bounds__(kThreads, 2)
-k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAtail,
+          const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   constexpr int ROWB = KC * 2;                                           // bytes per shared-memory row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = a.mt, N = a.Cout, halo = a.W + 3;
-  const int a_rows = (MT + 1) * 128;
+  const int a_rows = MT * 128 + a.tail_rows;
   const uint32_t a_chunk_bytes = (uint32_t)a_rows * ROWB;
-  const uint32_t b_stage_bytes = (uint32_t)N * ROWB;
-  uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)a.n_chunks * a_chunk_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kStages * b_stage_bytes);
-  uint64_t* a_full = bars;
-  uint64_t* b_full = bars + 1;
-  uint64_t* b_empty = bars + 1 + kStages;
-  uint64_t* acc_full = bars + 1 + 2 * kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * kStages);
-  float* s_scale = reinterpret_cast<float*>(bars + 4 + 2 * kStages);
-  float* s_shift = s_scale + N;
-  const long long m0 = (long long)blockIdx.x * MT * 128;                 // first row of this CTA (image-row space)
+  const uint32_t a_stage_bytes = (uint32_t)a.n_chunks * a_chunk_bytes;
+  const uint32_t b_block_bytes = (uint32_t)N * ROWB;
   const int NKB = 9 * a.n_chunks;
+  const int b_slots = a.b_resident ? NKB : kStages;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + 2 * (size_t)a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)b_slots * b_block_bytes);
+  uint64_t* a_full = bars;                 // [2]
+  uint64_t* a_empty = bars + 2;            // [2]
+  uint64_t* acc_full = bars + 4;           // [2]
+  uint64_t* acc_empty = bars + 6;          // [2]
+  uint64_t* b_full = bars + 8;             // [kStages] (ring) / [0] = resident weights landed
+  uint64_t* b_empty = bars + 8 + kStages;  // [kStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kStages);
+  float* s_scale = reinterpret_cast<float*>(bars + 10 + 2 * kStages);
+  float* s_shift = s_scale + N;
+  const long long n_super = (a.rows_valid + (long long)MT * 128 - 1) / ((long long)MT * 128);
 
   if (threadIdx.x == 0) {
-    mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps);
+    }
     for (int s = 0; s < kStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-    mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -132,6 +146,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < N; i += kThreads) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -139,62 +154,99 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- TMA producer: the activation rows once, then the weight k-blocks through the ring
-      mbar_expect_tx(a_full, (uint32_t)a.n_chunks * a_chunk_bytes);
-      for (int j = 0; j < a.n_chunks; ++j)
-        for (int box = 0; box <= MT; ++box)
-          tma_load_2d(smem_u32(sA + (size_t)j * a_chunk_bytes + (size_t)box * 128 * ROWB), &tmA, j * KC,
-                      (int)(m0 + (long long)box * 128), a_full);
-      for (int kb = 0; kb < NKB; ++kb) {
-        const int s = kb % kStages;
-        if (kb >= kStages) mbar_wait(b_empty + s, ((kb / kStages) - 1) & 1);
-        mbar_expect_tx(b_full + s, b_stage_bytes);
-        const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
-        tma_load_2d(smem_u32(sB + (size_t)s * b_stage_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full + s);
+      // ---------------- TMA producer
+      if (a.b_resident) {
+        mbar_expect_tx(b_full, (uint32_t)NKB * b_block_bytes);
+        for (int kb = 0; kb < NKB; ++kb) {
+          const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
+          tma_load_2d(smem_u32(sB + (size_t)kb * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full);
+        }
+      }
+      long long ring = 0;
+      int it = 0;
+      for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+        const int s = it & 1;
+        if (it >= 2) mbar_wait(a_empty + s, ((it >> 1) - 1) & 1);
+        const long long m0 = st * MT * 128;
+        mbar_expect_tx(a_full + s, a_stage_bytes);
+        for (int j = 0; j < a.n_chunks; ++j) {
+          uint8_t* dst = sA + (size_t)s * a_stage_bytes + (size_t)j * a_chunk_bytes;
+          for (int box = 0; box < MT; ++box)
+            tma_load_2d(smem_u32(dst + (size_t)box * 128 * ROWB), &tmA, j * KC, (int)(m0 + (long long)box * 128), a_full + s);
+          tma_load_2d(smem_u32(dst + (size_t)MT * 128 * ROWB), &tmAtail, j * KC, (int)(m0 + (long long)MT * 128), a_full + s);
+        }
+        if (!a.b_resident) {
+          for (int kb = 0; kb < NKB; ++kb, ++ring) {
+            const int rs = (int)(ring % kStages);
+            if (ring >= kStages) mbar_wait(b_empty + rs, (uint32_t)((ring / kStages) - 1) & 1);
+            mbar_expect_tx(b_full + rs, b_block_bytes);
+            const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
+            tma_load_2d(smem_u32(sB + (size_t)rs * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full + rs);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ---- MMA issuer: D[tile t] += A(shifted rows of tap) * B(tap, chunk)
+      // ---------------- MMA issuer
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-      mbar_wait(a_full, 0);
-      for (int kb = 0; kb < NKB; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(b_full + s, (kb / kStages) & 1);
+      if (a.b_resident) mbar_wait(b_full, 0);
+      long long ring = 0;
+      int it = 0;
+      for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+        const int s = it & 1;
+        mbar_wait(a_full + s, (it >> 1) & 1);
+        if (it >= 2) mbar_wait(acc_empty + s, ((it >> 1) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
-        const int shift = (tap / 3 - 1) * (a.W + 2) + (tap % 3 - 1);
-        const uint32_t b_addr = smem_u32(sB + (size_t)s * b_stage_bytes);
-        for (int t = 0; t < MT; ++t) {
-          const uint32_t a_addr = smem_u32(sA + (size_t)j * a_chunk_bytes) + (uint32_t)(halo + t * 128 + shift) * ROWB;
+        const uint32_t a_stage = smem_u32(sA + (size_t)s * a_stage_bytes);
+        const uint32_t d_base = tmem_base + (uint32_t)(s * MT * N);
+        for (int kb = 0; kb < NKB; ++kb) {
+          uint32_t b_addr;
+          int rs = 0;
+          if (a.b_resident) {
+            b_addr = smem_u32(sB + (size_t)kb * b_block_bytes);
+          } else {
+            rs = (int)(ring % kStages);
+            mbar_wait(b_full + rs, (uint32_t)(ring / kStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            b_addr = smem_u32(sB + (size_t)rs * b_block_bytes);
+            ++ring;
+          }
+          const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
+          const int shift = (tap / 3 - 1) * (a.W + 2) + (tap % 3 - 1);
+          for (int t = 0; t < MT; ++t) {
+            const uint32_t a_addr = a_stage + (uint32_t)j * a_chunk_bytes + (uint32_t)(halo + t * 128 + shift) * ROWB;
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k)
-            umma_bf16(tmem_base + (uint32_t)(t * N), make_desc<KC>(a_addr + k * 32), make_desc<KC>(b_addr + k * 32), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KC / 16; ++k)
+              umma_bf16(d_base + (uint32_t)(t * N), make_desc<KC>(a_addr + k * 32), make_desc<KC>(b_addr + k * 32), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (!a.b_resident) umma_commit(b_empty + rs);
         }
-        umma_commit(b_empty + s);               // frees this weight stage when the MMAs above retire
+        umma_commit(a_empty + s);              // activation stage reusable once these MMAs retire
+        umma_commit(acc_full + s);             // accumulators of this super-tile complete
       }
-      umma_commit(acc_full);
     }
   } else {
-    // ---- epilogue warps: TMEM lane quarter = warp % 4.  Per 64-column group: the residual row is requested
-    // first (one exposed global latency per group, not per chunk), then four 16-column TMEM loads are issued
-    // back to back behind a single wait.
-    const int q = warp & 3;
-    for (int i = threadIdx.x - 64; i < N; i += kThreads - 64) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
-    asm volatile("bar.sync 1, 128;" ::: "memory");             // epilogue warps only
-    mbar_wait(acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int t = 0; t < MT; ++t) {
-      const long long m = m0 + (long long)t * 128 + q * 32 + lane;
-      const int b = (int)(m / a.R_img);
-      const int rem = (int)(m % a.R_img);
-      const int yy = rem / (a.W + 2), xx = rem % (a.W + 2);
-      const bool valid = m < a.rows_valid && yy >= 1 && xx >= 1 && xx <= a.W;
-      const long long row_off = (m + halo) * (long long)N;
-      const float pl = (valid && a.plane) ? a.plane[b] : 0.0f;
-      const float* ptab = (valid && a.plane) ? a.plane_table + (size_t)((yy - 1) * a.W + (xx - 1)) * N : nullptr;
-      for (int g0 = 0; g0 < N; g0 += 64) {
+    // ---------------- epilogue warpgroups
+    const int q = warp & 3, group = (warp - 2) >> 2;
+    const int ncg = (N + 63) / 64;
+    int it = 0;
+    for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+      const int s = it & 1;
+      const long long m0 = st * MT * 128;
+      mbar_wait(acc_full + s, (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int item = group; item < MT * ncg; item += kEpiWarps / 4) {
+        const int t = item / ncg, g0 = (item % ncg) * 64;
+        const long long m = m0 + (long long)t * 128 + q * 32 + lane;
+        const int b = (int)(m / a.R_img);
+        const int rem = (int)(m % a.R_img);
+        const int yy = rem / (a.W + 2), xx = rem % (a.W + 2);
+        const bool valid = m < a.rows_valid && yy >= 1 && xx >= 1 && xx <= a.W;
+        const long long row_off = (m + halo) * (long long)N;
+        const float pl = (valid && a.plane) ? a.plane[b] : 0.0f;
+        const float* ptab = (valid && a.plane) ? a.plane_table + (size_t)((yy - 1) * a.W + (xx - 1)) * N : nullptr;
         const int gw = N - g0 < 64 ? N - g0 : 64;              // columns in this group (multiple of 16)
         uint4 res[8];
         if (valid && a.residual) {
@@ -203,7 +255,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int i = 0; i < 8; ++i) if (i * 8 < gw) res[i] = rp[i];
         }
         uint32_t v[64];
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * N + g0);
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * MT * N + t * N + g0);
 #pragma unroll
         for (int c = 0; c < 4; ++c) if (c * 16 < gw) tmem_ld16_nowait(tbase + c * 16, v + c * 16);
         tmem_wait_ld();
@@ -241,9 +293,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           op[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
       }
+      // this warp is done reading the TMEM stage: release it to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + s)) : "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -285,19 +341,29 @@ bool make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t ou
 
 int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
 
-int pick_mt(int cout, int n_chunks, int kc, int max_smem) {
-  for (int mt = 4; mt >= 1; mt >>= 1) {
-    if (mt * cout > 512) continue;
-    const size_t smem = (size_t)n_chunks * (mt + 1) * 128 * kc * 2 + (size_t)kStages * cout * kc * 2 + 1024 + 256 + 8 * (size_t)cout;
-    if (smem <= (size_t)max_smem) return mt;
-  }
-  return 0;
-}
+struct TcPlan { int kc, n_chunks, mt, tail_rows, b_resident, ncols; size_t smem; };
 
-// two CTAs per SM (epilogue of one overlaps the MMAs of the other) when a configuration fits in half the SM
-int pick_mt_auto(int cout, int n_chunks, int kc) {
-  const int two = pick_mt(cout, n_chunks, kc, 113 * 1024);
-  return two > 0 ? two : pick_mt(cout, n_chunks, kc, 227 * 1024);
+// Largest MT whose double-buffered activation stages, weights (resident if they fit, else a ring) and
+// 2 x MT x C_out TMEM columns fit in one SM.
+bool make_plan(int cin, int cout, int W, TcPlan* out) {
+  TcPlan p{};
+  p.kc = pick_kc(cin);
+  p.n_chunks = cin / p.kc;
+  p.tail_rows = 2 * (W + 3) <= 32 ? 32 : 128;
+  const size_t rowb = (size_t)p.kc * 2, limit = 225 * 1024;
+  const size_t b_all = (size_t)9 * p.n_chunks * cout * rowb, b_ring = (size_t)kStages * cout * rowb;
+  const size_t misc = 1024 + 512 + 8 * (size_t)cout;
+  for (int mt = 4; mt >= 1; mt >>= 1) {
+    if (2 * mt * cout > 512) continue;
+    const size_t a2 = 2 * (size_t)p.n_chunks * (mt * 128 + p.tail_rows) * rowb;
+    if (a2 + b_all + misc <= limit) { p.mt = mt; p.b_resident = 1; p.smem = a2 + b_all + misc; break; }
+    if (a2 + b_ring + misc <= limit) { p.mt = mt; p.b_resident = 0; p.smem = a2 + b_ring + misc; break; }
+  }
+  if (!p.mt) return false;
+  p.ncols = 32;
+  while (p.ncols < 2 * p.mt * cout) p.ncols <<= 1;
+  if (out) *out = p;
+  return true;
 }
 
 }  // namespace
@@ -307,36 +373,39 @@ extern "C" void mzb_conv_tc_enable(int on) { g_tc_enabled = on != 0; }
 
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
   return g_tc_enabled && cp.stride == 1 && cp.cin == cin_stride && cp.cin % 16 == 0 && cp.cout % 16 == 0 && cp.cout >= 16 &&
-         cp.cout <= 256 && W <= 61 && cp.w_bf16 != nullptr && encode_fn() != nullptr &&
-         pick_mt_auto(cp.cout, cp.cin / pick_kc(cp.cin), pick_kc(cp.cin)) > 0;
+         cp.cout <= 256 && W <= 61 && cp.w_bf16 != nullptr && encode_fn() != nullptr && make_plan(cp.cin, cp.cout, W, nullptr);
 }
 
 int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
                        const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream) {
-  const int kc = pick_kc(cp.cin), n_chunks = cp.cin / kc;
-  const int mt = pick_mt_auto(cp.cout, n_chunks, kc);
-  MZB_CHECK_ARG(mt > 0, "tensor-core convolution: no tile configuration fits");
+  TcPlan p;
+  MZB_CHECK_ARG(make_plan(cp.cin, cp.cout, W, &p), "tensor-core convolution: no tile configuration fits");
   const Geo g{H, W, cp.cin, 1};
   const long long rows_total = geo_rows_total(g, B);
-  CUtensorMap tmA, tmB;
-  if (!make_map_2d(&tmA, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)kc, 128, kc) ||
-      !make_map_2d(&tmB, cp.w_bf16, (uint64_t)9 * cp.cin, (uint64_t)cp.cout, (uint64_t)9 * cp.cin * 2, (uint32_t)kc,
-                   (uint32_t)cp.cout, kc)) {
+  CUtensorMap tmA, tmAtail, tmB;
+  if (!make_map_2d(&tmA, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)p.kc, 128, p.kc) ||
+      !make_map_2d(&tmAtail, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)p.kc,
+                   (uint32_t)p.tail_rows, p.kc) ||
+      !make_map_2d(&tmB, cp.w_bf16, (uint64_t)9 * cp.cin, (uint64_t)cp.cout, (uint64_t)9 * cp.cin * 2, (uint32_t)p.kc,
+                   (uint32_t)cp.cout, p.kc)) {
     mzb_set_error("cuTensorMapEncodeTiled failed (C_in=%d C_out=%d rows=%lld)", cp.cin, cp.cout, rows_total);
     return MZB_ECUDA;
   }
   TcArgs a{};
-  a.B = B; a.H = H; a.W = W; a.Cin = cp.cin; a.Cout = cp.cout; a.R_img = (H + 1) * (W + 2); a.mt = mt; a.n_chunks = n_chunks;
-  a.relu = relu;
-  int ncols = 32;
-  while (ncols < mt * cp.cout) ncols <<= 1;
-  a.ncols = ncols;
+  a.B = B; a.H = H; a.W = W; a.Cin = cp.cin; a.Cout = cp.cout; a.R_img = (H + 1) * (W + 2); a.mt = p.mt; a.n_chunks = p.n_chunks;
+  a.relu = relu; a.ncols = p.ncols; a.tail_rows = p.tail_rows; a.b_resident = p.b_resident;
   a.rows_valid = (long long)B * a.R_img;
   a.scale = cp.scale; a.shift = cp.shift; a.plane = cp.extra_plane ? plane : nullptr; a.plane_table = cp.plane_table;
   a.residual = residual; a.y = y;
-  const size_t smem = (size_t)n_chunks * (mt + 1) * 128 * kc * 2 + (size_t)kStages * cp.cout * kc * 2 + 1024 + 256 + 8 * (size_t)cp.cout;
-  const long long tiles = (a.rows_valid + 127) / 128;
-  const unsigned grid = (unsigned)((tiles + mt - 1) / mt);
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const long long n_super = (a.rows_valid + (long long)p.mt * 128 - 1) / ((long long)p.mt * 128);
+  const unsigned grid = (unsigned)(n_super < n_sm ? n_super : n_sm);      // persistent: one CTA per SM
 #define LAUNCH_KC(KCV)                                                                                              \
   {                                                                                                                 \
     static bool configured = false;                                                                                 \
@@ -344,9 +413,9 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
       MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));      \
       configured = true;                                                                                            \
     }                                                                                                               \
-    k_conv_tc<KCV><<<grid, kThreads, smem, stream>>>(tmA, tmB, a);                                                  \
+    k_conv_tc<KCV><<<grid, kThreads, p.smem, stream>>>(tmA, tmAtail, tmB, a);                                       \
   }
-  if (kc == 64) LAUNCH_KC(64) else if (kc == 32) LAUNCH_KC(32) else LAUNCH_KC(16)
+  if (p.kc == 64) LAUNCH_KC(64) else if (p.kc == 32) LAUNCH_KC(32) else LAUNCH_KC(16)
 #undef LAUNCH_KC
   MZB_LAUNCH_CHECK();
   return MZB_OK;
