@@ -32,6 +32,7 @@ struct TcArgs {
   long long rows_valid;                 // B * R_img
   const float* scale; const float* shift; const float* plane; const float* plane_table;
   const __nv_bfloat16* residual; __nv_bfloat16* y;
+  long long* debug;                     // optional timeline of CTA 0: [role][iteration][4] clock64 stamps
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,18 +44,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // bounded spin: a protocol bug traps (launch error) instead of hanging the GPU
-  for (uint32_t it = 0; it < (1u << 28); ++it) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (done) return;
-  }
-  __trap();
+  // One asm statement (no C++ control flow: the compiler keeps the surrounding role loop warp-uniform, so
+  // addresses and descriptors stay in uniform registers).  The spin is bounded: a protocol bug traps (launch
+  // error) instead of hanging the GPU.
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 spins;\n"
+      "mov.u32 spins, 0;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.lt.u32 p, spins, 0x08000000;\n"
+      "@p bra WAIT_%=;\n"
+      "trap;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -80,6 +86,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xFFFFFFFF;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -112,7 +128,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int ROWB = KC * 2;                                           // bytes per shared-memory row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index / TMEM base are broadcast through a shuffle so the compiler knows they are warp-uniform and keeps the
+  // role loops (addresses, descriptors, barrier phases) in uniform registers
+  const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int MT = a.mt, N = a.Cout, halo = a.W + 3;
   const int a_rows = MT * 128 + a.tail_rows;
   const uint32_t a_chunk_bytes = (uint32_t)a_rows * ROWB;
@@ -150,109 +168,151 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer
+    // ---------------- TMA producer.  The whole warp runs the (warp-uniform) control flow so that addresses and
+    // descriptors live in uniform registers; one elected lane issues the copies.
+    if (elect_one_sync()) {
+      const bool leader = true;
       if (a.b_resident) {
-        mbar_expect_tx(b_full, (uint32_t)NKB * b_block_bytes);
+        if (leader) mbar_expect_tx(b_full, (uint32_t)NKB * b_block_bytes);
         for (int kb = 0; kb < NKB; ++kb) {
           const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
-          tma_load_2d(smem_u32(sB + (size_t)kb * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full);
+          if (leader) tma_load_2d(smem_u32(sB + (size_t)kb * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full);
         }
       }
       long long ring = 0;
       int it = 0;
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
         const int s = it & 1;
+        const long long p0 = clock64();
         if (it >= 2) mbar_wait(a_empty + s, ((it >> 1) - 1) & 1);
+        if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (3 * 32 + it) * 4; d[0] = p0; d[1] = clock64(); }
         const long long m0 = st * MT * 128;
-        mbar_expect_tx(a_full + s, a_stage_bytes);
+        if (leader) mbar_expect_tx(a_full + s, a_stage_bytes);
         for (int j = 0; j < a.n_chunks; ++j) {
           uint8_t* dst = sA + (size_t)s * a_stage_bytes + (size_t)j * a_chunk_bytes;
           for (int box = 0; box < MT; ++box)
-            tma_load_2d(smem_u32(dst + (size_t)box * 128 * ROWB), &tmA, j * KC, (int)(m0 + (long long)box * 128), a_full + s);
-          tma_load_2d(smem_u32(dst + (size_t)MT * 128 * ROWB), &tmAtail, j * KC, (int)(m0 + (long long)MT * 128), a_full + s);
+            if (leader) tma_load_2d(smem_u32(dst + (size_t)box * 128 * ROWB), &tmA, j * KC, (int)(m0 + (long long)box * 128), a_full + s);
+          if (leader) tma_load_2d(smem_u32(dst + (size_t)MT * 128 * ROWB), &tmAtail, j * KC, (int)(m0 + (long long)MT * 128), a_full + s);
         }
         if (!a.b_resident) {
           for (int kb = 0; kb < NKB; ++kb, ++ring) {
             const int rs = (int)(ring % kStages);
             if (ring >= kStages) mbar_wait(b_empty + rs, (uint32_t)((ring / kStages) - 1) & 1);
-            mbar_expect_tx(b_full + rs, b_block_bytes);
+            if (leader) mbar_expect_tx(b_full + rs, b_block_bytes);
             const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
-            tma_load_2d(smem_u32(sB + (size_t)rs * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full + rs);
+            if (leader) tma_load_2d(smem_u32(sB + (size_t)rs * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full + rs);
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
+    // ---------------- MMA issuer: warp-uniform loop, tcgen05.mma / commit issued by one elected lane
+    if (elect_one_sync()) {
+      const bool leader = true;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t desc_hi = make_desc<KC>(0);
+      const uint64_t b_base_desc = desc_hi | (uint64_t)((smem_u32(sB) >> 4) & 0x3FFF);
       if (a.b_resident) mbar_wait(b_full, 0);
       long long ring = 0;
       int it = 0;
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
         const int s = it & 1;
+        const long long c0 = clock64();
         mbar_wait(a_full + s, (it >> 1) & 1);
+        const long long c1 = clock64();
         if (it >= 2) mbar_wait(acc_empty + s, ((it >> 1) - 1) & 1);
+        const long long c2 = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_stage = smem_u32(sA + (size_t)s * a_stage_bytes);
+        // descriptors differ only in the 14-bit start-address field (16-byte units): one add per MMA
+        const uint64_t a_stage_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)s * a_stage_bytes) >> 4) & 0x3FFF);
         const uint32_t d_base = tmem_base + (uint32_t)(s * MT * N);
         for (int kb = 0; kb < NKB; ++kb) {
-          uint32_t b_addr;
+          uint64_t bd;
           int rs = 0;
           if (a.b_resident) {
-            b_addr = smem_u32(sB + (size_t)kb * b_block_bytes);
+            bd = b_base_desc + (uint64_t)kb * (b_block_bytes >> 4);
           } else {
             rs = (int)(ring % kStages);
             mbar_wait(b_full + rs, (uint32_t)(ring / kStages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            b_addr = smem_u32(sB + (size_t)rs * b_block_bytes);
+            bd = b_base_desc + (uint64_t)rs * (b_block_bytes >> 4);
             ++ring;
           }
-          const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
+          const int tap = kb / a.n_chunks, j = kb - tap * a.n_chunks;
           const int shift = (tap / 3 - 1) * (a.W + 2) + (tap % 3 - 1);
-          for (int t = 0; t < MT; ++t) {
-            const uint32_t a_addr = a_stage + (uint32_t)j * a_chunk_bytes + (uint32_t)(halo + t * 128 + shift) * ROWB;
+          uint64_t ad = a_stage_desc + (uint64_t)(((uint32_t)j * a_chunk_bytes + (uint32_t)(halo + shift) * ROWB) >> 4);
+          uint32_t d = d_base;
+          for (int t = 0; t < MT; ++t, ad += (128 * ROWB) >> 4, d += (uint32_t)N) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
-              umma_bf16(d_base + (uint32_t)(t * N), make_desc<KC>(a_addr + k * 32), make_desc<KC>(b_addr + k * 32), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+              if (leader) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          if (!a.b_resident) umma_commit(b_empty + rs);
+          if (!a.b_resident && leader) umma_commit(b_empty + rs);
         }
-        umma_commit(a_empty + s);              // activation stage reusable once these MMAs retire
-        umma_commit(acc_full + s);             // accumulators of this super-tile complete
+        if (leader) {
+          umma_commit(a_empty + s);            // activation stage reusable once these MMAs retire
+          umma_commit(acc_full + s);           // accumulators of this super-tile complete
+        }
+        if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (0 * 32 + it) * 4; d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64(); }
       }
     }
   } else {
     // ---------------- epilogue warpgroups
     const int q = warp & 3, group = (warp - 2) >> 2;
-    const int ncg = (N + 63) / 64;
+    const int ncg = (N + 63) / 64, n_items = MT * ncg;
+    constexpr int NG = kEpiWarps / 4;
+    // row -> (image, y, x) of item `item` of super-tile starting at m0
+    auto decode = [&](long long m0, int item, long long& row_off, int& b, int& pos, bool& valid) {
+      const int t = item / ncg;
+      const long long m = m0 + (long long)t * 128 + q * 32 + lane;
+      b = (int)(m / a.R_img);
+      const int rem = (int)(m - (long long)b * a.R_img);
+      const int yy = rem / (a.W + 2), xx = rem - yy * (a.W + 2);
+      valid = m < a.rows_valid && yy >= 1 && xx >= 1 && xx <= a.W;
+      row_off = (m + halo) * (long long)N;
+      pos = (yy - 1) * a.W + (xx - 1);
+    };
     int it = 0;
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
       const int s = it & 1;
       const long long m0 = st * MT * 128;
-      mbar_wait(acc_full + s, (it >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int item = group; item < MT * ncg; item += kEpiWarps / 4) {
-        const int t = item / ncg, g0 = (item % ncg) * 64;
-        const long long m = m0 + (long long)t * 128 + q * 32 + lane;
-        const int b = (int)(m / a.R_img);
-        const int rem = (int)(m % a.R_img);
-        const int yy = rem / (a.W + 2), xx = rem % (a.W + 2);
-        const bool valid = m < a.rows_valid && yy >= 1 && xx >= 1 && xx <= a.W;
-        const long long row_off = (m + halo) * (long long)N;
-        const float pl = (valid && a.plane) ? a.plane[b] : 0.0f;
-        const float* ptab = (valid && a.plane) ? a.plane_table + (size_t)((yy - 1) * a.W + (xx - 1)) * N : nullptr;
-        const int gw = N - g0 < 64 ? N - g0 : 64;              // columns in this group (multiple of 16)
-        uint4 res[8];
+      // the residual rows do not depend on the MMAs: request the first item's now (hidden behind the accumulator
+      // wait) and pull the later items' lines towards L2
+      uint4 res[8];
+      long long row_off; int b, pos; bool valid;
+      if (a.residual) {
+        for (int item = group + NG; item < n_items; item += NG) {
+          decode(m0, item, row_off, b, pos, valid);
+          if (valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.residual + row_off + (item % ncg) * 64));
+        }
+      }
+      if (group < n_items) {
+        decode(m0, group, row_off, b, pos, valid);
         if (valid && a.residual) {
+          const int g0 = (group % ncg) * 64;
+          const int gw = N - g0 < 64 ? N - g0 : 64;
           const uint4* rp = reinterpret_cast<const uint4*>(a.residual + row_off + g0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) if (i * 8 < gw) res[i] = rp[i];
+          for (int i = 0; i < 8; ++i) if (i * 8 < gw) res[i] = __ldg(rp + i);
+        }
+      }
+      const long long e0 = clock64();
+      mbar_wait(acc_full + s, (it >> 1) & 1);
+      const long long e1 = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int item = group; item < n_items; item += NG) {
+        const int t = item / ncg, g0 = (item % ncg) * 64;
+        decode(m0, item, row_off, b, pos, valid);
+        const float pl = (valid && a.plane) ? a.plane[b] : 0.0f;
+        const float* ptab = (valid && a.plane) ? a.plane_table + (size_t)pos * N : nullptr;
+        const int gw = N - g0 < 64 ? N - g0 : 64;              // columns in this group (multiple of 16)
+        if (item != group && valid && a.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + row_off + g0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (i * 8 < gw) res[i] = __ldg(rp + i);
         }
         uint32_t v[64];
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * MT * N + t * N + g0);
@@ -264,12 +324,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int c = 0; c < 4; ++c) {
           if (c * 16 >= gw) break;
           float f[16];
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + g0 + c * 16);
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + g0 + c * 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = g0 + c * 16 + i;
-            float acc = __uint_as_float(v[c * 16 + i]);
-            if (ptab) acc = fmaf(pl, ptab[col], acc);
-            f[i] = fmaf(acc, s_scale[col], s_shift[col]);
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 sc = sc4[i4], sh = sh4[i4];
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i4 * 4 + j;
+              float acc = __uint_as_float(v[c * 16 + i]);
+              if (ptab) acc = fmaf(pl, ptab[g0 + c * 16 + i], acc);
+              f[i] = fmaf(acc, scv[j], shv[j]);
+            }
           }
           if (a.residual) {
             const uint32_t rw[8] = {res[2 * c].x, res[2 * c].y, res[2 * c].z, res[2 * c].w,
@@ -297,6 +364,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + s)) : "memory");
+      if (a.debug && blockIdx.x == 0 && it < 32 && lane == 0 && q == 2) { long long* d = a.debug + ((1 + group) * 32 + it) * 4; d[0] = e0; d[1] = e1; d[2] = clock64(); d[3] = 0; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -369,6 +437,8 @@ bool make_plan(int cin, int cout, int W, TcPlan* out) {
 }  // namespace
 
 static bool g_tc_enabled = true;
+static long long* g_tc_debug = nullptr;
+extern "C" void mzb_conv_tc_debug_buffer(long long* d_buf) { g_tc_debug = d_buf; }   // bring-up: 4*32*4 int64
 extern "C" void mzb_conv_tc_enable(int on) { g_tc_enabled = on != 0; }
 
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
@@ -397,6 +467,7 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   a.rows_valid = (long long)B * a.R_img;
   a.scale = cp.scale; a.shift = cp.shift; a.plane = cp.extra_plane ? plane : nullptr; a.plane_table = cp.plane_table;
   a.residual = residual; a.y = y;
+  a.debug = g_tc_debug;
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
