@@ -289,15 +289,19 @@ __global__ void __launch_bounds__(256) k_minmax_store(const T* __restrict__ x, i
     float lo[2 * MAXP], hi[2 * MAXP];
 #pragma unroll
     for (int k = 0; k < 2 * MAXP; ++k) { lo[k] = CUDART_INF_F; hi[k] = -CUDART_INF_F; }
-    for (int p = 0; p < HW; ++p) {
-      const T* row = x + geo_row(g, b, p / g.W, p % g.W) * C;
+    // pass 1: rows of one board line are contiguous; several independent row loads in flight per lane
+    for (int yy = 0; yy < g.H; ++yy) {
+      const T* line = x + geo_row(g, b, yy, 0) * C;
+#pragma unroll 4
+      for (int xx = 0; xx < g.W; ++xx) {
 #pragma unroll
-      for (int k = 0; k < MAXP; ++k) {
-        const int c2 = lane + 32 * k;
-        if (c2 < pairs) {
-          const float2 v = Pair<T>::ld(row + 2 * c2);
-          lo[2 * k] = fminf(lo[2 * k], v.x); hi[2 * k] = fmaxf(hi[2 * k], v.x);
-          lo[2 * k + 1] = fminf(lo[2 * k + 1], v.y); hi[2 * k + 1] = fmaxf(hi[2 * k + 1], v.y);
+        for (int k = 0; k < MAXP; ++k) {
+          const int c2 = lane + 32 * k;
+          if (c2 < pairs) {
+            const float2 v = Pair<T>::ld(line + (long long)xx * C + 2 * c2);
+            lo[2 * k] = fminf(lo[2 * k], v.x); hi[2 * k] = fmaxf(hi[2 * k], v.x);
+            lo[2 * k + 1] = fminf(lo[2 * k + 1], v.y); hi[2 * k + 1] = fmaxf(hi[2 * k + 1], v.y);
+          }
         }
       }
     }
@@ -307,27 +311,32 @@ __global__ void __launch_bounds__(256) k_minmax_store(const T* __restrict__ x, i
       if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
       hi[k] = scale;
     }
-    for (int p = 0; p < HW; ++p) {
-      const long long ro = geo_row(g, b, p / g.W, p % g.W) * C;
+    for (int yy = 0; yy < g.H; ++yy) {
+      const long long lo_off = geo_row(g, b, yy, 0) * C;
+#pragma unroll 4
+      for (int xx = 0; xx < g.W; ++xx) {
+        const long long ro = lo_off + (long long)xx * C;
+        const int p = yy * g.W + xx;
 #pragma unroll
-      for (int k = 0; k < MAXP; ++k) {
-        const int c2 = lane + 32 * k;
-        if (c2 < pairs) {
-          float2 v = Pair<T>::ld(x + ro + 2 * c2);
-          v.x = __fdiv_rn(__fsub_rn(v.x, lo[2 * k]), hi[2 * k]);
-          v.y = __fdiv_rn(__fsub_rn(v.y, lo[2 * k + 1]), hi[2 * k + 1]);
-          Pair<T>::st(y + ro + 2 * c2, v);
-          if (state) {
-            const int c = 2 * c2;
-            if (layout == 0) {
-              float* o = (float*)state + b * row_stride + off;
-              o[(long long)c * HW + p] = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(v.x)) : v.x;
-              o[(long long)(c + 1) * HW + p] = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(v.y)) : v.y;
-            } else if (layout == 1) {
-              *reinterpret_cast<float2*>((float*)state + b * row_stride + off + (long long)p * C + c) = v;
-            } else {
-              *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)state + b * row_stride + off + (long long)p * C + c) =
-                  __floats2bfloat162_rn(v.x, v.y);
+        for (int k = 0; k < MAXP; ++k) {
+          const int c2 = lane + 32 * k;
+          if (c2 < pairs) {
+            float2 v = Pair<T>::ld(x + ro + 2 * c2);
+            v.x = __fdiv_rn(__fsub_rn(v.x, lo[2 * k]), hi[2 * k]);
+            v.y = __fdiv_rn(__fsub_rn(v.y, lo[2 * k + 1]), hi[2 * k + 1]);
+            Pair<T>::st(y + ro + 2 * c2, v);
+            if (state) {
+              const int c = 2 * c2;
+              if (layout == 0) {
+                float* o = (float*)state + b * row_stride + off;
+                o[(long long)c * HW + p] = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(v.x)) : v.x;
+                o[(long long)(c + 1) * HW + p] = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(v.y)) : v.y;
+              } else if (layout == 1) {
+                *reinterpret_cast<float2*>((float*)state + b * row_stride + off + (long long)p * C + c) = v;
+              } else {
+                *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)state + b * row_stride + off + (long long)p * C + c) =
+                    __floats2bfloat162_rn(v.x, v.y);
+              }
             }
           }
         }
@@ -640,8 +649,7 @@ template <class T>
 void minmax_store(Runner& r, int cur, int nx, Geo g, const Outputs& o) {
   if (r.rc) return;
   if (g.C % 2 != 0 || g.C > 512) { mzb_set_error("min-max kernel needs an even channel count <= 512"); r.rc = MZB_EUNSUPPORTED; return; }
-  int grid = (r.B + 7) / 8;
-  if (grid > 148 * 8) grid = 148 * 8;
+  const int grid = (r.B + 7) / 8;                   // one image per warp
   if (g.C <= 64) k_minmax_store<T, 1><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
   else if (g.C <= 128) k_minmax_store<T, 2><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
   else k_minmax_store<T, 8><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
