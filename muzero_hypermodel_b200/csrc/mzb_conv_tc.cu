@@ -28,11 +28,15 @@ constexpr int kEpiWarps = 8;                       // two epilogue warpgroups
 constexpr int kThreads = 64 + kEpiWarps * 32;
 
 struct TcArgs {
-  int B, H, W, Cin, Cout, R_img, mt, n_chunks, relu, ncols, tail_rows, b_resident;
+  int B, H, W, Cin, Cout, R_img, mt, n_chunks, relu, ncols, tail_rows, b_resident, zero_pads;
   long long rows_valid;                 // B * R_img
+  long long rows_cover;                 // rows the super-tiles cover: rows_valid (+ the trailing halo when zero_pads)
   const float* scale; const float* shift; const float* plane; const float* plane_table;
   const __nv_bfloat16* residual; __nv_bfloat16* y;
   long long* debug;                     // optional timeline of CTA 0: [role][iteration][4] clock64 stamps
+  // fused head projection (the heads' 1x1 convolutions, models.py:398-404, 447-456): proj_out[b][r][pos] =
+  // sum_c y[b,pos,c] * proj_w[r][c] on the bf16-rounded outputs; bias is added by the head kernel
+  const float* proj_w; float* proj_out; int proj_r, proj_hw;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -150,7 +154,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kStages);
   float* s_scale = reinterpret_cast<float*>(bars + 10 + 2 * kStages);
   float* s_shift = s_scale + N;
-  const long long n_super = (a.rows_valid + (long long)MT * 128 - 1) / ((long long)MT * 128);
+  float* s_proj = s_shift + N;             // [proj_r][N]
+  const long long n_super = (a.rows_cover + (long long)MT * 128 - 1) / ((long long)MT * 128);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -165,6 +170,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < N; i += kThreads) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+  for (int i = threadIdx.x; i < a.proj_r * N; i += kThreads) s_proj[i] = a.proj_w[i];
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -265,9 +271,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int ncg = (N + 63) / 64, n_items = MT * ncg;
     constexpr int NG = kEpiWarps / 4;
     // row -> (image, y, x) of item `item` of super-tile starting at m0
+    long long m = 0;
     auto decode = [&](long long m0, int item, long long& row_off, int& b, int& pos, bool& valid) {
       const int t = item / ncg;
-      const long long m = m0 + (long long)t * 128 + q * 32 + lane;
+      m = m0 + (long long)t * 128 + q * 32 + lane;
       b = (int)(m / a.R_img);
       const int rem = (int)(m - (long long)b * a.R_img);
       const int yy = rem / (a.W + 2), xx = rem - yy * (a.W + 2);
@@ -319,7 +326,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
         for (int c = 0; c < 4; ++c) if (c * 16 < gw) tmem_ld16_nowait(tbase + c * 16, v + c * 16);
         tmem_wait_ld();
-        if (!valid) continue;
+        if (!valid) {
+          // stem mode: the buffers change resolution between layers, so the pad rows (and the trailing halo) are
+          // re-written as zeros by every layer instead of relying on a zeroed workspace
+          if (a.zero_pads && m < a.rows_cover) {
+            uint4* op = reinterpret_cast<uint4*>(a.y + row_off + g0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (i * 8 < gw) op[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
+        float pacc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) pacc[r] = 0.0f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c * 16 >= gw) break;
@@ -354,10 +373,35 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
             const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
             o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+            f[2 * i] = __uint_as_float(o[i] << 16); f[2 * i + 1] = __uint_as_float(o[i] & 0xFFFF0000u);
           }
           uint4* op = reinterpret_cast<uint4*>(a.y + row_off + g0 + c * 16);
           op[0] = make_uint4(o[0], o[1], o[2], o[3]);
           op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          if (a.proj_r > 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              if (r < a.proj_r) {
+                const float4* w4 = reinterpret_cast<const float4*>(s_proj + r * N + g0 + c * 16);
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const float4 ww = w4[i4];
+                  pacc[r] = fmaf(f[4 * i4], ww.x, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 1], ww.y, pacc[r]);
+                  pacc[r] = fmaf(f[4 * i4 + 2], ww.z, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 3], ww.w, pacc[r]);
+                }
+              }
+            }
+          }
+        }
+        if (a.proj_r > 0) {
+          float* po = a.proj_out + ((long long)b * a.proj_r) * a.proj_hw + pos;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (r < a.proj_r) {
+              if (ncg == 1) po[(long long)r * a.proj_hw] = pacc[r];
+              else atomicAdd(po + (long long)r * a.proj_hw, pacc[r]);     // two column groups: 0 + x + y, order-independent
+            }
+          }
         }
       }
       // this warp is done reading the TMEM stage: release it to the MMA issuer
@@ -420,7 +464,7 @@ bool make_plan(int cin, int cout, int W, TcPlan* out) {
   p.tail_rows = 2 * (W + 3) <= 32 ? 32 : 128;
   const size_t rowb = (size_t)p.kc * 2, limit = 225 * 1024;
   const size_t b_all = (size_t)9 * p.n_chunks * cout * rowb, b_ring = (size_t)kStages * cout * rowb;
-  const size_t misc = 1024 + 512 + 8 * (size_t)cout;
+  const size_t misc = 1024 + 512 + 8 * (size_t)cout + 32 * (size_t)cout;      // barriers, scale/shift, <= 8 projection rows
   for (int mt = 4; mt >= 1; mt >>= 1) {
     if (2 * mt * cout > 512) continue;
     const size_t a2 = 2 * (size_t)p.n_chunks * (mt * 128 + p.tail_rows) * rowb;
@@ -440,6 +484,7 @@ static bool g_tc_enabled = true;
 static long long* g_tc_debug = nullptr;
 extern "C" void mzb_conv_tc_debug_buffer(long long* d_buf) { g_tc_debug = d_buf; }   // bring-up: 4*32*4 int64
 extern "C" void mzb_conv_tc_enable(int on) { g_tc_enabled = on != 0; }
+bool mzb_conv_tc_enabled() { return g_tc_enabled && encode_fn() != nullptr; }
 
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
   return g_tc_enabled && cp.stride == 1 && cp.cin == cin_stride && cp.cin % 16 == 0 && cp.cout % 16 == 0 && cp.cout >= 16 &&
@@ -447,7 +492,8 @@ bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
 }
 
 int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
-                       const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream) {
+                       const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream, int zero_pads,
+                       const TcProj* proj) {
   TcPlan p;
   MZB_CHECK_ARG(make_plan(cp.cin, cp.cout, W, &p), "tensor-core convolution: no tile configuration fits");
   const Geo g{H, W, cp.cin, 1};
@@ -465,9 +511,16 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   a.B = B; a.H = H; a.W = W; a.Cin = cp.cin; a.Cout = cp.cout; a.R_img = (H + 1) * (W + 2); a.mt = p.mt; a.n_chunks = p.n_chunks;
   a.relu = relu; a.ncols = p.ncols; a.tail_rows = p.tail_rows; a.b_resident = p.b_resident;
   a.rows_valid = (long long)B * a.R_img;
+  a.zero_pads = zero_pads;
+  a.rows_cover = a.rows_valid + (zero_pads ? W + 3 : 0);
   a.scale = cp.scale; a.shift = cp.shift; a.plane = cp.extra_plane ? plane : nullptr; a.plane_table = cp.plane_table;
   a.residual = residual; a.y = y;
   a.debug = g_tc_debug;
+  if (proj && proj->r > 0) {
+    MZB_CHECK_ARG(proj->r <= 8 && proj->w && proj->out, "fused head projection: at most 8 rows");
+    a.proj_w = proj->w; a.proj_out = proj->out; a.proj_r = proj->r; a.proj_hw = H * W;
+    if (cp.cout > 64) MZB_CUDA(cudaMemsetAsync(proj->out, 0, sizeof(float) * (size_t)B * proj->r * H * W, stream));
+  }
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -475,7 +528,7 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  const long long n_super = (a.rows_valid + (long long)p.mt * 128 - 1) / ((long long)p.mt * 128);
+  const long long n_super = (a.rows_cover + (long long)p.mt * 128 - 1) / ((long long)p.mt * 128);
   const unsigned grid = (unsigned)(n_super < n_sm ? n_super : n_sm);      // persistent: one CTA per SM
 #define LAUNCH_KC(KCV)                                                                                              \
   {                                                                                                                 \

@@ -114,6 +114,135 @@ __global__ void k_avgpool(const T* __restrict__ x, int B, Geo gi, Geo go, T* __r
   stf(y + geo_row(go, b, oy, ox) * C + c, s / 9.0f);
 }
 
+// ---- bf16 DownSample stem (tensor-core path).  Every stem buffer is in the PADDED layout and every writer also
+// writes the pad rows and the trailing halo as zeros: the three rotating buffers change resolution from layer to
+// layer, so (unlike the latent path) the pads cannot be left to a zeroed workspace.
+//
+// Stride-2 3x3 convolution, padding 1 (DownSample.conv1 / conv2, models.py:236-255).  One thread per row of the
+// padded OUTPUT layout; 16 output channels per pass, weights [9*cin][go.C] broadcast from shared memory.
+// OBS: the input is the caller's fp32 NCHW observation (no staging copy); else padded NHWC bf16 rows of gi.C
+// channels of which the first `cin` (multiple of 8) are real.  Output channels >= cout are written as zeros.
+template <bool OBS>
+__global__ void __launch_bounds__(128) k_conv_s2(const void* __restrict__ xin, int B, Geo gi, int cin, const float* __restrict__ w,
+                                                 const float* __restrict__ scale, const float* __restrict__ shift, int cout,
+                                                 Geo go, __nv_bfloat16* __restrict__ y) {
+  extern __shared__ float sw[];
+  const int CO = go.C;
+  float* s_scale = sw + 9 * cin * CO;
+  float* s_shift = s_scale + CO;
+  for (int i = threadIdx.x; i < 9 * cin * CO; i += blockDim.x) {
+    const int k = i / CO, o = i % CO;
+    sw[i] = o < cout ? w[(size_t)k * cout + o] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < CO; i += blockDim.x) { s_scale[i] = i < cout ? scale[i] : 0.0f; s_shift[i] = i < cout ? shift[i] : 0.0f; }
+  __syncthreads();
+  const int Wp = go.W + 2;
+  const long long R_img = (long long)(go.H + 1) * Wp;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= (long long)B * R_img + (go.W + 3)) return;
+  const int b = (int)(m / R_img);
+  const int rem = (int)(m - (long long)b * R_img);
+  const int yy = rem / Wp, xx = rem - yy * Wp;
+  const bool valid = b < B && yy >= 1 && xx >= 1 && xx <= go.W;
+  uint4* out = reinterpret_cast<uint4*>(y + (m + go.W + 3) * CO);
+  if (!valid) {
+    for (int i = 0; i < CO / 8; ++i) out[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const int oy = yy - 1, ox = xx - 1;
+  for (int co0 = 0; co0 < CO; co0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+        const float* wt = sw + (size_t)(ky * 3 + kx) * cin * CO + co0;
+        if (OBS) {
+          if (iy < 0 || iy >= gi.H || ix < 0 || ix >= gi.W) continue;
+          const float* src = (const float*)xin + ((size_t)b * cin * gi.H + iy) * gi.W + ix;
+          for (int c = 0; c < cin; ++c) {
+            const float v = __bfloat162float(__float2bfloat16_rn(src[(size_t)c * gi.H * gi.W]));   // bf16 operands on this path
+            const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)c * CO);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 ww = w4[j4];
+              acc[4 * j4] = fmaf(v, ww.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(v, ww.y, acc[4 * j4 + 1]);
+              acc[4 * j4 + 2] = fmaf(v, ww.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(v, ww.w, acc[4 * j4 + 3]);
+            }
+          }
+        } else {
+          // out-of-image taps land on zero pad rows of the padded input: no bounds checks
+          const uint4* src = reinterpret_cast<const uint4*>((const __nv_bfloat16*)xin + geo_row(gi, b, iy, ix) * gi.C);
+          for (int c8 = 0; c8 < cin / 8; ++c8) {
+            const uint4 raw = src[c8];
+            const uint32_t r4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+              const float v = __uint_as_float((h & 1) ? (r4[h >> 1] & 0xFFFF0000u) : (r4[h >> 1] << 16));
+              const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)(c8 * 8 + h) * CO);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 ww = w4[j4];
+                acc[4 * j4] = fmaf(v, ww.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(v, ww.y, acc[4 * j4 + 1]);
+                acc[4 * j4 + 2] = fmaf(v, ww.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(v, ww.w, acc[4 * j4 + 3]);
+              }
+            }
+          }
+        }
+      }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __nv_bfloat162 pk = __floats2bfloat162_rn(fmaf(acc[2 * i], s_scale[co0 + 2 * i], s_shift[co0 + 2 * i]),
+                                                      fmaf(acc[2 * i + 1], s_scale[co0 + 2 * i + 1], s_shift[co0 + 2 * i + 1]));
+      o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+    }
+    out[co0 / 8] = make_uint4(o[0], o[1], o[2], o[3]);
+    out[co0 / 8 + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// AvgPool2d(kernel 3, stride 2, padding 1), count_include_pad, padded bf16 layouts on both sides (out-of-image taps
+// read the zero pads); one thread per (output row, 8-channel chunk), pad rows written as zeros.
+__global__ void __launch_bounds__(256) k_avgpool_pad(const __nv_bfloat16* __restrict__ x, int B, Geo gi, Geo go,
+                                                     __nv_bfloat16* __restrict__ y) {
+  const int cv = go.C / 8, Wp = go.W + 2;
+  const long long R_img = (long long)(go.H + 1) * Wp;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = i / cv;
+  const int ch = (int)(i - m * cv);
+  if (m >= (long long)B * R_img + (go.W + 3)) return;
+  const int b = (int)(m / R_img);
+  const int rem = (int)(m - (long long)b * R_img);
+  const int yy = rem / Wp, xx = rem - yy * Wp;
+  uint4* out = reinterpret_cast<uint4*>(y + (m + go.W + 3) * go.C) + ch;
+  if (!(b < B && yy >= 1 && xx >= 1 && xx <= go.W)) { *out = make_uint4(0u, 0u, 0u, 0u); return; }
+  const int oy = yy - 1, ox = xx - 1;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.0f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const uint4 raw = *(reinterpret_cast<const uint4*>(x + geo_row(gi, b, oy * 2 + ky - 1, ox * 2 + kx - 1) * gi.C) + ch);
+      const uint32_t r4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) { s[2 * h] += __uint_as_float(r4[h] << 16); s[2 * h + 1] += __uint_as_float(r4[h] & 0xFFFF0000u); }
+    }
+  uint32_t o[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const __nv_bfloat162 pk = __floats2bfloat162_rn(s[2 * h] / 9.0f, s[2 * h + 1] / 9.0f);
+    o[h] = *reinterpret_cast<const uint32_t*>(&pk);
+  }
+  *out = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // per-(image, channel) min-max scaling over H*W with the +1e-5 guard (models.py:525-549, 571-595)
 template <class T>
 __global__ void k_minmax(const T* __restrict__ x, int B, Geo g, T* __restrict__ y) {
@@ -169,7 +298,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <class T, int R>
 __global__ void __launch_bounds__(256) k_head(const T* __restrict__ x, int B, Geo g, HeadParams hp, int S, int mode,
                                               const uint8_t* __restrict__ legal, float* __restrict__ logits_out,
-                                              float* __restrict__ scalar_out, float* __restrict__ priors_out) {
+                                              float* __restrict__ scalar_out, float* __restrict__ priors_out,
+                                              const float* __restrict__ proj, long long proj_stride, int proj_off) {
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const HeadSmem L = head_smem(hp, warps);
@@ -186,7 +316,7 @@ __global__ void __launch_bounds__(256) k_head(const T* __restrict__ x, int B, Ge
   __syncthreads();
   float* bufA = sm + L.scratch + warp * L.per_warp;
   float* bufB = bufA + L.per_warp / 2;
-  const int n_flat = hp.r * hp.hw, n = hp.out;
+  const int n = hp.out;
   // conv1x1 mapping: a group of LPP lanes shares one position, each lane owns 16-byte channel chunks
   constexpr int V = 16 / (int)sizeof(T);
   const int cpr = hp.cin / V;                               // 16-byte chunks per row
@@ -194,6 +324,11 @@ __global__ void __launch_bounds__(256) k_head(const T* __restrict__ x, int B, Ge
   const int PPI = 32 / LPP;                                 // positions per warp iteration
   const int sub = lane % LPP;
   for (int b = blockIdx.x * warps + warp; b < B; b += gridDim.x * warps) {
+    if (proj) {
+      // the 1x1 convolution was computed by the producing convolution's epilogue (mzb_conv_tc.cu): add the bias
+      const float* pr = proj + (long long)b * proj_stride + proj_off;
+      for (int i = lane; i < hp.r * hp.hw; i += 32) bufA[i] = pr[i] + sm[L.b1 + i / hp.hw];
+    } else
     for (int p0 = 0; p0 < hp.hw; p0 += PPI) {
       const int p = p0 + lane / LPP;
       const bool valid = p < hp.hw;
@@ -345,6 +480,89 @@ __global__ void __launch_bounds__(256) k_minmax_store(const T* __restrict__ x, i
   }
 }
 
+// bf16 single-pass variant: one warp per image, lane = (row group, 16-byte channel chunk); the image's rows stay in
+// registers between the min/max reduction (shuffles across the row groups) and the rescale, so the activation is read
+// once with all loads in flight.  Same arithmetic as k_minmax_store.  C in {8,16,...,256} (C/8 a power of two).
+template <int MAXIT>
+__global__ void __launch_bounds__(256) k_minmax_store_bf16(const __nv_bfloat16* __restrict__ x, int B, Geo g,
+                                                           __nv_bfloat16* __restrict__ y, int layout, void* __restrict__ state,
+                                                           long long row_stride, long long off) {
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = g.C, HW = g.H * g.W, LPR = C / 8, RPI = 32 / LPR, sub = lane % LPR, rg = lane / LPR;
+  const int nit = (HW + RPI - 1) / RPI;
+  for (int b = blockIdx.x * warps + warp; b < B; b += gridDim.x * warps) {
+    uint4 v[MAXIT];
+    float lo[8], hi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { lo[k] = CUDART_INF_F; hi[k] = -CUDART_INF_F; }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int p = it * RPI + rg;
+      if (it < nit && p < HW) v[it] = *reinterpret_cast<const uint4*>(x + geo_row(g, b, p / g.W, p % g.W) * C + sub * 8);
+    }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int p = it * RPI + rg;
+      if (it < nit && p < HW) {
+        const uint32_t r4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float a = __uint_as_float(r4[h] << 16), c = __uint_as_float(r4[h] & 0xFFFF0000u);
+          lo[2 * h] = fminf(lo[2 * h], a); hi[2 * h] = fmaxf(hi[2 * h], a);
+          lo[2 * h + 1] = fminf(lo[2 * h + 1], c); hi[2 * h + 1] = fmaxf(hi[2 * h + 1], c);
+        }
+      }
+    }
+    for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
+        hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float scale = __fsub_rn(hi[k], lo[k]);
+      if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+      hi[k] = scale;
+    }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int p = it * RPI + rg;
+      if (it < nit && p < HW) {
+        const uint32_t r4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+        float f[8];
+        uint32_t o4[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          f[2 * h] = __fdiv_rn(__fsub_rn(__uint_as_float(r4[h] << 16), lo[2 * h]), hi[2 * h]);
+          f[2 * h + 1] = __fdiv_rn(__fsub_rn(__uint_as_float(r4[h] & 0xFFFF0000u), lo[2 * h + 1]), hi[2 * h + 1]);
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
+          o4[h] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+        const uint4 packed = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        *reinterpret_cast<uint4*>(y + geo_row(g, b, p / g.W, p % g.W) * C + sub * 8) = packed;
+        if (state) {
+          const int c = sub * 8;
+          if (layout == 2) {
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)state + b * row_stride + off + (long long)p * C + c) = packed;
+          } else if (layout == 1) {
+            float4* o = reinterpret_cast<float4*>((float*)state + b * row_stride + off + (long long)p * C + c);
+            o[0] = make_float4(f[0], f[1], f[2], f[3]); o[1] = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            float* o = (float*)state + b * row_stride + off;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              o[(long long)(c + 2 * h) * HW + p] = __uint_as_float(o4[h] << 16);
+              o[(long long)(c + 2 * h + 1) * HW + p] = __uint_as_float(o4[h] & 0xFFFF0000u);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void k_zero_reward(int B, int S, float* __restrict__ logits, float* __restrict__ scalar) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -437,6 +655,16 @@ int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* c) {
     for (auto& b : m->ds1) ok = ok && init_conv(m, b.c1, C / 2, C / 2, 1, 0, 0) && init_conv(m, b.c2, C / 2, C / 2, 1, 0, 0);
     for (auto& b : m->ds2) ok = ok && init_conv(m, b.c1, C, C, 1, 0, 0) && init_conv(m, b.c2, C, C, 1, 0, 0);
     for (auto& b : m->ds3) ok = ok && init_conv(m, b.c1, C, C, 1, 0, 0) && init_conv(m, b.c2, C, C, 1, 0, 0);
+    // bf16: the whole stem runs in the padded layout - stride-2 layers on a dedicated kernel, every residual block
+    // on the tcgen05 convolution (resblocks1 with its C/2 channels zero-padded to a multiple of 16)
+    const int w1 = (m->W - 1) / 2 + 1;
+    if (m->precision == 1 && C % 16 == 0 && (C / 2) % 8 == 0 && C <= 128 && w1 <= 61) {
+      m->stem_tc = 1;
+      m->stem_cp1 = (C / 2 + 15) / 16 * 16;
+      m->ds1_tc.resize(2);
+      for (auto& b : m->ds1_tc)
+        ok = ok && init_conv(m, b.c1, m->stem_cp1, m->stem_cp1, 1, 0, 0) && init_conv(m, b.c2, m->stem_cp1, m->stem_cp1, 1, 0, 0);
+    }
   }
   ok = ok && init_conv(m, m->rep_conv, m->Cobs, C, 1, 0, 0) && init_conv(m, m->dyn_conv, C, C, 1, 1, hw);
   m->rep_blocks.resize(m->blocks); m->dyn_blocks.resize(m->blocks); m->pred_blocks.resize(m->blocks);
@@ -445,6 +673,8 @@ int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* c) {
   ok = ok && init_head(m, m->reward, C, c->reduced_channels_reward, hw, c->fc_reward, c->n_fc_reward, m->full) &&
        init_head(m, m->value, C, c->reduced_channels_value, hw, c->fc_value, c->n_fc_value, m->full) &&
        init_head(m, m->policy, C, c->reduced_channels_policy, hw, c->fc_policy, c->n_fc_policy, m->A);
+  m->pv_w = (float*)dev_alloc(m, sizeof(float) * (size_t)(m->value.r + m->policy.r) * C);
+  ok = ok && m->pv_w;
   if (!ok) {
     mzb_resnet_destroy(m);
     mzb_set_error("resnet create: allocation failed or head mlp wider than 128");
@@ -487,8 +717,41 @@ struct Cursor {
 
 bool upload(void* dst, const void* src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess; }
 
-// conv weight [cout][cin(+extra)][3][3] -> fp32 [tap][cin+extra][cout], bf16 [cout][tap][cin]; plane table
-bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl) {
+// conv weight [cout][cin(+extra)][3][3] -> fp32 [tap][cin+extra][cout], bf16 [cout][tap][cin]; plane table.
+// `c` may be wider than the source tensor (src_cin x src_cout): the extra channels get zero weights, scale and shift.
+bool pack_conv(ConvParams& c, const float* w, int src_cin, int src_cout, const std::vector<float>& scale_src,
+               const std::vector<float>& shift_src, int Hl, int Wl) {
+  const int cw = c.cin + c.extra_plane, src_cw = src_cin + c.extra_plane;
+  std::vector<float> scale(c.cout, 0.0f), shift(c.cout, 0.0f);
+  for (int o = 0; o < src_cout; ++o) { scale[o] = scale_src[o]; shift[o] = shift_src[o]; }
+  std::vector<float> wp((size_t)9 * cw * c.cout, 0.0f);
+  std::vector<__nv_bfloat16> wb((size_t)9 * c.cin * c.cout, __float2bfloat16(0.0f));
+  for (int o = 0; o < src_cout; ++o)
+    for (int ci = 0; ci < src_cw; ++ci)
+      for (int tap = 0; tap < 9; ++tap) {
+        const float v = w[((size_t)o * src_cw + ci) * 9 + tap];
+        const int cd = ci < src_cin ? ci : c.cin;                  // the extra plane stays the last input channel
+        wp[((size_t)tap * cw + cd) * c.cout + o] = v;
+        if (ci < src_cin) wb[((size_t)o * 9 + tap) * c.cin + ci] = __float2bfloat16(v);
+      }
+  bool ok = upload(c.w, wp.data(), wp.size() * 4) && upload(c.w_bf16, wb.data(), wb.size() * 2) &&
+            upload(c.scale, scale.data(), scale.size() * 4) && upload(c.shift, shift.data(), shift.size() * 4);
+  if (c.extra_plane) {
+    std::vector<float> tab((size_t)Hl * Wl * c.cout, 0.0f);
+    for (int y = 0; y < Hl; ++y)
+      for (int x = 0; x < Wl; ++x)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const int iy = y + ky - 1, ix = x + kx - 1;
+            if (iy < 0 || iy >= Hl || ix < 0 || ix >= Wl) continue;
+            for (int o = 0; o < src_cout; ++o) tab[((size_t)y * Wl + x) * c.cout + o] += w[((size_t)o * src_cw + src_cin) * 9 + ky * 3 + kx];
+          }
+    ok = ok && upload(c.plane_table, tab.data(), tab.size() * 4);
+  }
+  return ok;
+}
+
+bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl, ConvParams* wide = nullptr) {
   const int cw = c.cin + c.extra_plane;
   const float* w = cur.take((int64_t)c.cout * cw * 9);
   std::vector<float> scale(c.cout, 1.0f), shift(c.cout, 0.0f);
@@ -502,30 +765,7 @@ bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl) {
     }
   }
   if (cur.bad) return false;
-  std::vector<float> wp((size_t)9 * cw * c.cout);
-  std::vector<__nv_bfloat16> wb((size_t)9 * c.cin * c.cout);
-  for (int o = 0; o < c.cout; ++o)
-    for (int ci = 0; ci < cw; ++ci)
-      for (int tap = 0; tap < 9; ++tap) {
-        const float v = w[((size_t)o * cw + ci) * 9 + tap];
-        wp[((size_t)tap * cw + ci) * c.cout + o] = v;
-        if (ci < c.cin) wb[((size_t)o * 9 + tap) * c.cin + ci] = __float2bfloat16(v);
-      }
-  bool ok = upload(c.w, wp.data(), wp.size() * 4) && upload(c.w_bf16, wb.data(), wb.size() * 2) &&
-            upload(c.scale, scale.data(), scale.size() * 4) && upload(c.shift, shift.data(), shift.size() * 4);
-  if (c.extra_plane) {
-    std::vector<float> tab((size_t)Hl * Wl * c.cout, 0.0f);
-    for (int y = 0; y < Hl; ++y)
-      for (int x = 0; x < Wl; ++x)
-        for (int ky = 0; ky < 3; ++ky)
-          for (int kx = 0; kx < 3; ++kx) {
-            const int iy = y + ky - 1, ix = x + kx - 1;
-            if (iy < 0 || iy >= Hl || ix < 0 || ix >= Wl) continue;
-            for (int o = 0; o < c.cout; ++o) tab[((size_t)y * Wl + x) * c.cout + o] += w[((size_t)o * cw + c.cin) * 9 + ky * 3 + kx];
-          }
-    ok = ok && upload(c.plane_table, tab.data(), tab.size() * 4);
-  }
-  return ok;
+  return pack_conv(c, w, c.cin, c.cout, scale, shift, Hl, Wl) && (!wide || pack_conv(*wide, w, c.cin, c.cout, scale, shift, Hl, Wl));
 }
 
 bool load_block(Cursor& cur, Block& b) { return load_conv(cur, b.c1, true, 0, 0) && load_conv(cur, b.c2, true, 0, 0); }
@@ -557,7 +797,11 @@ extern "C" int mzb_resnet_set_weights(mzb_resnet_model* m, const float* const* h
   // state_dict order = module registration order (models.py:300-429)
   if (m->downsample) {
     ok = ok && load_conv(cur, m->ds_conv1, false, 0, 0);
-    for (auto& b : m->ds1) ok = ok && load_block(cur, b);
+    for (size_t i = 0; i < m->ds1.size(); ++i) {
+      Block* wide = m->stem_tc ? &m->ds1_tc[i] : nullptr;
+      ok = ok && load_conv(cur, m->ds1[i].c1, true, 0, 0, wide ? &wide->c1 : nullptr) &&
+           load_conv(cur, m->ds1[i].c2, true, 0, 0, wide ? &wide->c2 : nullptr);
+    }
     ok = ok && load_conv(cur, m->ds_conv2, false, 0, 0);
     for (auto& b : m->ds2) ok = ok && load_block(cur, b);
     for (auto& b : m->ds3) ok = ok && load_block(cur, b);
@@ -569,6 +813,8 @@ extern "C" int mzb_resnet_set_weights(mzb_resnet_model* m, const float* const* h
   ok = ok && load_1x1(cur, m->reward) && load_fc(cur, m->reward);
   for (auto& b : m->pred_blocks) ok = ok && load_block(cur, b);
   ok = ok && load_1x1(cur, m->value) && load_1x1(cur, m->policy) && load_fc(cur, m->value) && load_fc(cur, m->policy);
+  ok = ok && cudaMemcpy(m->pv_w, m->value.w1x1, sizeof(float) * m->value.r * m->C, cudaMemcpyDeviceToDevice) == cudaSuccess &&
+       cudaMemcpy(m->pv_w + (size_t)m->value.r * m->C, m->policy.w1x1, sizeof(float) * m->policy.r * m->C, cudaMemcpyDeviceToDevice) == cudaSuccess;
   if (!ok || cur.bad || cur.i != n_tensors) {
     mzb_set_error("resnet set_weights: tensor %d has an unexpected size (or upload failed)", cur.i - 1);
     return MZB_EINVAL;
@@ -583,38 +829,51 @@ namespace {
 struct Runner {
   mzb_resnet_model* m; int B; cudaStream_t s; uint8_t* ws; size_t ws_bytes; size_t act_bytes;
   int rc = MZB_OK;
+  int zero_pads = 0;                 // stem mode: every layer re-writes its pad rows (see k_conv_s2)
+  long long cap_B = 0;               // batch the workspace was sized for (fixes the offsets inside it)
+  bool proj_fused = false;           // the last conv() computed the requested head projection in its epilogue
+  float* proj() { return reinterpret_cast<float*>(ws + 3 * act_bytes + mzb_align_up((size_t)cap_B * 4, 256)); }
   template <class T> T* buf(int i) { return reinterpret_cast<T*>(ws + (size_t)i * act_bytes); }
   float* plane() { return reinterpret_cast<float*>(ws + 3 * act_bytes); }
 };
 
 template <class T>
-void conv(Runner& r, const T* x, Geo gi, const ConvParams& cp, const float* plane, const T* res, int relu, Geo go, T* y) {
+void conv(Runner& r, const T* x, Geo gi, const ConvParams& cp, const float* plane, const T* res, int relu, Geo go, T* y,
+          const TcProj* proj = nullptr) {
+  r.proj_fused = false;
   if (r.rc) return;
   if (sizeof(T) == 2 && gi.pad && go.pad && mzb_conv_tc_supported(cp, gi.H, gi.W, gi.C)) {
     r.rc = mzb_conv_tc_launch(r.B, gi.H, gi.W, cp, (const __nv_bfloat16*)x, plane, (const __nv_bfloat16*)res, relu,
-                              (__nv_bfloat16*)y, r.s);
+                              (__nv_bfloat16*)y, r.s, r.zero_pads, proj);
+    r.proj_fused = proj != nullptr && proj->r > 0;
     return;
   }
+  if (r.zero_pads) { mzb_set_error("bf16 stem: layer %dx%d C %d->%d is not supported by the tensor-core kernel", gi.H, gi.W, cp.cin, cp.cout); r.rc = MZB_EUNSUPPORTED; return; }
   const long long n = (long long)r.B * go.H * go.W * cp.cout;
   k_conv3x3_direct<T><<<nblk(n, 128), 128, 0, r.s>>>(x, r.B, gi, cp, plane, res, relu, go, y);
   mzb_count_launch();
 }
 
 // residual tower: x -> blocks; uses the three rotating buffers, returns the buffer index holding the result
+// `proj`: head projection fused into the tower's last convolution (r.proj_fused tells whether it happened)
 template <class T>
-int tower(Runner& r, std::vector<Block>& blocks, Geo g, int cur) {
-  for (auto& b : blocks) {
+int tower(Runner& r, std::vector<Block>& blocks, Geo g, int cur, const TcProj* proj = nullptr) {
+  bool fused = false;
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    Block& b = blocks[i];
     const int t = (cur + 1) % 3, o = (cur + 2) % 3;
     conv<T>(r, r.buf<T>(cur), g, b.c1, nullptr, nullptr, 1, g, r.buf<T>(t));
-    conv<T>(r, r.buf<T>(t), g, b.c2, nullptr, r.buf<T>(cur), 1, g, r.buf<T>(o));
+    conv<T>(r, r.buf<T>(t), g, b.c2, nullptr, r.buf<T>(cur), 1, g, r.buf<T>(o), i + 1 == blocks.size() ? proj : nullptr);
+    fused = r.proj_fused;
     cur = o;
   }
+  r.proj_fused = fused;
   return cur;
 }
 
 template <class T>
 void head(Runner& r, const T* x, Geo g, const HeadParams& hp, int mode, const uint8_t* legal, float* logits,
-          float* scalar, float* priors) {
+          float* scalar, float* priors, const float* proj = nullptr, long long proj_stride = 0, int proj_off = 0) {
   if (r.rc || (!logits && !scalar && !priors)) return;
   const int warps = 8;
   const size_t smem = sizeof(float) * (size_t)head_smem(hp, warps).total;
@@ -633,9 +892,9 @@ void head(Runner& r, const T* x, Geo g, const HeadParams& hp, int mode, const ui
   }
   int grid = (r.B + warps - 1) / warps;
   if (grid > 148 * 4) grid = 148 * 4;                 // persistent: weights are staged once per block
-  if (hp.r <= 2) k_head<T, 2><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors);
-  else if (hp.r <= 4) k_head<T, 4><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors);
-  else k_head<T, 16><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors);
+  if (hp.r <= 2) k_head<T, 2><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors, proj, proj_stride, proj_off);
+  else if (hp.r <= 4) k_head<T, 4><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors, proj, proj_stride, proj_off);
+  else k_head<T, 16><<<grid, warps * 32, smem, r.s>>>(x, r.B, g, hp, r.m->S, mode, legal, logits, scalar, priors, proj, proj_stride, proj_off);
   mzb_count_launch();
 }
 
@@ -650,6 +909,14 @@ void minmax_store(Runner& r, int cur, int nx, Geo g, const Outputs& o) {
   if (r.rc) return;
   if (g.C % 2 != 0 || g.C > 512) { mzb_set_error("min-max kernel needs an even channel count <= 512"); r.rc = MZB_EUNSUPPORTED; return; }
   const int grid = (r.B + 7) / 8;                   // one image per warp
+  if (sizeof(T) == 2 && g.C % 8 == 0 && g.C <= 256 && ((g.C / 8) & (g.C / 8 - 1)) == 0) {
+    const int nit = (g.H * g.W + 32 / (g.C / 8) - 1) / (32 / (g.C / 8));
+    const __nv_bfloat16* x = (const __nv_bfloat16*)r.buf<T>(cur);
+    __nv_bfloat16* y = (__nv_bfloat16*)r.buf<T>(nx);
+    if (nit <= 4) { k_minmax_store_bf16<4><<<grid, 256, 0, r.s>>>(x, r.B, g, y, o.layout, o.state, o.row_stride, o.off); mzb_count_launch(); return; }
+    if (nit <= 12) { k_minmax_store_bf16<12><<<grid, 256, 0, r.s>>>(x, r.B, g, y, o.layout, o.state, o.row_stride, o.off); mzb_count_launch(); return; }
+    if (nit <= 20) { k_minmax_store_bf16<20><<<grid, 256, 0, r.s>>>(x, r.B, g, y, o.layout, o.state, o.row_stride, o.off); mzb_count_launch(); return; }
+  }
   if (g.C <= 64) k_minmax_store<T, 1><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
   else if (g.C <= 128) k_minmax_store<T, 2><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
   else k_minmax_store<T, 8><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
@@ -660,14 +927,63 @@ template <class T>
 void prediction_and_state(Runner& r, int cur, Geo g, const Outputs& o, const uint8_t* legal) {
   mzb_resnet_model* m = r.m;
   if (o.value_logits || o.policy_logits || o.value || o.priors) {
-    const int p = tower<T>(r, m->pred_blocks, g, cur);
-    head<T>(r, r.buf<T>(p), g, m->value, 0, nullptr, o.value_logits, o.value, nullptr);
-    head<T>(r, r.buf<T>(p), g, m->policy, 1, legal, o.policy_logits, nullptr, o.priors);
+    const int rv = m->value.r, rp = m->policy.r, hw = g.H * g.W;
+    const TcProj pj{m->pv_w, r.proj(), rv + rp};
+    const int p = tower<T>(r, m->pred_blocks, g, cur, (sizeof(T) == 2 && m->pv_w && rv + rp <= 8) ? &pj : nullptr);
+    const float* pr = r.proj_fused ? r.proj() : nullptr;
+    head<T>(r, r.buf<T>(p), g, m->value, 0, nullptr, o.value_logits, o.value, nullptr, pr, (long long)(rv + rp) * hw, 0);
+    head<T>(r, r.buf<T>(p), g, m->policy, 1, legal, o.policy_logits, nullptr, o.priors, pr, (long long)(rv + rp) * hw, rv * hw);
   }
 }
 
 // the latent-resolution geometry: padded on the tensor-core path
 template <class T> Geo latent_geo(const mzb_resnet_model* m) { return Geo{m->Hl, m->Wl, m->C, sizeof(T) == 2 ? 1 : 0}; }
+
+// DownSample.forward (models.py:264-275) on the bf16 path: padded layouts throughout, see k_conv_s2.
+// Returns the buffer holding the latent tensor in the padded latent geometry; all three buffers end with clean pads.
+int stem_tc(Runner& r, const float* obs) {
+  typedef __nv_bfloat16 T;
+  mzb_resnet_model* m = r.m;
+  const int B = r.B, C = m->C, Cp1 = m->stem_cp1;
+  const Geo g0{m->H, m->W, m->Cobs, 0};
+  const Geo g1{(g0.H - 1) / 2 + 1, (g0.W - 1) / 2 + 1, Cp1, 1};
+  const Geo g2{(g1.H - 1) / 2 + 1, (g1.W - 1) / 2 + 1, C, 1};
+  const Geo g3{(g2.H - 1) / 2 + 1, (g2.W - 1) / 2 + 1, C, 1};
+  const Geo gl{m->Hl, m->Wl, C, 1};
+  if ((g3.H - 1) / 2 + 1 != m->Hl || (g3.W - 1) / 2 + 1 != m->Wl) { mzb_set_error("latent size mismatch"); r.rc = MZB_EINVAL; return 0; }
+  auto out_rows = [&](const Geo& g) { return (long long)B * (g.H + 1) * (g.W + 2) + (g.W + 3); };
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_conv_s2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(k_conv_s2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    configured = true;
+  }
+  const size_t sm1 = sizeof(float) * ((size_t)9 * m->Cobs * Cp1 + 2 * Cp1), sm2 = sizeof(float) * ((size_t)9 * (C / 2) * C + 2 * C);
+  if (sm1 > 96 * 1024 || sm2 > 96 * 1024) { mzb_set_error("bf16 stem: stride-2 weights exceed 96 KiB of shared memory"); r.rc = MZB_EUNSUPPORTED; return 0; }
+  r.zero_pads = 1;
+  k_conv_s2<true><<<nblk(out_rows(g1), 128), 128, sm1, r.s>>>(obs, B, g0, m->Cobs, m->ds_conv1.w, m->ds_conv1.scale, m->ds_conv1.shift,
+                                                            C / 2, g1, r.buf<T>(1));
+  mzb_count_launch();
+  int cur = tower<T>(r, m->ds1_tc, g1, 1);
+  { const int nx = (cur + 1) % 3;
+    k_conv_s2<false><<<nblk(out_rows(g2), 128), 128, sm2, r.s>>>(r.buf<T>(cur), B, g1, C / 2, m->ds_conv2.w, m->ds_conv2.scale,
+                                                               m->ds_conv2.shift, C, g2, r.buf<T>(nx));
+    mzb_count_launch(); cur = nx; }
+  cur = tower<T>(r, m->ds2, g2, cur);
+  { const int nx = (cur + 1) % 3;
+    k_avgpool_pad<<<nblk(out_rows(g3) * (C / 8), 256), 256, 0, r.s>>>(r.buf<T>(cur), B, g2, g3, r.buf<T>(nx));
+    mzb_count_launch(); cur = nx; }
+  cur = tower<T>(r, m->ds3, g3, cur);
+  { const int nx = (cur + 1) % 3;
+    k_avgpool_pad<<<nblk(out_rows(gl) * (C / 8), 256), 256, 0, r.s>>>(r.buf<T>(cur), B, g3, gl, r.buf<T>(nx));
+    mzb_count_launch(); cur = nx; }
+  r.zero_pads = 0;
+  // the latent-resolution layers never write pads: clear the latent region of the two other buffers
+  const size_t latent_bytes = (size_t)geo_rows_total(gl, B) * C * sizeof(T);
+  cudaMemsetAsync(r.buf<T>((cur + 1) % 3), 0, latent_bytes, r.s);
+  cudaMemsetAsync(r.buf<T>((cur + 2) % 3), 0, latent_bytes, r.s);
+  return cur;
+}
 
 template <class T>
 int run_initial(Runner& r, const float* obs, const uint8_t* legal, const Outputs& o) {
@@ -675,7 +991,10 @@ int run_initial(Runner& r, const float* obs, const uint8_t* legal, const Outputs
   const int B = r.B, C = m->C;
   const Geo gl = latent_geo<T>(m);
   int cur = 0;
-  if (m->downsample) {                                               // DownSample.forward (models.py:264-275)
+  if (m->downsample && sizeof(T) == 2 && m->stem_tc && mzb_conv_tc_enabled()) {
+    cur = stem_tc(r, obs);
+    if (r.rc) return r.rc;
+  } else if (m->downsample) {                                        // DownSample.forward (models.py:264-275)
     Geo g0{m->H, m->W, m->Cobs, 0};
     {
       const long long n = (long long)B * g0.H * g0.W * g0.C;
@@ -751,8 +1070,11 @@ int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_r
   k_action_plane<<<nblk(B, 128), 128, 0, r.s>>>(action, B, m->A, r.plane());
   mzb_count_launch();
   conv<T>(r, r.buf<T>(0), gl, m->dyn_conv, r.plane(), nullptr, 1, gl, r.buf<T>(1));           // DynamicsNetwork.forward :377-387
-  int cur = tower<T>(r, m->dyn_blocks, gl, 1);
-  head<T>(r, r.buf<T>(cur), gl, m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr);   // reward on the un-normalised state
+  const bool want_reward = o.reward_logits || o.reward;
+  const TcProj pj{m->reward.w1x1, r.proj(), m->reward.r};
+  int cur = tower<T>(r, m->dyn_blocks, gl, 1, (sizeof(T) == 2 && want_reward && m->reward.r <= 8) ? &pj : nullptr);
+  head<T>(r, r.buf<T>(cur), gl, m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr,    // reward on the un-normalised state
+          r.proj_fused ? r.proj() : nullptr, (long long)m->reward.r * gl.H * gl.W, 0);
   const int nx = (cur + 1) % 3;
   minmax_store<T>(r, cur, nx, gl, o);
   prediction_and_state<T>(r, nx, gl, o, nullptr);
@@ -770,22 +1092,30 @@ size_t act_bytes_for(const mzb_resnet_model* m, long long B) {
     per = std::max(per, (long long)(m->H + 1) * (m->W + 2) * m->Cobs);
   }
   per = std::max(per, (long long)(m->Hl + 1) * (m->Wl + 2) * m->C);
-  const long long halo = 2ll * (m->Wl + 3) * std::max(m->C, m->Cobs) + 2ll * (m->W + 3) * m->Cobs;
+  long long halo = 2ll * (m->Wl + 3) * std::max(m->C, m->Cobs) + 2ll * (m->W + 3) * m->Cobs;
+  if (m->stem_tc) {                                        // padded bf16 stem stages (2 bytes per element: half of `per`)
+    const long long h1 = (m->H - 1) / 2 + 1, w1 = (m->W - 1) / 2 + 1, h2 = (h1 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1;
+    per = std::max(per, ((h1 + 1) * (w1 + 2) * m->stem_cp1 + 1) / 2);
+    per = std::max(per, ((h2 + 1) * (w2 + 2) * m->C + 1) / 2);
+    halo += (w1 + 3) * (long long)std::max(m->stem_cp1, m->C);
+  }
   return mzb_align_up((size_t)((per * B + halo) * 4 + 4096), 1024);      // sized for fp32; bf16 uses half
 }
 
 size_t ws_bytes_for(const mzb_resnet_model* m, long long B) {
-  return 3 * act_bytes_for(m, B) + mzb_align_up((size_t)B * 4, 256) + 1024;
+  const size_t proj_rows = (size_t)std::max(m->reward.r, m->value.r + m->policy.r) * m->Hl * m->Wl;
+  return 3 * act_bytes_for(m, B) + mzb_align_up((size_t)B * 4, 256) + mzb_align_up((size_t)B * proj_rows * 4, 256) + 1024;
 }
 
 // The buffer offsets inside a workspace must not depend on the batch of the call (the zero pad rows of the padded
 // layout sit at fixed places): derive them from the workspace CAPACITY = the largest batch it was sized for.
-size_t act_bytes_of_workspace(const mzb_resnet_model* m, size_t workspace_bytes) {
+size_t act_bytes_of_workspace(const mzb_resnet_model* m, size_t workspace_bytes, long long* cap_B) {
   long long lo = 1, hi = 1ll << 24;
   while (lo < hi) {
     const long long mid = (lo + hi + 1) / 2;
     if (ws_bytes_for(m, mid) <= workspace_bytes) lo = mid; else hi = mid - 1;
   }
+  *cap_B = lo;
   return act_bytes_for(m, lo);
 }
 
@@ -813,7 +1143,10 @@ int mzb_resnet_initial(mzb_resnet_model* m, int64_t B, const float* d_obs, const
   MZB_CHECK_ARG(B > 0 && B < (1ll << 24), "batch out of range");
   MZB_CHECK_ARG(workspace_bytes >= mzb_resnet_workspace_bytes(m, B), "workspace too small");
   MZB_CHECK_ARG(state_layout >= 0 && state_layout <= 2, "bad state layout");
-  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes_of_workspace(m, workspace_bytes)};
+  long long cap_B = 0;
+  const size_t act_bytes = act_bytes_of_workspace(m, workspace_bytes, &cap_B);
+  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes};
+  r.cap_B = cap_B;
   Outputs o{d_state_out, state_layout, out_row_stride, out_offset, d_value_logits, d_reward_logits, d_policy_logits,
             d_value, d_reward, d_priors};
   int rc = m->precision == 1 ? run_initial<__nv_bfloat16>(r, d_obs, d_legal, o) : run_initial<float>(r, d_obs, d_legal, o);
@@ -831,7 +1164,10 @@ int mzb_resnet_recurrent(mzb_resnet_model* m, int64_t B, const void* d_state_in,
   MZB_CHECK_ARG(B > 0 && B < (1ll << 24), "batch out of range");
   MZB_CHECK_ARG(workspace_bytes >= mzb_resnet_workspace_bytes(m, B), "workspace too small");
   MZB_CHECK_ARG(in_layout >= 0 && in_layout <= 2 && out_layout >= 0 && out_layout <= 2, "bad state layout");
-  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes_of_workspace(m, workspace_bytes)};
+  long long cap_B = 0;
+  const size_t act_bytes = act_bytes_of_workspace(m, workspace_bytes, &cap_B);
+  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes};
+  r.cap_B = cap_B;
   Outputs o{d_state_out, out_layout, out_row_stride, out_offset, d_value_logits, d_reward_logits, d_policy_logits,
             d_value, d_reward, d_priors};
   int rc = m->precision == 1

@@ -13,10 +13,17 @@ struct mzb_resnet_model {
   ConvParams rep_conv, dyn_conv, ds_conv1, ds_conv2;
   std::vector<Block> rep_blocks, dyn_blocks, pred_blocks, ds1, ds2, ds3;
   HeadParams reward, value, policy;
+  // bf16 DownSample stem on the tensor cores: resblocks1 with channels zero-padded C/2 -> stem_cp1 (multiple of 16)
+  float* pv_w = nullptr;           // value and policy 1x1 weights concatenated [r_value + r_policy][C] (fused projection)
+  int stem_tc = 0, stem_cp1 = 0;
+  std::vector<Block> ds1_tc;
   std::vector<void*> allocs;
 };
 
 // tcgen05 implicit-GEMM 3x3 convolution on NHWC bf16 (mzb_conv_tc.cu)
+bool mzb_conv_tc_enabled();
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride);
+struct TcProj { const float* w; float* out; int r; };   // fused 1x1 head projection: w [r][C_out] fp32, out [B][r][H*W] fp32
 int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
-                       const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream);
+                       const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream, int zero_pads = 0,
+                       const TcProj* proj = nullptr);
