@@ -316,7 +316,7 @@ def main():
         h_vis.copy_(o["visits"], non_blocking=True); h_rv.copy_(o["root_value"], non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the caller reads the visit counts before the next move
 
-    for _ in range(2 if is_fc else 1):
+    for _ in range(2):                          # resnet: first call plain launches, second captures the CUDA graph
         e2e_step()
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

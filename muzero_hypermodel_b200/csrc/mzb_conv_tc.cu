@@ -125,7 +125,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 //                 super-tile i+1 run while the epilogue drains super-tile i
 //   warps 2..9    two epilogue warpgroups (TMEM lane quarter = warp % 4); work items (tile, 64-column group) are
 //                 dealt round-robin to the groups
-template <int KC>
+// ZP / PR: the rarely used epilogue features (pad-row zeroing of the stem; fused head projection with PR rows, a
+// compile-time count so the dot products are straight-line code) are separate instantiations, so the common layer
+// keeps its register allocation.
+template <int KC, bool ZP, int PR>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAtail,
           const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -170,7 +173,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < N; i += kThreads) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
-  for (int i = threadIdx.x; i < a.proj_r * N; i += kThreads) s_proj[i] = a.proj_w[i];
+  if (PR > 0) for (int i = threadIdx.x; i < PR * N; i += kThreads) s_proj[i] = i < a.proj_r * N ? a.proj_w[i] : 0.0f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -329,16 +332,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (!valid) {
           // stem mode: the buffers change resolution between layers, so the pad rows (and the trailing halo) are
           // re-written as zeros by every layer instead of relying on a zeroed workspace
-          if (a.zero_pads && m < a.rows_cover) {
+          if (ZP && m < a.rows_cover) {
             uint4* op = reinterpret_cast<uint4*>(a.y + row_off + g0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) if (i * 8 < gw) op[i] = make_uint4(0u, 0u, 0u, 0u);
           }
           continue;
         }
-        float pacc[8];
+        float pacc[PR > 0 ? PR : 1];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) pacc[r] = 0.0f;
+        for (int r = 0; r < PR; ++r) pacc[r] = 0.0f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c * 16 >= gw) break;
@@ -373,30 +376,28 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
             const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
             o[i] = *reinterpret_cast<const uint32_t*>(&pk);
-            f[2 * i] = __uint_as_float(o[i] << 16); f[2 * i + 1] = __uint_as_float(o[i] & 0xFFFF0000u);
+            if (PR > 0) { f[2 * i] = __uint_as_float(o[i] << 16); f[2 * i + 1] = __uint_as_float(o[i] & 0xFFFF0000u); }
           }
           uint4* op = reinterpret_cast<uint4*>(a.y + row_off + g0 + c * 16);
           op[0] = make_uint4(o[0], o[1], o[2], o[3]);
           op[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          if (a.proj_r > 0) {
+          if (PR > 0) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              if (r < a.proj_r) {
-                const float4* w4 = reinterpret_cast<const float4*>(s_proj + r * N + g0 + c * 16);
+            for (int r = 0; r < PR; ++r) {
+              const float4* w4 = reinterpret_cast<const float4*>(s_proj + r * N + g0 + c * 16);
 #pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                  const float4 ww = w4[i4];
-                  pacc[r] = fmaf(f[4 * i4], ww.x, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 1], ww.y, pacc[r]);
-                  pacc[r] = fmaf(f[4 * i4 + 2], ww.z, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 3], ww.w, pacc[r]);
-                }
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 ww = w4[i4];
+                pacc[r] = fmaf(f[4 * i4], ww.x, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 1], ww.y, pacc[r]);
+                pacc[r] = fmaf(f[4 * i4 + 2], ww.z, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 3], ww.w, pacc[r]);
               }
             }
           }
         }
-        if (a.proj_r > 0) {
+        if (PR > 0) {
           float* po = a.proj_out + ((long long)b * a.proj_r) * a.proj_hw + pos;
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
+          for (int r = 0; r < PR; ++r) {
             if (r < a.proj_r) {
               if (ncg == 1) po[(long long)r * a.proj_hw] = pacc[r];
               else atomicAdd(po + (long long)r * a.proj_hw, pacc[r]);     // two column groups: 0 + x + y, order-independent
@@ -530,16 +531,28 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   }
   const long long n_super = (a.rows_cover + (long long)p.mt * 128 - 1) / ((long long)p.mt * 128);
   const unsigned grid = (unsigned)(n_super < n_sm ? n_super : n_sm);      // persistent: one CTA per SM
-#define LAUNCH_KC(KCV)                                                                                              \
+  const int pr = (a.proj_r + 1) / 2 * 2;              // instantiated projection heights: 2, 4, 6, 8
+  MZB_CHECK_ARG(!(zero_pads && pr), "pad zeroing and head projection are not combined");
+#define LAUNCH_ONE(KCV, ZPV, PRV)                                                                                   \
   {                                                                                                                 \
     static bool configured = false;                                                                                 \
     if (!configured) {                                                                                              \
-      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));      \
+      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV, ZPV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       configured = true;                                                                                            \
     }                                                                                                               \
-    k_conv_tc<KCV><<<grid, kThreads, p.smem, stream>>>(tmA, tmAtail, tmB, a);                                       \
+    k_conv_tc<KCV, ZPV, PRV><<<grid, kThreads, p.smem, stream>>>(tmA, tmAtail, tmB, a);                             \
+  }
+#define LAUNCH_KC(KCV)                                                                                              \
+  {                                                                                                                 \
+    if (zero_pads) LAUNCH_ONE(KCV, true, 0)                                                                         \
+    else if (pr == 0) LAUNCH_ONE(KCV, false, 0)                                                                     \
+    else if (pr == 2) LAUNCH_ONE(KCV, false, 2)                                                                     \
+    else if (pr == 4) LAUNCH_ONE(KCV, false, 4)                                                                     \
+    else if (pr == 6) LAUNCH_ONE(KCV, false, 6)                                                                     \
+    else LAUNCH_ONE(KCV, false, 8)                                                                                  \
   }
   if (p.kc == 64) LAUNCH_KC(64) else if (p.kc == 32) LAUNCH_KC(32) else LAUNCH_KC(16)
+#undef LAUNCH_ONE
 #undef LAUNCH_KC
   MZB_LAUNCH_CHECK();
   return MZB_OK;

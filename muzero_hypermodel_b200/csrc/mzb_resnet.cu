@@ -687,6 +687,7 @@ int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* c) {
 
 int mzb_resnet_destroy(mzb_resnet_model* m) {
   if (!m) return MZB_OK;
+  mzb_search_graph_forget(m);
   for (void* p : m->allocs) cudaFree(p);
   delete m;
   return MZB_OK;

@@ -457,6 +457,7 @@ int mzb_tree_create(mzb_tree** out, const mzb_tree_config* cfg, void* d_workspac
 
 int mzb_tree_destroy(mzb_tree* t) {
   if (!t) return MZB_OK;
+  mzb_search_graph_forget(t);
   cudaFree(t->d_log_lut);
   delete t;
   return MZB_OK;
