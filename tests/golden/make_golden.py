@@ -458,8 +458,127 @@ def gen_targets():
     print("targets.npz:", n, "cases")
 
 
+def obs_row(obs, n_rows=N_ROWS):
+    """Observation -> table row: crc32 of the float32 bytes (mirrored in tests/_tables.py)."""
+    import zlib
+    return zlib.crc32(np.ascontiguousarray(np.asarray(obs, dtype=np.float32)).tobytes()) % n_rows
+
+
+class EpisodeModel(TableModel):
+    """Table model whose root row is a hash of the observation: a whole game is a pure function of the tables."""
+
+    def __init__(self, V, Rw, L):
+        super().__init__(V, Rw, L)
+        self.step = -1
+
+    def initial_inference(self, observation):
+        self.step += 1          # one initial inference per move (self_play.py:288-292)
+        self.sim = 0
+        self.depth = 0
+        return self._out(obs_row(observation.cpu().numpy()[0]))
+
+
+def gen_episode():
+    """G7: whole games through the UNMODIFIED SelfPlay.play_game (self_play.py:110-184) - reset, observation
+    stacking, search, select_action, Game.step, store_search_statistics, history appends and the loop bounds -
+    with the reference's own Game classes, a table-driven network and injected randomness."""
+    self_play, models = ref_loader.load("self_play", "models")
+    rs = np.random.RandomState(SEED + 7)
+    out = {}
+    orig = (np.random.choice, np.random.dirichlet, models.support_to_scalar, self_play.MCTS.run, self_play.SelfPlay.__init__)
+    # game, simulations override, max_moves override, (temperature, temperature_threshold) per episode
+    plans = [("tictactoe", 25, None, [(1.0, None), (1.0, 4), (0.5, None), (0, None)]),
+             ("connect4", 40, None, [(1.0, None), (1.0, 10), (0.25, None)]),
+             ("gomoku", 20, 30, [(1.0, None), (0.5, 6)]),
+             ("cartpole", 50, None, [(1.0, None), (0.5, 12), (0.25, None)]),
+             ("cartpole", 20, 9, [(1.0, None)])]            # episode cut by max_moves (self_play.py:129-131)
+    n = 0
+    try:
+        for gname, sims, max_moves, episodes in plans:
+            gmod = ref_loader.load(f"games.{gname}")
+            cfg = gmod.MuZeroConfig()
+            cfg.num_simulations = sims
+            if max_moves is not None:
+                cfg.max_moves = max_moves
+            A = len(cfg.action_space)
+            V = rs.uniform(-3, 3, N_ROWS).astype(np.float32)
+            Rw = (rs.uniform(-1, 1, N_ROWS) * (rs.uniform(size=N_ROWS) < 0.5)).astype(np.float32)
+            L = rs.normal(0, 1.5, (N_ROWS, A)).astype(np.float32)
+            P = np.stack([torch.softmax(torch.tensor([torch.tensor(L)[r][a] for a in range(A)]), dim=0).numpy()
+                          for r in range(N_ROWS)]) if A <= 16 else \
+                np.stack([torch.softmax(torch.tensor(L[r]), dim=0).numpy() for r in range(N_ROWS)])
+            tab = f"tab{len([k for k in out if k.endswith('/V')])}"
+            out[f"{tab}/V"], out[f"{tab}/Rw"], out[f"{tab}/L"], out[f"{tab}/P"] = V, Rw, L, P
+            for ei, (T, T_thr) in enumerate(episodes):
+                slot, seed_env = 300 + n, 11 * n + 5
+                model = EpisodeModel(V, Rw, L)
+                roots = []          # per move: (row, legal, torch softmax over the legal logits = Node.expand's priors)
+
+                def choice(a, size=None, replace=True, p=None, _m=model):
+                    a = list(a)
+                    if p is None and not isinstance(a[0], (int, np.integer)):
+                        raise AssertionError("unexpected numpy.random.choice use")
+                    if p is not None or _m.sim >= cfg.num_simulations:
+                        # select_action (self_play.py:240-244): inverse CDF on the injected uniform / uniform pick
+                        u = rng.action_uniform(SEED, slot, _m.step)
+                        if p is None:
+                            return a[int(u * len(a))]
+                        cdf = np.cumsum(p)
+                        cdf /= cdf[-1]
+                        return a[int(np.searchsorted(cdf, u, side="right"))]
+                    i = rng.tie_index(SEED, slot, _m.step, _m.sim, _m.depth, len(a)) if len(a) > 1 else 0
+                    _m.depth += 1
+                    return a[i]
+
+                noises = {}
+
+                def dirichlet(alphas, _m=model, _slot=slot):
+                    nz = np.random.RandomState([SEED & 0x7FFFFFFF, _slot, _m.step]).dirichlet(alphas)
+                    noises[_m.step] = nz
+                    return nz
+
+                def run(self, mdl, observation, legal_actions, to_play, add_noise, override_root_with=None, _orig=orig[3]):
+                    row = obs_row(np.asarray(observation, dtype=np.float32))
+                    pri = torch.softmax(torch.tensor([torch.tensor(L[row:row + 1])[0][a] for a in legal_actions]), dim=0).numpy()
+                    roots.append((row, list(legal_actions), pri))
+                    return _orig(self, mdl, observation, legal_actions, to_play, add_noise, override_root_with)
+
+                def init(self, checkpoint, Game, config, seed, _m=model):
+                    self.config, self.game, self.model = config, Game(seed), _m
+
+                np.random.choice, np.random.dirichlet = choice, dirichlet
+                models.support_to_scalar = lambda logits, support_size: logits
+                self_play.MCTS.run = run
+                self_play.SelfPlay.__init__ = init
+                sp = self_play.SelfPlay(None, gmod.Game, cfg, seed_env)
+                gh = sp.play_game(T, T_thr, False, "self", 0)
+                pre = f"{n}/"
+                out[pre + "meta"] = np.array([A, len(cfg.players), sims, cfg.max_moves, cfg.discount, cfg.root_dirichlet_alpha,
+                                              float(T), float(T_thr or 0), slot, seed_env], dtype=np.float64)
+                out[pre + "game"] = np.array(gname)
+                out[pre + "table"] = np.array(tab)
+                out[pre + "actions"] = np.array(gh.action_history, dtype=np.int32)
+                out[pre + "rewards"] = np.array(gh.reward_history, dtype=np.float64)
+                out[pre + "to_play"] = np.array(gh.to_play_history, dtype=np.int32)
+                out[pre + "observations"] = np.array([np.asarray(o, dtype=np.float32) for o in gh.observation_history])
+                out[pre + "child_visits"] = np.array(gh.child_visits, dtype=np.float64)
+                out[pre + "root_values"] = np.array(gh.root_values, dtype=np.float64)
+                out[pre + "root_rows"] = np.array([r[0] for r in roots], dtype=np.int64)
+                for mi, (_, lg, pri) in enumerate(roots):
+                    out[pre + f"root_priors/{mi}"] = pri
+                    out[pre + f"noise/{mi}"] = noises[mi]
+                print(gname, "episode", ei, "moves", len(gh.action_history) - 1, "T", T, T_thr)
+                n += 1
+    finally:
+        (np.random.choice, np.random.dirichlet, models.support_to_scalar, self_play.MCTS.run,
+         self_play.SelfPlay.__init__) = orig
+    out["n"] = np.int64(n)
+    np.savez_compressed(os.path.join(HERE, "episode.npz"), **out)
+    print("episode.npz:", n, "games")
+
+
 FAMILIES = {"tree": gen_tree, "action": gen_action, "env": gen_env, "codec": gen_codec, "net": gen_net,
-            "targets": gen_targets}
+            "targets": gen_targets, "episode": gen_episode}
 
 if __name__ == "__main__":
     todo = sys.argv[1:] or list(FAMILIES)
