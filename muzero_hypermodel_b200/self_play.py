@@ -230,6 +230,29 @@ class MCTS:
         return root
 
 
+def decode_export(env):
+    """Empty the device export ring of `env` into reference-format GameHistory objects (self_play.py:480-495);
+    child_visits = count / sum(counts) in float64, bit-identical to store_search_statistics (:497-512)."""
+    ne, ng, h = env.drain_raw()
+    games = []
+    A = env.A
+    for k in range(ng):
+        s, n = int(h["start"][k]), int(h["len"][k])
+        gh = GameHistory()
+        gh.observation_history = [env.decode_observation(h["obs"][s + i]) for i in range(n + 1)]
+        gh.action_history = h["action"][s:s + n + 1].tolist()
+        gh.reward_history = [float(x) for x in h["reward"][s:s + n + 1]]
+        gh.reward_history[0] = 0
+        gh.to_play_history = h["to_play"][s:s + n + 1].astype(int).tolist()
+        v = h["visits"][s:s + n].astype(numpy.int64)
+        tot = v.sum(axis=1)
+        gh.child_visits = [[int(v[i, a]) / int(tot[i]) if v[i, a] else 0 for a in range(A)] for i in range(n)]
+        gh.root_values = h["root_value"][s:s + n].tolist()
+        gh.slot = int(h["slot"][k])
+        games.append(gh)
+    return games
+
+
 class SelfPlay:
     """Self-play worker.  `play_games` advances G games in lock-step on one GPU; `play_game` keeps the
     reference's one-game signature (self_play.py:110-184) on top of it."""
@@ -289,24 +312,8 @@ class SelfPlay:
 
     def drain(self):
         env, _ = self._setup()
-        ne, ng, h = env.drain_raw()
-        games = []
-        A = env.A
-        for k in range(ng):
-            s, n = int(h["start"][k]), int(h["len"][k])
-            gh = GameHistory()
-            gh.observation_history = [env.decode_observation(h["obs"][s + i]) for i in range(n + 1)]
-            gh.action_history = h["action"][s:s + n + 1].tolist()
-            gh.reward_history = [float(x) for x in h["reward"][s:s + n + 1]]
-            gh.reward_history[0] = 0
-            gh.to_play_history = h["to_play"][s:s + n + 1].astype(int).tolist()
-            v = h["visits"][s:s + n].astype(numpy.int64)
-            tot = v.sum(axis=1)
-            gh.child_visits = [[int(v[i, a]) / int(tot[i]) if v[i, a] else 0 for a in range(A)] for i in range(n)]
-            gh.root_values = h["root_value"][s:s + n].tolist()
-            gh.slot = int(h["slot"][k])
-            games.append(gh)
-        self.num_played_games += ng
+        games = decode_export(env)
+        self.num_played_games += len(games)
         self.num_played_steps += sum(len(g.root_values) for g in games)
         return games
 
