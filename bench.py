@@ -35,8 +35,28 @@ WORKLOADS = {
     "tictactoe": ("tictactoe_fc", "tictactoe", 4096 * 16, (3648, 5952)),
     "connect4": ("connect4", "connect4", 16384, (37372160, 40396160)),
     "gomoku": ("gomoku", "gomoku", 1024, (857557760, 892780160)),
-    "breakout": ("breakout", "breakout", 8192, (34192160, 1532480)),
+    "breakout": ("breakout", "breakout", 16384, (34192160, 1532480)),
 }
+# committed `ncu --set full` captures of the dominant kernel at the bench shape (profiles/): DRAM bytes per launch
+NCU_CAPTURE = {"cartpole": "r01_ncu_k_search_fc_cartpole.csv", "connect4": "r01_ncu_k_conv_tc_connect4.csv"}
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed capture, or None."""
+    name = NCU_CAPTURE.get(workload)
+    if not name:
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    try:
+        for ln in open(os.path.join(ROOT, "profiles", name)):
+            c = ln.strip().split(",")
+            if len(c) >= 3 and c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and c[1] in unit:
+                total += float(c[2]) * unit[c[1]]
+                seen += 1
+    except (OSError, ValueError):
+        return None
+    return total if seen == 2 else None
 
 
 def load_weights(tag):
@@ -287,15 +307,40 @@ def main():
     tflops = (flops[1] * S + flops[0]) * G / (k_ms * 1e-3) / 1e12
     if is_fc:
         roofline = {"bound": "hbm", "kernel": "k_search_fc (whole-search, fused)" if fused else "modular: k_select+k_fc_recurrent+k_expand_backup",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(args.workload) if (fused and G == WORKLOADS[args.workload][2]) else None,
+                    "traffic_source": ("profiles/" + NCU_CAPTURE[args.workload]) if args.workload in NCU_CAPTURE else None,
+                    "algorithmic_bytes_per_launch": bytes_per_sim * G * S,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                     "kernel_ms": k_ms, "bytes_per_sim": bytes_per_sim, "mean_path_nodes": L, "fp32_tflops": tflops,
                     "kernel_share_of_step": k_ms * args.steps / ms if world == 1 else None}
     else:
-        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        roofline = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM 3x3 conv) inside mzb_search_resnet",
-                    "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1400 TFLOP/s",
+        # the dominant kernel alone: the tower's C -> C convolution at the bench batch, timed live with CUDA events
+        # (activation buffers 3 x B x rows x C bf16 rotate through HBM; connect4: 3 x 132 MB > L2)
+        import ctypes as C
+        C_lat, H_lat, W_lat = (int(x) for x in sp.model.latent_shape)
+        ws = sp.model._workspace(G, dev)
+        iters = 20
+        probe = lambda: _lib.check(_lib.lib.mzb_resnet_conv_probe(sp.model.handle(), G, _lib.ptr(ws), ws.numel(), iters,
+                                                                   _lib.current_stream()))
+        probe()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); probe(); b.record()
+        torch.cuda.synchronize()
+        conv_ms = a.elapsed_time(b) / iters
+        conv_flop = 2.0 * G * H_lat * W_lat * C_lat * C_lat * 9
+        conv_tflops = conv_flop / (conv_ms * 1e-3) / 1e12
+        tpeak = float(peaks.get("bf16_tflops", 1650.0))
+        tpeak_s = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        roofline = {"bound": "tensor", "kernel": f"k_conv_tc (tcgen05 implicit-GEMM 3x3 conv, {C_lat}->{C_lat} ch, {H_lat}x{W_lat}, batch {G})",
+                    "achieved": conv_tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": conv_tflops / tpeak,
+                    "traffic": ncu_traffic(args.workload),
+                    "traffic_source": ("profiles/" + NCU_CAPTURE[args.workload]) if args.workload in NCU_CAPTURE else None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if peaks else "fallback 1650 TFLOP/s",
+                    "kernel_us": conv_ms * 1e3, "flop_per_launch": conv_flop,
+                    "whole_search": {"achieved": tflops, "peak": tpeak_s, "frac": tflops / tpeak_s,
+                                     "note": "all FLOPs of the search (BASELINE flop/sim) / search time, helper and tree kernels included; sustained peak"},
                     "search_ms": k_ms, "flop_per_sim": flops[1], "tree_bytes_per_sim": bytes_per_sim, "mean_path_nodes": L,
                     "tree_hbm_gbs": achieved, "search_share_of_step": k_ms * args.steps / ms if world == 1 else None}
 

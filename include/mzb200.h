@@ -317,6 +317,12 @@ int mzb_resnet_recurrent(mzb_resnet_model* m, int64_t B, const void* d_state_in,
                          int64_t out_offset, float* d_value_logits, float* d_reward_logits, float* d_policy_logits,
                          float* d_value, float* d_reward, float* d_priors, void* stream);
 
+/* Measurement hook for the roofline line of bench.py: launches the first residual-block convolution of the
+ * representation tower (C -> C, latent resolution, batch B; conv3x3 + BatchNorm2d + relu, models.py:206-229)
+ * `iters` times on the workspace's activation buffers, so the dominant kernel can be timed alone. */
+int mzb_resnet_conv_probe(mzb_resnet_model* m, int64_t B, void* d_workspace, size_t workspace_bytes, int32_t iters,
+                          void* stream);
+
 /* Batched MCTS.run for residual networks (self_play.py:261-362): as mzb_search_fc, with the tree kernels and
  * the resnet layer program launched per simulation.  d_hidden_pool: caller-owned hidden-state slots
  * [G][tree capacity + 1][H*W*C] dense NHWC, bf16 (precision 1) or fp32 (precision 0);

@@ -1179,6 +1179,30 @@ int mzb_resnet_recurrent(mzb_resnet_model* m, int64_t B, const void* d_state_in,
   return MZB_OK;
 }
 
+/* Measurement hook (bench.py roofline line): the first residual-block convolution of the representation tower
+ * (C -> C channels, latent resolution, batch B, + folded batch-norm + ReLU) launched `iters` times on the workspace's
+ * activation buffers - the dominant kernel of a resnet search, timed alone. */
+int mzb_resnet_conv_probe(mzb_resnet_model* m, int64_t B, void* d_workspace, size_t workspace_bytes, int32_t iters,
+                          void* stream) {
+  MZB_CHECK_ARG(m && d_workspace && iters > 0, "NULL argument");
+  MZB_CHECK_ARG(!m->rep_blocks.empty(), "model has no residual blocks");
+  MZB_CHECK_ARG(B > 0 && workspace_bytes >= mzb_resnet_workspace_bytes(m, B), "workspace too small");
+  long long cap_B = 0;
+  const size_t act_bytes = act_bytes_of_workspace(m, workspace_bytes, &cap_B);
+  Runner r{m, (int)B, (cudaStream_t)stream, (uint8_t*)d_workspace, workspace_bytes, act_bytes};
+  r.cap_B = cap_B;
+  for (int i = 0; i < iters && !r.rc; ++i) {
+    if (m->precision == 1) {
+      const Geo g = latent_geo<__nv_bfloat16>(m);
+      conv<__nv_bfloat16>(r, r.buf<__nv_bfloat16>(i & 1), g, m->rep_blocks[0].c1, nullptr, nullptr, 1, g, r.buf<__nv_bfloat16>(2));
+    } else {
+      const Geo g = latent_geo<float>(m);
+      conv<float>(r, r.buf<float>(i & 1), g, m->rep_blocks[0].c1, nullptr, nullptr, 1, g, r.buf<float>(2));
+    }
+  }
+  return r.rc;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------ debug / self-test

@@ -24,6 +24,8 @@ STREAM_NOISE = 1    # root Dirichlet noise (device generator)     (0, action / d
 STREAM_ACTION = 2   # temperature sampling of the played action   (0, 0)
 STREAM_RESET = 3    # environment reset (cartpole initial state)  (0, component)
 STREAM_PAD = 4      # random padding action in make_target        (0, row)
+STREAM_RGAME = 5    # replay: game draw of batch element `slot` in batch `step`
+STREAM_RPOS = 6     # replay: position draw of batch element `slot` in batch `step`
 
 
 def philox4x32(c0, c1, c2, c3, k0, k1):
@@ -89,3 +91,9 @@ def reset_uniforms(seed, slot, step, n=4):
 def pad_action(seed, slot, step, row, n_actions):
     r = draw(seed, slot, step, STREAM_PAD, 0, row)[0]
     return (r * n_actions) >> 32
+
+
+def replay_uniform(seed, element, batch, stream):
+    """float64 uniform of a replay draw: batch element `element` of the `batch`-th get_batch call."""
+    r = draw(seed, element, batch, stream)
+    return u01_double(r[0], r[1])

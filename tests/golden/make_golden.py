@@ -577,8 +577,125 @@ def gen_episode():
     print("episode.npz:", n, "games")
 
 
+def gen_replay():
+    """The unmodified reference ReplayBuffer (replay_buffer.py:33-220): save_game with initial PER priorities and FIFO
+    eviction, get_batch (sample_n_games / sample_position / make_target / weights / gradient scale) and
+    update_priorities, as a scripted sequence of operations with injected uniforms."""
+    self_play, replay_buffer = ref_loader.load("self_play", "replay_buffer")
+    rs = np.random.RandomState(SEED + 9)
+    out = {}
+    orig_choice = np.random.choice
+    cases = [("cartpole", True, 1), ("tictactoe", True, 2), ("connect4", False, 2), ("cartpole", True, 1)]
+    try:
+        for ci, (cname, per, players) in enumerate(cases):
+            cfg = _ref_config(cname)
+            cfg.PER = per
+            cfg.batch_size = 24
+            cfg.replay_buffer_size = 5 if ci < 3 else 400
+            if ci == 3:
+                cfg.PER_alpha = 1
+            A = len(cfg.action_space)
+            rb = replay_buffer.ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg)
+            ctx = {"batch": -1, "b": -1, "row": 0}
+
+            def choice(a, size=None, replace=True, p=None):
+                if size is not None:                                     # sample_n_games (:162-177)
+                    ids = list(a)
+                    ctx["b"] = -1
+                    u = [rng.replay_uniform(SEED, b, ctx["batch"], rng.STREAM_RGAME) for b in range(size)]
+                    if p is None:
+                        return np.array([ids[int(x * len(ids))] for x in u])
+                    cdf = np.cumsum(np.asarray(p, dtype=np.float64)); cdf /= cdf[-1]
+                    return np.array([ids[int(np.searchsorted(cdf, x, side="right"))] for x in u])
+                if isinstance(a, (int, np.integer)):                     # sample_position (:179-192)
+                    ctx["b"] += 1
+                    ctx["row"] = 0
+                    u = rng.replay_uniform(SEED, ctx["b"], ctx["batch"], rng.STREAM_RPOS)
+                    if p is None:
+                        return int(u * a)
+                    cdf = np.cumsum(np.asarray(p, dtype=np.float64)); cdf /= cdf[-1]
+                    return int(np.searchsorted(cdf, u, side="right"))
+                a = list(a)                                              # make_target padding action (:291)
+                k = ctx["row"]
+                ctx["row"] += 1
+                return a[rng.pad_action(SEED, ctx["b"], ctx["batch"], k, len(a))]
+
+            np.random.choice = choice
+            pre = f"{ci}/"
+            out[pre + "cfg"] = np.array([int(per), cfg.PER_alpha, cfg.replay_buffer_size, cfg.batch_size, cfg.num_unroll_steps,
+                                         cfg.td_steps, cfg.discount, A, players], dtype=np.float64)
+            out[pre + "game"] = np.array(cname)
+            n_games = 9 if ci < 3 else 300
+            script = (["save"] * 3 + ["batch", "batch", "update", "batch"] + ["save"] * 4 + ["batch", "update", "save", "save", "batch"]
+                      if ci < 3 else ["save"] * n_games + ["batch", "update", "batch"])
+            gi = bi = ui = 0
+            last_index = None
+            ops = []
+            for op in script:
+                if op == "save":
+                    T = int(rs.randint(1, min(cfg.max_moves, 90) + 1))
+                    gh = self_play.GameHistory()
+                    gh.action_history = [0] + rs.randint(A, size=T).tolist()
+                    gh.reward_history = [0] + np.round(rs.uniform(-1, 2, T), 3).tolist()
+                    gh.to_play_history = [int(i % players) for i in range(T + 1)]
+                    gh.root_values = rs.normal(0, 3, T).tolist()
+                    vis = rs.multinomial(cfg.num_simulations, rs.dirichlet([0.7] * A), size=T)
+                    gh.child_visits = [[int(v) / int(row.sum()) if v else 0 for v in row] for row in vis]
+                    gh.observation_history = [rs.uniform(-1, 1, cfg.observation_shape).astype(np.float32) for _ in range(T + 1)]
+                    g = f"{pre}game{gi}/"
+                    out[g + "actions"] = np.array(gh.action_history, dtype=np.int32)
+                    out[g + "rewards"] = np.array(gh.reward_history, dtype=np.float64)
+                    out[g + "to_play"] = np.array(gh.to_play_history, dtype=np.int32)
+                    out[g + "root_values"] = np.array(gh.root_values, dtype=np.float64)
+                    out[g + "visits"] = vis.astype(np.int32)
+                    out[g + "observations"] = np.array(gh.observation_history)
+                    rb.save_game(gh)
+                    if per:
+                        out[g + "priorities"] = np.array(gh.priorities, dtype=np.float32)
+                        out[g + "game_priority"] = np.float32(gh.game_priority)
+                    gi += 1
+                elif op == "batch":
+                    ctx["batch"] = bi
+                    index, (obs, act, val, rew, pol, w, gs) = rb.get_batch()
+                    b = f"{pre}batch{bi}/"
+                    out[b + "index"] = np.array(index, dtype=np.int64)
+                    out[b + "observations"] = np.array(obs, dtype=np.float32)
+                    out[b + "actions"] = np.array(act, dtype=np.int32)
+                    out[b + "values"] = np.array(val, dtype=np.float64)
+                    out[b + "rewards"] = np.array(rew, dtype=np.float64)
+                    out[b + "policies"] = np.array(pol, dtype=np.float64)
+                    out[b + "gradient_scale"] = np.array(gs, dtype=np.int32)
+                    if per:
+                        assert w.dtype == np.float32
+                        out[b + "weights"] = w
+                    out[b + "state"] = np.array([rb.total_samples, rb.num_played_games, len(rb.buffer)], dtype=np.int64)
+                    last_index = index
+                    bi += 1
+                else:                                                    # update_priorities with trainer-like values
+                    pr = np.abs(rs.normal(0, 2, (len(last_index), cfg.num_unroll_steps + 1))).astype(np.float32) ** cfg.PER_alpha
+                    pr = pr.astype(np.float32)
+                    if per:
+                        rb.update_priorities(pr, last_index)
+                    u = f"{pre}update{ui}/"
+                    out[u + "priorities"] = pr
+                    out[u + "index"] = np.array(last_index, dtype=np.int64)
+                    if per:
+                        for gid, gh in rb.buffer.items():
+                            out[u + f"after/{gid}"] = np.array(gh.priorities, dtype=np.float32)
+                            out[u + f"after_game/{gid}"] = np.float32(gh.game_priority)
+                    ui += 1
+                ops.append(op)
+            out[pre + "script"] = np.array(" ".join(ops))
+            print(cname, "PER" if per else "uniform", "games", gi, "batches", bi, "updates", ui)
+    finally:
+        np.random.choice = orig_choice
+    out["n"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
+    print("replay.npz", os.path.getsize(os.path.join(HERE, "replay.npz")) // 1024, "KiB")
+
+
 FAMILIES = {"tree": gen_tree, "action": gen_action, "env": gen_env, "codec": gen_codec, "net": gen_net,
-            "targets": gen_targets, "episode": gen_episode}
+            "targets": gen_targets, "episode": gen_episode, "replay": gen_replay}
 
 if __name__ == "__main__":
     todo = sys.argv[1:] or list(FAMILIES)
