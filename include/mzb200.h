@@ -46,6 +46,8 @@ void mzb_reset_launch_count(void);
 #define MZB_STREAM_ACTION 2
 #define MZB_STREAM_RESET 3
 #define MZB_STREAM_PAD 4
+#define MZB_STREAM_RGAME 5        /* replay: game draw of batch element (slot) in batch (step)     */
+#define MZB_STREAM_RPOS 6         /* replay: position draw                                         */
 /* Host-side evaluation (tests): out[4]. */
 void mzb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out);
 
@@ -332,6 +334,64 @@ int mzb_search_resnet(mzb_tree* t, mzb_resnet_model* m, const float* d_obs, cons
                       const uint32_t* d_step, int32_t num_simulations, void* d_hidden_pool, void* d_workspace,
                       size_t workspace_bytes, int32_t* d_visits, double* d_root_value, float* d_root_predicted_value,
                       int32_t* d_max_depth, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Replay store on the device: replaces ReplayBuffer (replay_buffer.py:11-220), the consumer
+ * of the self-play output and the producer of the trainer's batches.
+ * Games live in fixed slots (game id % capacity_games, FIFO eviction like the reference's dict :57-60) in the export
+ * layout of mzb_env / mzb_make_target; a game of n moves has n + 1 entries and must fit entry_stride.
+ * All float32 / float64 arithmetic of the reference (initial priorities :37-50, sampling probabilities :162-192,
+ * importance weights :117-121) is restated operation by operation; random draws are one float64 uniform per batch
+ * element and draw, injected (d_u_*) or Philox(seed; slot = element, step = batch counter; MZB_STREAM_RGAME/RPOS).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mzb_replay mzb_replay;
+typedef struct {
+  int32_t n_actions;         /* len(config.action_space)                                      */
+  int32_t obs_floats;        /* floats per stored observation (stacked_observations = 0)      */
+  int32_t capacity_games;    /* config.replay_buffer_size                                     */
+  int32_t entry_stride;      /* entries per slot >= max_moves + 1                             */
+  int32_t num_unroll_steps;  /* config.num_unroll_steps                                       */
+  int32_t td_steps;          /* config.td_steps                                               */
+  int32_t per;               /* config.PER                                                    */
+  int32_t max_batch;         /* largest batch get_batch / update_priorities will see          */
+  double per_alpha;          /* config.PER_alpha                                              */
+  uint64_t seed;             /* Philox key                                                    */
+} mzb_replay_config;
+
+size_t mzb_replay_workspace_bytes(const mzb_replay_config* cfg);
+/* h_discount_pow [td_steps + 1] = discount ** i as the caller's pow rounds it (replay_buffer.py:240, 253).
+ * d_workspace: caller-owned, 256-byte aligned, >= mzb_replay_workspace_bytes. */
+int mzb_replay_create(mzb_replay** out, const mzb_replay_config* cfg, void* d_workspace, size_t workspace_bytes,
+                      const double* h_discount_pow, void* stream);
+int mzb_replay_destroy(mzb_replay* r);
+/* save_game (replay_buffer.py:33-64) for n_games games given as entry arrays on the device (export layout: game g
+ * occupies source entries h_src_start[g] .. h_src_start[g] + h_len[g]); appended in order, the oldest games evicted
+ * beyond capacity.  PER: initial priorities |root_value - target_value| ** PER_alpha (float64 -> float32) and the
+ * game priority, or d_priorities [entries] f32 if the histories already carry them (:35-37).  Synchronises the
+ * stream once (staging of the per-game table). */
+int mzb_replay_save_games(mzb_replay* r, int32_t n_games, const int32_t* h_src_start, const int32_t* h_len,
+                          const float* d_obs, const int32_t* d_action, const float* d_reward, const int8_t* d_to_play,
+                          const double* d_root_value, const uint16_t* d_visits, const float* d_priorities, void* stream);
+/* get_batch (replay_buffer.py:69-140): sample_n_games + sample_position per element, then make_target, the
+ * observation of the position, gradient scale and (PER) importance weights normalised by their maximum.
+ * d_u_game / d_u_pos [batch] f64 inject the draws (NULL = Philox).  Outputs: d_game_id [B] i64 + d_pos [B] i32
+ * (index_batch), optional d_game_prob / d_pos_prob [B] f32, d_obs [B, obs_floats] f32, d_actions [B, K+1] i32,
+ * d_values / d_rewards [B, K+1] f64, d_policies [B, K+1, A] f64, d_weights [B] f32 (PER), d_gradient_scale
+ * [B, K+1] i32.  Output groups may be NULL.  Increments the batch counter. */
+int mzb_replay_get_batch(mzb_replay* r, int32_t batch, const double* d_u_game, const double* d_u_pos, int64_t* d_game_id,
+                         int32_t* d_pos, float* d_game_prob, float* d_pos_prob, float* d_obs, int32_t* d_actions,
+                         double* d_values, double* d_rewards, double* d_policies, float* d_weights,
+                         int32_t* d_gradient_scale, void* stream);
+/* update_priorities (replay_buffer.py:202-220): d_priorities [batch, K+1] f32 written to positions
+ * [pos, min(pos + K + 1, len)) of each still-buffered game, rows applied in order; game priority = max. */
+int mzb_replay_update_priorities(mzb_replay* r, int32_t batch, const float* d_priorities, const int64_t* d_game_id,
+                                 const int32_t* d_pos, void* stream);
+/* out5 = total_samples, num_played_games, num_played_steps, games in the buffer, id of the oldest game. */
+int mzb_replay_info(const mzb_replay* r, int64_t* out5);
+int mzb_replay_set_batch_counter(mzb_replay* r, uint32_t counter);
+/* Inspection (tests, checkpoints): priorities [len] and game priority of a buffered game. */
+int mzb_replay_game_priorities_sync(mzb_replay* r, int64_t game_id, float* h_priorities, float* h_game_priority,
+                                    int32_t* h_len, void* stream);
 
 #ifdef __cplusplus
 }

@@ -2,8 +2,12 @@
 
 `make_target_batch` builds the value / reward / policy / action targets of a batch of sampled
 positions on the GPU (K11, csrc/mzb_targets.cu) from games stored in the export layout of
-`envs.VectorEnv.drain_raw()`.  The replay store, PER sampling and Reanalyse are learner-side
-("next" rows) and are not part of this package yet.
+`envs.VectorEnv.drain_raw()`.
+
+`ReplayBuffer` is the reference's class (replay_buffer.py:11-220) with the game store, the PER sampling, the batch
+assembly and the priority updates on the device (csrc/mzb_replay.cu): same constructor, `save_game`, `get_batch`,
+`update_priorities`, counters.  Batches come back as device tensors (what the trainer moves to the GPU anyway,
+trainer.py:124-135).  Reanalyse is a later row.
 """
 import ctypes as C
 
@@ -14,6 +18,24 @@ from . import _lib
 from ._lib import check, ptr
 
 _vp, _i32 = C.c_void_p, C.c_int32
+_i64 = C.c_int64
+
+
+class ReplayConfig(C.Structure):
+    _fields_ = [("n_actions", _i32), ("obs_floats", _i32), ("capacity_games", _i32), ("entry_stride", _i32),
+                ("num_unroll_steps", _i32), ("td_steps", _i32), ("per", _i32), ("max_batch", _i32),
+                ("per_alpha", C.c_double), ("seed", C.c_uint64)]
+
+
+_lib.bind("mzb_replay_workspace_bytes", C.c_size_t, [C.POINTER(ReplayConfig)])
+_lib.bind("mzb_replay_create", C.c_int, [C.POINTER(_vp), C.POINTER(ReplayConfig), _vp, C.c_size_t, _vp, _vp])
+_lib.bind("mzb_replay_destroy", C.c_int, [_vp])
+_lib.bind("mzb_replay_save_games", C.c_int, [_vp, _i32, _vp, _vp] + [_vp] * 7 + [_vp])
+_lib.bind("mzb_replay_get_batch", C.c_int, [_vp, _i32] + [_vp] * 13 + [_vp])
+_lib.bind("mzb_replay_update_priorities", C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp])
+_lib.bind("mzb_replay_info", C.c_int, [_vp, C.POINTER(_i64)])
+_lib.bind("mzb_replay_set_batch_counter", C.c_int, [_vp, C.c_uint32])
+_lib.bind("mzb_replay_game_priorities_sync", C.c_int, [_vp, _i64, _vp, _vp, C.POINTER(_i32), _vp])
 _lib.bind("mzb_make_target", C.c_int, [_vp] * 8 + [_i32] + [_vp] * 4 + [_i32, _i32, _i32, _vp, C.c_uint64] + [_vp] * 5)
 
 
@@ -54,3 +76,133 @@ def make_target_batch(games, batch_game, batch_index, config, seed=0, batch_slot
                                        int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(tv), ptr(tr), ptr(tp), ptr(ta),
                                        _lib.current_stream()))
     return tv, tr, tp, ta
+
+
+class ReplayBuffer:
+    """ReplayBuffer(initial_checkpoint, initial_buffer, config) (replay_buffer.py:17-31) with the store on `device`."""
+
+    def __init__(self, initial_checkpoint, initial_buffer, config, device=None, max_batch=None):
+        self.config = config
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError("the replay store lives on a CUDA device (there is no CPU path)")
+        if int(getattr(config, "stacked_observations", 0)) != 0:
+            raise NotImplementedError("stacked_observations > 0 is not on the device path")
+        self.A = len(config.action_space)
+        self.obs_floats = int(np.prod(config.observation_shape))
+        self.K, self.td = int(config.num_unroll_steps), int(config.td_steps)
+        self.max_batch = int(max_batch or config.batch_size)
+        self.cfg = ReplayConfig(self.A, self.obs_floats, int(config.replay_buffer_size), int(config.max_moves) + 2, self.K,
+                                self.td, int(bool(config.PER)), self.max_batch, float(config.PER_alpha),
+                                int(config.seed) & 0xFFFFFFFFFFFFFFFF)
+        nbytes = _lib.lib.mzb_replay_workspace_bytes(C.byref(self.cfg))
+        if nbytes == 0:
+            check(-1)
+        # Python's own pow, so discount ** i matches replay_buffer.py:240, 253 bit-for-bit
+        dp = (C.c_double * (self.td + 1))(*[config.discount ** i for i in range(self.td + 1)])
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self.workspace.data_ptr() + 255) // 256 * 256
+            self._h = _vp()
+            check(_lib.lib.mzb_replay_create(C.byref(self._h), C.byref(self.cfg), _vp(base), nbytes, dp, _lib.current_stream()))
+        self.nbytes = nbytes
+        self._played0 = (int(initial_checkpoint["num_played_games"]), int(initial_checkpoint["num_played_steps"]))
+        for game_history in (initial_buffer or {}).values():
+            self.save_game(game_history)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                _lib.lib.mzb_replay_destroy(self._h)
+            except (AttributeError, TypeError):      # interpreter shutdown
+                pass
+            self._h = None
+
+    # -- counters (replay_buffer.py:20-24)
+    def _info(self):
+        out = (_i64 * 5)()
+        check(_lib.lib.mzb_replay_info(self._h, out))
+        return [int(x) for x in out]
+
+    total_samples = property(lambda self: self._info()[0])
+    num_played_games = property(lambda self: self._played0[0] + self._info()[1])
+    num_played_steps = property(lambda self: self._played0[1] + self._info()[2])
+
+    def __len__(self):
+        return self._info()[3]
+
+    # -- save_game (:33-64)
+    def save_game(self, game_history, shared_storage=None):
+        """One host GameHistory (self_play.py:480-495).  `child_visits` are ratios count / num_simulations; the store
+        keeps the integer counts (`game_history.visit_counts` if present, else recovered exactly by rounding)."""
+        n = len(game_history.root_values)
+        counts = getattr(game_history, "visit_counts", None)
+        if counts is None:
+            counts = np.rint(np.asarray(game_history.child_visits, dtype=np.float64) * self.config.num_simulations)
+        vis = np.zeros((n + 1, self.A), dtype=np.uint16)
+        vis[:n] = np.asarray(counts, dtype=np.int64)
+        obs = np.stack([np.asarray(o, dtype=np.float32).reshape(-1) for o in game_history.observation_history])
+        rv = np.zeros(n + 1, dtype=np.float64)
+        rv[:n] = game_history.root_values
+        pr = None
+        if self.config.PER and getattr(game_history, "priorities", None) is not None:
+            pr = np.zeros(n + 1, dtype=np.float32)
+            pr[:n] = game_history.priorities
+        self.save_games_device([0], [n], self._dev(obs, torch.float32), self._dev(game_history.action_history, torch.int32),
+                               self._dev(np.asarray(game_history.reward_history, dtype=np.float32), torch.float32),
+                               self._dev(game_history.to_play_history, torch.int8), self._dev(rv, torch.float64),
+                               torch.from_numpy(vis).to(self.device), None if pr is None else self._dev(pr, torch.float32))
+        if shared_storage:
+            shared_storage.set_info.remote("num_played_games", self.num_played_games)
+            shared_storage.set_info.remote("num_played_steps", self.num_played_steps)
+
+    def _dev(self, x, dt):
+        return torch.as_tensor(np.ascontiguousarray(x)).to(self.device, dt).contiguous()
+
+    def save_games_device(self, game_start, game_len, obs, action, reward, to_play, root_value, visits, priorities=None):
+        """Games already on the device as entry arrays in the export layout (envs.VectorEnv export ring)."""
+        n = len(game_len)
+        hs = (C.c_int32 * n)(*[int(x) for x in game_start])
+        hl = (C.c_int32 * n)(*[int(x) for x in game_len])
+        with torch.cuda.device(self.device):
+            check(_lib.lib.mzb_replay_save_games(self._h, n, hs, hl, ptr(obs), ptr(action), ptr(reward), ptr(to_play),
+                                                 ptr(root_value), ptr(visits), ptr(priorities), _lib.current_stream()))
+
+    # -- get_batch (:69-140)
+    def get_batch(self, batch_size=None, u_game=None, u_pos=None):
+        """Returns (index_batch [B,2] i64, (observation_batch, action_batch, value_batch, reward_batch, policy_batch,
+        weight_batch | None, gradient_scale_batch)) as device tensors.  u_game / u_pos [B] f64 inject the draws."""
+        B = int(batch_size or self.config.batch_size)
+        dev, K, A = self.device, self.K, self.A
+        gid = torch.empty(B, dtype=torch.int64, device=dev)
+        pos = torch.empty(B, dtype=torch.int32, device=dev)
+        obs = torch.empty((B,) + tuple(self.config.observation_shape), dtype=torch.float32, device=dev)
+        act = torch.empty((B, K + 1), dtype=torch.int32, device=dev)
+        val = torch.empty((B, K + 1), dtype=torch.float64, device=dev)
+        rew = torch.empty((B, K + 1), dtype=torch.float64, device=dev)
+        pol = torch.empty((B, K + 1, A), dtype=torch.float64, device=dev)
+        w = torch.empty(B, dtype=torch.float32, device=dev) if self.config.PER else None
+        gs = torch.empty((B, K + 1), dtype=torch.int32, device=dev)
+        ug = None if u_game is None else torch.as_tensor(u_game, dtype=torch.float64).to(dev).contiguous()
+        up = None if u_pos is None else torch.as_tensor(u_pos, dtype=torch.float64).to(dev).contiguous()
+        with torch.cuda.device(dev):
+            check(_lib.lib.mzb_replay_get_batch(self._h, B, ptr(ug), ptr(up), ptr(gid), ptr(pos), None, None, ptr(obs),
+                                                ptr(act), ptr(val), ptr(rew), ptr(pol), ptr(w), ptr(gs),
+                                                _lib.current_stream()))
+        return torch.stack([gid, pos.to(torch.int64)], dim=1), (obs, act, val, rew, pol, w, gs)
+
+    # -- update_priorities (:202-220)
+    def update_priorities(self, priorities, index_info):
+        pr = torch.as_tensor(priorities).to(self.device, torch.float32).contiguous()
+        idx = torch.as_tensor(np.asarray(index_info.cpu() if torch.is_tensor(index_info) else index_info, dtype=np.int64)).to(self.device)
+        gid = idx[:, 0].contiguous()
+        pos = idx[:, 1].to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            check(_lib.lib.mzb_replay_update_priorities(self._h, pr.shape[0], ptr(pr), ptr(gid), ptr(pos), _lib.current_stream()))
+
+    def game_priorities(self, game_id):
+        n = _i32()
+        buf = np.zeros(int(self.config.max_moves) + 2, dtype=np.float32)
+        gp = np.zeros(1, dtype=np.float32)
+        check(_lib.lib.mzb_replay_game_priorities_sync(self._h, int(game_id), ptr(buf), ptr(gp), C.byref(n), _lib.current_stream()))
+        return buf[:n.value].copy(), gp[0]

@@ -636,7 +636,8 @@ def gen_replay():
                     T = int(rs.randint(1, min(cfg.max_moves, 90) + 1))
                     gh = self_play.GameHistory()
                     gh.action_history = [0] + rs.randint(A, size=T).tolist()
-                    gh.reward_history = [0] + np.round(rs.uniform(-1, 2, T), 3).tolist()
+                    # float32-representable rewards (game rewards are small integers; the device store keeps float32)
+                    gh.reward_history = [0] + np.round(rs.uniform(-1, 2, T), 3).astype(np.float32).astype(np.float64).tolist()
                     gh.to_play_history = [int(i % players) for i in range(T + 1)]
                     gh.root_values = rs.normal(0, 3, T).tolist()
                     vis = rs.multinomial(cfg.num_simulations, rs.dirichlet([0.7] * A), size=T)

@@ -1,0 +1,106 @@
+"""Device replay store (csrc/mzb_replay.cu behind muzero_hypermodel_b200.replay_buffer.ReplayBuffer) vs the golden
+outputs of the UNMODIFIED reference ReplayBuffer (tests/golden/replay.npz): the scripted save_game / get_batch /
+update_priorities sequence with injected uniforms and with the device's own Philox draws - initial PER priorities,
+FIFO eviction, sampled indices, observations, targets, float32 importance weights, gradient scales and updated
+priorities are bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import _tables as T
+from oracle import rng
+from test_oracle_replay import Z, case_config
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+class _Cfg:
+    pass
+
+
+class _Game:
+    pass
+
+
+def make(ci):
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    per, alpha, size, batch, K, td, discount, A, players = case_config(ci)
+    cfg = _Cfg()
+    cfg.action_space = list(range(A)); cfg.PER, cfg.PER_alpha, cfg.replay_buffer_size, cfg.batch_size = per, alpha, size, batch
+    cfg.num_unroll_steps, cfg.td_steps, cfg.discount, cfg.seed, cfg.stacked_observations = K, td, discount, T.SEED, 0
+    cfg.observation_shape = tuple(Z[f"{ci}/game0/observations"].shape[1:])
+    cfg.max_moves, cfg.num_simulations = 100, int(Z[f"{ci}/game0/visits"][0].sum())
+    return ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg, device=DEV), cfg
+
+
+def load_game(ci, gi):
+    g, pre = _Game(), f"{ci}/game{gi}/"
+    g.observation_history = list(Z[pre + "observations"])
+    g.action_history, g.reward_history = Z[pre + "actions"].tolist(), Z[pre + "rewards"].tolist()
+    g.to_play_history, g.root_values = Z[pre + "to_play"].tolist(), Z[pre + "root_values"].tolist()
+    vis = Z[pre + "visits"]
+    g.child_visits = [[int(v) / int(row.sum()) if v else 0 for v in row] for row in vis]
+    g.priorities = None
+    return g
+
+
+@pytest.mark.parametrize("inject", [True, False])
+@pytest.mark.parametrize("ci", range(int(Z["n"])))
+def test_device_replay_equals_reference(ci, inject):
+    rb, cfg = make(ci)
+    per, batch = cfg.PER, cfg.batch_size
+    gi = bi = ui = 0
+    for op in str(Z[f"{ci}/script"]).split():
+        if op == "save":
+            rb.save_game(load_game(ci, gi))
+            if per:
+                pr, gp = rb.game_priorities(gi)
+                assert pr.tobytes() == Z[f"{ci}/game{gi}/priorities"].tobytes(), ("initial priorities", gi)
+                assert np.float32(gp).tobytes() == Z[f"{ci}/game{gi}/game_priority"].tobytes()
+            gi += 1
+        elif op == "batch":
+            b = f"{ci}/batch{bi}/"
+            ug = up = None
+            if inject:
+                ug = [rng.replay_uniform(T.SEED, e, bi, rng.STREAM_RGAME) for e in range(batch)]
+                up = [rng.replay_uniform(T.SEED, e, bi, rng.STREAM_RPOS) for e in range(batch)]
+            index, (obs, act, val, rew, pol, w, gs) = rb.get_batch(u_game=ug, u_pos=up)
+            assert index.cpu().numpy().tobytes() == Z[b + "index"].tobytes(), ("index", bi)
+            assert obs.cpu().numpy().tobytes() == Z[b + "observations"].tobytes()
+            assert act.cpu().numpy().tobytes() == Z[b + "actions"].tobytes()
+            assert val.cpu().numpy().tobytes() == Z[b + "values"].tobytes()
+            assert rew.cpu().numpy().tobytes() == Z[b + "rewards"].tobytes()
+            assert pol.cpu().numpy().tobytes() == Z[b + "policies"].tobytes()
+            assert gs.cpu().numpy().tobytes() == Z[b + "gradient_scale"].tobytes()
+            if per:
+                assert w.cpu().numpy().tobytes() == Z[b + "weights"].tobytes(), ("weights", bi)
+            else:
+                assert w is None
+            assert [rb.total_samples, rb.num_played_games, len(rb)] == Z[b + "state"].tolist()
+            bi += 1
+        else:
+            u = f"{ci}/update{ui}/"
+            if per:
+                rb.update_priorities(Z[u + "priorities"], Z[u + "index"])
+                first = rb._info()[4]
+                for gid in range(first, first + len(rb)):
+                    pr, gp = rb.game_priorities(gid)
+                    assert pr.tobytes() == Z[u + f"after/{gid}"].tobytes(), ("updated priorities", gid)
+                    assert np.float32(gp).tobytes() == Z[u + f"after_game/{gid}"].tobytes()
+            ui += 1
+
+
+def test_empty_buffer_and_oversize_game_are_refused():
+    from muzero_hypermodel_b200._lib import MzbError
+    rb, cfg = make(0)
+    with pytest.raises(MzbError):
+        rb.get_batch()
+    g = load_game(0, 0)
+    n = 200                                   # longer than max_moves + 1 entries
+    g.root_values = [0.0] * n
+    g.action_history, g.reward_history, g.to_play_history = [0] * (n + 1), [0.0] * (n + 1), [0] * (n + 1)
+    g.child_visits = [[1.0] + [0.0] * (len(cfg.action_space) - 1)] * n
+    g.observation_history = [g.observation_history[0]] * (n + 1)
+    with pytest.raises(MzbError):
+        rb.save_game(g)
