@@ -347,7 +347,11 @@ int mzb_search_resnet(mzb_tree* t, mzb_resnet_model* m, const float* d_obs, cons
 typedef struct mzb_replay mzb_replay;
 typedef struct {
   int32_t n_actions;         /* len(config.action_space)                                      */
-  int32_t obs_floats;        /* floats per stored observation (stacked_observations = 0)      */
+  int32_t obs_floats;        /* floats per stored observation record (stacked_observations = 0) */
+  int32_t obs_decode;        /* 0: the record IS the observation; 1: packed board record of mzb_env
+                              * (obs_h * obs_w int8 cells + int8 player, padded to obs_floats floats), decoded by
+                              * get_batch into the 3 planes [own, other, to-play] of the board games        */
+  int32_t obs_h, obs_w;      /* board size for obs_decode = 1                                 */
   int32_t capacity_games;    /* config.replay_buffer_size                                     */
   int32_t entry_stride;      /* entries per slot >= max_moves + 1                             */
   int32_t num_unroll_steps;  /* config.num_unroll_steps                                       */
@@ -386,6 +390,11 @@ int mzb_replay_get_batch(mzb_replay* r, int32_t batch, const double* d_u_game, c
  * [pos, min(pos + K + 1, len)) of each still-buffered game, rows applied in order; game priority = max. */
 int mzb_replay_update_priorities(mzb_replay* r, int32_t batch, const float* d_priorities, const int64_t* d_game_id,
                                  const int32_t* d_pos, void* stream);
+/* The device-to-device hop that replaces `replay_buffer.save_game.remote(game_history)` (self_play.py:52): every
+ * finished game in the export ring of `env` is appended to the store and the ring is emptied; only the per-game
+ * (start, length) table crosses to the host.  The store must have been created with the environment's record
+ * format (obs_floats = mzb_env_info's rec_floats, obs_decode = 1 for the board games). */
+int mzb_env_export_to_replay(mzb_env* env, mzb_replay* r, int32_t* h_n_games, void* stream);
 /* out5 = total_samples, num_played_games, num_played_steps, games in the buffer, id of the oldest game. */
 int mzb_replay_info(const mzb_replay* r, int64_t* out5);
 int mzb_replay_set_batch_counter(mzb_replay* r, uint32_t counter);

@@ -39,6 +39,7 @@ struct ExportView {
   float* obs; int* action; float* reward; int8_t* to_play; uint16_t* visits; double* root_value;
   int* game_start; int* game_len; uint32_t* game_slot;
   int* cursor;           // [2]: entries used, games used
+  int* plan;             // [G][2]: export entry offset (-1 = not exported) and game index, written by k_harvest_plan
 };
 
 struct mzb_env {
@@ -315,27 +316,58 @@ __global__ void k_act_step(EnvView e, const int* __restrict__ visits, const doub
 
 // Finished games: one warp per game copies the episode into the export ring (the GameHistory wire format
 // handed to ReplayBuffer.save_game, self_play.py:52) and restarts the game (auto-reset keeps the batch full).
+// Export placement of the finished games, in GAME ORDER (an ordered scan, not atomics: the ring contents - hence
+// everything downstream, e.g. the replay store's sampling - are reproducible from run to run).  One block.
+__global__ void __launch_bounds__(1024) k_harvest_plan(EnvView e, ExportView x) {
+  __shared__ int s_e[32], s_g[32], s_base[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_base[0] = x.cursor[0]; s_base[1] = x.cursor[1]; }
+  __syncthreads();
+  for (int g0 = 0; g0 < e.G; g0 += 1024) {
+    const int g = g0 + threadIdx.x;
+    const bool fin = g < e.G && e.finished[g];
+    const int len = fin ? e.h_len[g] : 0;
+    int ve = fin ? len + 1 : 0, vg = fin ? 1 : 0;          // inclusive warp scans
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int te = __shfl_up_sync(0xFFFFFFFFu, ve, o), tg = __shfl_up_sync(0xFFFFFFFFu, vg, o);
+      if (lane >= o) { ve += te; vg += tg; }
+    }
+    if (lane == 31) { s_e[warp] = ve; s_g[warp] = vg; }
+    __syncthreads();
+    if (warp == 0) {
+      int we = s_e[lane], wg = s_g[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int te = __shfl_up_sync(0xFFFFFFFFu, we, o), tg = __shfl_up_sync(0xFFFFFFFFu, wg, o);
+        if (lane >= o) { we += te; wg += tg; }
+      }
+      s_e[lane] = we; s_g[lane] = wg;
+    }
+    __syncthreads();
+    const int start = s_base[0] + (warp ? s_e[warp - 1] : 0) + ve - (fin ? len + 1 : 0);
+    const int gi = s_base[1] + (warp ? s_g[warp - 1] : 0) + vg - (fin ? 1 : 0);
+    if (fin) {
+      const bool ok = start + len + 1 <= x.cap_entries && gi < x.cap_games;
+      x.plan[2 * g] = ok ? start : -1;
+      x.plan[2 * g + 1] = gi;
+      if (ok) { x.game_start[gi] = start; x.game_len[gi] = len; x.game_slot[gi] = e.slot0 + (uint32_t)g; }
+      else atomicAdd(e.counters + 3, 1ull);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { s_base[0] += s_e[31]; s_base[1] += s_g[31]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { x.cursor[0] = s_base[0]; x.cursor[1] = s_base[1]; }
+}
+
 __global__ void k_harvest(EnvView e, ExportView x, int do_export) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
   if (warp >= e.G) return;
   const int g = warp;
   if (!e.finished[g]) return;
   const int len = e.h_len[g];
-  int start = -1;
-  if (do_export) {
-    if (lane == 0) {
-      start = atomicAdd(x.cursor, len + 1);
-      if (start + len + 1 > x.cap_entries) {
-        start = -1;
-      } else {
-        const int gi = atomicAdd(x.cursor + 1, 1);
-        if (gi < x.cap_games) { x.game_start[gi] = start; x.game_len[gi] = len; x.game_slot[gi] = e.slot0 + (uint32_t)g; }
-        else start = -1;
-      }
-      if (start < 0) atomicAdd(e.counters + 3, 1ull);
-    }
-    start = __shfl_sync(0xFFFFFFFFu, start, 0);
-  }
+  const int start = do_export ? x.plan[2 * g] : -1;
   const size_t h0 = (size_t)g * e.hist_cap;
   if (start >= 0) {
     const int n_obs = (len + 1) * e.rec_floats;
@@ -364,7 +396,7 @@ __global__ void k_harvest(EnvView e, ExportView x, int do_export) {
 
 struct Layout {
   size_t cp, elapsed, board, player, steps, h_obs, h_action, h_reward, h_to_play, h_visits, h_root, h_len, finished,
-      counters, x_obs, x_action, x_reward, x_to_play, x_visits, x_root, x_gstart, x_glen, x_gslot, x_cursor, total;
+      counters, x_obs, x_action, x_reward, x_to_play, x_visits, x_root, x_gstart, x_glen, x_gslot, x_cursor, x_plan, total;
 };
 
 int describe(const mzb_env_config& c, EnvView& v) {
@@ -396,6 +428,7 @@ Layout layout(const mzb_env_config& c, const EnvView& v) {
   o.x_obs = take(E * v.rec_floats * 4); o.x_action = take(E * 4); o.x_reward = take(E * 4); o.x_to_play = take(E);
   o.x_visits = take(E * A * 2); o.x_root = take(E * 8);
   o.x_gstart = take(XG * 4); o.x_glen = take(XG * 4); o.x_gslot = take(XG * 4); o.x_cursor = take(2 * 4);
+  o.x_plan = take(G * 2 * 4);
   o.total = off;
   return o;
 }
@@ -446,6 +479,7 @@ int mzb_env_create(mzb_env** out, const mzb_env_config* c, void* d_workspace, si
   x.to_play = (int8_t*)(w + o.x_to_play); x.visits = (uint16_t*)(w + o.x_visits); x.root_value = (double*)(w + o.x_root);
   x.game_start = (int*)(w + o.x_gstart); x.game_len = (int*)(w + o.x_glen); x.game_slot = (uint32_t*)(w + o.x_gslot);
   x.cursor = (int*)(w + o.x_cursor);
+  x.plan = (int*)(w + o.x_plan);
   cudaStream_t s = (cudaStream_t)stream;
   MZB_CUDA(cudaMemsetAsync(w + o.counters, 0, 64, s));
   MZB_CUDA(cudaMemsetAsync(w + o.x_cursor, 0, 8, s));
@@ -501,6 +535,10 @@ int mzb_env_act_step(mzb_env* e, const int32_t* d_visits, const double* d_root_v
 int mzb_env_harvest(mzb_env* e, int do_export, void* stream) {
   MZB_CHECK_ARG(e, "env is NULL");
   const long long threads = (long long)e->v.G * 32;
+  if (do_export) {
+    k_harvest_plan<<<1, 1024, 0, (cudaStream_t)stream>>>(e->v, e->x);
+    MZB_LAUNCH_CHECK();
+  }
   k_harvest<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->v, e->x, do_export);
   MZB_LAUNCH_CHECK();
   return MZB_OK;
@@ -554,6 +592,30 @@ int mzb_env_export_drain_sync(mzb_env* e, int32_t* h_n_entries, int32_t* h_n_gam
   }
   MZB_CUDA(cudaMemsetAsync(e->x.cursor, 0, 8, s));
   MZB_CUDA(cudaStreamSynchronize(s));
+  return MZB_OK;
+}
+
+int mzb_env_export_to_replay(mzb_env* e, mzb_replay* r, int32_t* h_n_games, void* stream) {
+  MZB_CHECK_ARG(e && r, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int cur[2];
+  MZB_CUDA(cudaMemcpyAsync(cur, e->x.cursor, 8, cudaMemcpyDeviceToHost, s));
+  MZB_CUDA(cudaStreamSynchronize(s));
+  const int ng = cur[1] < e->x.cap_games ? cur[1] : e->x.cap_games;
+  if (h_n_games) *h_n_games = ng;
+  if (ng > 0) {
+    std::vector<int> start((size_t)ng), len((size_t)ng);
+    MZB_CUDA(cudaMemcpyAsync(start.data(), e->x.game_start, (size_t)ng * 4, cudaMemcpyDeviceToHost, s));
+    MZB_CUDA(cudaMemcpyAsync(len.data(), e->x.game_len, (size_t)ng * 4, cudaMemcpyDeviceToHost, s));
+    MZB_CUDA(cudaStreamSynchronize(s));
+    for (int g0 = 0; g0 < ng; g0 += 1024) {
+      const int n = ng - g0 < 1024 ? ng - g0 : 1024;
+      const int rc = mzb_replay_save_games(r, n, start.data() + g0, len.data() + g0, e->x.obs, e->x.action, e->x.reward,
+                                           e->x.to_play, e->x.root_value, e->x.visits, nullptr, stream);
+      if (rc) return rc;
+    }
+  }
+  MZB_CUDA(cudaMemsetAsync(e->x.cursor, 0, 8, s));
   return MZB_OK;
 }
 

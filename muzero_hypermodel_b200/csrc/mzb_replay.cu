@@ -37,7 +37,7 @@ struct ReplayView {
   float* probs; double* cdf;
   double* discount_pow;
   int* b_slot; uint32_t* b_step; float* b_w;       // per batch element scratch [max_batch]
-  int A, obs_floats, cap, stride, K, td, per, max_batch;
+  int A, obs_floats, cap, stride, K, td, per, max_batch, decode, oh, ow;
   double alpha; RngKey key;
 };
 
@@ -227,7 +227,19 @@ __global__ void __launch_bounds__(256) k_replay_assemble(ReplayView v, int B, co
     const int slot = v.b_slot[b], s = v.g_start[slot], n = v.g_len[slot], p = pos[b];
     if (obs) {
       const float* src = v.obs + (long long)(s + p) * v.obs_floats;
-      for (int i = threadIdx.x; i < v.obs_floats; i += blockDim.x) obs[(long long)b * v.obs_floats + i] = src[i];
+      if (v.decode == 0) {
+        for (int i = threadIdx.x; i < v.obs_floats; i += blockDim.x) obs[(long long)b * v.obs_floats + i] = src[i];
+      } else {                                    // packed board record -> [board == 1, board == -1, player] planes
+        const int8_t* raw = reinterpret_cast<const int8_t*>(src);
+        const int cells = v.oh * v.ow;
+        const float player = (float)raw[cells];
+        float* o = obs + (long long)b * 3 * cells;
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+          o[i] = raw[i] == 1 ? 1.0f : 0.0f;
+          o[cells + i] = raw[i] == -1 ? 1.0f : 0.0f;
+          o[2 * cells + i] = player;
+        }
+      }
     }
     if (gscale) {
       const int gs = min(v.K, n + 1 - p);
@@ -307,7 +319,8 @@ Layout replay_layout(const mzb_replay_config& c) {
 
 bool config_ok(const mzb_replay_config* c) {
   return c && c->n_actions > 0 && c->n_actions <= 65535 && c->obs_floats > 0 && c->capacity_games > 0 && c->entry_stride > 1 &&
-         c->num_unroll_steps >= 0 && c->td_steps > 0 && c->max_batch > 0 && (c->per == 0 || c->per == 1) && c->per_alpha >= 0.0;
+         c->num_unroll_steps >= 0 && c->td_steps > 0 && c->max_batch > 0 && (c->per == 0 || c->per == 1) && c->per_alpha >= 0.0 &&
+         (c->obs_decode == 0 || (c->obs_decode == 1 && c->obs_h > 0 && c->obs_w > 0 && c->obs_h * c->obs_w + 1 <= 4 * c->obs_floats));
 }
 
 }  // namespace
@@ -335,6 +348,7 @@ int mzb_replay_create(mzb_replay** out, const mzb_replay_config* c, void* d_work
   v.discount_pow = (double*)(w + L.dpow); v.b_slot = (int*)(w + L.b_slot); v.b_step = (uint32_t*)(w + L.b_step);
   v.b_w = (float*)(w + L.b_w);
   v.A = c->n_actions; v.obs_floats = c->obs_floats; v.cap = c->capacity_games; v.stride = c->entry_stride;
+  v.decode = c->obs_decode; v.oh = c->obs_h; v.ow = c->obs_w;
   v.K = c->num_unroll_steps; v.td = c->td_steps; v.per = c->per; v.max_batch = c->max_batch; v.alpha = c->per_alpha;
   v.key = rng_key(c->seed);
   r->d_meta = (int*)(w + L.meta);

@@ -22,7 +22,8 @@ _i64 = C.c_int64
 
 
 class ReplayConfig(C.Structure):
-    _fields_ = [("n_actions", _i32), ("obs_floats", _i32), ("capacity_games", _i32), ("entry_stride", _i32),
+    _fields_ = [("n_actions", _i32), ("obs_floats", _i32), ("obs_decode", _i32), ("obs_h", _i32), ("obs_w", _i32),
+                ("capacity_games", _i32), ("entry_stride", _i32),
                 ("num_unroll_steps", _i32), ("td_steps", _i32), ("per", _i32), ("max_batch", _i32),
                 ("per_alpha", C.c_double), ("seed", C.c_uint64)]
 
@@ -34,6 +35,7 @@ _lib.bind("mzb_replay_save_games", C.c_int, [_vp, _i32, _vp, _vp] + [_vp] * 7 + 
 _lib.bind("mzb_replay_get_batch", C.c_int, [_vp, _i32] + [_vp] * 13 + [_vp])
 _lib.bind("mzb_replay_update_priorities", C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp])
 _lib.bind("mzb_replay_info", C.c_int, [_vp, C.POINTER(_i64)])
+_lib.bind("mzb_env_export_to_replay", C.c_int, [_vp, _vp, C.POINTER(_i32), _vp])
 _lib.bind("mzb_replay_set_batch_counter", C.c_int, [_vp, C.c_uint32])
 _lib.bind("mzb_replay_game_priorities_sync", C.c_int, [_vp, _i64, _vp, _vp, C.POINTER(_i32), _vp])
 _lib.bind("mzb_make_target", C.c_int, [_vp] * 8 + [_i32] + [_vp] * 4 + [_i32, _i32, _i32, _vp, C.c_uint64] + [_vp] * 5)
@@ -81,7 +83,9 @@ def make_target_batch(games, batch_game, batch_index, config, seed=0, batch_slot
 class ReplayBuffer:
     """ReplayBuffer(initial_checkpoint, initial_buffer, config) (replay_buffer.py:17-31) with the store on `device`."""
 
-    def __init__(self, initial_checkpoint, initial_buffer, config, device=None, max_batch=None):
+    def __init__(self, initial_checkpoint, initial_buffer, config, device=None, max_batch=None, record_env=None):
+        """record_env: an envs.VectorEnv whose export ring will feed this buffer with `ingest` - the store then keeps
+        the environment's compact observation records (packed int8 boards) and decodes them in get_batch."""
         self.config = config
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if self.device.type != "cuda":
@@ -92,7 +96,15 @@ class ReplayBuffer:
         self.obs_floats = int(np.prod(config.observation_shape))
         self.K, self.td = int(config.num_unroll_steps), int(config.td_steps)
         self.max_batch = int(max_batch or config.batch_size)
-        self.cfg = ReplayConfig(self.A, self.obs_floats, int(config.replay_buffer_size), int(config.max_moves) + 2, self.K,
+        decode, oh, ow, rec = 0, 0, 0, self.obs_floats
+        if record_env is not None:
+            rec = int(record_env.rec_floats)
+            if record_env.kind in ("tictactoe", "connect4", "gomoku"):
+                decode, (oh, ow) = 1, record_env.obs_shape[1:]
+            elif rec != self.obs_floats:
+                raise NotImplementedError(f"no record decoder for {record_env.kind!r} observations")
+        self.decode, self.rec_floats, self.board = decode, rec, (oh, ow)
+        self.cfg = ReplayConfig(self.A, rec, decode, oh, ow, int(config.replay_buffer_size), int(config.max_moves) + 2, self.K,
                                 self.td, int(bool(config.PER)), self.max_batch, float(config.PER_alpha),
                                 int(config.seed) & 0xFFFFFFFFFFFFFFFF)
         nbytes = _lib.lib.mzb_replay_workspace_bytes(C.byref(self.cfg))
@@ -141,7 +153,16 @@ class ReplayBuffer:
             counts = np.rint(np.asarray(game_history.child_visits, dtype=np.float64) * self.config.num_simulations)
         vis = np.zeros((n + 1, self.A), dtype=np.uint16)
         vis[:n] = np.asarray(counts, dtype=np.int64)
-        obs = np.stack([np.asarray(o, dtype=np.float32).reshape(-1) for o in game_history.observation_history])
+        if self.decode:           # [own, other, to-play] planes -> the environment's packed int8 record
+            oh, ow = self.board
+            raw = np.zeros((n + 1, self.rec_floats * 4), dtype=np.int8)
+            for i, o in enumerate(game_history.observation_history):
+                o = np.asarray(o)
+                raw[i, :oh * ow] = ((o[0] == 1).astype(np.int8) - (o[1] == 1).astype(np.int8)).reshape(-1)
+                raw[i, oh * ow] = int(o[2].flat[0])
+            obs = raw.view(np.float32)
+        else:
+            obs = np.stack([np.asarray(o, dtype=np.float32).reshape(-1) for o in game_history.observation_history])
         rv = np.zeros(n + 1, dtype=np.float64)
         rv[:n] = game_history.root_values
         pr = None
@@ -167,6 +188,14 @@ class ReplayBuffer:
         with torch.cuda.device(self.device):
             check(_lib.lib.mzb_replay_save_games(self._h, n, hs, hl, ptr(obs), ptr(action), ptr(reward), ptr(to_play),
                                                  ptr(root_value), ptr(visits), ptr(priorities), _lib.current_stream()))
+
+    def ingest(self, env):
+        """Append every finished game in `env`'s export ring (device to device) and empty the ring: the hop that
+        replaces `replay_buffer.save_game.remote(game_history)` (self_play.py:52).  Returns the number of games."""
+        n = _i32()
+        with torch.cuda.device(self.device):
+            check(_lib.lib.mzb_env_export_to_replay(env._h, self._h, C.byref(n), _lib.current_stream()))
+        return n.value
 
     # -- get_batch (:69-140)
     def get_batch(self, batch_size=None, u_game=None, u_pos=None):

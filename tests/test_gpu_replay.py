@@ -104,3 +104,46 @@ def test_empty_buffer_and_oversize_game_are_refused():
     g.observation_history = [g.observation_history[0]] * (n + 1)
     with pytest.raises(MzbError):
         rb.save_game(g)
+
+
+@pytest.mark.parametrize("kind", ["tictactoe", "cartpole"])
+def test_ingest_from_export_ring_equals_host_path(kind):
+    """Device-to-device hop: games exported by the self-play kernels and ingested straight into the store give the same
+    batches as the same games decoded to host GameHistory objects and saved one by one."""
+    import importlib
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    from muzero_hypermodel_b200.self_play import SelfPlay, decode_export
+    cfg = importlib.import_module(f"muzero_hypermodel_b200.games.{kind}").MuZeroConfig()
+    if kind == "tictactoe":
+        cfg.network = "fullyconnected"
+    cfg.num_simulations = 10
+    cfg.max_moves = min(cfg.max_moves, 25)
+    cfg.replay_buffer_size, cfg.batch_size, cfg.PER = 64, 32, True
+    z = T.load("net")
+    pre = ("tictactoe_fc" if kind == "tictactoe" else "cartpole") + "/w/"
+    sd = {k[len(pre):]: torch.tensor(z[k]) for k in z.files if k.startswith(pre)}
+    histories = []
+    buffers = []
+    for mode in ("device", "host"):
+        sp = SelfPlay({"weights": sd}, None, cfg, 5, n_games=16, device=DEV)
+        env, _ = sp._setup()
+        rb = ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg, device=DEV,
+                          record_env=env if mode == "device" else None)
+        for _ in range(cfg.max_moves + 1):
+            sp.step(1.0, None)
+            if mode == "device":
+                rb.ingest(env)
+            else:
+                for gh in decode_export(env):
+                    gh.priorities = None
+                    rb.save_game(gh)
+                    histories.append(gh)
+        buffers.append(rb)
+    dev_rb, host_rb = buffers
+    assert len(dev_rb) == len(host_rb) > 8 and dev_rb.total_samples == host_rb.total_samples
+    for _ in range(3):
+        ia, ba = dev_rb.get_batch()
+        ib, bb = host_rb.get_batch()
+        assert torch.equal(ia, ib)
+        for x, y in zip(ba, bb):
+            assert torch.equal(x, y)
