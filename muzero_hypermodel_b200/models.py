@@ -176,7 +176,7 @@ class MuZeroFullyConnectedNetwork(AbstractNetwork):
                 _lib.lib.mzb_fc_destroy(self._h)
             except (AttributeError, TypeError):      # interpreter shutdown
                 pass
-            self._h = None
+            object.__setattr__(self, "_h", None)     # not Module.__setattr__: torch may be half torn down at exit
 
     def __del__(self):
         self._free()

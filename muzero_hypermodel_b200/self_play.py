@@ -317,6 +317,56 @@ class SelfPlay:
         self.num_played_steps += sum(len(g.root_values) for g in games)
         return games
 
+    # -- the actor loop (self_play.py:30-108)
+    def continuous_self_play(self, shared_storage, replay_buffer, test_mode=False, max_moves=None):
+        """The reference's actor loop over G lock-step games: refresh the weights, play, hand finished games to the
+        replay buffer, respect self_play_delay / ratio.  `shared_storage` is anything with get_info / set_info (plain
+        methods or Ray-style `.remote`); a replay buffer with `ingest` (the device store, replay_buffer.ReplayBuffer)
+        receives the games device to device, any other through `save_game(game_history, shared_storage)`.
+        test_mode (greedy play against an opponent, :54-88) is a host-side evaluation mode and not on this path.
+        `max_moves` bounds the loop for callers without a trainer (None: until training_steps / terminate)."""
+        if test_mode:
+            raise NotImplementedError("test_mode evaluation is not on the device self-play path")
+        import time
+
+        def call(method, *args):
+            remote = getattr(method, "remote", None)
+            if remote is None:
+                return method(*args)
+            import ray
+            out = remote(*args)
+            return ray.get(out) if method.__name__.startswith("get") else out
+
+        cfg = self.config
+        env, _ = self._setup()
+        moves = 0
+        while (call(shared_storage.get_info, "training_step") < cfg.training_steps
+               and not call(shared_storage.get_info, "terminate")):
+            weights = call(shared_storage.get_info, "weights")
+            if weights is not None:
+                self.model.set_weights(weights)
+            T = cfg.visit_softmax_temperature_fn(trained_steps=call(shared_storage.get_info, "training_step"))
+            self.step(T, cfg.temperature_threshold)
+            if hasattr(replay_buffer, "ingest"):
+                n = replay_buffer.ingest(env)
+                if n:
+                    call(shared_storage.set_info, "num_played_games", replay_buffer.num_played_games)
+                    call(shared_storage.set_info, "num_played_steps", replay_buffer.num_played_steps)
+            else:
+                for game_history in self.drain():
+                    call(replay_buffer.save_game, game_history, shared_storage)
+            moves += 1
+            if max_moves is not None and moves >= max_moves:
+                break
+            if cfg.self_play_delay:
+                time.sleep(cfg.self_play_delay)
+            if cfg.ratio:
+                while (call(shared_storage.get_info, "training_step") / max(1, call(shared_storage.get_info, "num_played_steps")) < cfg.ratio
+                       and call(shared_storage.get_info, "training_step") < cfg.training_steps
+                       and not call(shared_storage.get_info, "terminate")):
+                    time.sleep(0.5)
+        self.close_game()
+
     # -- reference-compatible single game
     def play_game(self, temperature, temperature_threshold, render, opponent, muzero_player):
         """One complete game with G = 1 (self_play.py:110-184); `opponent` other than "self" is not on the

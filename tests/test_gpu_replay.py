@@ -147,3 +147,38 @@ def test_ingest_from_export_ring_equals_host_path(kind):
         assert torch.equal(ia, ib)
         for x, y in zip(ba, bb):
             assert torch.equal(x, y)
+
+
+def test_continuous_self_play_feeds_the_device_store():
+    """SelfPlay.continuous_self_play (self_play.py:30-108) with a plain-object shared storage: games flow from the
+    self-play kernels into the device replay store and a batch can be drawn."""
+    from muzero_hypermodel_b200.games.tictactoe import MuZeroConfig
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    from muzero_hypermodel_b200.self_play import SelfPlay
+    cfg = MuZeroConfig()
+    cfg.network, cfg.num_simulations, cfg.replay_buffer_size, cfg.batch_size = "fullyconnected", 8, 256, 64
+    cfg.self_play_delay, cfg.ratio = 0, None
+
+    class Storage:
+        def __init__(self):
+            self.info = {"training_step": 0, "terminate": False, "weights": None, "num_played_games": 0, "num_played_steps": 0}
+
+        def get_info(self, key):
+            return self.info[key]
+
+        def set_info(self, key, value=None):
+            self.info[key] = value
+
+    st = Storage()
+    sp = SelfPlay({"weights": None}, None, cfg, 3, n_games=64, device=DEV)
+    env, _ = sp._setup()
+    rb = ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg, device=DEV, record_env=env)
+    sp._env = env
+    sp.continuous_self_play(st, rb, max_moves=12)
+    assert len(rb) >= 64 and st.info["num_played_games"] == rb.num_played_games > 0
+    assert st.info["num_played_steps"] == rb.num_played_steps == rb.total_samples
+    index, (obs, act, val, rew, pol, w, gs) = rb.get_batch()
+    assert obs.shape == (64, 3, 3, 3) and pol.shape == (64, cfg.num_unroll_steps + 1, 9)
+    assert float(w.max()) == 1.0 and float(w.min()) > 0
+    assert torch.all((obs[:, 2] == 1) | (obs[:, 2] == -1))
+    np.testing.assert_allclose(pol.sum(-1).cpu().numpy(), 1.0, rtol=0, atol=1e-12)
