@@ -377,6 +377,28 @@ def main():
            "d2h_bytes_per_step": (h_vis.numel() * 4 + h_rv.numel() * 8) * world,
            "api": "BatchedMCTS.run == mzb_search_fc (G x MCTS.run) with pinned host buffers"}
 
+    # ---------------- learner-side collectives (off the self-play path): weight refresh + gradient all-reduce of this
+    # workload's parameter count, device-timed, max over ranks
+    collectives = None
+    if world > 1:
+        n_param = sum(int(v.numel()) for v in weights.values())
+        sd = {k: v.to(dev) for k, v in weights.items()}
+        grads = [torch.ones(n_param, device=dev)]
+        res = {}
+        for name, fn in (("weight_broadcast_ms", lambda: mdist.broadcast_weights(sd, 0, dev)),
+                         ("grad_allreduce_ms", lambda: mdist.allreduce_gradients(grads))):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                fn()
+            b.record()
+            barrier()
+            res[name] = mdist.max_over_ranks(a.elapsed_time(b) / 20, dev)
+        collectives = dict(res, parameters=n_param, backend="nccl", note="not on the self-play path (games are sharded, no data-path collective)")
+
     if rank == 0:
         line = {"metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -392,6 +414,8 @@ def main():
                 "clocks": clocks, "mean_search_path_nodes": L,
                 "games_finished_in_timed_region": c1["games"] - c0["games"],
                 "games_dropped": c1["dropped_games"] - c0["dropped_games"], "games_exported_after": len(finished)}
+        if collectives is not None:
+            line["collectives"] = collectives
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -65,3 +65,48 @@ def aggregate_throughput(units_this_rank, ms_this_rank, device="cpu"):
     units = sum_over_ranks(units_this_rank, device)
     ms = max_over_ranks(ms_this_rank, device)
     return units / (ms * 1e-3), ms
+
+
+# ---- the two collectives the learner side needs; neither is on the self-play data path
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def broadcast_weights(state_dict, src=0, device=None):
+    """Weight refresh (replaces `shared_storage.get_info.remote("weights")`, self_play.py:37): rank `src`'s state
+    dict reaches every rank as ONE flat float32 bucket (launch latency, not link count, is what a 1.5 K - 5.5 M
+    parameter model pays on NVSwitch).  Returns a state dict of tensors on `device` (same keys and shapes)."""
+    keys = list(state_dict.keys())
+    shapes = [tuple(state_dict[k].shape) for k in keys]
+    sizes = [int(torch.as_tensor(state_dict[k]).numel()) for k in keys]
+    dev = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() and dist.is_initialized()
+                                                          and dist.get_backend() == "nccl" else "cpu"))
+    flat = torch.cat([torch.as_tensor(state_dict[k]).reshape(-1).to(dev, torch.float32) for k in keys]) if keys else \
+        torch.zeros(0, device=dev)
+    if _world() > 1:
+        dist.broadcast(flat, src=src)
+    out, off = {}, 0
+    for k, shp, n in zip(keys, shapes, sizes):
+        out[k] = flat[off:off + n].reshape(shp)
+        off += n
+    return out
+
+
+def allreduce_gradients(grads, average=True):
+    """The trainer's gradient all-reduce (the only collective north_star names): the gradients are packed into one
+    flat float32 bucket, summed over the ranks (NCCL over NVLink / NVSwitch, in-switch reduction when NVLS is up) and
+    written back in place; `average` divides by the world size (data-parallel mean)."""
+    grads = [g for g in grads if g is not None]
+    if not grads:
+        return
+    world = _world()
+    flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if average:
+            flat /= world
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].reshape(g.shape))
+        off += n

@@ -31,7 +31,13 @@ def _worker(rank, world, port, G, out):
     ms = 10.0 + 5.0 * rank                        # rank 1 is slower
     value, ms_max = mdist.aggregate_throughput(G * 50, ms)
     total_games = mdist.sum_over_ranks(G)
-    out[rank] = (slot0, states, value, ms_max, total_games)
+    # the two learner-side collectives: weight refresh from rank 0, gradient all-reduce (mean)
+    torch.manual_seed(rank)
+    sd = {"a.weight": torch.randn(3, 4), "b.bias": torch.randn(5)}
+    got = mdist.broadcast_weights(sd, src=0, device="cpu")
+    grads = [torch.full((2, 3), float(rank + 1)), torch.full((4,), float(10 * (rank + 1)))]
+    mdist.allreduce_gradients(grads)
+    out[rank] = (slot0, states, value, ms_max, total_games, {k: v.clone() for k, v in got.items()}, [g.clone() for g in grads])
     torch.distributed.destroy_process_group()
 
 
@@ -46,7 +52,11 @@ def test_world_size_2_sharding_and_aggregation():
     single = ogames.CartPole(2 * G, seed=3, slot0=0).state64()
     np.testing.assert_array_equal(np.concatenate([out[0][1], out[1][1]]), single)
     for r in range(world):
-        slot0, _, value, ms_max, total_games = out[r]
+        slot0, _, value, ms_max, total_games, got, grads = out[r]
+        torch.manual_seed(0)
+        want = {"a.weight": torch.randn(3, 4), "b.bias": torch.randn(5)}
+        assert all(torch.equal(got[k], want[k]) for k in want)          # every rank holds rank 0's weights
+        assert torch.equal(grads[0], torch.full((2, 3), 1.5)) and torch.equal(grads[1], torch.full((4,), 15.0))
         assert ms_max == 15.0 and total_games == 2 * G                 # max over ranks, sum over ranks
         assert abs(value - (2 * G * 50) / 15e-3) < 1e-6                 # whole-job units / slowest rank's time
     from muzero_hypermodel_b200 import dist as mdist
