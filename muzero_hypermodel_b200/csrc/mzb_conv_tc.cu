@@ -18,6 +18,7 @@
 //     (tcgen05.ld 32x32b, scale/shift/plane/residual/ReLU, bf16 pack, 16-byte stores).
 // Rows that are pad positions compute garbage that is simply not stored (pads stay zero for the next layer).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "mzb_resnet_model.h"
 
@@ -270,132 +271,148 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else {
     // ---------------- epilogue warpgroups
+    // A group of four warps (TMEM lane quarter = warp % 4, thread = row) drains one 128-row tile at a time in steps of
+    // 32 columns.  The loop is software pipelined: the residual bytes of the NEXT step are requested before the current
+    // step's accumulators are converted, so the global-memory latency (the epilogue's dominant cost: it, not the MMA
+    // issue, set the kernel's period) hides behind the arithmetic of the step before.
     const int q = warp & 3, group = (warp - 2) >> 2;
     const int ncg = (N + 63) / 64, n_items = MT * ncg;
     constexpr int NG = kEpiWarps / 4;
-    // row -> (image, y, x) of item `item` of super-tile starting at m0
-    long long m = 0;
-    auto decode = [&](long long m0, int item, long long& row_off, int& b, int& pos, bool& valid) {
-      const int t = item / ncg;
-      m = m0 + (long long)t * 128 + q * 32 + lane;
-      b = (int)(m / a.R_img);
-      const int rem = (int)(m - (long long)b * a.R_img);
-      const int yy = rem / (a.W + 2), xx = rem - yy * (a.W + 2);
-      valid = m < a.rows_valid && yy >= 1 && xx >= 1 && xx <= a.W;
-      row_off = (m + halo) * (long long)N;
-      pos = (yy - 1) * a.W + (xx - 1);
+    const uint32_t s_scale_u32 = smem_u32(s_scale), s_shift_u32 = smem_u32(s_shift), s_proj_u32 = smem_u32(s_proj);
+    const uint32_t R_img = (uint32_t)a.R_img, Wp = (uint32_t)(a.W + 2);
+    struct Item { long long row_off; int b, pos, t, g0, gw; uint32_t m; bool valid; };
+    auto get_item = [&](uint32_t m0, int item, Item& I) {
+      I.t = item / ncg;
+      I.g0 = (item - I.t * ncg) * 64;
+      I.gw = N - I.g0 < 64 ? N - I.g0 : 64;                      // columns in this group (multiple of 16)
+      I.m = m0 + (uint32_t)(I.t * 128 + q * 32 + lane);           // rows_cover < 2^31 (checked by the host)
+      const uint32_t bb = I.m / R_img, rem = I.m - bb * R_img;
+      const uint32_t yy = rem / Wp, xx = rem - yy * Wp;
+      I.b = (int)bb;
+      I.valid = (long long)I.m < a.rows_valid && yy >= 1 && xx >= 1 && xx <= (uint32_t)a.W;
+      I.row_off = ((long long)I.m + halo) * (long long)N;
+      I.pos = (int)((yy - 1) * (uint32_t)a.W + (xx - 1));
+    };
+    auto load_res = [&](const Item& I, int hh, uint4 (&r)[4]) {
+      if (I.valid && a.residual) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.residual + I.row_off + I.g0 + hh * 32);
+        const int cw = I.gw - hh * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i * 8 < cw) r[i] = __ldg(rp + i);
+      }
     };
     int it = 0;
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
       const int s = it & 1;
-      const long long m0 = st * MT * 128;
-      // the residual rows do not depend on the MMAs: request the first item's now (hidden behind the accumulator
-      // wait) and pull the later items' lines towards L2
-      uint4 res[8];
-      long long row_off; int b, pos; bool valid;
-      if (a.residual) {
-        for (int item = group + NG; item < n_items; item += NG) {
-          decode(m0, item, row_off, b, pos, valid);
-          if (valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.residual + row_off + (item % ncg) * 64));
-        }
-      }
-      if (group < n_items) {
-        decode(m0, group, row_off, b, pos, valid);
-        if (valid && a.residual) {
-          const int g0 = (group % ncg) * 64;
-          const int gw = N - g0 < 64 ? N - g0 : 64;
-          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + row_off + g0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) if (i * 8 < gw) res[i] = __ldg(rp + i);
-        }
+      const uint32_t m0 = (uint32_t)(st * MT * 128);
+      // items are dealt round-robin over ALL super-tiles (not restarted per super-tile)
+      int item = (((group - it * n_items) % NG) + NG) % NG;
+      Item cur{}, nxt{};
+      uint4 res[4], resn[4];
+      bool have = item < n_items;
+      if (have) {
+        get_item(m0, item, cur);
+        load_res(cur, 0, res);                                    // independent of the MMAs: in flight during the wait
       }
       const long long e0 = clock64();
       mbar_wait(acc_full + s, (it >> 1) & 1);
       const long long e1 = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int item = group; item < n_items; item += NG) {
-        const int t = item / ncg, g0 = (item % ncg) * 64;
-        decode(m0, item, row_off, b, pos, valid);
-        const float pl = (valid && a.plane) ? a.plane[b] : 0.0f;
-        const float* ptab = (valid && a.plane) ? a.plane_table + (size_t)pos * N : nullptr;
-        const int gw = N - g0 < 64 ? N - g0 : 64;              // columns in this group (multiple of 16)
-        if (item != group && valid && a.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + row_off + g0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) if (i * 8 < gw) res[i] = __ldg(rp + i);
-        }
-        uint32_t v[64];
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * MT * N + t * N + g0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) if (c * 16 < gw) tmem_ld16_nowait(tbase + c * 16, v + c * 16);
-        tmem_wait_ld();
-        if (!valid) {
-          // stem mode: the buffers change resolution between layers, so the pad rows (and the trailing halo) are
-          // re-written as zeros by every layer instead of relying on a zeroed workspace
-          if (ZP && m < a.rows_cover) {
-            uint4* op = reinterpret_cast<uint4*>(a.y + row_off + g0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) if (i * 8 < gw) op[i] = make_uint4(0u, 0u, 0u, 0u);
-          }
-          continue;
-        }
+      while (have) {
+        const float pl = (cur.valid && a.plane) ? a.plane[cur.b] : 0.0f;
+        const float* ptab = (cur.valid && a.plane) ? a.plane_table + (size_t)cur.pos * N : nullptr;
         float pacc[PR > 0 ? PR : 1];
 #pragma unroll
         for (int r = 0; r < PR; ++r) pacc[r] = 0.0f;
+        const int n_half = (cur.gw + 31) / 32;
+        const int next_item = item + NG;
+        for (int hh = 0; hh < n_half; ++hh) {
+          const int c0 = cur.g0 + hh * 32, cw = cur.gw - hh * 32 < 32 ? cur.gw - hh * 32 : 32;   // 16 or 32 columns
+          uint32_t v[32];
+          const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * MT * N + cur.t * N + c0);
+          tmem_ld16_nowait(tbase, v);
+          if (cw > 16) tmem_ld16_nowait(tbase + 16, v + 16);
+          // request the next step's residual row before touching this step's accumulators
+          if (hh + 1 < n_half) {
+            load_res(cur, hh + 1, resn);
+          } else if (next_item < n_items) {
+            get_item(m0, next_item, nxt);
+            load_res(nxt, 0, resn);
+          }
+          tmem_wait_ld();
+          if (!cur.valid) {
+            // stem mode: the buffers change resolution between layers, so the pad rows (and the trailing halo) are
+            // re-written as zeros by every layer instead of relying on a zeroed workspace
+            if (ZP && (long long)cur.m < a.rows_cover) {
+              uint4* op = reinterpret_cast<uint4*>(a.y + cur.row_off + c0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c * 16 >= gw) break;
-          float f[16];
-          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + g0 + c * 16);
-          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + g0 + c * 16);
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 sc = sc4[i4], sh = sh4[i4];
-            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = i4 * 4 + j;
-              float acc = __uint_as_float(v[c * 16 + i]);
-              if (ptab) acc = fmaf(pl, ptab[g0 + c * 16 + i], acc);
-              f[i] = fmaf(acc, scv[j], shv[j]);
+              for (int i = 0; i < 4; ++i) if (i * 8 < cw) op[i] = make_uint4(0u, 0u, 0u, 0u);
             }
-          }
-          if (a.residual) {
-            const uint32_t rw[8] = {res[2 * c].x, res[2 * c].y, res[2 * c].z, res[2 * c].w,
-                                    res[2 * c + 1].x, res[2 * c + 1].y, res[2 * c + 1].z, res[2 * c + 1].w};
+          } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[2 * i] += __uint_as_float(rw[i] << 16);
-              f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
-            }
-          }
-          uint32_t o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float lo = f[2 * i], hi = f[2 * i + 1];
-            if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
-            const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-            o[i] = *reinterpret_cast<const uint32_t*>(&pk);
-            if (PR > 0) { f[2 * i] = __uint_as_float(o[i] << 16); f[2 * i + 1] = __uint_as_float(o[i] & 0xFFFF0000u); }
-          }
-          uint4* op = reinterpret_cast<uint4*>(a.y + row_off + g0 + c * 16);
-          op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          op[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          if (PR > 0) {
-#pragma unroll
-            for (int r = 0; r < PR; ++r) {
-              const float4* w4 = reinterpret_cast<const float4*>(s_proj + r * N + g0 + c * 16);
+            for (int c = 0; c < 2; ++c) {
+              if (c * 16 >= cw) break;
+              float f[16];
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 ww = w4[i4];
-                pacc[r] = fmaf(f[4 * i4], ww.x, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 1], ww.y, pacc[r]);
-                pacc[r] = fmaf(f[4 * i4 + 2], ww.z, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 3], ww.w, pacc[r]);
+                float4 sc, sh;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w)
+                             : "r"(s_scale_u32 + (uint32_t)(c0 + c * 16 + i4 * 4) * 4));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w)
+                             : "r"(s_shift_u32 + (uint32_t)(c0 + c * 16 + i4 * 4) * 4));
+                float4 pt = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (ptab) pt = __ldg(reinterpret_cast<const float4*>(ptab + c0 + c * 16 + i4 * 4));
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                const float ptv[4] = {pt.x, pt.y, pt.z, pt.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = i4 * 4 + j;
+                  float acc = __uint_as_float(v[c * 16 + i]);
+                  if (ptab) acc = fmaf(pl, ptv[j], acc);
+                  f[i] = fmaf(acc, scv[j], shv[j]);
+                }
+              }
+              if (a.residual) {
+                const uint32_t rw[8] = {res[2 * c].x, res[2 * c].y, res[2 * c].z, res[2 * c].w,
+                                        res[2 * c + 1].x, res[2 * c + 1].y, res[2 * c + 1].z, res[2 * c + 1].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  f[2 * i] += __uint_as_float(rw[i] << 16);
+                  f[2 * i + 1] += __uint_as_float(rw[i] & 0xFFFF0000u);
+                }
+              }
+              uint32_t o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float lo = f[2 * i], hi = f[2 * i + 1];
+                if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+                o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+                if (PR > 0) { f[2 * i] = __uint_as_float(o[i] << 16); f[2 * i + 1] = __uint_as_float(o[i] & 0xFFFF0000u); }
+              }
+              uint4* op = reinterpret_cast<uint4*>(a.y + cur.row_off + c0 + c * 16);
+              op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+              op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+              if (PR > 0) {
+#pragma unroll
+                for (int r = 0; r < PR; ++r) {
+#pragma unroll
+                  for (int i4 = 0; i4 < 4; ++i4) {
+                    float4 ww;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ww.x), "=f"(ww.y), "=f"(ww.z), "=f"(ww.w)
+                                 : "r"(s_proj_u32 + (uint32_t)(r * N + c0 + c * 16 + i4 * 4) * 4));
+                    pacc[r] = fmaf(f[4 * i4], ww.x, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 1], ww.y, pacc[r]);
+                    pacc[r] = fmaf(f[4 * i4 + 2], ww.z, pacc[r]); pacc[r] = fmaf(f[4 * i4 + 3], ww.w, pacc[r]);
+                  }
+                }
               }
             }
           }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) res[i] = resn[i];
         }
-        if (PR > 0) {
-          float* po = a.proj_out + ((long long)b * a.proj_r) * a.proj_hw + pos;
+        if (PR > 0 && cur.valid) {
+          float* po = a.proj_out + ((long long)cur.b * a.proj_r) * a.proj_hw + cur.pos;
 #pragma unroll
           for (int r = 0; r < PR; ++r) {
             if (r < a.proj_r) {
@@ -404,6 +421,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
         }
+        item = next_item;
+        have = item < n_items;
+        cur = nxt;
       }
       // this warp is done reading the TMEM stage: release it to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -514,6 +534,7 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   a.rows_valid = (long long)B * a.R_img;
   a.zero_pads = zero_pads;
   a.rows_cover = a.rows_valid + (zero_pads ? W + 3 : 0);
+  MZB_CHECK_ARG(a.rows_cover + 4 * 128 < (1ll << 31), "tensor-core convolution: %lld rows exceed the 32-bit row index", a.rows_cover);
   a.scale = cp.scale; a.shift = cp.shift; a.plane = cp.extra_plane ? plane : nullptr; a.plane_table = cp.plane_table;
   a.residual = residual; a.y = y;
   a.debug = g_tc_debug;
