@@ -325,8 +325,15 @@ def main():
                                                                    _lib.current_stream()))
         probe()
         torch.cuda.synchronize()
+        # replayed from a CUDA graph like the search itself: plain back-to-back launches are host-bound here (three
+        # tensor-map encodes + a launch per 80 us kernel) and would time the launch path, not the kernel
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            probe()
+        graph.replay()
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); probe(); b.record()
+        a.record(); graph.replay(); b.record()
         torch.cuda.synchronize()
         conv_ms = a.elapsed_time(b) / iters
         conv_flop = 2.0 * G * H_lat * W_lat * C_lat * C_lat * 9

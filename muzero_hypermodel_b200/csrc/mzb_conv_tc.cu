@@ -486,7 +486,10 @@ bool make_plan(int cin, int cout, int W, TcPlan* out) {
   const size_t rowb = (size_t)p.kc * 2, limit = 225 * 1024;
   const size_t b_all = (size_t)9 * p.n_chunks * cout * rowb, b_ring = (size_t)kStages * cout * rowb;
   const size_t misc = 1024 + 512 + 8 * (size_t)cout + 32 * (size_t)cout;      // barriers, scale/shift, <= 8 projection rows
-  for (int mt = 4; mt >= 1; mt >>= 1) {
+  // narrow layers (C_out <= 32) are bound by per-super-tile latencies, not by the MMAs: give them more rows per step
+  static int mt_narrow = -1;
+  if (mt_narrow < 0) { const char* e = getenv("MZB_TC_MT_NARROW"); mt_narrow = e ? atoi(e) : 8; }
+  for (int mt = cout <= 32 ? mt_narrow : 4; mt >= 1; mt >>= 1) {
     if (2 * mt * cout > 512) continue;
     const size_t a2 = 2 * (size_t)p.n_chunks * (mt * 128 + p.tail_rows) * rowb;
     if (a2 + b_all + misc <= limit) { p.mt = mt; p.b_resident = 1; p.smem = a2 + b_all + misc; break; }

@@ -12,7 +12,12 @@ sp = SelfPlay({"weights": w}, None, cfg, 0, n_games=16384, device="cuda:0")
 sp.step(); torch.cuda.synchronize()
 buf = torch.zeros(4 * 32 * 4, dtype=torch.int64, device="cuda:0")
 _lib.lib.mzb_conv_tc_debug_buffer(C.c_void_p(buf.data_ptr()))
-sp.step(); torch.cuda.synchronize()
+if len(sys.argv) > 1 and sys.argv[1] == "probe":        # the bench's probe layer (no residual) instead of a search
+    ws = sp.model._workspace(16384, torch.device("cuda:0"))
+    _lib.check(_lib.lib.mzb_resnet_conv_probe(sp.model.handle(), 16384, _lib.ptr(ws), ws.numel(), 1, _lib.current_stream()))
+else:
+    sp.step()
+torch.cuda.synchronize()
 _lib.lib.mzb_conv_tc_debug_buffer(None)
 d = buf.cpu().numpy().reshape(4, 32, 4)
 t0 = d[0, 0, 0]
