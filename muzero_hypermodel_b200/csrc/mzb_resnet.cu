@@ -118,91 +118,152 @@ __global__ void k_avgpool(const T* __restrict__ x, int B, Geo gi, Geo go, T* __r
 // writes the pad rows and the trailing halo as zeros: the three rotating buffers change resolution from layer to
 // layer, so (unlike the latent path) the pads cannot be left to a zeroed workspace.
 //
-// Stride-2 3x3 convolution, padding 1 (DownSample.conv1 / conv2, models.py:236-255).  One thread per row of the
-// padded OUTPUT layout; 16 output channels per pass, weights [9*cin][go.C] broadcast from shared memory.
-// OBS: the input is the caller's fp32 NCHW observation (no staging copy); else padded NHWC bf16 rows of gi.C
-// channels of which the first `cin` (multiple of 8) are real.  Output channels >= cout are written as zeros.
+// Stride-2 3x3 convolution, padding 1 (DownSample.conv1 / conv2, models.py:236-255).  Weights [9*cin][cout]
+// (cout a multiple of 8) are broadcast from shared memory, 8 output channels per pass.
+// OBS: the input is the caller's fp32 NCHW observation (no staging copy); else a padded NHWC bf16 tensor.
+// PIXEL-PAIR layout of the first stage (C/2 channels at half resolution): two horizontally adjacent pixels share one
+// row of 2*(C/2) channels, so an 8-channel stage still has the 16-channel rows the UMMA needs WITHOUT zero padding
+// (half the bytes of a channel-padded layout); a 3x3 convolution over pixels is a 3x3 convolution over pairs with a
+// structured-sparse weight matrix (pack_conv_pair).  out_pair: a thread owns pixel `po` of output pair-row m;
+// in_pair: input pixel (y, x) is row (y, x >> 1), channels (x & 1) * cin ...
 template <bool OBS>
-__global__ void __launch_bounds__(128) k_conv_s2(const void* __restrict__ xin, int B, Geo gi, int cin, const float* __restrict__ w,
-                                                 const float* __restrict__ scale, const float* __restrict__ shift, int cout,
-                                                 Geo go, __nv_bfloat16* __restrict__ y) {
+__global__ void __launch_bounds__(128) k_conv_s2(const void* __restrict__ xin, int B, Geo gi, int cin, int in_pair,
+                                                 const float* __restrict__ w, const float* __restrict__ scale,
+                                                 const float* __restrict__ shift, int cout, Geo go, int out_pair,
+                                                 __nv_bfloat16* __restrict__ y) {
   extern __shared__ float sw[];
-  const int CO = go.C;
-  float* s_scale = sw + 9 * cin * CO;
-  float* s_shift = s_scale + CO;
-  for (int i = threadIdx.x; i < 9 * cin * CO; i += blockDim.x) {
-    const int k = i / CO, o = i % CO;
-    sw[i] = o < cout ? w[(size_t)k * cout + o] : 0.0f;
-  }
-  for (int i = threadIdx.x; i < CO; i += blockDim.x) { s_scale[i] = i < cout ? scale[i] : 0.0f; s_shift[i] = i < cout ? shift[i] : 0.0f; }
+  float* s_scale = sw + 9 * cin * cout;
+  float* s_shift = s_scale + cout;
+  for (int i = threadIdx.x; i < 9 * cin * cout; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
   __syncthreads();
-  const int Wp = go.W + 2;
+  const int Wp = go.W + 2, CO = go.C, ppr = out_pair ? 2 : 1;                // pixels per output row
   const long long R_img = (long long)(go.H + 1) * Wp;
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long m = t / ppr;
+  const int po = (int)(t - m * ppr);
   if (m >= (long long)B * R_img + (go.W + 3)) return;
   const int b = (int)(m / R_img);
   const int rem = (int)(m - (long long)b * R_img);
   const int yy = rem / Wp, xx = rem - yy * Wp;
   const bool valid = b < B && yy >= 1 && xx >= 1 && xx <= go.W;
-  uint4* out = reinterpret_cast<uint4*>(y + (m + go.W + 3) * CO);
+  uint4* out = reinterpret_cast<uint4*>(y + (m + go.W + 3) * CO + po * cout);
   if (!valid) {
-    for (int i = 0; i < CO / 8; ++i) out[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < cout / 8; ++i) out[i] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
-  const int oy = yy - 1, ox = xx - 1;
-  for (int co0 = 0; co0 < CO; co0 += 16) {
-    float acc[16];
+  const int oy = yy - 1, ox = (xx - 1) * ppr + po;
+  for (int co0 = 0; co0 < cout; co0 += 8) {
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
-        const float* wt = sw + (size_t)(ky * 3 + kx) * cin * CO + co0;
+        const float* wt = sw + (size_t)(ky * 3 + kx) * cin * cout + co0;
         if (OBS) {
           if (iy < 0 || iy >= gi.H || ix < 0 || ix >= gi.W) continue;
           const float* src = (const float*)xin + ((size_t)b * cin * gi.H + iy) * gi.W + ix;
           for (int c = 0; c < cin; ++c) {
             const float v = __bfloat162float(__float2bfloat16_rn(src[(size_t)c * gi.H * gi.W]));   // bf16 operands on this path
-            const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)c * CO);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 ww = w4[j4];
-              acc[4 * j4] = fmaf(v, ww.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(v, ww.y, acc[4 * j4 + 1]);
-              acc[4 * j4 + 2] = fmaf(v, ww.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(v, ww.w, acc[4 * j4 + 3]);
-            }
+            const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)c * cout);
+            const float4 w0 = w4[0], w1 = w4[1];
+            acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+            acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
           }
         } else {
           // out-of-image taps land on zero pad rows of the padded input: no bounds checks
-          const uint4* src = reinterpret_cast<const uint4*>((const __nv_bfloat16*)xin + geo_row(gi, b, iy, ix) * gi.C);
+          const int ixr = in_pair ? (ix >> 1) : ix, coff = in_pair ? (ix & 1) * cin : 0;
+          const uint4* src = reinterpret_cast<const uint4*>((const __nv_bfloat16*)xin + geo_row(gi, b, iy, ixr) * gi.C + coff);
           for (int c8 = 0; c8 < cin / 8; ++c8) {
             const uint4 raw = src[c8];
             const uint32_t r4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
               const float v = __uint_as_float((h & 1) ? (r4[h >> 1] & 0xFFFF0000u) : (r4[h >> 1] << 16));
-              const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)(c8 * 8 + h) * CO);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 ww = w4[j4];
-                acc[4 * j4] = fmaf(v, ww.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(v, ww.y, acc[4 * j4 + 1]);
-                acc[4 * j4 + 2] = fmaf(v, ww.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(v, ww.w, acc[4 * j4 + 3]);
-              }
+              const float4* w4 = reinterpret_cast<const float4*>(wt + (size_t)(c8 * 8 + h) * cout);
+              const float4 w0 = w4[0], w1 = w4[1];
+              acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+              acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
             }
           }
         }
       }
     }
-    uint32_t o[8];
+    uint32_t o[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const __nv_bfloat162 pk = __floats2bfloat162_rn(fmaf(acc[2 * i], s_scale[co0 + 2 * i], s_shift[co0 + 2 * i]),
                                                       fmaf(acc[2 * i + 1], s_scale[co0 + 2 * i + 1], s_shift[co0 + 2 * i + 1]));
       o[i] = *reinterpret_cast<const uint32_t*>(&pk);
     }
     out[co0 / 8] = make_uint4(o[0], o[1], o[2], o[3]);
-    out[co0 / 8 + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// DownSample.conv1 specialised for the pixel-pair output (frame width a multiple of 4): a thread owns one output
+// PAIR, i.e. the input columns 4*xp-1 .. 4*xp+3 of three frame lines, fetched as one aligned float4 plus one scalar per
+// (line, plane) - consecutive lanes read consecutive 16-byte segments of the fp32 frame (the kernel is a 1.8 GB read
+// of the observation batch; the generic thread-per-pixel form issued 27 scattered 4-byte loads per pixel).
+__global__ void __launch_bounds__(128) k_stem_conv1_pair(const float* __restrict__ obs, int B, Geo gi, int cin,
+                                                         const float* __restrict__ w, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, int cout, Geo go,
+                                                         __nv_bfloat16* __restrict__ y) {
+  extern __shared__ float sw[];
+  float* s_scale = sw + 9 * cin * cout;
+  float* s_shift = s_scale + cout;
+  for (int i = threadIdx.x; i < 9 * cin * cout; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+  __syncthreads();
+  const int Wp = go.W + 2, CO = go.C;
+  const long long R_img = (long long)(go.H + 1) * Wp;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= (long long)B * R_img + (go.W + 3)) return;
+  const int b = (int)(m / R_img);
+  const int rem = (int)(m - (long long)b * R_img);
+  const int yy = rem / Wp, xx = rem - yy * Wp;
+  uint4* out = reinterpret_cast<uint4*>(y + (m + go.W + 3) * CO);
+  if (!(b < B && yy >= 1 && xx >= 1 && xx <= go.W)) {
+    for (int i = 0; i < CO / 8; ++i) out[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const int oy = yy - 1, xp = xx - 1;
+  auto bf = [](float v) { return __bfloat162float(__float2bfloat16_rn(v)); };      // bf16 operands on this path
+  for (int co0 = 0; co0 < cout; co0 += 8) {
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy + ky - 1;
+      if (iy < 0 || iy >= gi.H) continue;
+      for (int c = 0; c < cin; ++c) {
+        const float* line = obs + ((size_t)b * cin + c) * gi.H * gi.W + (size_t)iy * gi.W;
+        const float4 qv = *reinterpret_cast<const float4*>(line + 4 * xp);
+        const float in[5] = {xp > 0 ? bf(line[4 * xp - 1]) : 0.0f, bf(qv.x), bf(qv.y), bf(qv.z), bf(qv.w)};
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4* w4 = reinterpret_cast<const float4*>(sw + (size_t)((ky * 3 + kx) * cin + c) * cout + co0);
+          const float4 w0 = w4[0], w1 = w4[1];
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a0[j] = fmaf(in[kx], wv[j], a0[j]); a1[j] = fmaf(in[kx + 2], wv[j], a1[j]); }
+        }
+      }
+    }
+    uint32_t o0[4], o1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float sc0 = s_scale[co0 + 2 * i], sc1 = s_scale[co0 + 2 * i + 1], sh0 = s_shift[co0 + 2 * i], sh1 = s_shift[co0 + 2 * i + 1];
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(a0[2 * i], sc0, sh0), fmaf(a0[2 * i + 1], sc1, sh1));
+      const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(a1[2 * i], sc0, sh0), fmaf(a1[2 * i + 1], sc1, sh1));
+      o0[i] = *reinterpret_cast<const uint32_t*>(&p0);
+      o1[i] = *reinterpret_cast<const uint32_t*>(&p1);
+    }
+    out[co0 / 8] = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+    out[(cout + co0) / 8] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
   }
 }
 
@@ -658,9 +719,9 @@ int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* c) {
     // bf16: the whole stem runs in the padded layout - stride-2 layers on a dedicated kernel, every residual block
     // on the tcgen05 convolution (resblocks1 with its C/2 channels zero-padded to a multiple of 16)
     const int w1 = (m->W - 1) / 2 + 1;
-    if (m->precision == 1 && C % 16 == 0 && (C / 2) % 8 == 0 && C <= 128 && w1 <= 61) {
+    if (m->precision == 1 && C % 16 == 0 && (C / 2) % 8 == 0 && C <= 128 && w1 % 2 == 0 && w1 / 2 <= 61) {
       m->stem_tc = 1;
-      m->stem_cp1 = (C / 2 + 15) / 16 * 16;
+      m->stem_cp1 = C;                       // pixel-pair rows: 2 x (C/2) channels
       m->ds1_tc.resize(2);
       for (auto& b : m->ds1_tc)
         ok = ok && init_conv(m, b.c1, m->stem_cp1, m->stem_cp1, 1, 0, 0) && init_conv(m, b.c2, m->stem_cp1, m->stem_cp1, 1, 0, 0);
@@ -752,6 +813,33 @@ bool pack_conv(ConvParams& c, const float* w, int src_cin, int src_cout, const s
   return ok;
 }
 
+// Pixel-pair form of a C/2 -> C/2 3x3 convolution (see k_conv_s2): `c` has 2*src channels on both sides; output
+// channel po*src + co of pair tap kxp reads input channel pi*src + ci with the pixel tap dx = 2*(kxp-1) + pi - po + 1.
+bool pack_conv_pair(ConvParams& c, const float* w, int src, const std::vector<float>& scale_src, const std::vector<float>& shift_src) {
+  const int C2 = 2 * src;
+  std::vector<float> scale(C2), shift(C2);
+  for (int po = 0; po < 2; ++po)
+    for (int o = 0; o < src; ++o) { scale[po * src + o] = scale_src[o]; shift[po * src + o] = shift_src[o]; }
+  std::vector<float> wp((size_t)9 * C2 * C2, 0.0f);
+  std::vector<__nv_bfloat16> wb((size_t)9 * C2 * C2, __float2bfloat16(0.0f));
+  for (int po = 0; po < 2; ++po)
+    for (int pi = 0; pi < 2; ++pi)
+      for (int kxp = 0; kxp < 3; ++kxp) {
+        const int dx = 2 * (kxp - 1) + pi - po + 1;
+        if (dx < 0 || dx > 2) continue;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int o = 0; o < src; ++o)
+            for (int ci = 0; ci < src; ++ci) {
+              const float v = w[((size_t)o * src + ci) * 9 + ky * 3 + dx];
+              const int tap = ky * 3 + kxp, oc = po * src + o, ic = pi * src + ci;
+              wp[((size_t)tap * C2 + ic) * C2 + oc] = v;
+              wb[((size_t)oc * 9 + tap) * C2 + ic] = __float2bfloat16(v);
+            }
+      }
+  return upload(c.w, wp.data(), wp.size() * 4) && upload(c.w_bf16, wb.data(), wb.size() * 2) &&
+         upload(c.scale, scale.data(), scale.size() * 4) && upload(c.shift, shift.data(), shift.size() * 4);
+}
+
 bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl, ConvParams* wide = nullptr) {
   const int cw = c.cin + c.extra_plane;
   const float* w = cur.take((int64_t)c.cout * cw * 9);
@@ -766,7 +854,7 @@ bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl, ConvPar
     }
   }
   if (cur.bad) return false;
-  return pack_conv(c, w, c.cin, c.cout, scale, shift, Hl, Wl) && (!wide || pack_conv(*wide, w, c.cin, c.cout, scale, shift, Hl, Wl));
+  return pack_conv(c, w, c.cin, c.cout, scale, shift, Hl, Wl) && (!wide || pack_conv_pair(*wide, w, c.cin, scale, shift));
 }
 
 bool load_block(Cursor& cur, Block& b) { return load_conv(cur, b.c1, true, 0, 0) && load_conv(cur, b.c2, true, 0, 0); }
@@ -947,8 +1035,9 @@ int stem_tc(Runner& r, const float* obs) {
   mzb_resnet_model* m = r.m;
   const int B = r.B, C = m->C, Cp1 = m->stem_cp1;
   const Geo g0{m->H, m->W, m->Cobs, 0};
-  const Geo g1{(g0.H - 1) / 2 + 1, (g0.W - 1) / 2 + 1, Cp1, 1};
-  const Geo g2{(g1.H - 1) / 2 + 1, (g1.W - 1) / 2 + 1, C, 1};
+  const int h1 = (g0.H - 1) / 2 + 1, w1 = (g0.W - 1) / 2 + 1;
+  const Geo g1{h1, w1 / 2, Cp1, 1};                         // pixel pairs: w1/2 rows of 2*(C/2) channels per line
+  const Geo g2{(h1 - 1) / 2 + 1, (w1 - 1) / 2 + 1, C, 1};
   const Geo g3{(g2.H - 1) / 2 + 1, (g2.W - 1) / 2 + 1, C, 1};
   const Geo gl{m->Hl, m->Wl, C, 1};
   if ((g3.H - 1) / 2 + 1 != m->Hl || (g3.W - 1) / 2 + 1 != m->Wl) { mzb_set_error("latent size mismatch"); r.rc = MZB_EINVAL; return 0; }
@@ -957,18 +1046,23 @@ int stem_tc(Runner& r, const float* obs) {
   if (!configured) {
     cudaFuncSetAttribute(k_conv_s2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(k_conv_s2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(k_stem_conv1_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     configured = true;
   }
-  const size_t sm1 = sizeof(float) * ((size_t)9 * m->Cobs * Cp1 + 2 * Cp1), sm2 = sizeof(float) * ((size_t)9 * (C / 2) * C + 2 * C);
+  const size_t sm1 = sizeof(float) * ((size_t)9 * m->Cobs * (C / 2) + C), sm2 = sizeof(float) * ((size_t)9 * (C / 2) * C + 2 * C);
   if (sm1 > 96 * 1024 || sm2 > 96 * 1024) { mzb_set_error("bf16 stem: stride-2 weights exceed 96 KiB of shared memory"); r.rc = MZB_EUNSUPPORTED; return 0; }
   r.zero_pads = 1;
-  k_conv_s2<true><<<nblk(out_rows(g1), 128), 128, sm1, r.s>>>(obs, B, g0, m->Cobs, m->ds_conv1.w, m->ds_conv1.scale, m->ds_conv1.shift,
-                                                            C / 2, g1, r.buf<T>(1));
+  if (g0.W % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0)
+    k_stem_conv1_pair<<<nblk(out_rows(g1), 128), 128, sm1, r.s>>>(obs, B, g0, m->Cobs, m->ds_conv1.w, m->ds_conv1.scale,
+                                                                m->ds_conv1.shift, C / 2, g1, r.buf<T>(1));
+  else
+    k_conv_s2<true><<<nblk(2 * out_rows(g1), 128), 128, sm1, r.s>>>(obs, B, g0, m->Cobs, 0, m->ds_conv1.w, m->ds_conv1.scale,
+                                                                  m->ds_conv1.shift, C / 2, g1, 1, r.buf<T>(1));
   mzb_count_launch();
   int cur = tower<T>(r, m->ds1_tc, g1, 1);
   { const int nx = (cur + 1) % 3;
-    k_conv_s2<false><<<nblk(out_rows(g2), 128), 128, sm2, r.s>>>(r.buf<T>(cur), B, g1, C / 2, m->ds_conv2.w, m->ds_conv2.scale,
-                                                               m->ds_conv2.shift, C, g2, r.buf<T>(nx));
+    k_conv_s2<false><<<nblk(out_rows(g2), 128), 128, sm2, r.s>>>(r.buf<T>(cur), B, g1, C / 2, 1, m->ds_conv2.w, m->ds_conv2.scale,
+                                                               m->ds_conv2.shift, C, g2, 0, r.buf<T>(nx));
     mzb_count_launch(); cur = nx; }
   cur = tower<T>(r, m->ds2, g2, cur);
   { const int nx = (cur + 1) % 3;
@@ -1096,7 +1190,7 @@ size_t act_bytes_for(const mzb_resnet_model* m, long long B) {
   long long halo = 2ll * (m->Wl + 3) * std::max(m->C, m->Cobs) + 2ll * (m->W + 3) * m->Cobs;
   if (m->stem_tc) {                                        // padded bf16 stem stages (2 bytes per element: half of `per`)
     const long long h1 = (m->H - 1) / 2 + 1, w1 = (m->W - 1) / 2 + 1, h2 = (h1 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1;
-    per = std::max(per, ((h1 + 1) * (w1 + 2) * m->stem_cp1 + 1) / 2);
+    per = std::max(per, ((h1 + 1) * (w1 / 2 + 2) * m->stem_cp1 + 1) / 2);
     per = std::max(per, ((h2 + 1) * (w2 + 2) * m->C + 1) / 2);
     halo += (w1 + 3) * (long long)std::max(m->stem_cp1, m->C);
   }
