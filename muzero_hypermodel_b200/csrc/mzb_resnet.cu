@@ -368,10 +368,7 @@ __global__ void __launch_bounds__(256) k_head(const T* __restrict__ x, int B, Ge
   for (int i = threadIdx.x; i < hp.r; i += blockDim.x) sm[L.b1 + i] = hp.b1x1[i];
   for (int l = 0; l < hp.n_fc; ++l) {
     const int in = hp.fc_in[l], out = hp.fc_out[l];
-    for (int i = threadIdx.x; i < in * out; i += blockDim.x) {        // [out][in] -> [in][out]
-      const int o = i / in, k = i % in;
-      sm[L.fw[l] + k * out + o] = hp.fc_w[l][i];
-    }
+    for (int i = threadIdx.x; i < in * out; i += blockDim.x) sm[L.fw[l] + i] = hp.fc_w[l][i];     // already [in][out]
     for (int i = threadIdx.x; i < out; i += blockDim.x) sm[L.fb[l] + i] = hp.fc_b[l][i];
   }
   __syncthreads();
@@ -432,8 +429,17 @@ __global__ void __launch_bounds__(256) k_head(const T* __restrict__ x, int B, Ge
       const int ni = hp.fc_in[l], no = hp.fc_out[l];
       const float* w = sm + L.fw[l];
       for (int o = lane; o < no; o += 32) {
-        float acc = sm[L.fb[l] + o];
-        for (int k = 0; k < ni; ++k) acc = fmaf(in[k], w[k * no + o], acc);
+        // four interleaved partial sums: the dot products are short dependent FMA chains otherwise
+        float a0 = sm[L.fb[l] + o], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        int k = 0;
+        for (; k + 4 <= ni; k += 4) {
+          a0 = fmaf(in[k], w[k * no + o], a0);
+          a1 = fmaf(in[k + 1], w[(k + 1) * no + o], a1);
+          a2 = fmaf(in[k + 2], w[(k + 2) * no + o], a2);
+          a3 = fmaf(in[k + 3], w[(k + 3) * no + o], a3);
+        }
+        for (; k < ni; ++k) a0 = fmaf(in[k], w[k * no + o], a0);
+        const float acc = (a0 + a1) + (a2 + a3);
         out[o] = l < hp.n_fc - 1 ? elu_f32(acc) : acc;
       }
       __syncwarp();
@@ -868,7 +874,10 @@ bool load_fc(Cursor& cur, HeadParams& h) {
   for (int l = 0; l < h.n_fc; ++l) {
     const float* w = cur.take((int64_t)h.fc_in[l] * h.fc_out[l]); const float* b = cur.take(h.fc_out[l]);
     if (cur.bad) return false;
-    if (!upload(h.fc_w[l], w, sizeof(float) * h.fc_in[l] * h.fc_out[l]) || !upload(h.fc_b[l], b, sizeof(float) * h.fc_out[l])) return false;
+    std::vector<float> wt((size_t)h.fc_in[l] * h.fc_out[l]);                    // torch [out][in] -> [in][out]
+    for (int o = 0; o < h.fc_out[l]; ++o)
+      for (int k = 0; k < h.fc_in[l]; ++k) wt[(size_t)k * h.fc_out[l] + o] = w[(size_t)o * h.fc_in[l] + k];
+    if (!upload(h.fc_w[l], wt.data(), sizeof(float) * wt.size()) || !upload(h.fc_b[l], b, sizeof(float) * h.fc_out[l])) return false;
   }
   return true;
 }

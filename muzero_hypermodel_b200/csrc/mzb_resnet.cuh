@@ -47,7 +47,7 @@ struct HeadParams {
   int fc_in[4], fc_out[4];
   float* w1x1;                    // [r][cin]
   float* b1x1;                    // [r]
-  float* fc_w[4];                 // [out][in]
+  float* fc_w[4];                 // [in][out]: transposed at set_weights so lanes = outputs read consecutive floats
   float* fc_b[4];
   int out;                        // logits width
 };
