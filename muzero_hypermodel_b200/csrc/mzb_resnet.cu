@@ -630,6 +630,98 @@ __global__ void __launch_bounds__(256) k_minmax_store_bf16(const __nv_bfloat16* 
   }
 }
 
+// Block-per-image variant for large images or small batches (gomoku: 121 positions x 128 channels, 1,024 images - one
+// warp per image would leave most of the GPU idle): 256 threads = (row group, 16-byte channel chunk), rows in registers,
+// min/max reduced with shuffles inside a warp and through shared memory across the warps.  Same arithmetic.
+template <int MAXIT>
+__global__ void __launch_bounds__(256) k_minmax_store_bf16_block(const __nv_bfloat16* __restrict__ x, int B, Geo g,
+                                                                 __nv_bfloat16* __restrict__ y, int layout,
+                                                                 void* __restrict__ state, long long row_stride, long long off) {
+  __shared__ float s_lo[8][256], s_hi[8][256];          // [warp][channel]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = g.C, HW = g.H * g.W, LPR = C / 8, RPB = 256 / LPR, sub = threadIdx.x % LPR, rg = threadIdx.x / LPR;
+  const int nit = (HW + RPB - 1) / RPB;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    uint4 v[MAXIT];
+    float lo[8], hi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { lo[k] = CUDART_INF_F; hi[k] = -CUDART_INF_F; }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int p = it * RPB + rg;
+      if (it < nit && p < HW) v[it] = *reinterpret_cast<const uint4*>(x + geo_row(g, b, p / g.W, p % g.W) * C + sub * 8);
+    }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int p = it * RPB + rg;
+      if (it < nit && p < HW) {
+        const uint32_t r4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float a = __uint_as_float(r4[h] << 16), c = __uint_as_float(r4[h] & 0xFFFF0000u);
+          lo[2 * h] = fminf(lo[2 * h], a); hi[2 * h] = fmaxf(hi[2 * h], a);
+          lo[2 * h + 1] = fminf(lo[2 * h + 1], c); hi[2 * h + 1] = fmaxf(hi[2 * h + 1], c);
+        }
+      }
+    }
+    for (int o = LPR; o < 32; o <<= 1) {                 // row groups that share a warp (LPR < 32)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        lo[k] = fminf(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
+        hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
+      }
+    }
+    __syncthreads();                                     // previous image's readers are done with the scratch
+    if (lane < LPR) {                                   // LPR <= 32 divides 32: every warp holds all channel chunks
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s_lo[warp][sub * 8 + k] = lo[k]; s_hi[warp][sub * 8 + k] = hi[k]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float l = CUDART_INF_F, h = -CUDART_INF_F;
+      for (int w2 = 0; w2 < 8; ++w2) { l = fminf(l, s_lo[w2][sub * 8 + k]); h = fmaxf(h, s_hi[w2][sub * 8 + k]); }
+      float scale = __fsub_rn(h, l);
+      if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
+      lo[k] = l; hi[k] = scale;
+    }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int p = it * RPB + rg;
+      if (it < nit && p < HW) {
+        const uint32_t r4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+        float f[8];
+        uint32_t o4[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          f[2 * h] = __fdiv_rn(__fsub_rn(__uint_as_float(r4[h] << 16), lo[2 * h]), hi[2 * h]);
+          f[2 * h + 1] = __fdiv_rn(__fsub_rn(__uint_as_float(r4[h] & 0xFFFF0000u), lo[2 * h + 1]), hi[2 * h + 1]);
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
+          o4[h] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+        const uint4 packed = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        *reinterpret_cast<uint4*>(y + geo_row(g, b, p / g.W, p % g.W) * C + sub * 8) = packed;
+        if (state) {
+          const int c = sub * 8;
+          if (layout == 2) {
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)state + b * row_stride + off + (long long)p * C + c) = packed;
+          } else if (layout == 1) {
+            float4* o = reinterpret_cast<float4*>((float*)state + b * row_stride + off + (long long)p * C + c);
+            o[0] = make_float4(f[0], f[1], f[2], f[3]); o[1] = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            float* o = (float*)state + b * row_stride + off;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              o[(long long)(c + 2 * h) * HW + p] = __uint_as_float(o4[h] << 16);
+              o[(long long)(c + 2 * h + 1) * HW + p] = __uint_as_float(o4[h] & 0xFFFF0000u);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void k_zero_reward(int B, int S, float* __restrict__ logits, float* __restrict__ scalar) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -1014,6 +1106,12 @@ void minmax_store(Runner& r, int cur, int nx, Geo g, const Outputs& o) {
     if (nit <= 4) { k_minmax_store_bf16<4><<<grid, 256, 0, r.s>>>(x, r.B, g, y, o.layout, o.state, o.row_stride, o.off); mzb_count_launch(); return; }
     if (nit <= 12) { k_minmax_store_bf16<12><<<grid, 256, 0, r.s>>>(x, r.B, g, y, o.layout, o.state, o.row_stride, o.off); mzb_count_launch(); return; }
     if (nit <= 20) { k_minmax_store_bf16<20><<<grid, 256, 0, r.s>>>(x, r.B, g, y, o.layout, o.state, o.row_stride, o.off); mzb_count_launch(); return; }
+    const int lpr = g.C / 8, rpb = 256 / lpr;                       // block per image: rows per block iteration
+    if (lpr <= 32 && (g.H * g.W + rpb - 1) / rpb <= 8) {
+      k_minmax_store_bf16_block<8><<<r.B, 256, 0, r.s>>>(x, r.B, g, y, o.layout, o.state, o.row_stride, o.off);
+      mzb_count_launch();
+      return;
+    }
   }
   if (g.C <= 64) k_minmax_store<T, 1><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
   else if (g.C <= 128) k_minmax_store<T, 2><<<grid, 256, 0, r.s>>>(r.buf<T>(cur), r.B, g, r.buf<T>(nx), o.layout, o.state, o.row_stride, o.off);
