@@ -34,7 +34,7 @@ WORKLOADS = {
     "cartpole": ("cartpole_shipped", "cartpole", 262144, (1312, 2752)),
     "tictactoe": ("tictactoe_fc", "tictactoe", 4096 * 16, (3648, 5952)),
     "connect4": ("connect4", "connect4", 16384, (37372160, 40396160)),
-    "gomoku": ("gomoku", "gomoku", 1024, (857557760, 892780160)),
+    "gomoku": ("gomoku", "gomoku", 4096, (857557760, 892780160)),      # 51 GB bf16 hidden-state pool (401 slots x 31 KB x 4096)
     "breakout": ("breakout", "breakout", 16384, (34192160, 1532480)),
 }
 # committed `ncu --set full` captures of the dominant kernel at the bench shape (profiles/): DRAM bytes per launch
