@@ -398,6 +398,10 @@ int mzb_env_export_to_replay(mzb_env* env, mzb_replay* r, int32_t* h_n_games, vo
 /* out5 = total_samples, num_played_games, num_played_steps, games in the buffer, id of the oldest game. */
 int mzb_replay_info(const mzb_replay* r, int64_t* out5);
 int mzb_replay_set_batch_counter(mzb_replay* r, uint32_t counter);
+/* get_buffer (replay_buffer.py:66-67, persisted as replay_buffer.pkl by muzero.py:315-323): one buffered game back
+ * to the host as entry arrays (len + 1 entries; root values and visit counts for the len moves). */
+int mzb_replay_export_game_sync(mzb_replay* r, int64_t game_id, int32_t* h_len, float* h_obs, int32_t* h_action,
+                                float* h_reward, int8_t* h_to_play, double* h_root_value, uint16_t* h_visits, void* stream);
 /* Inspection (tests, checkpoints): priorities [len] and game priority of a buffered game. */
 int mzb_replay_game_priorities_sync(mzb_replay* r, int64_t game_id, float* h_priorities, float* h_game_priority,
                                     int32_t* h_len, void* stream);

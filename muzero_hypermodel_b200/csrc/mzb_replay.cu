@@ -476,4 +476,23 @@ int mzb_replay_game_priorities_sync(mzb_replay* r, int64_t game_id, float* h_pri
   return MZB_OK;
 }
 
+int mzb_replay_export_game_sync(mzb_replay* r, int64_t game_id, int32_t* h_len, float* h_obs, int32_t* h_action,
+                                float* h_reward, int8_t* h_to_play, double* h_root_value, uint16_t* h_visits, void* stream) {
+  MZB_CHECK_ARG(r && h_len, "NULL argument");
+  MZB_CHECK_ARG(game_id >= r->first_id && game_id < r->first_id + r->n_games, "game %lld is not in the buffer", (long long)game_id);
+  const int slot = (int)(game_id % r->cfg.capacity_games), n = r->h_len[slot];
+  const size_t e0 = (size_t)slot * r->cfg.entry_stride;
+  cudaStream_t s = (cudaStream_t)stream;
+  *h_len = n;
+  const ReplayView& v = r->v;
+  if (h_obs) MZB_CUDA(cudaMemcpyAsync(h_obs, v.obs + e0 * v.obs_floats, sizeof(float) * (n + 1) * v.obs_floats, cudaMemcpyDeviceToHost, s));
+  if (h_action) MZB_CUDA(cudaMemcpyAsync(h_action, v.action + e0, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, s));
+  if (h_reward) MZB_CUDA(cudaMemcpyAsync(h_reward, v.reward + e0, sizeof(float) * (n + 1), cudaMemcpyDeviceToHost, s));
+  if (h_to_play) MZB_CUDA(cudaMemcpyAsync(h_to_play, v.to_play + e0, (size_t)(n + 1), cudaMemcpyDeviceToHost, s));
+  if (h_root_value) MZB_CUDA(cudaMemcpyAsync(h_root_value, v.root_value + e0, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (h_visits) MZB_CUDA(cudaMemcpyAsync(h_visits, v.visits + e0 * v.A, sizeof(uint16_t) * (size_t)n * v.A, cudaMemcpyDeviceToHost, s));
+  MZB_CUDA(cudaStreamSynchronize(s));
+  return MZB_OK;
+}
+
 }  // extern "C"

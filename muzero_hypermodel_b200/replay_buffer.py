@@ -37,6 +37,7 @@ _lib.bind("mzb_replay_update_priorities", C.c_int, [_vp, _i32, _vp, _vp, _vp, _v
 _lib.bind("mzb_replay_info", C.c_int, [_vp, C.POINTER(_i64)])
 _lib.bind("mzb_env_export_to_replay", C.c_int, [_vp, _vp, C.POINTER(_i32), _vp])
 _lib.bind("mzb_replay_set_batch_counter", C.c_int, [_vp, C.c_uint32])
+_lib.bind("mzb_replay_export_game_sync", C.c_int, [_vp, _i64, C.POINTER(_i32)] + [_vp] * 6 + [_vp])
 _lib.bind("mzb_replay_game_priorities_sync", C.c_int, [_vp, _i64, _vp, _vp, C.POINTER(_i32), _vp])
 _lib.bind("mzb_make_target", C.c_int, [_vp] * 8 + [_i32] + [_vp] * 4 + [_i32, _i32, _i32, _vp, C.c_uint64] + [_vp] * 5)
 
@@ -228,6 +229,44 @@ class ReplayBuffer:
         pos = idx[:, 1].to(torch.int32).contiguous()
         with torch.cuda.device(self.device):
             check(_lib.lib.mzb_replay_update_priorities(self._h, pr.shape[0], ptr(pr), ptr(gid), ptr(pos), _lib.current_stream()))
+
+    # -- get_buffer (:66-67): what muzero.py pickles into replay_buffer.pkl and hands back as `initial_buffer`
+    def get_buffer(self):
+        """{game_id: GameHistory} of every buffered game, host objects in the reference's format (self_play.py:480-495)
+        with `priorities` / `game_priority` (PER) and the integer `visit_counts` the device store keeps."""
+        from .self_play import GameHistory
+        E = int(self.config.max_moves) + 2
+        obs = np.empty((E, self.rec_floats), np.float32); act = np.empty(E, np.int32); rew = np.empty(E, np.float32)
+        tp = np.empty(E, np.int8); rv = np.empty(E, np.float64); vis = np.empty((E, self.A), np.uint16)
+        out = {}
+        first, n_games = self._info()[4], len(self)
+        for gid in range(first, first + n_games):
+            n = _i32()
+            check(_lib.lib.mzb_replay_export_game_sync(self._h, gid, C.byref(n), ptr(obs), ptr(act), ptr(rew), ptr(tp), ptr(rv),
+                                                       ptr(vis), _lib.current_stream()))
+            n = n.value
+            gh = GameHistory()
+            gh.observation_history = [self._decode_record(obs[i]) for i in range(n + 1)]
+            gh.action_history = act[:n + 1].tolist()
+            gh.reward_history = [0] + [float(x) for x in rew[1:n + 1]]
+            gh.to_play_history = tp[:n + 1].astype(int).tolist()
+            v = vis[:n].astype(np.int64)
+            tot = v.sum(axis=1)
+            gh.child_visits = [[int(v[i, a]) / int(tot[i]) if v[i, a] else 0 for a in range(self.A)] for i in range(n)]
+            gh.visit_counts = v.copy()
+            gh.root_values = rv[:n].tolist()
+            if self.config.PER:
+                gh.priorities, gh.game_priority = self.game_priorities(gid)
+            out[self._played0[0] + gid] = gh
+        return out
+
+    def _decode_record(self, rec):
+        if not self.decode:
+            return rec.reshape(tuple(self.config.observation_shape)).copy()
+        oh, ow = self.board
+        raw = rec.view(np.int8)
+        board = raw[:oh * ow].reshape(oh, ow)
+        return np.array([board == 1, board == -1, np.full((oh, ow), int(raw[oh * ow]))], dtype=np.float32)
 
     def game_priorities(self, game_id):
         n = _i32()

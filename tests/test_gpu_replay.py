@@ -182,3 +182,23 @@ def test_continuous_self_play_feeds_the_device_store():
     assert float(w.max()) == 1.0 and float(w.min()) > 0
     assert torch.all((obs[:, 2] == 1) | (obs[:, 2] == -1))
     np.testing.assert_allclose(pol.sum(-1).cpu().numpy(), 1.0, rtol=0, atol=1e-12)
+
+
+def test_get_buffer_round_trip():
+    """get_buffer() -> host GameHistory dict (what muzero.py pickles) -> a new store built from it as `initial_buffer`
+    draws the same batches: counts, float32 priorities and observations survive the round trip exactly."""
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    rb, cfg = make(1)
+    for gi in range(5):
+        rb.save_game(load_game(1, gi))
+    buf = rb.get_buffer()
+    assert sorted(buf) == [0, 1, 2, 3, 4] and all(g.priorities is not None for g in buf.values())
+    rb2 = ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, buf, cfg, device=DEV)
+    assert len(rb2) == 5 and rb2.total_samples == rb.total_samples
+    for gid in range(5):
+        np.testing.assert_array_equal(rb.game_priorities(gid)[0], rb2.game_priorities(gid)[0])
+    ia, ba = rb.get_batch()
+    ib, bb = rb2.get_batch()
+    assert torch.equal(ia, ib)
+    for x, y in zip(ba, bb):
+        assert torch.equal(x, y)
