@@ -398,6 +398,13 @@ int mzb_env_export_to_replay(mzb_env* env, mzb_replay* r, int32_t* h_n_games, vo
 /* out5 = total_samples, num_played_games, num_played_steps, games in the buffer, id of the oldest game. */
 int mzb_replay_info(const mzb_replay* r, int64_t* out5);
 int mzb_replay_set_batch_counter(mzb_replay* r, uint32_t counter);
+/* Reanalyse (replay_buffer.py:298-361).  mzb_replay_game_observations writes the len observations of a buffered game
+ * as network input d_obs [len, observation floats] (board records decoded; d_obs may be NULL to query len);
+ * mzb_replay_set_reanalysed stores fresh root-value predictions d_values [len] f32 as the game's
+ * `reanalysed_predicted_root_values`: get_batch's n-step targets then bootstrap from them (:229-233, accumulated in
+ * float64).  A game evicted in the meantime is ignored (update_game_history :194-200). */
+int mzb_replay_game_observations(mzb_replay* r, int64_t game_id, float* d_obs, int32_t* h_len, void* stream);
+int mzb_replay_set_reanalysed(mzb_replay* r, int64_t game_id, const float* d_values, void* stream);
 /* get_buffer (replay_buffer.py:66-67, persisted as replay_buffer.pkl by muzero.py:315-323): one buffered game back
  * to the host as entry arrays (len + 1 entries; root values and visit counts for the len moves). */
 int mzb_replay_export_game_sync(mzb_replay* r, int64_t game_id, int32_t* h_len, float* h_obs, int32_t* h_action,

@@ -33,6 +33,7 @@ namespace {
 
 struct ReplayView {
   float* obs; int* action; float* reward; int8_t* to_play; double* root_value; uint16_t* visits; float* priority;
+  double* reanalysed;          // GameHistory.reanalysed_predicted_root_values; = root_value until Reanalyse writes it
   int* g_start; int* g_len; float* g_priority;
   float* probs; double* cdf;
   double* discount_pow;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) k_replay_save(ReplayView v, SaveArgs a) {
     v.reward[dst + i] = a.reward[src + i];
     v.to_play[dst + i] = a.to_play[src + i];
     v.root_value[dst + i] = i < n ? a.root_value[src + i] : 0.0;
+    v.reanalysed[dst + i] = i < n ? a.root_value[src + i] : 0.0;
   }
   for (long long i = threadIdx.x; i < (long long)(n + 1) * v.obs_floats; i += blockDim.x)
     v.obs[(long long)dst * v.obs_floats + i] = a.obs[(long long)src * v.obs_floats + i];
@@ -249,6 +251,26 @@ __global__ void __launch_bounds__(256) k_replay_assemble(ReplayView v, int B, co
   }
 }
 
+// The observations of one stored game as network input [n, obs_out] (Reanalyse, replay_buffer.py:337-349).
+__global__ void k_replay_game_obs(ReplayView v, int slot, float* out) {
+  const int s = v.g_start[slot], n = v.g_len[slot];
+  const int cells = v.oh * v.ow, per = v.decode ? 3 * cells : v.obs_floats;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * per) return;
+  const int e = (int)(i / per), k = (int)(i - (long long)e * per);
+  const float* src = v.obs + (long long)(s + e) * v.obs_floats;
+  if (!v.decode) { out[i] = src[k]; return; }
+  const int8_t* raw = reinterpret_cast<const int8_t*>(src);
+  const int plane = k / cells, c = k - plane * cells;
+  out[i] = plane == 0 ? (raw[c] == 1 ? 1.0f : 0.0f) : (plane == 1 ? (raw[c] == -1 ? 1.0f : 0.0f) : (float)raw[cells]);
+}
+
+__global__ void k_replay_set_reanalysed(ReplayView v, int slot, const float* values) {
+  const int s = v.g_start[slot], n = v.g_len[slot];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v.reanalysed[s + i] = (double)values[i];
+}
+
 // update_priorities (:202-220).  The reference applies the batch rows in order (a later row overwrites an earlier one
 // where their windows overlap), so one thread writes; the per-game maxima are then recomputed in parallel.
 __global__ void __launch_bounds__(256) k_replay_update(ReplayView v, int B, const float* prio, const long long* game_id,
@@ -289,7 +311,7 @@ struct mzb_replay {
 
 namespace {
 
-struct Layout { size_t obs, action, reward, to_play, root_value, visits, priority, g_start, g_len, g_priority, probs, cdf, dpow, b_slot, b_step, b_w, meta, total; };
+struct Layout { size_t obs, action, reward, to_play, root_value, reanalysed, visits, priority, g_start, g_len, g_priority, probs, cdf, dpow, b_slot, b_step, b_w, meta, total; };
 
 Layout replay_layout(const mzb_replay_config& c) {
   Layout L{};
@@ -301,6 +323,7 @@ Layout replay_layout(const mzb_replay_config& c) {
   L.reward = take(E * sizeof(float));
   L.to_play = take(E);
   L.root_value = take(E * sizeof(double));
+  L.reanalysed = take(E * sizeof(double));
   L.visits = take(E * c.n_actions * sizeof(uint16_t));
   L.priority = take(E * sizeof(float));
   L.g_start = take((size_t)c.capacity_games * sizeof(int));
@@ -342,7 +365,7 @@ int mzb_replay_create(mzb_replay** out, const mzb_replay_config* c, void* d_work
   uint8_t* w = (uint8_t*)d_workspace;
   ReplayView& v = r->v;
   v.obs = (float*)(w + L.obs); v.action = (int*)(w + L.action); v.reward = (float*)(w + L.reward);
-  v.to_play = (int8_t*)(w + L.to_play); v.root_value = (double*)(w + L.root_value); v.visits = (uint16_t*)(w + L.visits);
+  v.to_play = (int8_t*)(w + L.to_play); v.root_value = (double*)(w + L.root_value); v.reanalysed = (double*)(w + L.reanalysed); v.visits = (uint16_t*)(w + L.visits);
   v.priority = (float*)(w + L.priority); v.g_start = (int*)(w + L.g_start); v.g_len = (int*)(w + L.g_len);
   v.g_priority = (float*)(w + L.g_priority); v.probs = (float*)(w + L.probs); v.cdf = (double*)(w + L.cdf);
   v.discount_pow = (double*)(w + L.dpow); v.b_slot = (int*)(w + L.b_slot); v.b_step = (uint32_t*)(w + L.b_step);
@@ -426,7 +449,7 @@ int mzb_replay_get_batch(mzb_replay* r, int32_t batch, const double* d_u_game, c
   MZB_LAUNCH_CHECK();
   if (d_actions || d_values || d_rewards || d_policies) {
     MZB_CHECK_ARG(d_actions && d_values && d_rewards && d_policies, "targets: all four outputs or none");
-    const int rc = mzb_make_target(r->v.reward, r->v.to_play, r->v.root_value, nullptr, r->v.visits, r->v.action, r->v.g_start,
+    const int rc = mzb_make_target(r->v.reward, r->v.to_play, r->v.root_value, r->v.reanalysed, r->v.visits, r->v.action, r->v.g_start,
                                    r->v.g_len, r->v.A, r->v.b_slot, d_pos, nullptr, r->v.b_step, batch, r->v.K, r->v.td,
                                    r->v.discount_pow, r->cfg.seed, d_values, d_rewards, d_policies, d_actions, stream);
     if (rc) return rc;
@@ -473,6 +496,28 @@ int mzb_replay_game_priorities_sync(mzb_replay* r, int64_t game_id, float* h_pri
   if (h_priorities) MZB_CUDA(cudaMemcpyAsync(h_priorities, r->v.priority + (size_t)slot * r->cfg.entry_stride, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
   if (h_game_priority) MZB_CUDA(cudaMemcpyAsync(h_game_priority, r->v.g_priority + slot, sizeof(float), cudaMemcpyDeviceToHost, s));
   MZB_CUDA(cudaStreamSynchronize(s));
+  return MZB_OK;
+}
+
+int mzb_replay_game_observations(mzb_replay* r, int64_t game_id, float* d_obs, int32_t* h_len, void* stream) {
+  MZB_CHECK_ARG(r && h_len, "NULL argument");
+  MZB_CHECK_ARG(game_id >= r->first_id && game_id < r->first_id + r->n_games, "game %lld is not in the buffer", (long long)game_id);
+  const int slot = (int)(game_id % r->cfg.capacity_games), n = r->h_len[slot];
+  *h_len = n;
+  if (d_obs) {
+    const long long per = r->v.decode ? 3ll * r->v.oh * r->v.ow : r->v.obs_floats;
+    k_replay_game_obs<<<(unsigned)((n * per + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r->v, slot, d_obs);
+    MZB_LAUNCH_CHECK();
+  }
+  return MZB_OK;
+}
+
+int mzb_replay_set_reanalysed(mzb_replay* r, int64_t game_id, const float* d_values, void* stream) {
+  MZB_CHECK_ARG(r && d_values, "NULL argument");
+  if (game_id < r->first_id || game_id >= r->first_id + r->n_games) return MZB_OK;     // evicted meanwhile (:194-196)
+  const int slot = (int)(game_id % r->cfg.capacity_games), n = r->h_len[slot];
+  k_replay_set_reanalysed<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->v, slot, d_values);
+  MZB_LAUNCH_CHECK();
   return MZB_OK;
 }
 

@@ -37,6 +37,8 @@ _lib.bind("mzb_replay_update_priorities", C.c_int, [_vp, _i32, _vp, _vp, _vp, _v
 _lib.bind("mzb_replay_info", C.c_int, [_vp, C.POINTER(_i64)])
 _lib.bind("mzb_env_export_to_replay", C.c_int, [_vp, _vp, C.POINTER(_i32), _vp])
 _lib.bind("mzb_replay_set_batch_counter", C.c_int, [_vp, C.c_uint32])
+_lib.bind("mzb_replay_game_observations", C.c_int, [_vp, _i64, _vp, C.POINTER(_i32), _vp])
+_lib.bind("mzb_replay_set_reanalysed", C.c_int, [_vp, _i64, _vp, _vp])
 _lib.bind("mzb_replay_export_game_sync", C.c_int, [_vp, _i64, C.POINTER(_i32)] + [_vp] * 6 + [_vp])
 _lib.bind("mzb_replay_game_priorities_sync", C.c_int, [_vp, _i64, _vp, _vp, C.POINTER(_i32), _vp])
 _lib.bind("mzb_make_target", C.c_int, [_vp] * 8 + [_i32] + [_vp] * 4 + [_i32, _i32, _i32, _vp, C.c_uint64] + [_vp] * 5)
@@ -230,6 +232,30 @@ class ReplayBuffer:
         with torch.cuda.device(self.device):
             check(_lib.lib.mzb_replay_update_priorities(self._h, pr.shape[0], ptr(pr), ptr(gid), ptr(pos), _lib.current_stream()))
 
+    # -- Reanalyse support (:141-160, 194-200, 298-361)
+    def sample_game(self, force_uniform=True, u=None):
+        """A uniformly drawn buffered game id (the only form Reanalyse uses, :332-334)."""
+        if not force_uniform:
+            raise NotImplementedError("prioritised single-game draws go through get_batch")
+        first, n = self._info()[4], len(self)
+        u = float(np.random.random_sample()) if u is None else float(u)
+        return first + int(u * n)
+
+    def game_observations(self, game_id):
+        """[len, C, H, W] float32 device tensor: the stored observations of a game as network input."""
+        n = _i32()
+        check(_lib.lib.mzb_replay_game_observations(self._h, int(game_id), None, C.byref(n), _lib.current_stream()))
+        obs = torch.empty((n.value,) + tuple(self.config.observation_shape), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(_lib.lib.mzb_replay_game_observations(self._h, int(game_id), ptr(obs), C.byref(n), _lib.current_stream()))
+        return obs
+
+    def set_reanalysed_values(self, game_id, values):
+        """game_history.reanalysed_predicted_root_values = values (float32 [len]); ignored if the game was evicted."""
+        v = torch.as_tensor(values).to(self.device, torch.float32).reshape(-1).contiguous()
+        with torch.cuda.device(self.device):
+            check(_lib.lib.mzb_replay_set_reanalysed(self._h, int(game_id), ptr(v), _lib.current_stream()))
+
     # -- get_buffer (:66-67): what muzero.py pickles into replay_buffer.pkl and hands back as `initial_buffer`
     def get_buffer(self):
         """{game_id: GameHistory} of every buffered game, host objects in the reference's format (self_play.py:480-495)
@@ -274,3 +300,47 @@ class ReplayBuffer:
         gp = np.zeros(1, dtype=np.float32)
         check(_lib.lib.mzb_replay_game_priorities_sync(self._h, int(game_id), ptr(buf), ptr(gp), C.byref(n), _lib.current_stream()))
         return buf[:n.value].copy(), gp[0]
+
+
+class Reanalyse:
+    """Reanalyse(initial_checkpoint, config) (replay_buffer.py:298-361) against the device store: whole stored games go
+    through one batched `initial_inference` on the CUDA kernels and their fresh value predictions become the bootstrap
+    values of later batches, without the games leaving the GPU."""
+
+    def __init__(self, initial_checkpoint, config, device=None):
+        from . import models
+        self.config = config
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        np.random.seed(config.seed)
+        torch.manual_seed(config.seed)
+        self.model = models.MuZeroNetwork(config)
+        if initial_checkpoint.get("weights") is not None:
+            self.model.set_weights(initial_checkpoint["weights"])
+        self.model.to(self.device)
+        self.model.eval()
+        self.num_reanalysed_games = int(initial_checkpoint.get("num_reanalysed_games", 0))
+
+    def reanalyse_game(self, replay_buffer, game_id):
+        from . import models
+        if self.config.use_last_model_value:
+            obs = replay_buffer.game_observations(game_id)
+            values = models.support_to_scalar(self.model.initial_inference(obs)[0], self.config.support_size)
+            replay_buffer.set_reanalysed_values(game_id, values.reshape(-1))
+        self.num_reanalysed_games += 1
+
+    def reanalyse(self, replay_buffer, shared_storage, max_games=None):
+        """The reference's loop (:321-361) over plain `get_info` / `set_info` objects."""
+        import time
+        while shared_storage.get_info("num_played_games") < 1:
+            time.sleep(0.1)
+        done = 0
+        while (shared_storage.get_info("training_step") < self.config.training_steps
+               and not shared_storage.get_info("terminate")):
+            weights = shared_storage.get_info("weights")
+            if weights is not None:
+                self.model.set_weights(weights)
+            self.reanalyse_game(replay_buffer, replay_buffer.sample_game(force_uniform=True))
+            shared_storage.set_info("num_reanalysed_games", self.num_reanalysed_games)
+            done += 1
+            if max_games is not None and done >= max_games:
+                break

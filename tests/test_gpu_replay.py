@@ -202,3 +202,43 @@ def test_get_buffer_round_trip():
     assert torch.equal(ia, ib)
     for x, y in zip(ba, bb):
         assert torch.equal(x, y)
+
+
+def test_reanalyse_replaces_bootstrap_values():
+    """Reanalyse (replay_buffer.py:298-361): a stored game goes through one batched initial_inference on the CUDA
+    kernels, its value predictions become reanalysed_predicted_root_values, and later batches bootstrap from them -
+    targets equal the oracle's make_target fed the same values (float64 accumulation)."""
+    from muzero_hypermodel_b200 import models
+    from muzero_hypermodel_b200.games.cartpole import MuZeroConfig
+    from muzero_hypermodel_b200.replay_buffer import Reanalyse, ReplayBuffer
+    from oracle import targets as otargets
+    cfg = MuZeroConfig()
+    cfg.PER, cfg.batch_size, cfg.replay_buffer_size, cfg.td_steps, cfg.max_moves = False, 16, 8, 5, 100
+    z = T.load("net")
+    pre = "cartpole_shipped/w/"
+    sd = {k[len(pre):]: torch.tensor(z[k]) for k in z.files if k.startswith(pre)}
+    rb = ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg, device=DEV)
+    games = []
+    for gi in range(3):
+        g = load_game(0, gi)
+        rb.save_game(g)
+        games.append(g)
+    ra = Reanalyse({"weights": sd, "num_reanalysed_games": 0}, cfg, device=DEV)
+    ra.reanalyse_game(rb, 1)
+    assert ra.num_reanalysed_games == 1
+    obs = torch.tensor(np.array(games[1].observation_history[:len(games[1].root_values)]), device=DEV)
+    assert torch.equal(rb.game_observations(1), obs)
+    net = models.MuZeroNetwork(cfg); net.set_weights(sd); net.to(DEV)
+    fresh = models.support_to_scalar(net.initial_inference(obs)[0], cfg.support_size).reshape(-1).cpu().numpy()
+    assert np.abs(fresh - np.array(games[1].root_values)).max() > 1e-3      # the network disagrees with the stored values
+    ug = [(1 + 0.5) / 3] * 16                                                # always game 1 (uniform draw floor(u * 3))
+    up = [(i + 0.5) / 16 for i in range(16)]
+    index, (_, act, val, rew, pol, w, gs) = rb.get_batch(u_game=ug, u_pos=up)
+    g = games[1]
+    for b in range(16):
+        pos = int(index[b, 1])
+        ev, er, ep, ea = otargets.make_target(g.root_values, [float(np.float32(x)) for x in g.reward_history], g.to_play_history,
+                                              g.child_visits, g.action_history, pos, cfg.num_unroll_steps, cfg.td_steps,
+                                              cfg.discount, 2, reanalysed_root_values=[float(x) for x in fresh],
+                                              pad_action=lambda row: int(act[b, row]))
+        assert np.array(ev, dtype=np.float64).tobytes() == val[b].cpu().numpy().tobytes(), (b, pos)
