@@ -413,6 +413,17 @@ int mzb_replay_export_game_sync(mzb_replay* r, int64_t game_id, int32_t* h_len, 
 int mzb_replay_game_priorities_sync(mzb_replay* r, int64_t game_id, float* h_priorities, float* h_game_priority,
                                     int32_t* h_len, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser step on one flat float32 bucket: the trainer keeps all parameters and all
+ * gradients as views into two flat buffers, all-reduces the gradient bucket (NCCL) and applies ONE of these launches.
+ * Replaces torch.optim.Adam / SGD as configured in trainer.py:35-52 (L2 weight decay added to the gradient; Adam
+ * without amsgrad; SGD with momentum, no dampening / nesterov).  step counts from 1; grad_scale multiplies the
+ * gradient first (1 / world size for the data-parallel mean). */
+int mzb_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int64_t step, double grad_scale, void* stream);
+int mzb_sgd_step(float* d_param, const float* d_grad, float* d_momentum_buffer, int64_t n, double lr, double momentum,
+                 double weight_decay, int64_t step, double grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,331 @@
+"""Trainer: the reference's class (trainer.py:11-298) on one GPU per rank.
+
+Same constructor, `update_lr`, `update_weights(batch)`, `continuous_update_weights(replay_buffer, shared_storage)`,
+loss definition (cross-entropy on the categorical support, value loss weight, PER importance weights, 0.5 gradient
+scaling into the dynamics function, per-sample 1 / gradient_scale) and return values.
+
+What runs where - stated plainly, because this row is NOT yet on hand-written kernels end to end:
+  * the unrolled forward / backward is PyTorch autograd over the parameter-holder modules of `models` / `resnet`
+    (library kernels: cuBLAS / cuDNN), in the reference's own operation order;
+  * `scalar_to_support` / `support_to_scalar` are this package's device kernels;
+  * every parameter and every gradient is a VIEW into one flat float32 bucket each, so the data-parallel step is one
+    NCCL all-reduce of the gradient bucket (`dist.allreduce_gradients`' collective, here without the pack / unpack
+    copies) followed by ONE launch of the hand-written flat optimiser kernel (csrc/mzb_optim.cu) instead of
+    torch.optim's per-tensor launches;
+  * batches come from the device replay store as device tensors (no host hop) and priorities go back the same way.
+"""
+import ctypes as C
+import time
+
+import numpy
+import torch
+import torch.distributed as tdist
+
+from . import _lib, models
+from ._lib import check, ptr
+
+_vp, _i64, _f64 = C.c_void_p, C.c_int64, C.c_double
+_lib.bind("mzb_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _f64, _vp])
+_lib.bind("mzb_sgd_step", C.c_int, [_vp, _vp, _vp, _i64, _f64, _f64, _f64, _i64, _f64, _vp])
+
+F = torch.nn.functional
+
+
+# ------------------------------------------------------------------------------------------ differentiable forward
+def _minmax(x):
+    """Per-sample min-max scaling over everything but the batch dimension with the +1e-5 guard
+    (models.py:138-145 for vectors, :525-549 for [B, C, H, W]: per sample AND channel)."""
+    if x.dim() == 2:
+        lo, hi = x.min(1, keepdim=True)[0], x.max(1, keepdim=True)[0]
+    else:
+        flat = x.reshape(x.shape[0], x.shape[1], -1)
+        lo, hi = flat.min(2, keepdim=True)[0].unsqueeze(-1), flat.max(2, keepdim=True)[0].unsqueeze(-1)
+    scale = hi - lo
+    scale = torch.where(scale < 1e-5, scale + 1e-5, scale)
+    return (x - lo) / scale
+
+
+def _block(b, x):
+    out = F.relu(b.bn1(b.conv1(x)))
+    out = b.bn2(b.conv2(out))
+    return F.relu(out + x)
+
+
+class _FcGraph:
+    """MuZeroFullyConnectedNetwork.forward pieces (models.py:128-195)."""
+
+    def __init__(self, net):
+        self.n = net
+
+    def initial(self, obs):
+        n = self.n
+        state = _minmax(n.representation_network(obs.reshape(obs.shape[0], -1).float()))
+        policy, value = n.prediction_policy_network(state), n.prediction_value_network(state)
+        reward = torch.full((obs.shape[0], n.full_support_size), -float("inf"), device=obs.device)
+        reward[:, n.full_support_size // 2] = 0.0            # log of the one-hot centre bin (:176-183)
+        return value, reward, policy, state
+
+    def recurrent(self, state, action):
+        n = self.n
+        onehot = torch.zeros((action.shape[0], n.action_space_size), device=action.device)
+        onehot.scatter_(1, action.long(), 1.0)
+        nxt = n.dynamics_encoded_state_network(torch.cat((state, onehot), dim=1))
+        reward = n.dynamics_reward_network(nxt)              # on the un-normalised state (:157-159)
+        nxt = _minmax(nxt)
+        return n.prediction_value_network(nxt), reward, n.prediction_policy_network(nxt), nxt
+
+
+class _ResnetGraph:
+    """MuZeroResidualNetwork.forward pieces (models.py:206-619)."""
+
+    def __init__(self, net):
+        self.n = net
+
+    def _represent(self, obs):
+        r = self.n.representation_network.module
+        if hasattr(r, "downsample_net"):
+            d = r.downsample_net
+            x = d.conv1(obs)
+            for b in d.resblocks1:
+                x = _block(b, x)
+            x = d.conv2(x)
+            for b in d.resblocks2:
+                x = _block(b, x)
+            x = F.avg_pool2d(x, kernel_size=3, stride=2, padding=1)
+            for b in d.resblocks3:
+                x = _block(b, x)
+            x = F.avg_pool2d(x, kernel_size=3, stride=2, padding=1)
+        else:
+            x = F.relu(r.bn(r.conv(obs)))
+        for b in r.resblocks:
+            x = _block(b, x)
+        return _minmax(x)
+
+    def _predict(self, state):
+        p = self.n.prediction_network.module
+        x = state
+        for b in p.resblocks:
+            x = _block(b, x)
+        value = p.fc_value(p.conv1x1_value(x).reshape(x.shape[0], -1))
+        policy = p.fc_policy(p.conv1x1_policy(x).reshape(x.shape[0], -1))
+        return policy, value
+
+    def initial(self, obs):
+        n = self.n
+        state = self._represent(obs.float())
+        policy, value = self._predict(state)
+        reward = torch.full((obs.shape[0], n.full_support_size), -float("inf"), device=obs.device)
+        reward[:, n.full_support_size // 2] = 0.0
+        return value, reward, policy, state
+
+    def recurrent(self, state, action):
+        n, d = self.n, self.n.dynamics_network.module
+        plane = (action.float() / n.action_space_size).reshape(-1, 1, 1, 1).expand(-1, 1, state.shape[2], state.shape[3])
+        x = F.relu(d.bn(d.conv(torch.cat((state, plane), dim=1))))
+        for b in d.resblocks:
+            x = _block(b, x)
+        reward = d.fc(d.conv1x1_reward(x).reshape(x.shape[0], -1))
+        nxt = _minmax(x)
+        policy, value = self._predict(nxt)
+        return value, reward, policy, nxt
+
+
+# ------------------------------------------------------------------------------------------ loss of one batch
+def loss_function(value, reward, policy_logits, target_value, target_reward, target_policy):
+    """Cross-entropy against the categorical targets (trainer.py:267-284)."""
+    value_loss = (-target_value * F.log_softmax(value, dim=1)).sum(1)
+    reward_loss = (-target_reward * F.log_softmax(reward, dim=1)).sum(1)
+    policy_loss = (-target_policy * F.log_softmax(policy_logits, dim=1)).sum(1)
+    return value_loss, reward_loss, policy_loss
+
+
+def unrolled_loss(graph, cfg, tensors, scalar_to_support=None, support_to_scalar=None):
+    """The training objective of one batch (trainer.py:140-243): initial inference + K recurrent steps, per-step
+    cross-entropies with the 0.5 gradient scale into the dynamics function and 1 / gradient_scale per sample, value loss
+    weight, PER importance weights, batch mean.  `tensors` = (observation [B,...], action [B,K+1] i64, target value /
+    reward [B,K+1], target policy [B,K+1,A], weight [B] | None, gradient scale [B,K+1]) on one device.
+    Returns (loss, value_loss [B], reward_loss [B], policy_loss [B], priorities [B,K+1]).
+    The codec callables default to this package's device kernels."""
+    scalar_to_support = scalar_to_support or models.scalar_to_support
+    support_to_scalar = support_to_scalar or models.support_to_scalar
+    observation_batch, action_batch, target_value_scalar, target_reward, target_policy, weight_batch, gradient_scale_batch = tensors
+    action_batch = action_batch.unsqueeze(-1)
+    target_value = scalar_to_support(target_value_scalar, cfg.support_size)
+    target_reward = scalar_to_support(target_reward, cfg.support_size)
+    priorities = torch.zeros_like(target_value_scalar)
+
+    value, reward, policy_logits, hidden_state = graph.initial(observation_batch)
+    predictions = [(value, reward, policy_logits)]
+    for i in range(1, action_batch.shape[1]):
+        value, reward, policy_logits, hidden_state = graph.recurrent(hidden_state, action_batch[:, i])
+        hidden_state.register_hook(lambda grad: grad * 0.5)        # gradient scale into the dynamics function
+        predictions.append((value, reward, policy_logits))
+
+    # the reference's per-step hooks all divide by the LAST column of gradient_scale_batch (late-binding closure,
+    # trainer.py:207-215); the columns of a row are equal by construction (replay_buffer.py:103-110)
+    gscale = gradient_scale_batch[:, action_batch.shape[1] - 1]
+    value, reward, policy_logits = predictions[0]
+    value_loss, _, policy_loss = loss_function(value, reward, policy_logits, target_value[:, 0], target_reward[:, 0], target_policy[:, 0])
+    reward_loss = torch.zeros_like(value_loss)
+    priorities[:, 0] = (support_to_scalar(value.detach(), cfg.support_size).reshape(-1) - target_value_scalar[:, 0]).abs() ** cfg.PER_alpha
+    for i in range(1, len(predictions)):
+        value, reward, policy_logits = predictions[i]
+        cv, cr, cp = loss_function(value, reward, policy_logits, target_value[:, i], target_reward[:, i], target_policy[:, i])
+        for x in (cv, cr, cp):
+            x.register_hook(lambda grad: grad / gscale)
+        value_loss = value_loss + cv
+        reward_loss = reward_loss + cr
+        policy_loss = policy_loss + cp
+        priorities[:, i] = (support_to_scalar(value.detach(), cfg.support_size).reshape(-1) - target_value_scalar[:, i]).abs() ** cfg.PER_alpha
+    loss = value_loss * cfg.value_loss_weight + reward_loss + policy_loss
+    if cfg.PER:
+        loss = loss * weight_batch
+    return loss.mean(), value_loss, reward_loss, policy_loss, priorities
+
+
+def training_graph(model, cfg):
+    """The differentiable forward of a `models.MuZeroNetwork` (autograd over its parameter-holder modules)."""
+    return _FcGraph(model) if cfg.network == "fullyconnected" else _ResnetGraph(model)
+
+
+# ------------------------------------------------------------------------------------------ trainer
+class Trainer:
+    def __init__(self, initial_checkpoint, config, device=None):
+        self.config = config
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError("Trainer: the B200 path has no CPU fallback")
+        numpy.random.seed(config.seed)
+        torch.manual_seed(config.seed)
+        self.model = models.MuZeroNetwork(config)
+        if initial_checkpoint.get("weights") is not None:
+            self.model.set_weights(initial_checkpoint["weights"])
+        self.model.to(self.device)
+        self.model.train()
+        self.training_step = int(initial_checkpoint.get("training_step", 0))
+        if config.optimizer not in ("Adam", "SGD"):
+            raise NotImplementedError(f"{config.optimizer} is not implemented. You can change the optimizer manually in trainer.py.")
+        self.graph = training_graph(self.model, config)
+        # flat buckets: parameters and gradients become views (the DDP bucket idea, for the whole model at once)
+        unused = set()
+        if config.network == "resnet" and config.downsample:        # never reached by forward (models.py:338-345):
+            r = self.model.representation_network.module             # torch.optim skips parameters without a gradient
+            unused = {id(p) for p in list(r.conv.parameters()) + list(r.bn.parameters())}
+        self.params = [p for p in self.model.parameters() if p.requires_grad and id(p) not in unused]
+        total = sum(p.numel() for p in self.params)
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            self.flat_param[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + n].view_as(p)
+            p.grad = self.flat_grad[off:off + n].view_as(p)
+            off += n
+        self.state1 = torch.zeros(total, dtype=torch.float32, device=self.device)        # Adam exp_avg / SGD momentum buffer
+        self.state2 = torch.zeros(total, dtype=torch.float32, device=self.device)        # Adam exp_avg_sq
+        self.opt_step = 0
+        self.lr = float(config.lr_init)
+        st = initial_checkpoint.get("optimizer_state")
+        if st is not None:
+            self.load_optimizer_state(st)
+
+    # -- optimiser state in torch.optim's state_dict format (shared_storage / model.checkpoint compatibility)
+    def optimizer_state(self):
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            if self.opt_step > 0:
+                if self.config.optimizer == "Adam":
+                    state[i] = {"step": torch.tensor(float(self.opt_step)), "exp_avg": self.state1[off:off + n].view_as(p).cpu().clone(),
+                                "exp_avg_sq": self.state2[off:off + n].view_as(p).cpu().clone()}
+                else:
+                    state[i] = {"momentum_buffer": self.state1[off:off + n].view_as(p).cpu().clone()}
+            off += n
+        group = {"lr": self.lr, "weight_decay": self.config.weight_decay, "params": list(range(len(self.params)))}
+        if self.config.optimizer == "Adam":
+            group.update(betas=(0.9, 0.999), eps=1e-8, amsgrad=False)
+        else:
+            group.update(momentum=self.config.momentum, dampening=0, nesterov=False)
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state(self, st):
+        off = 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            s = st["state"].get(i)
+            if s:
+                if "exp_avg" in s:
+                    self.state1[off:off + n].copy_(s["exp_avg"].reshape(-1))
+                    self.state2[off:off + n].copy_(s["exp_avg_sq"].reshape(-1))
+                    self.opt_step = int(float(s["step"]))
+                elif s.get("momentum_buffer") is not None:
+                    self.state1[off:off + n].copy_(s["momentum_buffer"].reshape(-1))
+                    self.opt_step = max(self.opt_step, 1)
+            off += n
+
+    # -- trainer.py:257-265
+    def update_lr(self):
+        self.lr = self.config.lr_init * self.config.lr_decay_rate ** (self.training_step / self.config.lr_decay_steps)
+
+    loss_function = staticmethod(loss_function)
+
+    # -- trainer.py:124-255
+    def update_weights(self, batch):
+        dev = self.device
+        t = lambda x, dt: None if x is None else torch.as_tensor(numpy.asarray(x) if not torch.is_tensor(x) else x).to(dev, dt)
+        observation_batch, action_batch, target_value, target_reward, target_policy, weight_batch, gradient_scale_batch = batch
+        tensors = (t(observation_batch, torch.float32), t(action_batch, torch.int64), t(target_value, torch.float32),
+                   t(target_reward, torch.float32), t(target_policy, torch.float32),
+                   t(weight_batch, torch.float32) if self.config.PER else None, t(gradient_scale_batch, torch.float32))
+        loss, value_loss, reward_loss, policy_loss, priorities = unrolled_loss(self.graph, self.config, tensors)
+        self.flat_grad.zero_()
+        loss.backward()
+        self._step()
+        self.training_step += 1
+        return priorities, loss.item(), value_loss.mean().item(), reward_loss.mean().item(), policy_loss.mean().item()
+
+    def _step(self):
+        """Gradient all-reduce over the ranks + one fused optimiser launch on the flat bucket."""
+        world = tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
+        if world > 1:
+            tdist.all_reduce(self.flat_grad, op=tdist.ReduceOp.SUM)
+        self.opt_step += 1
+        n, cfg = self.flat_param.numel(), self.config
+        with torch.cuda.device(self.device):
+            if cfg.optimizer == "Adam":
+                check(_lib.lib.mzb_adam_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.state1), ptr(self.state2), n,
+                                             self.lr, 0.9, 0.999, 1e-8, float(cfg.weight_decay), self.opt_step, 1.0 / world,
+                                             _lib.current_stream()))
+            else:
+                check(_lib.lib.mzb_sgd_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.state1), n, self.lr,
+                                            float(cfg.momentum), float(cfg.weight_decay), self.opt_step, 1.0 / world,
+                                            _lib.current_stream()))
+        self.model._synced = None          # the inference kernels re-pack the weights on their next call
+
+    # -- trainer.py:55-122 over plain get_info / set_info objects
+    def continuous_update_weights(self, replay_buffer, shared_storage, max_steps=None):
+        while shared_storage.get_info("num_played_games") < 1:
+            time.sleep(0.1)
+        done = 0
+        while self.training_step < self.config.training_steps and not shared_storage.get_info("terminate"):
+            index_batch, batch = replay_buffer.get_batch()
+            self.update_lr()
+            priorities, total_loss, value_loss, reward_loss, policy_loss = self.update_weights(batch)
+            if self.config.PER:
+                replay_buffer.update_priorities(priorities, index_batch)
+            if self.training_step % self.config.checkpoint_interval == 0:
+                shared_storage.set_info("weights", self.model.get_weights())
+                shared_storage.set_info("optimizer_state", self.optimizer_state())
+            for k, v in (("training_step", self.training_step), ("lr", self.lr), ("total_loss", total_loss),
+                         ("value_loss", value_loss), ("reward_loss", reward_loss), ("policy_loss", policy_loss)):
+                shared_storage.set_info(k, v)
+            done += 1
+            if max_steps is not None and done >= max_steps:
+                break
+            if self.config.training_delay:
+                time.sleep(self.config.training_delay)
+            if self.config.ratio:
+                while (self.training_step / max(1, shared_storage.get_info("num_played_steps")) > self.config.ratio
+                       and self.training_step < self.config.training_steps and not shared_storage.get_info("terminate")):
+                    time.sleep(0.5)

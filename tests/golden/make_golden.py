@@ -695,7 +695,65 @@ def gen_replay():
     print("replay.npz", os.path.getsize(os.path.join(HERE, "replay.npz")) // 1024, "KiB")
 
 
-FAMILIES = {"tree": gen_tree, "action": gen_action, "env": gen_env, "codec": gen_codec, "net": gen_net,
+def gen_trainer():
+    """Two consecutive steps of the UNMODIFIED reference Trainer.update_weights (trainer.py:124-255) on CPU: losses,
+    priorities and the updated weights, for a batch drawn by the reference ReplayBuffer."""
+    self_play, replay_buffer, trainer, models = ref_loader.load("self_play", "replay_buffer", "trainer", "models")
+    rs = np.random.RandomState(SEED + 11)
+    out = {}
+    orig_choice = np.random.choice
+    cases = [("cartpole", {}), ("tictactoe", {}), ("connect4", {"optimizer": "SGD", "blocks": 1, "channels": 16, "lr_init": 0.01}),
+             ("breakout", {"batch_size": 4, "num_unroll_steps": 2})]
+    try:
+        for ci, (cname, over) in enumerate(cases):
+            cfg = _ref_config(cname, **over)
+            cfg.batch_size = over.get("batch_size", 12)
+            cfg.train_on_gpu = False
+            A, players = len(cfg.action_space), len(cfg.players)
+            rb = replay_buffer.ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg)
+            np.random.choice = orig_choice
+            for _ in range(4):
+                T = int(rs.randint(3, min(cfg.max_moves, 30) + 1))
+                gh = self_play.GameHistory()
+                gh.action_history = [0] + rs.randint(A, size=T).tolist()
+                gh.reward_history = [0] + np.round(rs.uniform(-1, 2, T), 3).astype(np.float32).astype(np.float64).tolist()
+                gh.to_play_history = [int(i % players) for i in range(T + 1)]
+                gh.root_values = rs.normal(0, 3, T).tolist()
+                vis = rs.multinomial(cfg.num_simulations, rs.dirichlet([0.7] * A), size=T)
+                gh.child_visits = [[int(v) / int(row.sum()) if v else 0 for v in row] for row in vis]
+                gh.observation_history = [rs.uniform(0, 1, cfg.observation_shape).astype(np.float32) for _ in range(T + 1)]
+                rb.save_game(gh)
+            np.random.seed(ci)
+            index, batch = rb.get_batch()
+            torch.manual_seed(100 + ci)
+            model = models.MuZeroNetwork(cfg)
+            w0 = {k: v.clone() for k, v in model.state_dict().items()}
+            tr = trainer.Trainer({"weights": w0, "training_step": 0, "optimizer_state": None}, cfg)
+            pre = f"{ci}/"
+            out[pre + "game"] = np.array(cname)
+            out[pre + "over"] = np.array(repr(over))
+            for k, v in w0.items():
+                out[pre + "w0/" + k] = v.numpy()
+            names = ["observation", "action", "value", "reward", "policy", "weight", "gradient_scale"]
+            for nm, arr in zip(names, batch):
+                if arr is not None:
+                    out[pre + "batch/" + nm] = np.array(arr, dtype=np.float32 if nm != "action" else np.int64)
+            for step in range(2):
+                tr.update_lr()
+                pr, total, vl, rl, pl = tr.update_weights(batch)
+                out[pre + f"step{step}/losses"] = np.array([total, vl, rl, pl, tr.optimizer.param_groups[0]["lr"]], dtype=np.float64)
+                out[pre + f"step{step}/priorities"] = np.array(pr, dtype=np.float32)
+            for k, v in tr.model.state_dict().items():
+                out[pre + "w2/" + k] = v.detach().numpy()
+            print(cname, over, "losses", out[pre + "step0/losses"][:4], out[pre + "step1/losses"][:4])
+    finally:
+        np.random.choice = orig_choice
+    out["n"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(HERE, "trainer.npz"), **out)
+    print("trainer.npz", os.path.getsize(os.path.join(HERE, "trainer.npz")) // 1024, "KiB")
+
+
+FAMILIES = {"trainer": gen_trainer, "tree": gen_tree, "action": gen_action, "env": gen_env, "codec": gen_codec, "net": gen_net,
             "targets": gen_targets, "episode": gen_episode, "replay": gen_replay}
 
 if __name__ == "__main__":
