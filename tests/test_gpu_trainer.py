@@ -121,3 +121,41 @@ def test_flat_optimiser_kernel_equals_torch_optim(kind):
         else:
             _lib.check(_lib.lib.mzb_sgd_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(s1), n, lr, mom, wd, step, 1.0, _lib.current_stream()))
         torch.testing.assert_close(p, p_ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_self_play_replay_train_loop():
+    """The whole loop on one GPU with plain-object shared storage: batched self-play feeds the device replay store, the
+    trainer draws batches from it, writes priorities back and publishes weights, self-play picks them up."""
+    from muzero_hypermodel_b200.games.cartpole import MuZeroConfig
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    from muzero_hypermodel_b200.self_play import SelfPlay
+    from muzero_hypermodel_b200.trainer import Trainer
+    cfg = MuZeroConfig()
+    cfg.num_simulations, cfg.max_moves, cfg.batch_size, cfg.replay_buffer_size = 10, 40, 64, 512
+    cfg.checkpoint_interval, cfg.self_play_delay, cfg.training_delay, cfg.ratio = 2, 0, 0, None
+
+    class Storage:
+        def __init__(self):
+            self.info = {"training_step": 0, "terminate": False, "weights": None, "optimizer_state": None,
+                         "num_played_games": 0, "num_played_steps": 0}
+
+        def get_info(self, key):
+            return self.info[key]
+
+        def set_info(self, key, value=None):
+            self.info[key] = value
+
+    st = Storage()
+    sp = SelfPlay({"weights": None}, None, cfg, 1, n_games=128, device=DEV)
+    env, _ = sp._setup()
+    rb = ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg, device=DEV, record_env=env)
+    tr = Trainer({"weights": sp.model.get_weights(), "training_step": 0, "optimizer_state": None}, cfg, device=DEV)
+    w_before = {k: v.clone() for k, v in sp.model.get_weights().items()}
+    sp.continuous_self_play(st, rb, max_moves=45)
+    assert st.info["num_played_games"] >= 128 and len(rb) >= 128
+    tr.continuous_update_weights(rb, st, max_steps=6)
+    assert tr.training_step == 6 == st.info["training_step"] and np.isfinite(st.info["total_loss"])
+    assert st.info["weights"] is not None and st.info["optimizer_state"]["state"]
+    sp2 = SelfPlay({"weights": None}, None, cfg, 1, n_games=128, device=DEV)
+    sp2.continuous_self_play(st, rb, max_moves=2)           # refreshes the weights from the storage (self_play.py:37)
+    assert any(not torch.equal(w_before[k], v) for k, v in sp2.model.get_weights().items())
