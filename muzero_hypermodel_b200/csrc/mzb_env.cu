@@ -319,19 +319,26 @@ __global__ void k_act_step(EnvView e, const int* __restrict__ visits, const doub
 // Export placement of the finished games, in GAME ORDER (an ordered scan, not atomics: the ring contents - hence
 // everything downstream, e.g. the replay store's sampling - are reproducible from run to run).  One block.
 __global__ void __launch_bounds__(1024) k_harvest_plan(EnvView e, ExportView x) {
+  constexpr int ITEMS = 8;                                  // consecutive games per thread and pass
   __shared__ int s_e[32], s_g[32], s_base[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { s_base[0] = x.cursor[0]; s_base[1] = x.cursor[1]; }
   __syncthreads();
-  for (int g0 = 0; g0 < e.G; g0 += 1024) {
-    const int g = g0 + threadIdx.x;
-    const bool fin = g < e.G && e.finished[g];
-    const int len = fin ? e.h_len[g] : 0;
-    int ve = fin ? len + 1 : 0, vg = fin ? 1 : 0;          // inclusive warp scans
+  for (int g0 = 0; g0 < e.G; g0 += 1024 * ITEMS) {
+    const int gfirst = g0 + threadIdx.x * ITEMS;
+    int len[ITEMS];
+    int te = 0, tg = 0;                                     // this thread's totals
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int g = gfirst + k;
+      len[k] = (g < e.G && e.finished[g]) ? e.h_len[g] : -1;
+      if (len[k] >= 0) { te += len[k] + 1; tg += 1; }
+    }
+    int ve = te, vg = tg;                                   // inclusive scans over the threads of the block
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int te = __shfl_up_sync(0xFFFFFFFFu, ve, o), tg = __shfl_up_sync(0xFFFFFFFFu, vg, o);
-      if (lane >= o) { ve += te; vg += tg; }
+      const int ue = __shfl_up_sync(0xFFFFFFFFu, ve, o), ug = __shfl_up_sync(0xFFFFFFFFu, vg, o);
+      if (lane >= o) { ve += ue; vg += ug; }
     }
     if (lane == 31) { s_e[warp] = ve; s_g[warp] = vg; }
     __syncthreads();
@@ -339,20 +346,25 @@ __global__ void __launch_bounds__(1024) k_harvest_plan(EnvView e, ExportView x) 
       int we = s_e[lane], wg = s_g[lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int te = __shfl_up_sync(0xFFFFFFFFu, we, o), tg = __shfl_up_sync(0xFFFFFFFFu, wg, o);
-        if (lane >= o) { we += te; wg += tg; }
+        const int ue = __shfl_up_sync(0xFFFFFFFFu, we, o), ug = __shfl_up_sync(0xFFFFFFFFu, wg, o);
+        if (lane >= o) { we += ue; wg += ug; }
       }
       s_e[lane] = we; s_g[lane] = wg;
     }
     __syncthreads();
-    const int start = s_base[0] + (warp ? s_e[warp - 1] : 0) + ve - (fin ? len + 1 : 0);
-    const int gi = s_base[1] + (warp ? s_g[warp - 1] : 0) + vg - (fin ? 1 : 0);
-    if (fin) {
-      const bool ok = start + len + 1 <= x.cap_entries && gi < x.cap_games;
+    int start = s_base[0] + (warp ? s_e[warp - 1] : 0) + ve - te;
+    int gi = s_base[1] + (warp ? s_g[warp - 1] : 0) + vg - tg;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      if (len[k] < 0) continue;
+      const int g = gfirst + k;
+      const bool ok = start + len[k] + 1 <= x.cap_entries && gi < x.cap_games;
       x.plan[2 * g] = ok ? start : -1;
       x.plan[2 * g + 1] = gi;
-      if (ok) { x.game_start[gi] = start; x.game_len[gi] = len; x.game_slot[gi] = e.slot0 + (uint32_t)g; }
+      if (ok) { x.game_start[gi] = start; x.game_len[gi] = len[k]; x.game_slot[gi] = e.slot0 + (uint32_t)g; }
       else atomicAdd(e.counters + 3, 1ull);
+      start += len[k] + 1;
+      gi += 1;
     }
     __syncthreads();
     if (threadIdx.x == 0) { s_base[0] += s_e[31]; s_base[1] += s_g[31]; }
