@@ -12,11 +12,14 @@
 //     start address is shifted by (halo + dy*(W+2) + dx) rows.  The swizzle XOR is a function of the absolute
 //     shared-memory address bits (measured: every row shift is exact with descriptor base_offset = 0 for
 //     SWIZZLE_128B/64B/32B, tests/debug_conv_tc.py), so the im2col matrix is never materialised;
-//   * the B operand (weights [C_out][9*C_in], K-major) streams through a 4-stage TMA/mbarrier ring, each
-//     k-block feeding all MT accumulators (MT*C_out TMEM columns);
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2-5 = epilogue
-//     (tcgen05.ld 32x32b, scale/shift/plane/residual/ReLU, bf16 pack, 16-byte stores).
-// Rows that are pad positions compute garbage that is simply not stored (pads stay zero for the next layer).
+//   * the B operand (weights [C_out][9*C_in], K-major) stays resident in shared memory when it fits (loaded once
+//     per CTA) and streams through a 4-stage TMA/mbarrier ring otherwise, each k-block feeding all MT accumulators;
+//   * the kernel is persistent (one CTA per SM loops over super-tiles of MT tiles) and warp specialised:
+//     warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2-9 = two epilogue
+//     warpgroups (tcgen05.ld 32x32b, scale/shift/plane/residual/ReLU, bf16 pack, 16-byte stores), with the
+//     activation stages and the TMEM accumulators double buffered.
+// Rows that are pad positions compute garbage that is not stored (pads stay zero for the next layer) - or, in the
+// stem's ZP instantiation, are stored as zeros.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -82,15 +85,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
   asm volatile(

@@ -47,22 +47,6 @@ __global__ void k_gather_nhwc(const T* __restrict__ in, long long in_row_stride,
   *reinterpret_cast<uint4*>(out + geo_row(g, b, p / g.W, p % g.W) * g.C + c) = v;
 }
 
-// NHWC T in geometry g -> state rows in the requested layout: 0 NCHW fp32, 1 dense NHWC fp32, 2 dense NHWC bf16
-template <class T>
-__global__ void k_store_state(const T* __restrict__ in, int B, Geo g, int layout, void* __restrict__ out,
-                              long long out_row_stride, long long out_off) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int HW = g.H * g.W, C = g.C;
-  if (i >= (long long)B * HW * C) return;
-  const int c = (int)(i % C);
-  const int p = (int)((i / C) % HW);
-  const int b = (int)(i / ((long long)C * HW));
-  const float v = ldf(in + geo_row(g, b, p / g.W, p % g.W) * C + c);
-  if (layout == 0) ((float*)out)[b * out_row_stride + out_off + (long long)c * HW + p] = v;
-  else if (layout == 1) ((float*)out)[b * out_row_stride + out_off + (long long)p * C + c] = v;
-  else ((__nv_bfloat16*)out)[b * out_row_stride + out_off + (long long)p * C + c] = __float2bfloat16_rn(v);
-}
-
 // 3x3 convolution, padding 1, stride s, + folded batch-norm + residual + ReLU.  Direct fp32-accumulate form:
 // one thread per (position, output channel); x reads broadcast across the warp, weight reads coalesced.
 template <class T>
@@ -302,26 +286,6 @@ __global__ void __launch_bounds__(256) k_avgpool_pad(const __nv_bfloat16* __rest
     o[h] = *reinterpret_cast<const uint32_t*>(&pk);
   }
   *out = make_uint4(o[0], o[1], o[2], o[3]);
-}
-
-// per-(image, channel) min-max scaling over H*W with the +1e-5 guard (models.py:525-549, 571-595)
-template <class T>
-__global__ void k_minmax(const T* __restrict__ x, int B, Geo g, T* __restrict__ y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int C = g.C, HW = g.H * g.W;
-  if (i >= B * C) return;
-  const int b = i / C, c = i % C;
-  float lo = CUDART_INF_F, hi = -CUDART_INF_F;
-  for (int k = 0; k < HW; ++k) {
-    const float v = ldf(x + geo_row(g, b, k / g.W, k % g.W) * C + c);
-    lo = fminf(lo, v); hi = fmaxf(hi, v);
-  }
-  float scale = __fsub_rn(hi, lo);
-  if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
-  for (int k = 0; k < HW; ++k) {
-    const long long o = geo_row(g, b, k / g.W, k % g.W) * C + c;
-    stf(y + o, __fdiv_rn(__fsub_rn(ldf(x + o), lo), scale));
-  }
 }
 
 // Head: conv1x1(+bias) -> flatten (channel-major, like .view on NCHW) -> mlp -> logits -> decode.
