@@ -349,7 +349,10 @@ __global__ void __launch_bounds__(256) k_head(const T* __restrict__ x, int B, Ge
     if (proj) {
       // the 1x1 convolution was computed by the producing convolution's epilogue (mzb_conv_tc.cu): add the bias
       const float* pr = proj + (long long)b * proj_stride + proj_off;
-      for (int i = lane; i < hp.r * hp.hw; i += 32) bufA[i] = pr[i] + sm[L.b1 + i / hp.hw];
+      for (int rr = 0; rr < hp.r; ++rr) {
+        const float bias = sm[L.b1 + rr];
+        for (int i = lane; i < hp.hw; i += 32) bufA[rr * hp.hw + i] = pr[rr * hp.hw + i] + bias;
+      }
     } else
     for (int p0 = 0; p0 < hp.hw; p0 += PPI) {
       const int p = p0 + lane / LPP;
@@ -396,11 +399,13 @@ __global__ void __launch_bounds__(256) k_head(const T* __restrict__ x, int B, Ge
         // four interleaved partial sums: the dot products are short dependent FMA chains otherwise
         float a0 = sm[L.fb[l] + o], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
         int k = 0;
-        for (; k + 4 <= ni; k += 4) {
-          a0 = fmaf(in[k], w[k * no + o], a0);
-          a1 = fmaf(in[k + 1], w[(k + 1) * no + o], a1);
-          a2 = fmaf(in[k + 2], w[(k + 2) * no + o], a2);
-          a3 = fmaf(in[k + 3], w[(k + 3) * no + o], a3);
+        const float* wk = w + o;
+        for (; k + 4 <= ni; k += 4, wk += 4 * no) {
+          const float4 x4 = *reinterpret_cast<const float4*>(in + k);      // one broadcast load for four inputs
+          a0 = fmaf(x4.x, wk[0], a0);
+          a1 = fmaf(x4.y, wk[no], a1);
+          a2 = fmaf(x4.z, wk[2 * no], a2);
+          a3 = fmaf(x4.w, wk[3 * no], a3);
         }
         for (; k < ni; ++k) a0 = fmaf(in[k], w[k * no + o], a0);
         const float acc = (a0 + a1) + (a2 + a3);
@@ -513,7 +518,8 @@ __global__ void __launch_bounds__(256) k_minmax_store(const T* __restrict__ x, i
 
 // bf16 single-pass variant: one warp per image, lane = (row group, 16-byte channel chunk); the image's rows stay in
 // registers between the min/max reduction (shuffles across the row groups) and the rescale, so the activation is read
-// once with all loads in flight.  Same arithmetic as k_minmax_store.  C in {8,16,...,256} (C/8 a power of two).
+// once with all loads in flight.  The rescale multiplies by one reciprocal per channel (the fp32 path divides per
+// element like the reference; here the bf16 rounding of the result is 2^-9, the reciprocal's error 2^-23).  C in {8,16,...,256} (C/8 a power of two).
 template <int MAXIT>
 __global__ void __launch_bounds__(256) k_minmax_store_bf16(const __nv_bfloat16* __restrict__ x, int B, Geo g,
                                                            __nv_bfloat16* __restrict__ y, int layout, void* __restrict__ state,
@@ -523,13 +529,17 @@ __global__ void __launch_bounds__(256) k_minmax_store_bf16(const __nv_bfloat16* 
   const int nit = (HW + RPI - 1) / RPI;
   for (int b = blockIdx.x * warps + warp; b < B; b += gridDim.x * warps) {
     uint4 v[MAXIT];
+    long long ro[MAXIT];                                  // element offset of this lane's chunk, per iteration
     float lo[8], hi[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { lo[k] = CUDART_INF_F; hi[k] = -CUDART_INF_F; }
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int p = it * RPI + rg;
-      if (it < nit && p < HW) v[it] = *reinterpret_cast<const uint4*>(x + geo_row(g, b, p / g.W, p % g.W) * C + sub * 8);
+      if (it < nit && p < HW) {
+        ro[it] = geo_row(g, b, p / g.W, p % g.W) * C + sub * 8;
+        v[it] = *reinterpret_cast<const uint4*>(x + ro[it]);
+      }
     }
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
@@ -555,7 +565,7 @@ __global__ void __launch_bounds__(256) k_minmax_store_bf16(const __nv_bfloat16* 
     for (int k = 0; k < 8; ++k) {
       float scale = __fsub_rn(hi[k], lo[k]);
       if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
-      hi[k] = scale;
+      hi[k] = 1.0f / scale;                               // bf16 path: one reciprocal per channel, not a division per element
     }
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
@@ -566,13 +576,13 @@ __global__ void __launch_bounds__(256) k_minmax_store_bf16(const __nv_bfloat16* 
         uint32_t o4[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          f[2 * h] = __fdiv_rn(__fsub_rn(__uint_as_float(r4[h] << 16), lo[2 * h]), hi[2 * h]);
-          f[2 * h + 1] = __fdiv_rn(__fsub_rn(__uint_as_float(r4[h] & 0xFFFF0000u), lo[2 * h + 1]), hi[2 * h + 1]);
+          f[2 * h] = (__uint_as_float(r4[h] << 16) - lo[2 * h]) * hi[2 * h];
+          f[2 * h + 1] = (__uint_as_float(r4[h] & 0xFFFF0000u) - lo[2 * h + 1]) * hi[2 * h + 1];
           const __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
           o4[h] = *reinterpret_cast<const uint32_t*>(&pk);
         }
         const uint4 packed = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-        *reinterpret_cast<uint4*>(y + geo_row(g, b, p / g.W, p % g.W) * C + sub * 8) = packed;
+        *reinterpret_cast<uint4*>(y + ro[it]) = packed;
         if (state) {
           const int c = sub * 8;
           if (layout == 2) {
@@ -607,13 +617,17 @@ __global__ void __launch_bounds__(256) k_minmax_store_bf16_block(const __nv_bflo
   const int nit = (HW + RPB - 1) / RPB;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     uint4 v[MAXIT];
+    long long ro[MAXIT];
     float lo[8], hi[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { lo[k] = CUDART_INF_F; hi[k] = -CUDART_INF_F; }
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int p = it * RPB + rg;
-      if (it < nit && p < HW) v[it] = *reinterpret_cast<const uint4*>(x + geo_row(g, b, p / g.W, p % g.W) * C + sub * 8);
+      if (it < nit && p < HW) {
+        ro[it] = geo_row(g, b, p / g.W, p % g.W) * C + sub * 8;
+        v[it] = *reinterpret_cast<const uint4*>(x + ro[it]);
+      }
     }
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
@@ -647,7 +661,7 @@ __global__ void __launch_bounds__(256) k_minmax_store_bf16_block(const __nv_bflo
       for (int w2 = 0; w2 < 8; ++w2) { l = fminf(l, s_lo[w2][sub * 8 + k]); h = fmaxf(h, s_hi[w2][sub * 8 + k]); }
       float scale = __fsub_rn(h, l);
       if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
-      lo[k] = l; hi[k] = scale;
+      lo[k] = l; hi[k] = 1.0f / scale;
     }
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
@@ -658,13 +672,13 @@ __global__ void __launch_bounds__(256) k_minmax_store_bf16_block(const __nv_bflo
         uint32_t o4[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          f[2 * h] = __fdiv_rn(__fsub_rn(__uint_as_float(r4[h] << 16), lo[2 * h]), hi[2 * h]);
-          f[2 * h + 1] = __fdiv_rn(__fsub_rn(__uint_as_float(r4[h] & 0xFFFF0000u), lo[2 * h + 1]), hi[2 * h + 1]);
+          f[2 * h] = (__uint_as_float(r4[h] << 16) - lo[2 * h]) * hi[2 * h];
+          f[2 * h + 1] = (__uint_as_float(r4[h] & 0xFFFF0000u) - lo[2 * h + 1]) * hi[2 * h + 1];
           const __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
           o4[h] = *reinterpret_cast<const uint32_t*>(&pk);
         }
         const uint4 packed = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-        *reinterpret_cast<uint4*>(y + geo_row(g, b, p / g.W, p % g.W) * C + sub * 8) = packed;
+        *reinterpret_cast<uint4*>(y + ro[it]) = packed;
         if (state) {
           const int c = sub * 8;
           if (layout == 2) {
