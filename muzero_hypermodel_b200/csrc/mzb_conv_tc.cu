@@ -155,6 +155,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   float* s_proj = s_shift + N;             // [proj_r][N]
   const long long n_super = (a.rows_cover + (long long)MT * 128 - 1) / ((long long)MT * 128);
 
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as this grid's CTAs free
+  // their SMs (its prologue - barrier setup, TMEM allocation, weight loads - then overlaps this grid's tail); every
+  // thread that reads a predecessor's output executes griddepcontrol.wait first.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps);
@@ -186,6 +190,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (leader) tma_load_2d(smem_u32(sB + (size_t)kb * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full);
         }
       }
+      asm volatile("griddepcontrol.wait;" ::: "memory");      // the activations come from the preceding kernel
       long long ring = 0;
       int it = 0;
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
@@ -295,6 +300,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int i = 0; i < 4; ++i) if (i * 8 < cw) r[i] = __ldg(rp + i);
       }
     };
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // residual / plane reads below: earlier kernels' outputs
     int it = 0;
     for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
       const int s = it & 1;
@@ -466,6 +472,13 @@ bool make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t ou
             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// MZB_PDL=0 launches the convolutions without the programmatic-dependent-launch attribute (comparison knob)
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MZB_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
+}
+
 int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
 
 struct TcPlan { int kc, n_chunks, mt, tail_rows, b_resident, ncols; size_t smem; };
@@ -558,7 +571,13 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
       MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV, ZPV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       configured = true;                                                                                            \
     }                                                                                                               \
-    k_conv_tc<KCV, ZPV, PRV><<<grid, kThreads, p.smem, stream>>>(tmA, tmAtail, tmB, a);                             \
+    cudaLaunchConfig_t lc = {};                                                                                     \
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = p.smem; lc.stream = stream;        \
+    cudaLaunchAttribute la[1];                                                                                      \
+    la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                  \
+    la[0].val.programmaticStreamSerializationAllowed = 1;                                                           \
+    lc.attrs = la; lc.numAttrs = pdl_enabled() ? 1 : 0;                                                             \
+    MZB_CUDA(cudaLaunchKernelEx(&lc, k_conv_tc<KCV, ZPV, PRV>, tmA, tmAtail, tmB, a));                              \
   }
 #define LAUNCH_KC(KCV)                                                                                              \
   {                                                                                                                 \
