@@ -328,7 +328,10 @@ int mzb_resnet_conv_probe(mzb_resnet_model* m, int64_t B, void* d_workspace, siz
 /* Batched MCTS.run for residual networks (self_play.py:261-362): as mzb_search_fc, with the tree kernels and
  * the resnet layer program launched per simulation.  d_hidden_pool: caller-owned hidden-state slots
  * [G][tree capacity + 1][H*W*C] dense NHWC, bf16 (precision 1) or fp32 (precision 0);
- * d_workspace as for mzb_resnet_recurrent with batch G. */
+ * d_workspace as for mzb_resnet_recurrent with batch G.
+ * From the second call with an identical argument set (same handles and buffers - the self-play loop) the launch
+ * sequence of the whole search is captured once into a CUDA graph and replayed; everything that varies from move to
+ * move is read through the device pointers.  MZB_NO_GRAPH=1 in the environment disables this. */
 int mzb_search_resnet(mzb_tree* t, mzb_resnet_model* m, const float* d_obs, const uint8_t* d_legal,
                       const int8_t* d_to_play, const double* d_noise, double alpha, double frac, const uint32_t* d_slot,
                       const uint32_t* d_step, int32_t num_simulations, void* d_hidden_pool, void* d_workspace,
