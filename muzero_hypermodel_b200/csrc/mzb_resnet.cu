@@ -1103,7 +1103,8 @@ void prediction_and_state(Runner& r, int cur, Geo g, const Outputs& o, const uin
   if (o.value_logits || o.policy_logits || o.value || o.priors) {
     const int rv = m->value.r, rp = m->policy.r, hw = g.H * g.W;
     const TcProj pj{m->pv_w, r.proj(), rv + rp};
-    const int p = tower<T>(r, m->pred_blocks, g, cur, (sizeof(T) == 2 && m->pv_w && rv + rp <= 8) ? &pj : nullptr);
+    // narrow layers (C < 64) are epilogue-bound: there the heads keep their own (cheap) 1x1 convolution
+    const int p = tower<T>(r, m->pred_blocks, g, cur, (sizeof(T) == 2 && m->pv_w && rv + rp <= 8 && m->C >= 64) ? &pj : nullptr);
     const float* pr = r.proj_fused ? r.proj() : nullptr;
     head<T>(r, r.buf<T>(p), g, m->value, 0, nullptr, o.value_logits, o.value, nullptr, pr, (long long)(rv + rp) * hw, 0);
     head<T>(r, r.buf<T>(p), g, m->policy, 1, legal, o.policy_logits, nullptr, o.priors, pr, (long long)(rv + rp) * hw, rv * hw);
@@ -1252,7 +1253,7 @@ int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_r
   conv<T>(r, r.buf<T>(0), gl, m->dyn_conv, r.plane(), nullptr, 1, gl, r.buf<T>(1));           // DynamicsNetwork.forward :377-387
   const bool want_reward = o.reward_logits || o.reward;
   const TcProj pj{m->reward.w1x1, r.proj(), m->reward.r};
-  int cur = tower<T>(r, m->dyn_blocks, gl, 1, (sizeof(T) == 2 && want_reward && m->reward.r <= 8) ? &pj : nullptr);
+  int cur = tower<T>(r, m->dyn_blocks, gl, 1, (sizeof(T) == 2 && want_reward && m->reward.r <= 8 && m->C >= 64) ? &pj : nullptr);
   head<T>(r, r.buf<T>(cur), gl, m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr,    // reward on the un-normalised state
           r.proj_fused ? r.proj() : nullptr, (long long)m->reward.r * gl.H * gl.W, 0);
   const int nx = (cur + 1) % 3;
