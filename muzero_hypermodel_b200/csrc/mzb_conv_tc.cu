@@ -28,8 +28,8 @@
 namespace {
 
 constexpr int kStages = 4;
-constexpr int kEpiWarps = 8;                       // two epilogue warpgroups
-constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kEpiWarpsWide = 8;                   // two epilogue warpgroups: layers with C_out >= 64
+constexpr int kEpiWarpsNarrow = 16;                // four for narrow layers, whose pace the per-tile epilogue latency sets
 
 struct TcArgs {
   int B, H, W, Cin, Cout, R_img, mt, n_chunks, relu, ncols, tail_rows, b_resident, zero_pads;
@@ -123,11 +123,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 // ZP / PR: the rarely used epilogue features (pad-row zeroing of the stem; fused head projection with PR rows, a
 // compile-time count so the dot products are straight-line code) are separate instantiations, so the common layer
 // keeps its register allocation.
-template <int KC, bool ZP, int PR>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int KC, bool ZP, int PR, int kEpiWarps>
+__global__ void __launch_bounds__(64 + kEpiWarps * 32, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAtail,
           const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   constexpr int ROWB = KC * 2;                                           // bytes per shared-memory row
+  constexpr int kThreads = 64 + kEpiWarps * 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // warp index / TMEM base are broadcast through a shuffle so the compiler knows they are warp-uniform and keeps the
@@ -563,21 +564,31 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   const long long n_super = (a.rows_cover + (long long)p.mt * 128 - 1) / ((long long)p.mt * 128);
   const unsigned grid = (unsigned)(n_super < n_sm ? n_super : n_sm);      // persistent: one CTA per SM
   const int pr = (a.proj_r + 1) / 2 * 2;              // instantiated projection heights: 2, 4, 6, 8
+  static int narrow_on = -1;
+  if (narrow_on < 0) { const char* e = getenv("MZB_TC_NARROW_EPI"); narrow_on = (e && atoi(e) == 0) ? 0 : 1; }
+  const bool narrow = narrow_on && cp.cout <= 32;
   MZB_CHECK_ARG(!(zero_pads && pr), "pad zeroing and head projection are not combined");
-#define LAUNCH_ONE(KCV, ZPV, PRV)                                                                                   \
+#define LAUNCH_EW(KCV, ZPV, PRV, EWV)                                                                               \
   {                                                                                                                 \
     static bool configured = false;                                                                                 \
     if (!configured) {                                                                                              \
-      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV, ZPV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV, ZPV, PRV, EWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       configured = true;                                                                                            \
     }                                                                                                               \
     cudaLaunchConfig_t lc = {};                                                                                     \
-    lc.gridDim = dim3(grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = p.smem; lc.stream = stream;        \
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(64 + EWV * 32); lc.dynamicSmemBytes = p.smem; lc.stream = stream;   \
     cudaLaunchAttribute la[1];                                                                                      \
     la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                  \
     la[0].val.programmaticStreamSerializationAllowed = 1;                                                           \
     lc.attrs = la; lc.numAttrs = pdl_enabled() ? 1 : 0;                                                             \
-    MZB_CUDA(cudaLaunchKernelEx(&lc, k_conv_tc<KCV, ZPV, PRV>, tmA, tmAtail, tmB, a));                              \
+    MZB_CUDA(cudaLaunchKernelEx(&lc, k_conv_tc<KCV, ZPV, PRV, EWV>, tmA, tmAtail, tmB, a));                         \
+  }
+#define LAUNCH_ONE(KCV, ZPV, PRV)                                                                                   \
+  {                                                                                                                 \
+    if constexpr (PRV == 0) {                                                                                       \
+      if (narrow) LAUNCH_EW(KCV, ZPV, PRV, kEpiWarpsNarrow)                                                         \
+      else LAUNCH_EW(KCV, ZPV, PRV, kEpiWarpsWide)                                                                  \
+    } else LAUNCH_EW(KCV, ZPV, PRV, kEpiWarpsWide)                                                                  \
   }
 #define LAUNCH_KC(KCV)                                                                                              \
   {                                                                                                                 \
@@ -590,6 +601,7 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   }
   if (p.kc == 64) LAUNCH_KC(64) else if (p.kc == 32) LAUNCH_KC(32) else LAUNCH_KC(16)
 #undef LAUNCH_ONE
+#undef LAUNCH_EW
 #undef LAUNCH_KC
   MZB_LAUNCH_CHECK();
   return MZB_OK;
