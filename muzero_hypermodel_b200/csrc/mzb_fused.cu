@@ -119,6 +119,70 @@ __device__ __forceinline__ void priors_regs(const float (&logit)[A], const uint8
   for (int a = 0; a < A; ++a) p[a] = __fdiv_rn(p[a], sum);
 }
 
+// ---- vectorised tree accesses.  One thread owns one game, so every global access of a warp touches 32 different
+// lines: the load/store unit then needs one pass per lane and REQUEST COUNT, not bytes, is what the kernel pays for
+// (the scalar form issued ~100 requests per simulation and kept the L1 pipe ~70 % busy).  A node record is 24*A
+// contiguous bytes (mzb_tree.cuh), 16-byte aligned when A is even and 8-byte aligned otherwise; hidden states are
+// ENC contiguous floats.
+template <int A>
+struct Rec {
+  static constexpr int WORDS = 6 * A;                    // value_sum f64[A] | prior f32[A] | visit i32[A] | reward f32[A] | child i32[A]
+  uint32_t w[WORDS];
+  __device__ __forceinline__ void load(const uint8_t* r) {
+    if constexpr (A % 2 == 0) {
+      const uint4* p = reinterpret_cast<const uint4*>(r);
+#pragma unroll
+      for (int i = 0; i < WORDS / 4; ++i) { const uint4 q = p[i]; w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w; }
+    } else {
+      const uint2* p = reinterpret_cast<const uint2*>(r);
+#pragma unroll
+      for (int i = 0; i < WORDS / 2; ++i) { const uint2 q = p[i]; w[2 * i] = q.x; w[2 * i + 1] = q.y; }
+    }
+  }
+  __device__ __forceinline__ void store(uint8_t* r) const {
+    if constexpr (A % 2 == 0) {
+      uint4* p = reinterpret_cast<uint4*>(r);
+#pragma unroll
+      for (int i = 0; i < WORDS / 4; ++i) p[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    } else {
+      uint2* p = reinterpret_cast<uint2*>(r);
+#pragma unroll
+      for (int i = 0; i < WORDS / 2; ++i) p[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+    }
+  }
+  __device__ __forceinline__ double vs(int a) const { return __hiloint2double((int)w[2 * a + 1], (int)w[2 * a]); }
+  __device__ __forceinline__ float pr(int a) const { return __uint_as_float(w[2 * A + a]); }
+  __device__ __forceinline__ int vi(int a) const { return (int)w[3 * A + a]; }
+  __device__ __forceinline__ float rw(int a) const { return __uint_as_float(w[4 * A + a]); }
+  __device__ __forceinline__ int ch(int a) const { return (int)w[5 * A + a]; }
+  __device__ __forceinline__ void set(int a, double value_sum, float prior, int visit, float reward, int child) {
+    w[2 * a] = (uint32_t)__double2loint(value_sum); w[2 * a + 1] = (uint32_t)__double2hiint(value_sum);
+    w[2 * A + a] = __float_as_uint(prior); w[3 * A + a] = (uint32_t)visit; w[4 * A + a] = __float_as_uint(reward);
+    w[5 * A + a] = (uint32_t)child;
+  }
+};
+
+template <int N>
+__device__ __forceinline__ void load_floats(const float* __restrict__ p, float (&x)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) { const float4 q = reinterpret_cast<const float4*>(p)[i]; x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = p[i];
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_floats(float* __restrict__ p, const float (&x)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = x[i];
+  }
+}
+
 struct SearchIO {
   const float* obs; const uint8_t* legal; const int8_t* to_play; const double* noise;
   double alpha, frac;
@@ -164,13 +228,11 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
   float root_reward = 0.0f;
   if (active) {
     float ob[SH::OBS];
-#pragma unroll
-    for (int i = 0; i < SH::OBS; ++i) ob[i] = io.obs[(size_t)g * SH::OBS + i];
+    load_floats<SH::OBS>(io.obs + (size_t)g * SH::OBS, ob);
     float st[ENC];
     SH::Rep::run(pack + SH::OFF_REP, ob, -1, st);
     minmax_regs(st);
-#pragma unroll
-    for (int i = 0; i < ENC; ++i) hid[i] = st[i];
+    store_floats<ENC>(hid, st);
     float pl[A], pri[A];
     SH::Pol::run(pack + SH::OFF_POL, st, -1, pl);
     priors_regs<A>(pl, legal, pri);
@@ -184,15 +246,14 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
     for (int i = 0; i < FULL; ++i) zl[i] = (i == SH::SUP) ? 0.0f : -CUDART_INF_F;
     root_reward = s2s_regs<SH::SUP>(zl);
     // root record
-    uint8_t* r = t.rec(g, 0);
+    {
+      Rec<A> rr;
 #pragma unroll
-    for (int a = 0; a < A; ++a) {
-      const bool ok = !legal || legal[a];
-      t.value_sum(r)[a] = 0.0;
-      t.prior(r)[a] = ok ? pri[a] : 0.0f;
-      t.visit(r)[a] = 0;
-      t.reward(r)[a] = 0.0f;
-      t.child(r)[a] = ok ? MZB_CHILD_NONE : MZB_CHILD_ILLEGAL;
+      for (int a = 0; a < A; ++a) {
+        const bool ok = !legal || legal[a];
+        rr.set(a, 0.0, ok ? pri[a] : 0.0f, 0, 0.0f, ok ? MZB_CHILD_NONE : MZB_CHILD_ILLEGAL);
+      }
+      rr.store(t.rec(g, 0));
     }
     if (io.frac > 0.0) {
       const double keep = __dsub_rn(1.0, io.frac);
@@ -236,9 +297,11 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
     while (active) {
       uint8_t* r = t.rec(g, node);
       double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
+      {
+        Rec<A> rr;
+        rr.load(r);
 #pragma unroll
-      for (int a = 0; a < A; ++a) {
-        vs[a] = t.value_sum(r)[a]; pr[a] = t.prior(r)[a]; vi[a] = t.visit(r)[a]; rw[a] = t.reward(r)[a]; ch[a] = t.child(r)[a];
+        for (int a = 0; a < A; ++a) { vs[a] = rr.vs(a); pr[a] = rr.pr(a); vi[a] = rr.vi(a); rw[a] = rr.rw(a); ch[a] = rr.ch(a); }
       }
       const double pbc0 = PB_LUT ? 0.0 : lut[N];
       const double sqrtN = PB_LUT ? 0.0 : __dsqrt_rn((double)N);
@@ -288,9 +351,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
     float value, reward, pri[A];
     {
       float st[ENC];
-      const float* hp = hid + (size_t)node * ENC;
-#pragma unroll
-      for (int i = 0; i < ENC; ++i) st[i] = hp[i];
+      load_floats<ENC>(hid + (size_t)node * ENC, st);
       float nx[ENC];
       SH::Dyn::run(pack + SH::OFF_DYN, st, action, nx);
       {
@@ -299,9 +360,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
         reward = s2s_regs<SH::SUP>(rl);
       }
       minmax_regs(nx);
-      float* ho = hid + (size_t)fresh * ENC;
-#pragma unroll
-      for (int i = 0; i < ENC; ++i) ho[i] = nx[i];
+      store_floats<ENC>(hid + (size_t)fresh * ENC, nx);
       {
         float pl[A];
         SH::Pol::run(pack + SH::OFF_POL, nx, -1, pl);
@@ -316,12 +375,10 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
 
     // ---------------- expand (self_play.py:346-352)
     {
-      uint8_t* r = t.rec(g, fresh);
+      Rec<A> rr;
 #pragma unroll
-      for (int a = 0; a < A; ++a) {
-        t.value_sum(r)[a] = 0.0; t.prior(r)[a] = pri[a]; t.visit(r)[a] = 0; t.reward(r)[a] = 0.0f;
-        t.child(r)[a] = MZB_CHILD_NONE;
-      }
+      for (int a = 0; a < A; ++a) rr.set(a, 0.0, pri[a], 0, 0.0f, MZB_CHILD_NONE);
+      rr.store(t.rec(g, fresh));
       uint8_t* pr_ = t.rec(g, node);
       t.reward(pr_)[action] = reward;
       t.child(pr_)[action] = fresh;
