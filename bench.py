@@ -14,8 +14,11 @@ parameters); observations come from the device CartPole-v1 environments (synthet
 JSON line keys: see the task contract; `value` = simulations/s over all GPUs with state resident in HBM,
 `e2e` = the same searches driven through the batched MCTS.run entry point with HOST observation /
 legal-action / to-play buffers (pinned H2D before, D2H of visit counts + root values after, every step),
-`roofline` = the whole-search kernel against the measured HBM copy peak, `cpu_baseline` = the oracle
-port of SelfPlay.play_game on the host cores (bounded sample).
+`roofline` = the dominant kernel alone, timed live with CUDA events: the whole-search kernel against the measured
+HBM copy peak (FC workloads; `traffic` = DRAM bytes per launch from the committed ncu capture), or the tower's
+C->C tcgen05 convolution replayed from a CUDA graph against the measured bf16 burst peak (resnet workloads;
+`roofline.whole_search` keeps the all-in figure), `cpu_baseline` = the oracle port of SelfPlay.play_game on the
+host cores (bounded sample), `collectives` (N > 1) = device time of the two learner-side collectives.
 """
 import argparse
 import json
