@@ -247,13 +247,29 @@ def main():
     is_fc = cfg.network == "fullyconnected"
     fused = is_fc and bool(_lib.lib.mzb_search_fc_is_fused(sp.model.handle())) and not args.modular
 
+    # the games self-play finishes are consumed like in the real pipeline: every 4th move the export ring is ingested,
+    # device to device, by the replay store (one 8-byte D2H + the per-game table per ingest)
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    try:
+        rb = ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg, device=dev, record_env=env)
+    except NotImplementedError:                    # synthetic frames are regenerated, not stored
+        rb = None
+    moves = [0]
+
     def step():
         sp.step(temperature=1.0, temperature_threshold=None, add_exploration_noise=True, export=True,
                 allow_fused=not args.modular)
+        moves[0] += 1
+        if rb is not None and moves[0] % 4 == 0:
+            rb.ingest(env)
 
     for _ in range(args.warmup):
         step()
-    sp.drain()
+    if rb is not None:
+        rb.ingest(env)
+    else:
+        sp.drain()
+    ingested0 = rb.num_played_games if rb is not None else 0
     mcts.tree.counters(reset=True)
     barrier()
 
@@ -278,7 +294,11 @@ def main():
     value = sims_total / (ms * 1e-3)
     env_steps = args.steps * G * world / (ms * 1e-3)
     mean_path = tc["path_length_sum"] / max(1, tc["simulations"])
-    finished = sp.drain()
+    if rb is not None:
+        rb.ingest(env)
+        ingested = rb.num_played_games - ingested0
+    else:
+        ingested = len(sp.drain())
 
     # ---------------- the dominant kernel alone: search launches timed with events (same inputs every launch;
     # the tree store it streams through is G*(S+1)*(24A + 4H) bytes >> L2, no L2 flush needed)
@@ -423,7 +443,8 @@ def main():
                 "env_steps_per_sec": env_steps, "e2e": e2e, "roofline": roofline, "gpu_launches": launches,
                 "clocks": clocks, "mean_search_path_nodes": L,
                 "games_finished_in_timed_region": c1["games"] - c0["games"],
-                "games_dropped": c1["dropped_games"] - c0["dropped_games"], "games_exported_after": len(finished)}
+                "games_dropped": c1["dropped_games"] - c0["dropped_games"],
+                "games_ingested_by_replay_store": ingested}
         if collectives is not None:
             line["collectives"] = collectives
         if cpu is not None:

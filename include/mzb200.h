@@ -348,6 +348,7 @@ int mzb_search_resnet(mzb_tree* t, mzb_resnet_model* m, const float* d_obs, cons
  * element and draw, injected (d_u_*) or Philox(seed; slot = element, step = batch counter; MZB_STREAM_RGAME/RPOS).
  * ------------------------------------------------------------------------------------------- */
 typedef struct mzb_replay mzb_replay;
+#define MZB_REPLAY_MAX_SAVE 65536   /* games per mzb_replay_save_games call */
 typedef struct {
   int32_t n_actions;         /* len(config.action_space)                                      */
   int32_t obs_floats;        /* floats per stored observation record (stacked_observations = 0) */

@@ -620,8 +620,8 @@ int mzb_env_export_to_replay(mzb_env* e, mzb_replay* r, int32_t* h_n_games, void
     MZB_CUDA(cudaMemcpyAsync(start.data(), e->x.game_start, (size_t)ng * 4, cudaMemcpyDeviceToHost, s));
     MZB_CUDA(cudaMemcpyAsync(len.data(), e->x.game_len, (size_t)ng * 4, cudaMemcpyDeviceToHost, s));
     MZB_CUDA(cudaStreamSynchronize(s));
-    for (int g0 = 0; g0 < ng; g0 += 1024) {
-      const int n = ng - g0 < 1024 ? ng - g0 : 1024;
+    for (int g0 = 0; g0 < ng; g0 += MZB_REPLAY_MAX_SAVE) {
+      const int n = ng - g0 < MZB_REPLAY_MAX_SAVE ? ng - g0 : MZB_REPLAY_MAX_SAVE;
       const int rc = mzb_replay_save_games(r, n, start.data() + g0, len.data() + g0, e->x.obs, e->x.action, e->x.reward,
                                            e->x.to_play, e->x.root_value, e->x.visits, nullptr, stream);
       if (rc) return rc;

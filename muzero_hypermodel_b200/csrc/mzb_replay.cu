@@ -335,7 +335,7 @@ Layout replay_layout(const mzb_replay_config& c) {
   L.b_slot = take((size_t)c.max_batch * sizeof(int));
   L.b_step = take((size_t)c.max_batch * sizeof(uint32_t));
   L.b_w = take((size_t)c.max_batch * sizeof(float));
-  L.meta = take((size_t)3 * 1024 * sizeof(int));
+  L.meta = take((size_t)3 * MZB_REPLAY_MAX_SAVE * sizeof(int));
   L.total = off;
   return L;
 }
@@ -375,7 +375,7 @@ int mzb_replay_create(mzb_replay** out, const mzb_replay_config* c, void* d_work
   v.K = c->num_unroll_steps; v.td = c->td_steps; v.per = c->per; v.max_batch = c->max_batch; v.alpha = c->per_alpha;
   v.key = rng_key(c->seed);
   r->d_meta = (int*)(w + L.meta);
-  r->max_save = 1024;
+  r->max_save = MZB_REPLAY_MAX_SAVE;
   r->h_len.assign((size_t)c->capacity_games, 0);
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemcpyAsync(v.discount_pow, h_discount_pow, sizeof(double) * (c->td_steps + 1), cudaMemcpyHostToDevice, s);
@@ -418,11 +418,17 @@ int mzb_replay_save_games(mzb_replay* r, int32_t n_games, const int32_t* h_src_s
     r->total_samples += h_len[g];
     meta[g] = h_src_start[g]; meta[n_games + g] = h_len[g]; meta[2 * n_games + g] = slot;
   }
-  MZB_CUDA(cudaMemcpyAsync(r->d_meta, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice, s));
-  MZB_CUDA(cudaStreamSynchronize(s));                     // `meta` is a stack-lifetime staging buffer
-  SaveArgs a{d_obs, d_action, d_reward, d_to_play, d_root_value, d_visits, d_priorities, r->d_meta, r->d_meta + n_games,
-             r->d_meta + 2 * n_games};
-  k_replay_save<<<n_games, 256, 0, s>>>(r->v, a);
+  // more games than slots in one call: the early ones are evicted by the later ones of the same call (the counters
+  // above already say so) - only the last `capacity` games are materialised, so no two blocks write one slot
+  const int first = n_games > r->cfg.capacity_games ? n_games - r->cfg.capacity_games : 0, n_copy = n_games - first;
+  std::vector<int> packed((size_t)3 * n_copy);
+  for (int g = 0; g < n_copy; ++g)
+    for (int k = 0; k < 3; ++k) packed[(size_t)k * n_copy + g] = meta[(size_t)k * n_games + first + g];
+  MZB_CUDA(cudaMemcpyAsync(r->d_meta, packed.data(), sizeof(int) * packed.size(), cudaMemcpyHostToDevice, s));
+  MZB_CUDA(cudaStreamSynchronize(s));                     // `packed` is a stack-lifetime staging buffer
+  SaveArgs a{d_obs, d_action, d_reward, d_to_play, d_root_value, d_visits, d_priorities, r->d_meta, r->d_meta + n_copy,
+             r->d_meta + 2 * n_copy};
+  k_replay_save<<<n_copy, 256, 0, s>>>(r->v, a);
   MZB_LAUNCH_CHECK();
   r->cdf_valid = false;
   return MZB_OK;

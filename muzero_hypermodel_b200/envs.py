@@ -58,7 +58,8 @@ class VectorEnv:
         if export_games is None:
             export_games = max(1024, self.G)
         if export_entries is None:
-            export_entries = int(min(2 ** 30, max(4 * (self.max_moves + 1), self.G * min(self.max_moves + 1, 32))))
+            # worst case: every game ends in the same step with a full-length history (cartpole: 262,144 x 501 entries, 5 GB)
+            export_entries = int(min(2 ** 30, max(4 * (self.max_moves + 1), self.G * (self.max_moves + 1))))
         self.cfg = EnvConfig(KINDS[kind], self.G, self.max_moves, int(export_entries), int(export_games),
                              int(first_slot), int(seed) & 0xFFFFFFFFFFFFFFFF)
         nbytes = _lib.lib.mzb_env_workspace_bytes(C.byref(self.cfg))

@@ -242,3 +242,34 @@ def test_reanalyse_replaces_bootstrap_values():
                                               cfg.discount, 2, reanalysed_root_values=[float(x) for x in fresh],
                                               pad_action=lambda row: int(act[b, row]))
         assert np.array(ev, dtype=np.float64).tobytes() == val[b].cpu().numpy().tobytes(), (b, pos)
+
+
+def test_one_call_with_more_games_than_slots_equals_sequential_saves():
+    """save_games_device with 9 games into 5 slots in ONE call = 9 sequential save_game calls (FIFO eviction inside the
+    call, no two games racing for a slot): same counters, same priorities, same batches."""
+    rb_seq, cfg = make(1)
+    rb_one, _ = make(1)
+    games = [load_game(1, gi) for gi in range(9)]
+    for g in games:
+        rb_seq.save_game(g)
+    A = len(cfg.action_space)
+    obs, act, rew, tp, rv, vis, start, length = [], [], [], [], [], [], [], []
+    for g in games:
+        n = len(g.root_values)
+        start.append(sum(len(x) for x in act)); length.append(n)
+        obs.append(np.stack([np.asarray(o, dtype=np.float32).reshape(-1) for o in g.observation_history]))
+        act.append(np.array(g.action_history, dtype=np.int32)); rew.append(np.array(g.reward_history, dtype=np.float32))
+        tp.append(np.array(g.to_play_history, dtype=np.int8)); rv.append(np.concatenate([g.root_values, [0.0]]))
+        counts = np.rint(np.array(g.child_visits) * cfg.num_simulations).astype(np.uint16)
+        vis.append(np.concatenate([counts, np.zeros((1, A), dtype=np.uint16)]))
+    dev = lambda x, dt: torch.as_tensor(np.concatenate(x)).to(DEV, dt).contiguous()
+    rb_one.save_games_device(start, length, dev(obs, torch.float32), dev(act, torch.int32), dev(rew, torch.float32),
+                             dev(tp, torch.int8), dev(rv, torch.float64), torch.from_numpy(np.concatenate(vis)).to(DEV))
+    assert rb_one._info() == rb_seq._info() and len(rb_one) == 5
+    first = rb_one._info()[4]
+    for gid in range(first, first + 5):
+        a, b = rb_one.game_priorities(gid), rb_seq.game_priorities(gid)
+        assert a[0].tobytes() == b[0].tobytes() and np.float32(a[1]).tobytes() == np.float32(b[1]).tobytes()
+    ia, ba = rb_one.get_batch()
+    ib, bb = rb_seq.get_batch()
+    assert torch.equal(ia, ib) and all(torch.equal(x, y) for x, y in zip(ba, bb))
