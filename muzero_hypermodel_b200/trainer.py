@@ -226,6 +226,8 @@ class Trainer:
         self.state2 = torch.zeros(total, dtype=torch.float32, device=self.device)        # Adam exp_avg_sq
         self.opt_step = 0
         self.lr = float(config.lr_init)
+        self.use_cuda_graph = True
+        self._graphs = {}
         st = initial_checkpoint.get("optimizer_state")
         if st is not None:
             self.load_optimizer_state(st)
@@ -278,12 +280,51 @@ class Trainer:
         tensors = (t(observation_batch, torch.float32), t(action_batch, torch.int64), t(target_value, torch.float32),
                    t(target_reward, torch.float32), t(target_policy, torch.float32),
                    t(weight_batch, torch.float32) if self.config.PER else None, t(gradient_scale_batch, torch.float32))
-        loss, value_loss, reward_loss, policy_loss, priorities = unrolled_loss(self.graph, self.config, tensors)
-        self.flat_grad.zero_()
-        loss.backward()
+        loss, value_loss, reward_loss, policy_loss, priorities = self._forward_backward(tensors)
         self._step()
         self.training_step += 1
         return priorities, loss.item(), value_loss.mean().item(), reward_loss.mean().item(), policy_loss.mean().item()
+
+    def _forward_backward(self, tensors):
+        """Gradients of one batch into the flat bucket.  The unrolled graph is hundreds of small kernels (launch-bound:
+        13 ms per cartpole step eagerly), so from the second batch of a given shape on it is replayed from a CUDA graph
+        captured over static input buffers; the optimiser launch stays outside (its step count and learning rate
+        are host scalars)."""
+        sig = tuple(None if t is None else (tuple(t.shape), t.dtype) for t in tensors)
+        st = self._graphs.get(sig) if self.use_cuda_graph else None
+        if st is None:
+            self.flat_grad.zero_()
+            out = unrolled_loss(self.graph, self.config, tensors)
+            out[0].backward()
+            if self.use_cuda_graph:
+                self._graphs[sig] = "seen"
+            return out
+        if st == "seen":
+            static = [None if t is None else t.clone() for t in tensors]
+            # capture needs a few warm-up passes on a side stream (cuDNN plans, allocator pools); they must not count
+            # as training passes: batch-norm running statistics are restored afterwards
+            buffers = [b.clone() for b in self.model.buffers()]
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.flat_grad.zero_()
+                    unrolled_loss(self.graph, self.config, static)[0].backward()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.flat_grad.zero_()
+                out = unrolled_loss(self.graph, self.config, static)
+                out[0].backward()
+            for b, saved in zip(self.model.buffers(), buffers):
+                b.copy_(saved)
+            st = self._graphs[sig] = (g, static, out)
+        g, static, out = st
+        for dst, src in zip(static, tensors):
+            if dst is not None:
+                dst.copy_(src)
+        g.replay()
+        return out
 
     def _step(self):
         """Gradient all-reduce over the ranks + one fused optimiser launch on the flat bucket."""
