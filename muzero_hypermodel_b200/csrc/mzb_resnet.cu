@@ -741,7 +741,7 @@ static bool init_conv(mzb_resnet_model* m, ConvParams& c, int cin, int cout, int
 }
 
 static bool init_head(mzb_resnet_model* m, HeadParams& h, int cin, int r, int hw, const int32_t* hidden, int n_hidden, int out) {
-  h.cin = cin; h.r = r; h.hw = hw; h.out = out; h.n_fc = n_hidden + 1;
+  h.cin = cin; h.r = r; h.hw = hw; h.out = out; h.n_fc = n_hidden + 1; h.mma = nullptr;
   h.w1x1 = (float*)dev_alloc(m, sizeof(float) * (size_t)r * cin);
   h.b1x1 = (float*)dev_alloc(m, sizeof(float) * r);
   int cur = r * hw;
@@ -825,6 +825,7 @@ int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* c) {
 int mzb_resnet_destroy(mzb_resnet_model* m) {
   if (!m) return MZB_OK;
   mzb_search_graph_forget(m);
+  for (HeadParams* h : {&m->reward, &m->value, &m->policy}) if (h->mma) { mzb_head_mma_free(h->mma); h->mma = nullptr; }
   for (void* p : m->allocs) cudaFree(p);
   delete m;
   return MZB_OK;
@@ -940,7 +941,8 @@ bool load_1x1(Cursor& cur, HeadParams& h) {
   if (cur.bad) return false;
   return upload(h.w1x1, w, sizeof(float) * h.r * h.cin) && upload(h.b1x1, b, sizeof(float) * h.r);
 }
-bool load_fc(Cursor& cur, HeadParams& h) {
+bool load_fc(Cursor& cur, HeadParams& h, mzb_resnet_model* m) {
+  std::vector<std::vector<float>> w_host, b_host;
   for (int l = 0; l < h.n_fc; ++l) {
     const float* w = cur.take((int64_t)h.fc_in[l] * h.fc_out[l]); const float* b = cur.take(h.fc_out[l]);
     if (cur.bad) return false;
@@ -948,6 +950,12 @@ bool load_fc(Cursor& cur, HeadParams& h) {
     for (int o = 0; o < h.fc_out[l]; ++o)
       for (int k = 0; k < h.fc_in[l]; ++k) wt[(size_t)k * h.fc_out[l] + o] = w[(size_t)o * h.fc_in[l] + k];
     if (!upload(h.fc_w[l], wt.data(), sizeof(float) * wt.size()) || !upload(h.fc_b[l], b, sizeof(float) * h.fc_out[l])) return false;
+    w_host.push_back(std::move(wt));
+    b_host.emplace_back(b, b + h.fc_out[l]);
+  }
+  if (m->precision == 1) {                                // bf16 path: the mlp also goes to the tensor-core head kernel
+    void* pk = h.mma;
+    if (mzb_head_mma_pack(m, h, w_host, b_host, &pk)) h.mma = pk; else { mzb_head_mma_free(pk); h.mma = nullptr; }
   }
   return true;
 }
@@ -978,9 +986,9 @@ extern "C" int mzb_resnet_set_weights(mzb_resnet_model* m, const float* const* h
   for (auto& b : m->rep_blocks) ok = ok && load_block(cur, b);
   ok = ok && load_conv(cur, m->dyn_conv, true, m->Hl, m->Wl);
   for (auto& b : m->dyn_blocks) ok = ok && load_block(cur, b);
-  ok = ok && load_1x1(cur, m->reward) && load_fc(cur, m->reward);
+  ok = ok && load_1x1(cur, m->reward) && load_fc(cur, m->reward, m);
   for (auto& b : m->pred_blocks) ok = ok && load_block(cur, b);
-  ok = ok && load_1x1(cur, m->value) && load_1x1(cur, m->policy) && load_fc(cur, m->value) && load_fc(cur, m->policy);
+  ok = ok && load_1x1(cur, m->value) && load_1x1(cur, m->policy) && load_fc(cur, m->value, m) && load_fc(cur, m->policy, m);
   ok = ok && cudaMemcpy(m->pv_w, m->value.w1x1, sizeof(float) * m->value.r * m->C, cudaMemcpyDeviceToDevice) == cudaSuccess &&
        cudaMemcpy(m->pv_w + (size_t)m->value.r * m->C, m->policy.w1x1, sizeof(float) * m->policy.r * m->C, cudaMemcpyDeviceToDevice) == cudaSuccess;
   if (!ok || cur.bad || cur.i != n_tensors) {
@@ -1043,6 +1051,10 @@ template <class T>
 void head(Runner& r, const T* x, Geo g, const HeadParams& hp, int mode, const uint8_t* legal, float* logits,
           float* scalar, float* priors, const float* proj = nullptr, long long proj_stride = 0, int proj_off = 0) {
   if (r.rc || (!logits && !scalar && !priors)) return;
+  if (sizeof(T) == 2 && hp.mma && proj && mzb_conv_tc_enabled()) {     // bf16 path: mlp on the tensor cores
+    r.rc = mzb_head_mma_launch(hp.mma, proj, proj_stride, proj_off, r.B, r.m->S, mode, legal, logits, scalar, priors, r.s);
+    return;
+  }
   const int warps = 8;
   const size_t smem = sizeof(float) * (size_t)head_smem(hp, warps).total;
   static bool configured = false;

@@ -50,6 +50,7 @@ struct HeadParams {
   float* fc_w[4];                 // [in][out]: transposed at set_weights so lanes = outputs read consecutive floats
   float* fc_b[4];
   int out;                        // logits width
+  void* mma;                      // bf16 path: the mlp packed for the tensor-core head kernel (mzb_head_mma.cu), or NULL
 };
 
 struct Block { ConvParams c1, c2; };

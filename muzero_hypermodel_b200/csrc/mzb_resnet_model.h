@@ -27,3 +27,10 @@ struct TcProj { const float* w; float* out; int r; };   // fused 1x1 head projec
 int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
                        const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream, int zero_pads = 0,
                        const TcProj* proj = nullptr);
+
+// head mlp on mma.sync (mzb_head_mma.cu); w_host[l] = fc weights [in][out] fp32 on the host
+bool mzb_head_mma_pack(mzb_resnet_model* m, const HeadParams& hp, const std::vector<std::vector<float>>& w_host,
+                       const std::vector<std::vector<float>>& b_host, void** opaque);
+void mzb_head_mma_free(void* opaque);
+int mzb_head_mma_launch(void* opaque, const float* proj, long long proj_stride, int proj_off, int B, int S, int mode,
+                        const uint8_t* legal, float* logits, float* scalar, float* priors, cudaStream_t stream);
