@@ -22,8 +22,10 @@ It restates, on the CPU, the algorithms of the reference hot path
                       support codec (models.py:641-685).
 * `oracle.targets`  - compute_target_value / make_target (replay_buffer.py:222-295).
 * `oracle.selfplay` - play_game episode loop (self_play.py:110-184).
-* `oracle/csrc`     - a plain-C restatement of the FC search used as the strong
-                      multi-threaded CPU baseline.
+* `oracle.replay`   - ReplayBuffer save_game / get_batch / update_priorities
+                      (replay_buffer.py:33-220), incl. numpy's float32 pairwise sum.
+* `oracle.cpu_baseline` - the port timed as the CPU baseline (one process per host
+                      core, batch-1 numpy network).
 
 Parity pinning: the reference ships no tests or golden vectors, so
 the oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, produced in the

@@ -1,6 +1,6 @@
 """Generate the committed golden vectors by running the UNMODIFIED reference (build container only).
 
-    python tests/golden/make_golden.py [family ...]      families: tree env codec net targets action episode
+    python tests/golden/make_golden.py [family ...]      families: tree env codec net targets action episode replay trainer
 
 The reference ships no tests or golden vectors, so every fixture here is an
 output of the reference's own code under /root/reference, imported through
