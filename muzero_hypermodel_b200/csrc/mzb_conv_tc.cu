@@ -4,12 +4,12 @@
 // DynamicsNetwork's first convolution with the action plane (:363, :551-568).
 //
 // Formulation.  Activations live in the PADDED NHWC layout of mzb_resnet.cuh: flat rows of C channels,
-// (H+1)*(W+2) rows per image with zero pad rows, so the 3x3 neighbour (dy,dx) of EVERY row is the row at
-// flat offset dy*(W+2)+dx.  One CTA owns MT tiles of 128 consecutive rows (M = 128 per UMMA):
+// (H+1)*(W+1) rows per image with zero pad rows, so the 3x3 neighbour (dy,dx) of EVERY row is the row at
+// flat offset dy*(W+1)+dx.  One CTA owns MT tiles of 128 consecutive rows (M = 128 per UMMA):
 //   * TMA loads the rows [m0 - halo, m0 + MT*128 + halo) ONCE into shared memory (SWIZZLE_128B/64B/32B by
 //     channel-chunk width) - the input is read from L2/HBM once, not once per tap;
 //   * the A operand of tap (dy,dx) is the SAME shared-memory tile addressed through a UMMA descriptor whose
-//     start address is shifted by (halo + dy*(W+2) + dx) rows.  The swizzle XOR is a function of the absolute
+//     start address is shifted by (halo + dy*(W+1) + dx) rows.  The swizzle XOR is a function of the absolute
 //     shared-memory address bits (measured: every row shift is exact with descriptor base_offset = 0 for
 //     SWIZZLE_128B/64B/32B, tests/debug_conv_tc.py), so the im2col matrix is never materialised;
 //   * the B operand (weights [C_out][9*C_in], K-major) stays resident in shared memory when it fits (loaded once
@@ -134,7 +134,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // warp index / TMEM base are broadcast through a shuffle so the compiler knows they are warp-uniform and keeps the
   // role loops (addresses, descriptors, barrier phases) in uniform registers
   const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int MT = a.mt, N = a.Cout, halo = a.W + 3;
+  const int MT = a.mt, N = a.Cout, halo = geo_halo(a.W);
   const int a_rows = MT * 128 + a.tail_rows;
   const uint32_t a_chunk_bytes = (uint32_t)a_rows * ROWB;
   const uint32_t a_stage_bytes = (uint32_t)a.n_chunks * a_chunk_bytes;
@@ -252,7 +252,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             ++ring;
           }
           const int tap = kb / a.n_chunks, j = kb - tap * a.n_chunks;
-          const int shift = (tap / 3 - 1) * (a.W + 2) + (tap % 3 - 1);
+          const int shift = (tap / 3 - 1) * geo_pitch(a.W) + (tap % 3 - 1);
           uint64_t ad = a_stage_desc + (uint64_t)(((uint32_t)j * a_chunk_bytes + (uint32_t)(halo + shift) * ROWB) >> 4);
           uint32_t d = d_base;
           for (int t = 0; t < MT; ++t, ad += (128 * ROWB) >> 4, d += (uint32_t)N) {
@@ -279,7 +279,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int ncg = (N + 63) / 64, n_items = MT * ncg;
     constexpr int NG = kEpiWarps / 4;
     const uint32_t s_scale_u32 = smem_u32(s_scale), s_shift_u32 = smem_u32(s_shift), s_proj_u32 = smem_u32(s_proj);
-    const uint32_t R_img = (uint32_t)a.R_img, Wp = (uint32_t)(a.W + 2);
+    const uint32_t R_img = (uint32_t)a.R_img, Wp = (uint32_t)geo_pitch(a.W);
     struct Item { long long row_off; int b, pos, t, g0, gw; uint32_t m; bool valid; };
     auto get_item = [&](uint32_t m0, int item, Item& I) {
       I.t = item / ncg;
@@ -289,9 +289,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t bb = I.m / R_img, rem = I.m - bb * R_img;
       const uint32_t yy = rem / Wp, xx = rem - yy * Wp;
       I.b = (int)bb;
-      I.valid = (long long)I.m < a.rows_valid && yy >= 1 && xx >= 1 && xx <= (uint32_t)a.W;
+      I.valid = (long long)I.m < a.rows_valid && geo_is_pixel((int)yy, (int)xx, a.W);
       I.row_off = ((long long)I.m + halo) * (long long)N;
-      I.pos = (int)((yy - 1) * (uint32_t)a.W + (xx - 1));
+      I.pos = (int)((yy - 1) * (uint32_t)a.W + xx);
     };
     auto load_res = [&](const Item& I, int hh, uint4 (&r)[4]) {
       if (I.valid && a.residual) {
@@ -490,7 +490,7 @@ bool make_plan(int cin, int cout, int W, TcPlan* out) {
   TcPlan p{};
   p.kc = pick_kc(cin);
   p.n_chunks = cin / p.kc;
-  p.tail_rows = 2 * (W + 3) <= 32 ? 32 : 128;
+  p.tail_rows = 2 * geo_halo(W) <= 32 ? 32 : 128;
   const size_t rowb = (size_t)p.kc * 2, limit = 225 * 1024;
   const size_t b_all = (size_t)9 * p.n_chunks * cout * rowb, b_ring = (size_t)kStages * cout * rowb;
   const size_t misc = 1024 + 512 + 8 * (size_t)cout + 32 * (size_t)cout;      // barriers, scale/shift, <= 8 projection rows
@@ -540,11 +540,11 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
     return MZB_ECUDA;
   }
   TcArgs a{};
-  a.B = B; a.H = H; a.W = W; a.Cin = cp.cin; a.Cout = cp.cout; a.R_img = (H + 1) * (W + 2); a.mt = p.mt; a.n_chunks = p.n_chunks;
+  a.B = B; a.H = H; a.W = W; a.Cin = cp.cin; a.Cout = cp.cout; a.R_img = geo_rows_per_image(H, W); a.mt = p.mt; a.n_chunks = p.n_chunks;
   a.relu = relu; a.ncols = p.ncols; a.tail_rows = p.tail_rows; a.b_resident = p.b_resident;
   a.rows_valid = (long long)B * a.R_img;
   a.zero_pads = zero_pads;
-  a.rows_cover = a.rows_valid + (zero_pads ? W + 3 : 0);
+  a.rows_cover = a.rows_valid + (zero_pads ? geo_halo(W) : 0);
   MZB_CHECK_ARG(a.rows_cover + 4 * 128 < (1ll << 31), "tensor-core convolution: %lld rows exceed the 32-bit row index", a.rows_cover);
   a.scale = cp.scale; a.shift = cp.shift; a.plane = cp.extra_plane ? plane : nullptr; a.plane_table = cp.plane_table;
   a.residual = residual; a.y = y;

@@ -121,22 +121,22 @@ __global__ void __launch_bounds__(128) k_conv_s2(const void* __restrict__ xin, i
   for (int i = threadIdx.x; i < 9 * cin * cout; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
   __syncthreads();
-  const int Wp = go.W + 2, CO = go.C, ppr = out_pair ? 2 : 1;                // pixels per output row
-  const long long R_img = (long long)(go.H + 1) * Wp;
+  const int Wp = geo_pitch(go.W), CO = go.C, ppr = out_pair ? 2 : 1;         // pixels per output row
+  const long long R_img = geo_rows_per_image(go.H, go.W);
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long m = t / ppr;
   const int po = (int)(t - m * ppr);
-  if (m >= (long long)B * R_img + (go.W + 3)) return;
+  if (m >= (long long)B * R_img + geo_halo(go.W)) return;
   const int b = (int)(m / R_img);
   const int rem = (int)(m - (long long)b * R_img);
   const int yy = rem / Wp, xx = rem - yy * Wp;
-  const bool valid = b < B && yy >= 1 && xx >= 1 && xx <= go.W;
-  uint4* out = reinterpret_cast<uint4*>(y + (m + go.W + 3) * CO + po * cout);
+  const bool valid = b < B && geo_is_pixel(yy, xx, go.W);
+  uint4* out = reinterpret_cast<uint4*>(y + (m + geo_halo(go.W)) * CO + po * cout);
   if (!valid) {
     for (int i = 0; i < cout / 8; ++i) out[i] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
-  const int oy = yy - 1, ox = (xx - 1) * ppr + po;
+  const int oy = yy - 1, ox = xx * ppr + po;
   for (int co0 = 0; co0 < cout; co0 += 8) {
     float acc[8];
 #pragma unroll
@@ -201,19 +201,19 @@ __global__ void __launch_bounds__(128) k_stem_conv1_pair(const float* __restrict
   for (int i = threadIdx.x; i < 9 * cin * cout; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
   __syncthreads();
-  const int Wp = go.W + 2, CO = go.C;
-  const long long R_img = (long long)(go.H + 1) * Wp;
+  const int Wp = geo_pitch(go.W), CO = go.C;
+  const long long R_img = geo_rows_per_image(go.H, go.W);
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= (long long)B * R_img + (go.W + 3)) return;
+  if (m >= (long long)B * R_img + geo_halo(go.W)) return;
   const int b = (int)(m / R_img);
   const int rem = (int)(m - (long long)b * R_img);
   const int yy = rem / Wp, xx = rem - yy * Wp;
-  uint4* out = reinterpret_cast<uint4*>(y + (m + go.W + 3) * CO);
-  if (!(b < B && yy >= 1 && xx >= 1 && xx <= go.W)) {
+  uint4* out = reinterpret_cast<uint4*>(y + (m + geo_halo(go.W)) * CO);
+  if (!(b < B && geo_is_pixel(yy, xx, go.W))) {
     for (int i = 0; i < CO / 8; ++i) out[i] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
-  const int oy = yy - 1, xp = xx - 1;
+  const int oy = yy - 1, xp = xx;
   auto bf = [](float v) { return __bfloat162float(__float2bfloat16_rn(v)); };      // bf16 operands on this path
   for (int co0 = 0; co0 < cout; co0 += 8) {
     float a0[8], a1[8];
@@ -255,18 +255,18 @@ __global__ void __launch_bounds__(128) k_stem_conv1_pair(const float* __restrict
 // read the zero pads); one thread per (output row, 8-channel chunk), pad rows written as zeros.
 __global__ void __launch_bounds__(256) k_avgpool_pad(const __nv_bfloat16* __restrict__ x, int B, Geo gi, Geo go,
                                                      __nv_bfloat16* __restrict__ y) {
-  const int cv = go.C / 8, Wp = go.W + 2;
-  const long long R_img = (long long)(go.H + 1) * Wp;
+  const int cv = go.C / 8, Wp = geo_pitch(go.W);
+  const long long R_img = geo_rows_per_image(go.H, go.W);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long m = i / cv;
   const int ch = (int)(i - m * cv);
-  if (m >= (long long)B * R_img + (go.W + 3)) return;
+  if (m >= (long long)B * R_img + geo_halo(go.W)) return;
   const int b = (int)(m / R_img);
   const int rem = (int)(m - (long long)b * R_img);
   const int yy = rem / Wp, xx = rem - yy * Wp;
-  uint4* out = reinterpret_cast<uint4*>(y + (m + go.W + 3) * go.C) + ch;
-  if (!(b < B && yy >= 1 && xx >= 1 && xx <= go.W)) { *out = make_uint4(0u, 0u, 0u, 0u); return; }
-  const int oy = yy - 1, ox = xx - 1;
+  uint4* out = reinterpret_cast<uint4*>(y + (m + geo_halo(go.W)) * go.C) + ch;
+  if (!(b < B && geo_is_pixel(yy, xx, go.W))) { *out = make_uint4(0u, 0u, 0u, 0u); return; }
+  const int oy = yy - 1, ox = xx;
   float s[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.0f;
@@ -1139,7 +1139,7 @@ int stem_tc(Runner& r, const float* obs) {
   const Geo g3{(g2.H - 1) / 2 + 1, (g2.W - 1) / 2 + 1, C, 1};
   const Geo gl{m->Hl, m->Wl, C, 1};
   if ((g3.H - 1) / 2 + 1 != m->Hl || (g3.W - 1) / 2 + 1 != m->Wl) { mzb_set_error("latent size mismatch"); r.rc = MZB_EINVAL; return 0; }
-  auto out_rows = [&](const Geo& g) { return (long long)B * (g.H + 1) * (g.W + 2) + (g.W + 3); };
+  auto out_rows = [&](const Geo& g) { return (long long)B * geo_rows_per_image(g.H, g.W) + geo_halo(g.W); };
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_conv_s2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
