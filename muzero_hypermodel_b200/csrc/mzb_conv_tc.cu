@@ -113,7 +113,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
-// Persistent, warp-specialised kernel.  A CTA loops over super-tiles (MT tiles of 128 rows):
+// Persistent, warp-specialised kernel.  A CTA owns a contiguous range of 128-row tiles and loops over it in super-tiles
+// (up to MT tiles of 128 rows):
 //   warp 0        TMA producer: activation rows of super-tile i+1 are loaded while i is multiplied (2 A stages);
 //                 weights either stay resident in shared memory (loaded once) or stream through a ring
 //   warp 1        MMA issuer; accumulators are double buffered in TMEM (2 x MT x C_out columns), so the MMAs of
@@ -154,7 +155,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   float* s_scale = reinterpret_cast<float*>(bars + 10 + 2 * kStages);
   float* s_shift = s_scale + N;
   float* s_proj = s_shift + N;             // [proj_r][N]
-  const long long n_super = (a.rows_cover + (long long)MT * 128 - 1) / ((long long)MT * 128);
+  // Work split: every CTA owns one CONTIGUOUS range of 128-row tiles (sizes differ by at most one tile) and walks it in
+  // super-tiles of up to MT tiles; only the range's last super-tile may be short.  A strided split in whole super-tiles
+  // would leave a tail wave in which most SMs idle (connect4: 12.1 waves of work took 13).
+  const long long total_tiles = (a.rows_cover + 127) / 128;
+  const long long t_base = total_tiles / gridDim.x, t_rem = total_tiles % gridDim.x;
+  const long long tile_begin = (long long)blockIdx.x * t_base + ((long long)blockIdx.x < t_rem ? (long long)blockIdx.x : t_rem);
+  const long long tile_end = tile_begin + t_base + ((long long)blockIdx.x < t_rem ? 1 : 0);
 
   // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as this grid's CTAs free
   // their SMs (its prologue - barrier setup, TMEM allocation, weight loads - then overlaps this grid's tail); every
@@ -194,18 +201,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       asm volatile("griddepcontrol.wait;" ::: "memory");      // the activations come from the preceding kernel
       long long ring = 0;
       int it = 0;
-      for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+      for (long long tile0 = tile_begin; tile0 < tile_end; tile0 += MT, ++it) {
         const int s = it & 1;
+        const int mt_cur = tile_end - tile0 < MT ? (int)(tile_end - tile0) : MT;
         const long long p0 = clock64();
         if (it >= 2) mbar_wait(a_empty + s, ((it >> 1) - 1) & 1);
         if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (3 * 32 + it) * 4; d[0] = p0; d[1] = clock64(); }
-        const long long m0 = st * MT * 128;
-        if (leader) mbar_expect_tx(a_full + s, a_stage_bytes);
+        const long long m0 = tile0 * 128;
+        if (leader) mbar_expect_tx(a_full + s, (uint32_t)a.n_chunks * (uint32_t)(mt_cur * 128 + a.tail_rows) * ROWB);
         for (int j = 0; j < a.n_chunks; ++j) {
           uint8_t* dst = sA + (size_t)s * a_stage_bytes + (size_t)j * a_chunk_bytes;
-          for (int box = 0; box < MT; ++box)
+          for (int box = 0; box < mt_cur; ++box)
             if (leader) tma_load_2d(smem_u32(dst + (size_t)box * 128 * ROWB), &tmA, j * KC, (int)(m0 + (long long)box * 128), a_full + s);
-          if (leader) tma_load_2d(smem_u32(dst + (size_t)MT * 128 * ROWB), &tmAtail, j * KC, (int)(m0 + (long long)MT * 128), a_full + s);
+          if (leader) tma_load_2d(smem_u32(dst + (size_t)mt_cur * 128 * ROWB), &tmAtail, j * KC, (int)(m0 + (long long)mt_cur * 128), a_full + s);
         }
         if (!a.b_resident) {
           for (int kb = 0; kb < NKB; ++kb, ++ring) {
@@ -228,8 +236,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (a.b_resident) mbar_wait(b_full, 0);
       long long ring = 0;
       int it = 0;
-      for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+      for (long long tile0 = tile_begin; tile0 < tile_end; tile0 += MT, ++it) {
         const int s = it & 1;
+        const int mt_cur = tile_end - tile0 < MT ? (int)(tile_end - tile0) : MT;
         const long long c0 = clock64();
         mbar_wait(a_full + s, (it >> 1) & 1);
         const long long c1 = clock64();
@@ -255,7 +264,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const int shift = (tap / 3 - 1) * geo_pitch(a.W) + (tap % 3 - 1);
           uint64_t ad = a_stage_desc + (uint64_t)(((uint32_t)j * a_chunk_bytes + (uint32_t)(halo + shift) * ROWB) >> 4);
           uint32_t d = d_base;
-          for (int t = 0; t < MT; ++t, ad += (128 * ROWB) >> 4, d += (uint32_t)N) {
+          for (int t = 0; t < mt_cur; ++t, ad += (128 * ROWB) >> 4, d += (uint32_t)N) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
               if (leader) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -276,7 +285,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // step's accumulators are converted, so the global-memory latency (the epilogue's dominant cost: it, not the MMA
     // issue, set the kernel's period) hides behind the arithmetic of the step before.
     const int q = warp & 3, group = (warp - 2) >> 2;
-    const int ncg = (N + 63) / 64, n_items = MT * ncg;
+    const int ncg = (N + 63) / 64;
     constexpr int NG = kEpiWarps / 4;
     const uint32_t s_scale_u32 = smem_u32(s_scale), s_shift_u32 = smem_u32(s_shift), s_proj_u32 = smem_u32(s_proj);
     const uint32_t R_img = (uint32_t)a.R_img, Wp = (uint32_t)geo_pitch(a.W);
@@ -302,12 +311,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     };
     asm volatile("griddepcontrol.wait;" ::: "memory");        // residual / plane reads below: earlier kernels' outputs
-    int it = 0;
-    for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++it) {
+    int it = 0, item_base = 0;
+    for (long long tile0 = tile_begin; tile0 < tile_end; tile0 += MT, ++it) {
       const int s = it & 1;
-      const uint32_t m0 = (uint32_t)(st * MT * 128);
+      const int n_items = (tile_end - tile0 < MT ? (int)(tile_end - tile0) : MT) * ncg;
+      const uint32_t m0 = (uint32_t)(tile0 * 128);
       // items are dealt round-robin over ALL super-tiles (not restarted per super-tile)
-      int item = (((group - it * n_items) % NG) + NG) % NG;
+      int item = (((group - item_base) % NG) + NG) % NG;
+      item_base = (item_base + n_items) % NG;
       Item cur{}, nxt{};
       uint4 res[4], resn[4];
       bool have = item < n_items;
@@ -561,8 +572,8 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  const long long n_super = (a.rows_cover + (long long)p.mt * 128 - 1) / ((long long)p.mt * 128);
-  const unsigned grid = (unsigned)(n_super < n_sm ? n_super : n_sm);      // persistent: one CTA per SM
+  const long long total_tiles = (a.rows_cover + 127) / 128;
+  const unsigned grid = (unsigned)(total_tiles < n_sm ? total_tiles : n_sm);   // persistent: one CTA per SM
   const int pr = (a.proj_r + 1) / 2 * 2;              // instantiated projection heights: 2, 4, 6, 8
   static int narrow_on = -1;
   if (narrow_on < 0) { const char* e = getenv("MZB_TC_NARROW_EPI"); narrow_on = (e && atoi(e) == 0) ? 0 : 1; }
