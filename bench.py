@@ -361,6 +361,10 @@ def main():
         conv_ms = a.elapsed_time(b) / iters
         conv_flop = 2.0 * G * H_lat * W_lat * C_lat * C_lat * 9
         conv_tflops = conv_flop / (conv_ms * 1e-3) / 1e12
+        # the same launch against the other roof: it reads every row of the padded NHWC layout ((H+1)(W+1) rows per
+        # image) once and writes the H*W pixel rows; at C=64 its intensity (~250 flop/B) sits on the ridge
+        conv_bytes = 2.0 * G * C_lat * ((H_lat + 1) * (W_lat + 1) + H_lat * W_lat)
+        conv_gbs = conv_bytes / (conv_ms * 1e-3) / 1e9
         tpeak = float(peaks.get("bf16_tflops", 1650.0))
         tpeak_s = float(peaks.get("bf16_tflops_sustained", 1400.0))
         roofline = {"bound": "tensor", "kernel": f"k_conv_tc (tcgen05 implicit-GEMM 3x3 conv, {C_lat}->{C_lat} ch, {H_lat}x{W_lat}, batch {G})",
@@ -369,6 +373,8 @@ def main():
                     "traffic_source": ("profiles/" + NCU_CAPTURE[args.workload]) if args.workload in NCU_CAPTURE else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if peaks else "fallback 1650 TFLOP/s",
                     "kernel_us": conv_ms * 1e3, "flop_per_launch": conv_flop,
+                    "hbm_side": {"algorithmic_bytes_per_launch": conv_bytes, "achieved": conv_gbs, "peak": peak, "unit": "GB/s",
+                                 "frac": conv_gbs / peak, "flop_per_byte": conv_flop / conv_bytes},
                     "whole_search": {"achieved": tflops, "peak": tpeak_s, "frac": tflops / tpeak_s,
                                      "note": "all FLOPs of the search (BASELINE flop/sim) / search time, helper and tree kernels included; sustained peak"},
                     "search_ms": k_ms, "flop_per_sim": flops[1], "tree_bytes_per_sim": bytes_per_sim, "mean_path_nodes": L,
