@@ -234,7 +234,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint64_t desc_hi = make_desc<KC>(0);
       const uint64_t b_base_desc = desc_hi | (uint64_t)((smem_u32(sB) >> 4) & 0x3FFF);
       if (a.b_resident) mbar_wait(b_full, 0);
-      long long ring = 0;
+      uint32_t ring = 0;
       int it = 0;
       for (long long tile0 = tile_begin; tile0 < tile_end; tile0 += MT, ++it) {
         const int s = it & 1;
@@ -249,30 +249,40 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint64_t a_stage_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)s * a_stage_bytes) >> 4) & 0x3FFF);
         const uint32_t d_base = tmem_base + (uint32_t)(s * MT * N);
         long long b_wait = 0;                  // bring-up timeline: cycles this super-tile waited for weight blocks
-        for (int kb = 0; kb < NKB; ++kb) {
-          uint64_t bd;
-          int rs = 0;
-          if (a.b_resident) {
-            bd = b_base_desc + (uint64_t)kb * (b_block_bytes >> 4);
-          } else {
-            rs = (int)(ring % kStages);
-            const long long w0 = a.debug ? clock64() : 0;
-            mbar_wait(b_full + rs, (uint32_t)(ring / kStages) & 1);
-            if (a.debug) b_wait += clock64() - w0;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            bd = b_base_desc + (uint64_t)rs * (b_block_bytes >> 4);
-            ++ring;
-          }
-          const int tap = kb / a.n_chunks, j = kb - tap * a.n_chunks;
-          const int shift = (tap / 3 - 1) * geo_pitch(a.W) + (tap % 3 - 1);
-          uint64_t ad = a_stage_desc + (uint64_t)(((uint32_t)j * a_chunk_bytes + (uint32_t)(halo + shift) * ROWB) >> 4);
-          uint32_t d = d_base;
-          for (int t = 0; t < mt_cur; ++t, ad += (128 * ROWB) >> 4, d += (uint32_t)N) {
+        // The k-block loop is unrolled over the 9 taps so that the tap's row shift is a compile-time expression and the
+        // per-block bookkeeping stays a handful of uniform-datapath adds: descriptor arithmetic in vector registers
+        // (a division by n_chunks, R2UR moves) sat between the MMA bursts and was NOT overlapped with them - the in-situ
+        // cost per MMA was 73 cycles against the 51 the same instruction stream takes alone (tests/ubench_umma.cu).
+        const uint32_t blk16 = b_block_bytes >> 4, chunk16 = a_chunk_bytes >> 4;
+        const int pitch = geo_pitch(a.W);
+        int kb = 0;
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k)
-              if (leader) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int shift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
+          const uint64_t a_tap_desc = a_stage_desc + (uint64_t)(((uint32_t)(halo + shift) * ROWB) >> 4);
+          for (int j = 0; j < a.n_chunks; ++j, ++kb) {
+            uint64_t bd;
+            int rs = 0;
+            if (a.b_resident) {
+              bd = b_base_desc + (uint64_t)((uint32_t)kb * blk16);
+            } else {
+              rs = (int)(ring % kStages);
+              const long long w0 = a.debug ? clock64() : 0;
+              mbar_wait(b_full + rs, (ring / kStages) & 1);
+              if (a.debug) b_wait += clock64() - w0;
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              bd = b_base_desc + (uint64_t)((uint32_t)rs * blk16);
+              ++ring;
+            }
+            uint64_t ad = a_tap_desc + (uint64_t)((uint32_t)j * chunk16);
+            uint32_t d = d_base;
+            for (int t = 0; t < mt_cur; ++t, ad += (128 * ROWB) >> 4, d += (uint32_t)N) {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                if (leader) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            if (!a.b_resident && leader) umma_commit(b_empty + rs);
           }
-          if (!a.b_resident && leader) umma_commit(b_empty + rs);
         }
         if (leader) {
           umma_commit(a_empty + s);            // activation stage reusable once these MMAs retire
