@@ -166,6 +166,14 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def count(self):
+        """Samples written so far."""
+        try:
+            with open(self.f.name) as g:
+                return sum(1 for ln in g if ln.count(",") >= 8)
+        except OSError:
+            return 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
@@ -286,9 +294,21 @@ def main():
     barrier()
     ms = ev[0].elapsed_time(ev[1])
     launches = int(_lib.lib.mzb_launch_count())
-    clocks = sampler.stop() if sampler else None
     c1 = env.counters()
     tc = mcts.tree.counters()
+    ingested_end = rb.num_played_games if rb is not None else 0
+    # a timed region shorter than a few 50 ms sampling periods (breakout: 3 steps of 19 ms) would leave the clocks
+    # line empty: keep the same load running, untimed, until the sampler has seen it
+    extra = 0
+    if sampler is not None and sampler.p is not None:
+        t_end = time.time() + 3.0
+        while sampler.count() < 3 and time.time() < t_end:
+            step()
+            torch.cuda.synchronize()
+            extra += 1
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None and extra:
+        clocks["untimed_load_steps_for_sampling"] = extra
     ms = mdist.max_over_ranks(ms, dev)
     sims_total = args.steps * G * S * world
     value = sims_total / (ms * 1e-3)
@@ -296,7 +316,7 @@ def main():
     mean_path = tc["path_length_sum"] / max(1, tc["simulations"])
     if rb is not None:
         rb.ingest(env)
-        ingested = rb.num_played_games - ingested0
+        ingested = ingested_end - ingested0
     else:
         ingested = len(sp.drain())
 
