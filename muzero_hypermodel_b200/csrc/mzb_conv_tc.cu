@@ -248,7 +248,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // descriptors differ only in the 14-bit start-address field (16-byte units): one add per MMA
         const uint64_t a_stage_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)s * a_stage_bytes) >> 4) & 0x3FFF);
         const uint32_t d_base = tmem_base + (uint32_t)(s * MT * N);
-        long long b_wait = 0;                  // bring-up timeline: cycles this super-tile waited for weight blocks
         // The k-block loop is unrolled over the 9 taps so that the tap's row shift is a compile-time expression and the
         // per-block bookkeeping stays a handful of uniform-datapath adds: descriptor arithmetic in vector registers
         // (a division by n_chunks, R2UR moves) sat between the MMA bursts and was NOT overlapped with them - the in-situ
@@ -267,9 +266,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               bd = b_base_desc + (uint64_t)((uint32_t)kb * blk16);
             } else {
               rs = (int)(ring % kStages);
-              const long long w0 = a.debug ? clock64() : 0;
               mbar_wait(b_full + rs, (ring / kStages) & 1);
-              if (a.debug) b_wait += clock64() - w0;
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               bd = b_base_desc + (uint64_t)((uint32_t)rs * blk16);
               ++ring;
@@ -288,7 +285,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           umma_commit(a_empty + s);            // activation stage reusable once these MMAs retire
           umma_commit(acc_full + s);           // accumulators of this super-tile complete
         }
-        if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (0 * 32 + it) * 4; d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64(); a.debug[(3 * 32 + it) * 4 + 2] = b_wait; }
+        if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (0 * 32 + it) * 4; d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64(); }
       }
     }
   } else {

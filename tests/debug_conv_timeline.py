@@ -28,5 +28,5 @@ for it in range(12): print("  ", it, *(int(x - t0) for x in d[0, it]))
 for g in (1, 2):
     print(f"EPI group {g-1}: it  wait_start  acc_full  done")
     for it in range(12): print("  ", it, *(int(x - t0) for x in d[g, it, :3]))
-print("PRODUCER: it  start  a_empty_ok   | MMA issuer: cycles waiting for weight blocks in this super-tile")
-for it in range(12): print("  ", it, *(int(x - t0) for x in d[3, it, :2]), "|", int(d[3, it, 2]))
+print("PRODUCER: it  start  a_empty_ok")
+for it in range(12): print("  ", it, *(int(x - t0) for x in d[3, it, :2]))

@@ -32,6 +32,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 // shared-memory region, `copy` of them in flight, to see what concurrent TMA writes cost the MMA's operand reads.
 // mode 0: tap shifts of a W = 7 board ((tap/3-1)*8 + tap%3-1 rows); mode 1: no shift (8-row aligned starts);
 // mode 2: like 0 but every MMA of a k-block goes to ONE accumulator tile (MT = 1 behaviour, dependent chain)
+// mode 3: like 0 plus the streaming-weights protocol per k-block: try_wait on the barrier committed 4 blocks ago
+//         (always complete by then), tcgen05.fence::after_thread_sync, the MMAs, tcgen05.commit to the slot's barrier
 template <int KC>
 __global__ void __launch_bounds__(64 + 8 * 32, 1) k_ubench(int N, int MT, int supers, int mode, long long* out, const uint8_t* src, int copy) {
   extern __shared__ uint8_t smem_raw[];
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(64 + 8 * 32, 1) k_ubench(int N, int MT, int su
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
   uint64_t* cbar = bar + 2;                                    // [8] copy-slot barriers
   volatile int* stop = reinterpret_cast<volatile int*>(bar + 10);
-  uint8_t* sC = reinterpret_cast<uint8_t*>(bar + 16);          // copy ring: `copy` slots of 16 KB (16-byte aligned)
+  uint8_t* sC = reinterpret_cast<uint8_t*>(bar + 32);          // copy ring: `copy` slots of 16 KB (16-byte aligned)
   for (int i = threadIdx.x; i < (a_rows + nb * N) * ROWB / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
   // warp index / TMEM base through a shuffle: known warp-uniform, so the issue loop lives in uniform registers (a
   // divergent `threadIdx.x == 32` loop needs five R2UR moves + ELECT per MMA and measures its own issue overhead)
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(64 + 8 * 32, 1) k_ubench(int N, int MT, int su
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
     for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(cbar + i)) : "memory");
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 12 + i)) : "memory");
     *stop = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -116,8 +119,16 @@ __global__ void __launch_bounds__(64 + 8 * 32, 1) k_ubench(int N, int MT, int su
     const uint64_t a_desc = make_desc<KC>(smem_u32(sA)), b_desc = make_desc<KC>(smem_u32(sB));
     const int n_kb = 9 * (64 / KC);                            // 64 input channels
     long long t0 = clock64();
+    uint32_t ring = 0;
     for (int it = 0; it < supers; ++it) {
       for (int kb = 0; kb < n_kb; ++kb) {
+        const uint32_t rs = ring & 3;
+        if (mode == 3) {
+          if (ring >= 4)
+            asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra W_%=;\n}\n"
+                         ::"r"(smem_u32(bar + 12 + rs)), "r"(((ring >> 2) - 1) & 1) : "memory");
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         const int tap = kb % 9;
         const int shift = mode == 1 ? 8 : 9 + (tap / 3 - 1) * 8 + (tap % 3 - 1);
         const uint64_t bd = b_desc + (uint64_t)((kb % nb) * N * ROWB >> 4);
@@ -127,6 +138,9 @@ __global__ void __launch_bounds__(64 + 8 * 32, 1) k_ubench(int N, int MT, int su
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) umma(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
+        if (mode == 3)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + 12 + rs)) : "memory");
+        ++ring;
       }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -182,6 +196,10 @@ int main() {
   // the gomoku shape (N = 128, MT = 2) with the weight ring's traffic beside it
   for (int copy : {0, 1, 2, 4}) run<64>(128, 2, 0, 148, d_out, d_src, copy);
   for (int copy : {0, 2}) run<64>(64, 4, 0, 148, d_out, d_src, copy);
+  // the streaming protocol (wait / fence / commit per k-block) at the gomoku and connect4 shapes
+  run<64>(128, 2, 3, 148, d_out);
+  run<64>(128, 2, 3, 148, d_out, d_src, 2, 8);
+  run<64>(64, 4, 3, 148, d_out);
   // ... and with epilogue warps reading TMEM meanwhile (accumulators use columns [0, MT*N) <= 256 here)
   for (int readers : {4, 8}) {
     run<64>(64, 4, 0, 148, d_out, d_src, 0, readers);
