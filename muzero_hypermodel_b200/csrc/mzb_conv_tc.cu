@@ -123,8 +123,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 //                 dealt round-robin to the groups
 // ZP / PR: the rarely used epilogue features (pad-row zeroing of the stem; fused head projection with PR rows, a
 // compile-time count so the dot products are straight-line code) are separate instantiations, so the common layer
-// keeps its register allocation.
-template <int KC, bool ZP, int PR, int kEpiWarps>
+// keeps its register allocation.  RES: weights resident in shared memory (true) or streamed through the ring (false) -
+// compile-time because the MMA stream is issue-bound and every instruction between two bursts of MMAs shows.
+template <int KC, bool ZP, int PR, int kEpiWarps, bool RES>
 __global__ void __launch_bounds__(64 + kEpiWarps * 32, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAtail,
           const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -141,7 +142,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t a_stage_bytes = (uint32_t)a.n_chunks * a_chunk_bytes;
   const uint32_t b_block_bytes = (uint32_t)N * ROWB;
   const int NKB = 9 * a.n_chunks;
-  const int b_slots = a.b_resident ? NKB : kStages;
+  const int b_slots = RES ? NKB : kStages;
   uint8_t* sA = smem;
   uint8_t* sB = sA + 2 * (size_t)a_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)b_slots * b_block_bytes);
@@ -191,7 +192,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // descriptors live in uniform registers; one elected lane issues the copies.
     if (elect_one_sync()) {
       const bool leader = true;
-      if (a.b_resident) {
+      if (RES) {
         if (leader) mbar_expect_tx(b_full, (uint32_t)NKB * b_block_bytes);
         for (int kb = 0; kb < NKB; ++kb) {
           const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
@@ -215,7 +216,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (leader) tma_load_2d(smem_u32(dst + (size_t)box * 128 * ROWB), &tmA, j * KC, (int)(m0 + (long long)box * 128), a_full + s);
           if (leader) tma_load_2d(smem_u32(dst + (size_t)mt_cur * 128 * ROWB), &tmAtail, j * KC, (int)(m0 + (long long)mt_cur * 128), a_full + s);
         }
-        if (!a.b_resident) {
+        if (!RES) {
           for (int kb = 0; kb < NKB; ++kb, ++ring) {
             const int rs = (int)(ring % kStages);
             if (ring >= kStages) mbar_wait(b_empty + rs, (uint32_t)((ring / kStages) - 1) & 1);
@@ -233,7 +234,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
       const uint64_t desc_hi = make_desc<KC>(0);
       const uint64_t b_base_desc = desc_hi | (uint64_t)((smem_u32(sB) >> 4) & 0x3FFF);
-      if (a.b_resident) mbar_wait(b_full, 0);
+      if (RES) mbar_wait(b_full, 0);
       uint32_t ring = 0;
       int it = 0;
       for (long long tile0 = tile_begin; tile0 < tile_end; tile0 += MT, ++it) {
@@ -262,7 +263,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int j = 0; j < a.n_chunks; ++j, ++kb) {
             uint64_t bd;
             int rs = 0;
-            if (a.b_resident) {
+            if (RES) {
               bd = b_base_desc + (uint64_t)((uint32_t)kb * blk16);
             } else {
               rs = (int)(ring % kStages);
@@ -278,7 +279,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               for (int k = 0; k < KC / 16; ++k)
                 if (leader) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
-            if (!a.b_resident && leader) umma_commit(b_empty + rs);
+            if (!RES && leader) umma_commit(b_empty + rs);
           }
         }
         if (leader) {
@@ -589,11 +590,11 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   if (narrow_on < 0) { const char* e = getenv("MZB_TC_NARROW_EPI"); narrow_on = (e && atoi(e) == 0) ? 0 : 1; }
   const bool narrow = narrow_on && cp.cout <= 32;
   MZB_CHECK_ARG(!(zero_pads && pr), "pad zeroing and head projection are not combined");
-#define LAUNCH_EW(KCV, ZPV, PRV, EWV)                                                                               \
+#define LAUNCH_RES(KCV, ZPV, PRV, EWV, RESV)                                                                             \
   {                                                                                                                 \
     static bool configured = false;                                                                                 \
     if (!configured) {                                                                                              \
-      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV, ZPV, PRV, EWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV, ZPV, PRV, EWV, RESV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       configured = true;                                                                                            \
     }                                                                                                               \
     cudaLaunchConfig_t lc = {};                                                                                     \
@@ -602,7 +603,12 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
     la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                  \
     la[0].val.programmaticStreamSerializationAllowed = 1;                                                           \
     lc.attrs = la; lc.numAttrs = pdl_enabled() ? 1 : 0;                                                             \
-    MZB_CUDA(cudaLaunchKernelEx(&lc, k_conv_tc<KCV, ZPV, PRV, EWV>, tmA, tmAtail, tmB, a));                         \
+    MZB_CUDA(cudaLaunchKernelEx(&lc, k_conv_tc<KCV, ZPV, PRV, EWV, RESV>, tmA, tmAtail, tmB, a));                         \
+  }
+#define LAUNCH_EW(KCV, ZPV, PRV, EWV)                                                                               \
+  {                                                                                                                 \
+    if (p.b_resident) LAUNCH_RES(KCV, ZPV, PRV, EWV, true)                                                          \
+    else LAUNCH_RES(KCV, ZPV, PRV, EWV, false)                                                                      \
   }
 #define LAUNCH_ONE(KCV, ZPV, PRV)                                                                                   \
   {                                                                                                                 \
@@ -623,6 +629,7 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   if (p.kc == 64) LAUNCH_KC(64) else if (p.kc == 32) LAUNCH_KC(32) else LAUNCH_KC(16)
 #undef LAUNCH_ONE
 #undef LAUNCH_EW
+#undef LAUNCH_RES
 #undef LAUNCH_KC
   MZB_LAUNCH_CHECK();
   return MZB_OK;
