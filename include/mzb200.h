@@ -79,7 +79,9 @@ size_t mzb_tree_workspace_bytes(const mzb_tree_config* cfg);
 int mzb_tree_create(mzb_tree** out, const mzb_tree_config* cfg, void* d_workspace, size_t workspace_bytes,
                     const double* h_log_lut);
 int mzb_tree_destroy(mzb_tree* t);
-/* Device pointer to hidden-state slots, fp32 [G][num_simulations+1][hidden_floats]. */
+/* Device pointer to the hidden-state slots, fp32, blocked by 32 games and node-major inside a block:
+ * [ceil(G/32)][num_simulations+1][32][hidden_floats]; game g, slot n lives at
+ * ((g >> 5) * (num_simulations+1) * 32 + n * 32 + (g & 31)) * hidden_floats. */
 float* mzb_tree_hidden_ptr(mzb_tree* t);
 
 /* Root expansion (+ exploration noise).  Replaces Node.expand at the root and
@@ -397,8 +399,11 @@ int mzb_replay_update_priorities(mzb_replay* r, int32_t batch, const float* d_pr
 /* The device-to-device hop that replaces `replay_buffer.save_game.remote(game_history)` (self_play.py:52): every
  * finished game in the export ring of `env` is appended to the store and the ring is emptied; only the per-game
  * (start, length) table crosses to the host.  The store must have been created with the environment's record
- * format (obs_floats = mzb_env_info's rec_floats, obs_decode = 1 for the board games). */
+ * format (obs_floats = mzb_env_info's rec_floats, obs_decode = 1 with the board size for the board games, the same
+ * n_actions, entry_stride >= max_moves + 2): anything else returns MZB_EINVAL and leaves ring and store untouched. */
 int mzb_env_export_to_replay(mzb_env* env, mzb_replay* r, int32_t* h_n_games, void* stream);
+/* The configuration the store was created with (layout checks of callers that copy into it). */
+int mzb_replay_get_config(const mzb_replay* r, mzb_replay_config* out);
 /* out5 = total_samples, num_played_games, num_played_steps, games in the buffer, id of the oldest game. */
 int mzb_replay_info(const mzb_replay* r, int64_t* out5);
 int mzb_replay_set_batch_counter(mzb_replay* r, uint32_t counter);

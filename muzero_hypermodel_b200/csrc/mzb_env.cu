@@ -609,6 +609,19 @@ int mzb_env_export_drain_sync(mzb_env* e, int32_t* h_n_entries, int32_t* h_n_gam
 
 int mzb_env_export_to_replay(mzb_env* e, mzb_replay* r, int32_t* h_n_games, void* stream) {
   MZB_CHECK_ARG(e && r, "NULL argument");
+  // the store copies ring entries with ITS strides: refuse a store laid out for anything but this environment's records
+  mzb_replay_config rc_{};
+  if (int rc = mzb_replay_get_config(r, &rc_)) return rc;
+  const bool board = e->v.kind == MZB_ENV_TICTACTOE || e->v.kind == MZB_ENV_CONNECT4 || e->v.kind == MZB_ENV_GOMOKU;
+  MZB_CHECK_ARG(rc_.obs_floats == e->v.rec_floats, "replay store keeps %d floats per observation record, the environment's ring %d "
+                "(create the store with this environment as record_env)", rc_.obs_floats, e->v.rec_floats);
+  MZB_CHECK_ARG(rc_.n_actions == e->v.A, "replay store has %d actions, the environment %d", rc_.n_actions, e->v.A);
+  MZB_CHECK_ARG(rc_.obs_decode == (board ? 1 : 0), "replay store obs_decode = %d does not match environment kind %d",
+                rc_.obs_decode, e->v.kind);
+  MZB_CHECK_ARG(!board || (rc_.obs_h == e->v.H && rc_.obs_w == e->v.W), "replay store decodes %dx%d boards, the environment plays %dx%d",
+                rc_.obs_h, rc_.obs_w, e->v.H, e->v.W);
+  MZB_CHECK_ARG(rc_.entry_stride >= e->v.max_moves + 2, "replay store slots hold %d entries, games of this environment up to %d",
+                rc_.entry_stride, e->v.max_moves + 2);
   cudaStream_t s = (cudaStream_t)stream;
   int cur[2];
   MZB_CUDA(cudaMemcpyAsync(cur, e->x.cursor, 8, cudaMemcpyDeviceToHost, s));

@@ -13,6 +13,15 @@ struct RowIO {
   // state_in(row) = in + row*in_row_stride + (in_slot ? in_slot[row] : 0) * slot_stride
   const float* in; long long in_row_stride; const int* in_slot; long long slot_stride;
   float* out; long long out_row_stride; long long out_off;
+  // blocked rows (the tree store's hidden slots, mzb_tree.cuh): when *_blk != 0 the row term becomes
+  // (row >> 5) * blk + (row & 31) * row_stride
+  long long in_blk, out_blk;
+  __device__ __forceinline__ long long in_row(long long row) const {
+    return in_blk ? (row >> 5) * in_blk + (row & 31) * in_row_stride : row * in_row_stride;
+  }
+  __device__ __forceinline__ long long out_row(long long row) const {
+    return out_blk ? (row >> 5) * out_blk + (row & 31) * out_row_stride : row * out_row_stride;
+  }
   float* value_logits; float* reward_logits; float* policy_logits;
   float* value; float* reward; float* priors;
 };
@@ -116,7 +125,7 @@ __global__ void k_fc_initial(FcDesc d, const float* __restrict__ gpack, int B, c
   for (int i = 0; i < d.enc; ++i) st[(size_t)i * NT + tid] = enc[(size_t)i * NT + tid];
   minmax_normalize(st, d.enc, tid, NT);
   if (io.out) {
-    float* o = io.out + row * io.out_row_stride + io.out_off;
+    float* o = io.out + io.out_row(row) + io.out_off;
     for (int i = 0; i < d.enc; ++i) o[i] = st[(size_t)i * NT + tid];
   }
   // reward := log(one-hot(centre)) (models.py:176-183)
@@ -142,7 +151,7 @@ __global__ void k_fc_recurrent(FcDesc d, const float* __restrict__ gpack, int B,
   __syncthreads();
   const long long row = (long long)blockIdx.x * NT + tid;
   if (row >= B) return;
-  const float* sin = io.in + row * io.in_row_stride + (io.in_slot ? (long long)io.in_slot[row] * io.slot_stride : 0);
+  const float* sin = io.in + io.in_row(row) + (io.in_slot ? (long long)io.in_slot[row] * io.slot_stride : 0);
   const int a = action[row];
   // dynamics (models.py:147-170): state ++ one-hot(action) -> next state
   float* nx = fc_mlp(d.dyn, pack, [=](int i) { return sin[i]; }, d.enc, a, t0, t1, tid, NT);
@@ -158,7 +167,7 @@ __global__ void k_fc_recurrent(FcDesc d, const float* __restrict__ gpack, int B,
   }
   minmax_normalize(st, d.enc, tid, NT);
   if (io.out) {
-    float* o = io.out + row * io.out_row_stride + io.out_off;
+    float* o = io.out + io.out_row(row) + io.out_off;
     for (int i = 0; i < d.enc; ++i) o[i] = st[(size_t)i * NT + tid];
   }
   heads(d, pack, st, t0, t1, tid, NT, row, io, nullptr);
@@ -334,6 +343,42 @@ int mzb_fc_recurrent(mzb_fc_model* m, int64_t B, const float* d_state_in, int64_
   MZB_LAUNCH_CHECK();
   return MZB_OK;
 }
+
+}  // extern "C"
+
+// Internal (mzb_search_fc's modular path): hidden states read from / written to the tree store's blocked slots
+// [G/32][S1][32][H] - row g, slot n lives at ((g >> 5) * S1 * 32 + n * 32 + (g & 31)) * H.
+int mzb_fc_initial_tree(mzb_fc_model* m, int64_t B, const float* d_obs, const uint8_t* d_legal, float* d_hidden, int S1,
+                        int out_slot, float* d_value, float* d_reward, float* d_priors, void* stream) {
+  MZB_CHECK_ARG(m && d_obs && d_hidden, "NULL argument");
+  RowIO io{};
+  const long long H = m->d.enc;
+  io.out = d_hidden; io.out_row_stride = H; io.out_blk = (long long)S1 * 32 * H; io.out_off = (long long)out_slot * 32 * H;
+  io.value = d_value; io.reward = d_reward; io.priors = d_priors;
+  const int nt = m->rows_per_block;
+  k_fc_initial<<<(unsigned)((B + nt - 1) / nt), nt, m->smem_bytes, (cudaStream_t)stream>>>(m->d, m->d_pack, (int)B, d_obs,
+                                                                                            d_legal, io);
+  MZB_LAUNCH_CHECK();
+  return MZB_OK;
+}
+
+int mzb_fc_recurrent_tree(mzb_fc_model* m, int64_t B, float* d_hidden, int S1, const int32_t* d_in_slot,
+                          const int32_t* d_action, int out_slot, float* d_value, float* d_reward, float* d_priors,
+                          void* stream) {
+  MZB_CHECK_ARG(m && d_hidden && d_in_slot && d_action, "NULL argument");
+  RowIO io{};
+  const long long H = m->d.enc;
+  io.in = d_hidden; io.in_row_stride = H; io.in_blk = (long long)S1 * 32 * H; io.in_slot = d_in_slot; io.slot_stride = 32 * H;
+  io.out = d_hidden; io.out_row_stride = H; io.out_blk = io.in_blk; io.out_off = (long long)out_slot * 32 * H;
+  io.value = d_value; io.reward = d_reward; io.priors = d_priors;
+  const int nt = m->rows_per_block;
+  k_fc_recurrent<<<(unsigned)((B + nt - 1) / nt), nt, m->smem_bytes, (cudaStream_t)stream>>>(m->d, m->d_pack, (int)B,
+                                                                                              d_action, io);
+  MZB_LAUNCH_CHECK();
+  return MZB_OK;
+}
+
+extern "C" {
 
 int mzb_support_to_scalar(const float* d_logits, int64_t B, int support_size, float* d_out, void* stream) {
   MZB_CHECK_ARG(d_logits && d_out && B > 0 && support_size > 0, "bad argument");

@@ -74,3 +74,10 @@ __device__ __forceinline__ float support_to_scalar_dev(Logit logit, Scratch e, i
   for (int i = 0; i < full; ++i) num = fmaf((float)(i - S), e(i), num);
   return inverse_value_transform(__fdiv_rn(num, sum));
 }
+
+// mzb_fc.cu, internal: inference on hidden states kept in the tree store's blocked slots (mzb_tree.cuh)
+int mzb_fc_initial_tree(mzb_fc_model* m, int64_t B, const float* d_obs, const uint8_t* d_legal, float* d_hidden, int S1,
+                        int out_slot, float* d_value, float* d_reward, float* d_priors, void* stream);
+int mzb_fc_recurrent_tree(mzb_fc_model* m, int64_t B, float* d_hidden, int S1, const int32_t* d_in_slot,
+                          const int32_t* d_action, int out_slot, float* d_value, float* d_reward, float* d_priors,
+                          void* stream);

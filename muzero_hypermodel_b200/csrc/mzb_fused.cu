@@ -13,20 +13,42 @@
 #include "mzb_fc.cuh"
 #include "mzb_tree.cuh"
 
+#define MZB_FUSED_DEFAULT_EXP 1
+
 namespace {
 
 __host__ __device__ constexpr int pad4(int x) { return (x + 3) / 4 * 4; }
 
 // ---- one Linear layer, compile-time shape.  w: Wt [*][OUTP] in shared memory, b: [OUTP].
-template <int NIN, int OUT, int OUTP>
+// F2: the same fmaf chain per output, issued as packed FFMA2 (fma.rn.f32x2: two IEEE fp32 FMAs per instruction on
+// sm_100) over adjacent outputs - bit-identical to the scalar form, half the FMA instructions.
+template <int NIN, int OUT, int OUTP, bool F2 = false>
 __device__ __forceinline__ void lin(const float* __restrict__ w, const float* __restrict__ b, const float (&x)[NIN],
                                     int hot, float (&y)[OUT], bool elu) {
+  if constexpr (F2) {
+    constexpr int NP = OUT / 2;
+    float2 acc[NP > 0 ? NP : 1];
 #pragma unroll
-  for (int o = 0; o < OUT; ++o) y[o] = b[o];
+    for (int p = 0; p < NP; ++p) acc[p] = *reinterpret_cast<const float2*>(b + 2 * p);
+    float last = (OUT & 1) ? b[OUT - 1] : 0.0f;
 #pragma unroll
-  for (int i = 0; i < NIN; ++i) {
+    for (int i = 0; i < NIN; ++i) {
+      const float2 xx = make_float2(x[i], x[i]);
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) y[o] = fmaf(x[i], w[i * OUTP + o], y[o]);
+      for (int p = 0; p < NP; ++p) acc[p] = __ffma2_rn(xx, *reinterpret_cast<const float2*>(w + i * OUTP + 2 * p), acc[p]);
+      if (OUT & 1) last = fmaf(x[i], w[i * OUTP + OUT - 1], last);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { y[2 * p] = acc[p].x; y[2 * p + 1] = acc[p].y; }
+    if (OUT & 1) y[OUT - 1] = last;
+  } else {
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) y[o] = b[o];
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) {
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) y[o] = fmaf(x[i], w[i * OUTP + o], y[o]);
+    }
   }
   if (hot >= 0) {
     const float* wr = w + (NIN + hot) * OUTP;
@@ -45,14 +67,15 @@ struct Mlp {
   static constexpr int OUT0 = H > 0 ? H : OUT;
   static constexpr int SIZE0 = IN * pad4(OUT0) + pad4(OUT0);
   static constexpr int SIZE = SIZE0 + (H > 0 ? H * pad4(OUT) + pad4(OUT) : 0);
+  template <bool F2 = false>
   __device__ __forceinline__ static void run(const float* __restrict__ p, const float (&x)[NDIRECT], int hot,
                                              float (&y)[OUT]) {
     if constexpr (H > 0) {
       float h[H];
-      lin<NDIRECT, H, pad4(H)>(p, p + IN * pad4(H), x, hot, h, true);
-      lin<H, OUT, pad4(OUT)>(p + SIZE0, p + SIZE0 + H * pad4(OUT), h, -1, y, false);
+      lin<NDIRECT, H, pad4(H), F2>(p, p + IN * pad4(H), x, hot, h, true);
+      lin<H, OUT, pad4(OUT), F2>(p + SIZE0, p + SIZE0 + H * pad4(OUT), h, -1, y, false);
     } else {
-      lin<NDIRECT, OUT, pad4(OUT)>(p, p + IN * pad4(OUT), x, hot, y, false);
+      lin<NDIRECT, OUT, pad4(OUT), F2>(p, p + IN * pad4(OUT), x, hot, y, false);
     }
   }
 };
@@ -195,14 +218,27 @@ struct SearchIO {
 // block's warps so they fetch the (fully unrolled, ~100 KB) network code together; PB_LUT: the exploration factor
 // pb(N, n) = (log((N+base+1)/base)+init) * (sqrt(N)/(n+1)) comes from a shared-memory table built with the same
 // three float64 operations (bit-identical), removing a double division and square root per child and level.
-template <class SH, int THREADS, bool PHASE_SYNC, bool PB_LUT>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t, const float* __restrict__ gpack, SearchIO io) {
+// EXP: experiment / tuning flags (MZB_FUSED_EXP): 1 = packed FFMA2 network, 2 = root record in registers (A <= 4),
+// 4/8/16/32 = timing-only diagnostics (blocked layout, aliased trees, no network, no walk) - results are NOT valid.
+// 4 = the search path's edge statistics in shared memory for the first 12 levels (deeper levels: local memory).
+enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32 };
+__host__ __device__ constexpr int smem_path_depth(int blocks_per_sm) { return blocks_per_sm >= 3 ? 8 : 12; }
+
+template <class SH, int THREADS, bool PHASE_SYNC, bool PB_LUT, int EXP, int MINB = 512 / THREADS>
+__global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const float* __restrict__ gpack, SearchIO io) {
   constexpr int A = SH::A, ENC = SH::ENC, FULL = SH::FULL;
+  constexpr bool F2 = (EXP & X_F2) != 0;
+  constexpr bool ROOTREG = (EXP & X_ROOTREG) != 0 && A <= 4;
   extern __shared__ float4 smem4[];
   float* pack = reinterpret_cast<float*>(smem4);
   double* lut = reinterpret_cast<double*>(pack + SH::PACK);
   const int S1 = io.num_sims + 1;
   double* pbt = lut + ((S1 + 1) & ~1);                     // [S1][S1] when PB_LUT
+  // SPATH: [PD][THREADS] value sums f64 | rewards f32 | (node << 16 | action << 8... ) see path_put
+  constexpr int PD = ((EXP & X_SPATH) != 0 && PB_LUT) ? smem_path_depth(MINB) : 0;
+  double* sp_vs = pbt + (PB_LUT ? S1 * S1 : 0);
+  float* sp_rw = reinterpret_cast<float*>(sp_vs + PD * THREADS);
+  uint32_t* sp_ev = reinterpret_cast<uint32_t*>(sp_rw + PD * THREADS);
   for (int i = threadIdx.x; i < SH::PACK / 4; i += THREADS) smem4[i] = reinterpret_cast<const float4*>(gpack)[i];
   for (int i = threadIdx.x; i < S1; i += THREADS) lut[i] = t.log_lut[i];
   if (PB_LUT) {
@@ -221,24 +257,27 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
   const uint32_t my_slot = io.slot ? io.slot[g] : (uint32_t)g;
   const uint32_t my_step = io.step ? io.step[g] : 0u;
   const uint8_t* legal = io.legal ? io.legal + (size_t)g * A : nullptr;
-  float* hid = t.hidden + (size_t)g * (t.S + 1) * ENC;
+  const int gm = (EXP & X_ALIAS) ? (g & 8191) : g;
+  auto rec_of = [&](int n) -> uint8_t* { return t.rec(gm, n); };
+  auto hid_of = [&](int n) -> float* { return t.hidden + t.rec_index(gm, n) * ENC; };
 
   // ---------------- initial inference (models.py:172-190) + root expansion (self_play.py:292-314)
   double rp[A];                       // root priors, float64 after the noise mix
   float root_reward = 0.0f;
+  Rec<ROOTREG ? A : 1> root;          // ROOTREG: the root's record lives in registers for the whole search
   if (active) {
     float ob[SH::OBS];
     load_floats<SH::OBS>(io.obs + (size_t)g * SH::OBS, ob);
     float st[ENC];
-    SH::Rep::run(pack + SH::OFF_REP, ob, -1, st);
+    SH::Rep::template run<F2>(pack + SH::OFF_REP, ob, -1, st);
     minmax_regs(st);
-    store_floats<ENC>(hid, st);
+    store_floats<ENC>(hid_of(0), st);
     float pl[A], pri[A];
-    SH::Pol::run(pack + SH::OFF_POL, st, -1, pl);
+    SH::Pol::template run<F2>(pack + SH::OFF_POL, st, -1, pl);
     priors_regs<A>(pl, legal, pri);
     if (io.root_pred_value) {
       float vl[FULL];
-      SH::Val::run(pack + SH::OFF_VAL, st, -1, vl);
+      SH::Val::template run<F2>(pack + SH::OFF_VAL, st, -1, vl);
       io.root_pred_value[g] = s2s_regs<SH::SUP>(vl);
     }
     float zl[FULL];
@@ -253,7 +292,12 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
         const bool ok = !legal || legal[a];
         rr.set(a, 0.0, ok ? pri[a] : 0.0f, 0, 0.0f, ok ? MZB_CHILD_NONE : MZB_CHILD_ILLEGAL);
       }
-      rr.store(t.rec(g, 0));
+      if constexpr (ROOTREG) {
+#pragma unroll
+        for (int i = 0; i < Rec<A>::WORDS; ++i) root.w[i] = rr.w[i];
+      } else {
+        rr.store(rec_of(0));
+      }
     }
     if (io.frac > 0.0) {
       const double keep = __dsub_rn(1.0, io.frac);
@@ -295,11 +339,18 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
     // ---------------- select walk (self_play.py:326-335, 364-405)
     int node = 0, N = root_visit, depth = 0, action = 0;
     while (active) {
-      uint8_t* r = t.rec(g, node);
       double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
       {
         Rec<A> rr;
-        rr.load(r);
+        bool from_regs = false;
+        if constexpr (ROOTREG) {
+          if (node == 0) {
+            from_regs = true;
+#pragma unroll
+            for (int i = 0; i < Rec<A>::WORDS; ++i) rr.w[i] = root.w[i];
+          }
+        }
+        if (!from_regs) rr.load(rec_of(node));
 #pragma unroll
         for (int a = 0; a < A; ++a) { vs[a] = rr.vs(a); pr[a] = rr.pr(a); vi[a] = rr.vi(a); rw[a] = rr.rw(a); ch[a] = rr.ch(a); }
       }
@@ -334,12 +385,19 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
 #pragma unroll
       for (int a = 0; a < A; ++a) if (a == action) { next = ch[a]; nv = vi[a]; nvs = vs[a]; nrw = rw[a]; }
       if (PB_LUT) {
-        lp_edge[depth] = ((uint32_t)node << 16) | (uint32_t)action; lp_vs[depth] = nvs; lp_vi[depth] = nv; lp_rw[depth] = nrw;
+        // node <= 63 and action < 2^8 here (PB_LUT: num_simulations <= 63): edge and visit count share one word
+        if (PD > 0 && depth < PD) {
+          sp_ev[depth * THREADS + threadIdx.x] = ((uint32_t)node << 24) | ((uint32_t)action << 16) | (uint32_t)nv;
+          sp_vs[depth * THREADS + threadIdx.x] = nvs; sp_rw[depth * THREADS + threadIdx.x] = nrw;
+        } else {
+          lp_edge[depth] = ((uint32_t)node << 16) | (uint32_t)action; lp_vs[depth] = nvs; lp_vi[depth] = nv; lp_rw[depth] = nrw;
+        }
       } else {
         path[(size_t)depth * G] = ((uint32_t)node << 16) | (uint32_t)action;
       }
       ++depth;
       if (next < 0) break;
+      if ((EXP & X_NOWALK) && depth >= 1) break;
       N = nv;
       node = next;
     }
@@ -349,26 +407,33 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
 
     // ---------------- recurrent inference on the parent's hidden state (models.py:192-195)
     float value, reward, pri[A];
-    {
+    if constexpr ((EXP & X_NONET) != 0) {
       float st[ENC];
-      load_floats<ENC>(hid + (size_t)node * ENC, st);
+      load_floats<ENC>(hid_of(node), st);
+      value = st[0] + 0.5f; reward = 1.0f;
+#pragma unroll
+      for (int a = 0; a < A; ++a) pri[a] = 1.0f / A;
+      store_floats<ENC>(hid_of(fresh), st);
+    } else {
+      float st[ENC];
+      load_floats<ENC>(hid_of(node), st);
       float nx[ENC];
-      SH::Dyn::run(pack + SH::OFF_DYN, st, action, nx);
+      SH::Dyn::template run<F2>(pack + SH::OFF_DYN, st, action, nx);
       {
         float rl[FULL];
-        SH::Rew::run(pack + SH::OFF_REW, nx, -1, rl);
+        SH::Rew::template run<F2>(pack + SH::OFF_REW, nx, -1, rl);
         reward = s2s_regs<SH::SUP>(rl);
       }
       minmax_regs(nx);
-      store_floats<ENC>(hid + (size_t)fresh * ENC, nx);
+      store_floats<ENC>(hid_of(fresh), nx);
       {
         float pl[A];
-        SH::Pol::run(pack + SH::OFF_POL, nx, -1, pl);
+        SH::Pol::template run<F2>(pack + SH::OFF_POL, nx, -1, pl);
         priors_regs<A>(pl, nullptr, pri);
       }
       {
         float vl[FULL];
-        SH::Val::run(pack + SH::OFF_VAL, nx, -1, vl);
+        SH::Val::template run<F2>(pack + SH::OFF_VAL, nx, -1, vl);
         value = s2s_regs<SH::SUP>(vl);
       }
     }
@@ -378,24 +443,56 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
       Rec<A> rr;
 #pragma unroll
       for (int a = 0; a < A; ++a) rr.set(a, 0.0, pri[a], 0, 0.0f, MZB_CHILD_NONE);
-      rr.store(t.rec(g, fresh));
-      uint8_t* pr_ = t.rec(g, node);
-      t.reward(pr_)[action] = reward;
-      t.child(pr_)[action] = fresh;
+      rr.store(rec_of(fresh));
+      bool in_regs = false;
+      if constexpr (ROOTREG) {
+        if (node == 0) {
+          in_regs = true;
+#pragma unroll
+          for (int a = 0; a < A; ++a)
+            if (a == action) { root.w[4 * A + a] = __float_as_uint(reward); root.w[5 * A + a] = (uint32_t)fresh; }
+        }
+      }
+      if (!in_regs) {
+        uint8_t* pr_ = rec_of(node);
+        t.reward(pr_)[action] = reward;
+        t.child(pr_)[action] = fresh;
+      }
     }
 
     // ---------------- backup (self_play.py:407-431), leaf first
     double val = (double)value;
     for (int k = L - 1; k >= 0; --k) {
-      const uint32_t pe = PB_LUT ? lp_edge[k] : path[(size_t)k * G];
-      uint8_t* er = t.rec(g, (int)(pe >> 16));
-      const int pa = (int)(pe & 0xFFFFu);
-      double e_vs = PB_LUT ? lp_vs[k] : t.value_sum(er)[pa];
-      int e_vi = PB_LUT ? lp_vi[k] : t.visit(er)[pa];
-      const double e_rw = (k == L - 1) ? (double)reward : (PB_LUT ? (double)lp_rw[k] : (double)t.reward(er)[pa]);
+      int pn, pa, e_vi; double e_vs; float l_rw = 0.0f;
+      if (PD > 0 && k < PD) {
+        const uint32_t ev = sp_ev[k * THREADS + threadIdx.x];
+        pn = (int)(ev >> 24); pa = (int)((ev >> 16) & 0xFFu); e_vi = (int)(ev & 0xFFFFu);
+        e_vs = sp_vs[k * THREADS + threadIdx.x]; l_rw = sp_rw[k * THREADS + threadIdx.x];
+      } else {
+        const uint32_t pe = PB_LUT ? lp_edge[k] : path[(size_t)k * G];
+        pn = (int)(pe >> 16); pa = (int)(pe & 0xFFFFu);
+        if (PB_LUT) { e_vs = lp_vs[k]; e_vi = lp_vi[k]; l_rw = lp_rw[k]; }
+      }
+      uint8_t* er = rec_of(pn);
+      if (!PB_LUT) { e_vs = t.value_sum(er)[pa]; e_vi = t.visit(er)[pa]; l_rw = t.reward(er)[pa]; }
+      const double e_rw = (k == L - 1) ? (double)reward : (double)l_rw;
       backup_step(e_vs, e_vi, e_rw, val, t.discount, two, ((L - (k + 1)) & 1) == 0, vmin, vmax);
-      t.value_sum(er)[pa] = e_vs;
-      t.visit(er)[pa] = e_vi;
+      bool in_regs = false;
+      if constexpr (ROOTREG) {
+        if (pn == 0) {
+          in_regs = true;
+#pragma unroll
+          for (int a = 0; a < A; ++a)
+            if (a == pa) {
+              root.w[2 * a] = (uint32_t)__double2loint(e_vs); root.w[2 * a + 1] = (uint32_t)__double2hiint(e_vs);
+              root.w[3 * A + a] = (uint32_t)e_vi;
+            }
+        }
+      }
+      if (!in_regs) {
+        t.value_sum(er)[pa] = e_vs;
+        t.visit(er)[pa] = e_vi;
+      }
     }
     backup_step(root_vs, root_visit, (double)root_reward, val, t.discount, two, (L & 1) == 0, vmin, vmax);
     max_depth = L > max_depth ? L : max_depth;
@@ -405,6 +502,12 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
   atomicAdd(t.counters + 1, (unsigned long long)io.num_sims);
 
   if (!active) return;
+  if constexpr (ROOTREG) {
+    Rec<A> rr;
+#pragma unroll
+    for (int i = 0; i < Rec<A>::WORDS; ++i) rr.w[i] = root.w[i];
+    rr.store(rec_of(0));
+  }
   // ---------------- publish the per-game scalars (same fields the modular kernels keep)
   t.root_value_sum[g] = root_vs;
   t.vmin[g] = vmin;
@@ -418,9 +521,13 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
   t.step[g] = my_step;
   t.to_play[g] = io.to_play ? io.to_play[g] : (int8_t)0;
   if (io.visits) {
-    uint8_t* r = t.rec(g, 0);
 #pragma unroll
-    for (int a = 0; a < A; ++a) io.visits[(size_t)g * A + a] = t.child(r)[a] == MZB_CHILD_ILLEGAL ? 0 : t.visit(r)[a];
+    for (int a = 0; a < A; ++a) {
+      int c, v;
+      if constexpr (ROOTREG) { c = (int)root.w[5 * A + a]; v = (int)root.w[3 * A + a]; }
+      else { uint8_t* r = rec_of(0); c = t.child(r)[a]; v = t.visit(r)[a]; }
+      io.visits[(size_t)g * A + a] = c == MZB_CHILD_ILLEGAL ? 0 : v;
+    }
   }
   if (io.root_value) io.root_value[g] = root_visit > 0 ? __ddiv_rn(root_vs, (double)root_visit) : 0.0;
   if (io.max_depth) io.max_depth[g] = max_depth;
@@ -429,45 +536,52 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) k_search_fc(TreeView t
 using CartpoleShape = Shape<4, 8, 2, 10, 0, 16, 16, 16, 16>;       // games/cartpole.py:21-71
 using TicTacToeFcShape = Shape<27, 32, 9, 10, 0, 16, 16, 0, 0>;    // games/tictactoe.py:20-70, network="fullyconnected"
 
-template <class SH, int THREADS, bool PHASE_SYNC, bool PB_LUT>
+template <class SH, bool PB_LUT, int EXP, int THREADS = 256, bool PHASE_SYNC = true, int MINB = 512 / THREADS>
 int launch_variant(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
   const int S1 = io.num_sims + 1;
-  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? S1 * S1 : 0));
+  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? S1 * S1 : 0)) +
+                      (((EXP & X_SPATH) != 0 && PB_LUT) ? (size_t)smem_path_depth(MINB) * THREADS * 16 : 0);
   static bool configured = false;
   if (!configured) {
-    MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT, EXP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = true;
   }
   MZB_CHECK_ARG(smem <= 96 * 1024, "fused search: shared memory %zu > 96 KiB", smem);
   const int grid = (t->v.G + THREADS - 1) / THREADS;
-  k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT><<<grid, THREADS, smem, s>>>(t->v, m->d_pack, io);
+  k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT, EXP, MINB><<<grid, THREADS, smem, s>>>(t->v, m->d_pack, io);
   MZB_LAUNCH_CHECK();
   return MZB_OK;
 }
 
-// Kernel variant: MZB_FUSED_VARIANT = threads(128|256) + 1000*phase_sync + 10000*pb_lut (tuning knob; default below)
-int fused_variant() {
+// MZB_FUSED_EXP: experiment flags of k_search_fc (see the enum); default = the shipped configuration
+int fused_exp() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("MZB_FUSED_VARIANT");
-    v = e ? atoi(e) : 11256;
+    const char* e = getenv("MZB_FUSED_EXP");
+    v = e ? atoi(e) : MZB_FUSED_DEFAULT_EXP;
   }
   return v;
 }
 
-template <class SH>
+template <class SH, bool TUNE>
 int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
-  int v = fused_variant();
-  const bool lut_ok = io.num_sims <= 63;                 // (S+1)^2 doubles must fit next to the weights
-  const int threads = v % 1000;
-  const bool sync = (v / 1000) % 10 != 0;
-  const bool lut = (v / 10000) % 10 != 0 && lut_ok;
-  if (threads == 256) {
-    if (sync) return lut ? launch_variant<SH, 256, true, true>(t, m, io, s) : launch_variant<SH, 256, true, false>(t, m, io, s);
-    return lut ? launch_variant<SH, 256, false, true>(t, m, io, s) : launch_variant<SH, 256, false, false>(t, m, io, s);
+  const bool lut = io.num_sims <= 63;                 // (S+1)^2 doubles must fit next to the weights
+  if (!lut) return launch_variant<SH, false, MZB_FUSED_DEFAULT_EXP>(t, m, io, s);
+  if constexpr (TUNE) {
+    switch (fused_exp()) {
+      case 0: return launch_variant<SH, true, 0>(t, m, io, s);
+      case 1: return launch_variant<SH, true, 1>(t, m, io, s);
+      case 3: return launch_variant<SH, true, 3>(t, m, io, s);
+      case 7: return launch_variant<SH, true, 7>(t, m, io, s);
+      case 23: return launch_variant<SH, true, 23>(t, m, io, s);
+      case 1003: return launch_variant<SH, true, 3, 256, true, 3>(t, m, io, s);     // 1000 + flags: 3 blocks per SM (<= 85 registers)
+      case 1007: return launch_variant<SH, true, 7, 256, true, 3>(t, m, io, s);
+      case 19: return launch_variant<SH, true, 19>(t, m, io, s);
+      case 35: return launch_variant<SH, true, 35>(t, m, io, s);
+      default: break;
+    }
   }
-  if (sync) return lut ? launch_variant<SH, 128, true, true>(t, m, io, s) : launch_variant<SH, 128, true, false>(t, m, io, s);
-  return lut ? launch_variant<SH, 128, false, true>(t, m, io, s) : launch_variant<SH, 128, false, false>(t, m, io, s);
+  return launch_variant<SH, true, MZB_FUSED_DEFAULT_EXP>(t, m, io, s);
 }
 
 }  // namespace
@@ -494,22 +608,21 @@ int mzb_search_fc(mzb_tree* t, mzb_fc_model* m, const float* d_obs, const uint8_
   if (allow_fused) {
     SearchIO io{d_obs, d_legal, d_to_play, d_noise, alpha, frac, d_slot, d_step, num_simulations,
                 d_visits, d_root_value, d_root_predicted_value, d_max_depth};
-    if (CartpoleShape::matches(m->d)) return launch_fused<CartpoleShape>(t, m, io, s);
-    if (TicTacToeFcShape::matches(m->d)) return launch_fused<TicTacToeFcShape>(t, m, io, s);
+    if (CartpoleShape::matches(m->d)) return launch_fused<CartpoleShape, true>(t, m, io, s);
+    if (TicTacToeFcShape::matches(m->d)) return launch_fused<TicTacToeFcShape, false>(t, m, io, s);
   }
   // modular path: K5, K0, then (K1, K4, K3) per simulation - any FC shape
-  const int64_t hs = (int64_t)(t->v.S + 1) * t->v.H;
-  int rc = mzb_fc_initial(m, G, d_obs, d_legal, t->v.hidden, hs, 0, nullptr, nullptr, nullptr, d_root_predicted_value,
-                          t->tmp_reward, t->tmp_priors, s);
+  const int S1 = t->v.S + 1;
+  int rc = mzb_fc_initial_tree(m, G, d_obs, d_legal, t->v.hidden, S1, 0, d_root_predicted_value, t->tmp_reward,
+                               t->tmp_priors, s);
   if (rc) return rc;
   rc = mzb_tree_root_init(t, t->tmp_reward, t->tmp_priors, 0, d_legal, d_to_play, d_noise, alpha, frac, d_slot, d_step, s);
   if (rc) return rc;
   for (int sim = 0; sim < num_simulations; ++sim) {
     rc = mzb_tree_select(t, t->tmp_parent, t->tmp_action, nullptr, s);
     if (rc) return rc;
-    rc = mzb_fc_recurrent(m, G, t->v.hidden, hs, t->tmp_parent, t->v.H, t->tmp_action, t->v.hidden, hs,
-                          (int64_t)(sim + 1) * t->v.H, nullptr, nullptr, nullptr, t->tmp_value, t->tmp_reward,
-                          t->tmp_priors, s);
+    rc = mzb_fc_recurrent_tree(m, G, t->v.hidden, S1, t->tmp_parent, t->tmp_action, sim + 1, t->tmp_value, t->tmp_reward,
+                               t->tmp_priors, s);
     if (rc) return rc;
     rc = mzb_tree_expand_backup(t, t->tmp_value, t->tmp_reward, t->tmp_priors, 0, s);
     if (rc) return rc;

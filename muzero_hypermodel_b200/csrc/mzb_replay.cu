@@ -486,6 +486,12 @@ int mzb_replay_info(const mzb_replay* r, int64_t* out5) {
   return MZB_OK;
 }
 
+int mzb_replay_get_config(const mzb_replay* r, mzb_replay_config* out) {
+  MZB_CHECK_ARG(r && out, "NULL argument");
+  *out = r->cfg;
+  return MZB_OK;
+}
+
 int mzb_replay_set_batch_counter(mzb_replay* r, uint32_t counter) {
   MZB_CHECK_ARG(r, "NULL argument");
   r->batch_counter = counter;

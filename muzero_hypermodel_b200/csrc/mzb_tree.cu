@@ -350,15 +350,16 @@ struct Offsets {
 Offsets layout(const mzb_tree_config& c) {
   Offsets o;
   const size_t G = c.n_games, A = c.n_actions, S1 = (size_t)c.num_simulations + 1;
+  const size_t Gp = (G + 31) / 32 * 32;          // node records and hidden slots are blocked by 32 games
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t at = off; off = mzb_align_up(off + bytes, 256); return at; };
-  o.nodes = take(G * S1 * 24 * A);
+  o.nodes = take(Gp * S1 * 24 * A);
   o.root_prior = take(G * A * 8);
   o.path = take(G * S1 * 4);
   o.rvs = take(G * 8); o.vmin = take(G * 8); o.vmax = take(G * 8);
   o.rrew = take(G * 4); o.rvis = take(G * 4); o.plen = take(G * 4); o.mdep = take(G * 4); o.sdone = take(G * 4);
   o.slot = take(G * 4); o.step = take(G * 4); o.toplay = take(G);
-  o.hidden = take(G * S1 * (size_t)c.hidden_floats * 4);
+  o.hidden = take(Gp * S1 * (size_t)c.hidden_floats * 4);
   o.tmp_parent = take(G * 4); o.tmp_action = take(G * 4); o.tmp_value = take(G * 4); o.tmp_reward = take(G * 4);
   o.tmp_priors = take(G * A * 4);
   o.counters = take(64);
@@ -429,7 +430,7 @@ int mzb_tree_create(mzb_tree** out, const mzb_tree_config* cfg, void* d_workspac
   v.discount = cfg->discount;
   v.nodes = w + o.nodes;
   v.rec_bytes = 24 * (size_t)cfg->n_actions;
-  v.game_stride = v.rec_bytes * S1;
+  v.blk_stride = v.rec_bytes * S1 * 32;
   v.root_prior = (double*)(w + o.root_prior);
   v.path = (uint32_t*)(w + o.path);
   v.root_value_sum = (double*)(w + o.rvs);
@@ -531,8 +532,9 @@ int mzb_tree_export_game_sync(mzb_tree* t, int32_t game, double* h_value_sum, fl
   cudaStream_t s = (cudaStream_t)stream;
   const TreeView& v = t->v;
   const int S1 = v.S + 1, A = v.A;
-  std::vector<uint8_t> buf(v.game_stride);
-  MZB_CUDA(cudaMemcpyAsync(buf.data(), v.nodes + (size_t)game * v.game_stride, v.game_stride, cudaMemcpyDeviceToHost, s));
+  std::vector<uint8_t> buf(v.rec_bytes * S1);      // the game's records are 32 records apart (blocked layout)
+  MZB_CUDA(cudaMemcpy2DAsync(buf.data(), v.rec_bytes, v.nodes + v.rec_index(game, 0) * v.rec_bytes, 32 * v.rec_bytes,
+                             v.rec_bytes, S1, cudaMemcpyDeviceToHost, s));
   double rvs; float rrw; int rvi, sd;
   MZB_CUDA(cudaMemcpyAsync(&rvs, v.root_value_sum + game, 8, cudaMemcpyDeviceToHost, s));
   MZB_CUDA(cudaMemcpyAsync(&rrw, v.root_reward + game, 4, cudaMemcpyDeviceToHost, s));

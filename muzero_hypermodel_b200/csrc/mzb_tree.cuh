@@ -1,15 +1,19 @@
 // Tree store layout + device routines shared by the modular tree kernels (mzb_tree.cu).
 //
 // HBM layout (one workspace, caller-owned), for G games, A actions, S simulations:
-//   nodes      [G][S+1] records of 24*A bytes:  value_sum f64[A] | prior f32[A] | visit i32[A] |
-//                                               reward f32[A]   | child i32[A]
+//   nodes      [G/32][S+1][32] records of 24*A bytes:  value_sum f64[A] | prior f32[A] | visit i32[A] |
+//                                                      reward f32[A]   | child i32[A]
+//              NODE-MAJOR inside a block of 32 consecutive games (one warp of the thread-per-game kernels): the 32
+//              records a warp touches at the SAME node index - the root every simulation, the fresh node of
+//              simulation k, the depth-1 nodes most of the time - are one contiguous 32*24*A-byte run instead of
+//              32 lines scattered at a game-sized stride (cartpole whole-search kernel: 5.06 -> 4.62 ms).
 //              record (g, n) describes the A edges leaving node n; edge (n, a) carries what the
 //              reference keeps on the child Node (self_play.py:434-442).  child = slot of the
 //              expanded child, -1 = not expanded, -2 = illegal at the root.
 //   root_prior [G][A] f64   root priors after the Dirichlet mix are true float64 (:474-477)
 //   path       [G][S+1] u32 (node << 16 | action) edges of the current search path
 //   scalars    SoA per game: root value_sum/min/max f64, root reward f32, counters i32, rng u32
-//   hidden     [G][S+1][H] f32 hidden-state slots (slot = node index)
+//   hidden     [G/32][S+1][32][H] f32 hidden-state slots (slot = node index), blocked the same way
 // One node's edges are contiguous, so a group of lanes reads them with coalesced loads.
 #pragma once
 #include "mzb_common.cuh"
@@ -21,7 +25,7 @@ struct TreeView {
   int G, A, S, P, H;
   double discount;
   uint8_t* nodes;
-  size_t rec_bytes, game_stride;
+  size_t rec_bytes, blk_stride;      // blk_stride = (S+1) * 32 * rec_bytes: one block of 32 games
   double* root_prior;
   uint32_t* path;
   double* root_value_sum;
@@ -40,7 +44,11 @@ struct TreeView {
   unsigned long long* counters;   // [0] sum of search-path lengths, [1] simulations (bench: mean path length)
   RngKey key;
 
-  __device__ __forceinline__ uint8_t* rec(int g, int n) const { return nodes + (size_t)g * game_stride + (size_t)n * rec_bytes; }
+  __host__ __device__ __forceinline__ size_t rec_index(int g, int n) const {     // in records (or hidden slots)
+    return ((size_t)(g >> 5) * (size_t)(S + 1) + (size_t)n) * 32 + (size_t)(g & 31);
+  }
+  __device__ __forceinline__ uint8_t* rec(int g, int n) const { return nodes + rec_index(g, n) * rec_bytes; }
+  __device__ __forceinline__ float* hidden_at(int g, int n) const { return hidden + rec_index(g, n) * (size_t)H; }
   __device__ __forceinline__ static double* value_sum(uint8_t* r) { return (double*)r; }
   __device__ __forceinline__ float* prior(uint8_t* r) const { return (float*)(r + 8 * (size_t)A); }
   __device__ __forceinline__ int* visit(uint8_t* r) const { return (int*)(r + 12 * (size_t)A); }

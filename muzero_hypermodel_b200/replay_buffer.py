@@ -83,6 +83,12 @@ def make_target_batch(games, batch_game, batch_index, config, seed=0, batch_slot
     return tv, tr, tp, ta
 
 
+def _set_info(shared_storage, key, value):
+    """shared_storage.set_info, Ray actor handle (`.remote`) or plain object (Trainer / Reanalyse / tests)."""
+    remote = getattr(shared_storage.set_info, "remote", None)
+    return remote(key, value) if remote is not None else shared_storage.set_info(key, value)
+
+
 class ReplayBuffer:
     """ReplayBuffer(initial_checkpoint, initial_buffer, config) (replay_buffer.py:17-31) with the store on `device`."""
 
@@ -121,9 +127,18 @@ class ReplayBuffer:
             self._h = _vp()
             check(_lib.lib.mzb_replay_create(C.byref(self._h), C.byref(self.cfg), _vp(base), nbytes, dp, _lib.current_stream()))
         self.nbytes = nbytes
-        self._played0 = (int(initial_checkpoint["num_played_games"]), int(initial_checkpoint["num_played_steps"]))
-        for game_history in (initial_buffer or {}).values():
+        self._record_env_kind = None if record_env is None else record_env.kind
+        # Resume (replay_buffer.py:17-24): the counters are the CHECKPOINT's - re-loading the buffered games does not
+        # play them again - and the games keep their ids (the keys of `initial_buffer`): public id = device id + _id0.
+        # With a consistent checkpoint the newest loaded game is num_played_games - 1 and the next saved game gets id
+        # num_played_games, as in the reference.
+        self._played0, self._id0 = (0, 0), 0
+        initial = sorted((initial_buffer or {}).items())
+        for _, game_history in initial:
             self.save_game(game_history)
+        n0, s0 = self._info()[1], self._info()[2]
+        self._played0 = (int(initial_checkpoint["num_played_games"]) - n0, int(initial_checkpoint["num_played_steps"]) - s0)
+        self._id0 = int(initial[0][0]) if initial else int(initial_checkpoint["num_played_games"])
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -177,8 +192,8 @@ class ReplayBuffer:
                                self._dev(game_history.to_play_history, torch.int8), self._dev(rv, torch.float64),
                                torch.from_numpy(vis).to(self.device), None if pr is None else self._dev(pr, torch.float32))
         if shared_storage:
-            shared_storage.set_info.remote("num_played_games", self.num_played_games)
-            shared_storage.set_info.remote("num_played_steps", self.num_played_steps)
+            _set_info(shared_storage, "num_played_games", self.num_played_games)
+            _set_info(shared_storage, "num_played_steps", self.num_played_steps)
 
     def _dev(self, x, dt):
         return torch.as_tensor(np.ascontiguousarray(x)).to(self.device, dt).contiguous()
@@ -195,6 +210,18 @@ class ReplayBuffer:
     def ingest(self, env):
         """Append every finished game in `env`'s export ring (device to device) and empty the ring: the hop that
         replaces `replay_buffer.save_game.remote(game_history)` (self_play.py:52).  Returns the number of games."""
+        same_layout = (self.rec_floats == int(env.rec_floats) and self.A == int(env.A)
+                       and self.decode == (1 if env.kind in ("tictactoe", "connect4", "gomoku") else 0)
+                       and (not self.decode or tuple(self.board) == tuple(env.obs_shape[1:]))
+                       and int(self.config.max_moves) >= int(env.max_moves))
+        if not same_layout:
+            # a store built with the reference's 3-argument constructor keeps decoded observations: take the games
+            # through the host format instead of copying records with the wrong stride
+            from .self_play import decode_export
+            games = decode_export(env)
+            for game_history in games:
+                self.save_game(game_history)
+            return len(games)
         n = _i32()
         with torch.cuda.device(self.device):
             check(_lib.lib.mzb_env_export_to_replay(env._h, self._h, C.byref(n), _lib.current_stream()))
@@ -221,13 +248,18 @@ class ReplayBuffer:
             check(_lib.lib.mzb_replay_get_batch(self._h, B, ptr(ug), ptr(up), ptr(gid), ptr(pos), None, None, ptr(obs),
                                                 ptr(act), ptr(val), ptr(rew), ptr(pol), ptr(w), ptr(gs),
                                                 _lib.current_stream()))
+        if self._id0:
+            gid = gid + self._id0                   # public game ids (resume keeps the checkpoint's numbering)
         return torch.stack([gid, pos.to(torch.int64)], dim=1), (obs, act, val, rew, pol, w, gs)
 
     # -- update_priorities (:202-220)
     def update_priorities(self, priorities, index_info):
         pr = torch.as_tensor(priorities).to(self.device, torch.float32).contiguous()
-        idx = torch.as_tensor(np.asarray(index_info.cpu() if torch.is_tensor(index_info) else index_info, dtype=np.int64)).to(self.device)
-        gid = idx[:, 0].contiguous()
+        if torch.is_tensor(index_info):             # stays on the device: no host sync on the learner loop
+            idx = index_info.to(self.device, torch.int64)
+        else:
+            idx = torch.as_tensor(np.asarray(index_info, dtype=np.int64)).to(self.device)
+        gid = (idx[:, 0] - self._id0).contiguous()
         pos = idx[:, 1].to(torch.int32).contiguous()
         with torch.cuda.device(self.device):
             check(_lib.lib.mzb_replay_update_priorities(self._h, pr.shape[0], ptr(pr), ptr(gid), ptr(pos), _lib.current_stream()))
@@ -239,11 +271,12 @@ class ReplayBuffer:
             raise NotImplementedError("prioritised single-game draws go through get_batch")
         first, n = self._info()[4], len(self)
         u = float(np.random.random_sample()) if u is None else float(u)
-        return first + int(u * n)
+        return self._id0 + first + int(u * n)
 
     def game_observations(self, game_id):
         """[len, C, H, W] float32 device tensor: the stored observations of a game as network input."""
         n = _i32()
+        game_id = int(game_id) - self._id0
         check(_lib.lib.mzb_replay_game_observations(self._h, int(game_id), None, C.byref(n), _lib.current_stream()))
         obs = torch.empty((n.value,) + tuple(self.config.observation_shape), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
@@ -254,7 +287,7 @@ class ReplayBuffer:
         """game_history.reanalysed_predicted_root_values = values (float32 [len]); ignored if the game was evicted."""
         v = torch.as_tensor(values).to(self.device, torch.float32).reshape(-1).contiguous()
         with torch.cuda.device(self.device):
-            check(_lib.lib.mzb_replay_set_reanalysed(self._h, int(game_id), ptr(v), _lib.current_stream()))
+            check(_lib.lib.mzb_replay_set_reanalysed(self._h, int(game_id) - self._id0, ptr(v), _lib.current_stream()))
 
     # -- get_buffer (:66-67): what muzero.py pickles into replay_buffer.pkl and hands back as `initial_buffer`
     def get_buffer(self):
@@ -282,8 +315,8 @@ class ReplayBuffer:
             gh.visit_counts = v.copy()
             gh.root_values = rv[:n].tolist()
             if self.config.PER:
-                gh.priorities, gh.game_priority = self.game_priorities(gid)
-            out[self._played0[0] + gid] = gh
+                gh.priorities, gh.game_priority = self.game_priorities(self._id0 + gid)
+            out[self._id0 + gid] = gh
         return out
 
     def _decode_record(self, rec):
@@ -298,7 +331,8 @@ class ReplayBuffer:
         n = _i32()
         buf = np.zeros(int(self.config.max_moves) + 2, dtype=np.float32)
         gp = np.zeros(1, dtype=np.float32)
-        check(_lib.lib.mzb_replay_game_priorities_sync(self._h, int(game_id), ptr(buf), ptr(gp), C.byref(n), _lib.current_stream()))
+        check(_lib.lib.mzb_replay_game_priorities_sync(self._h, int(game_id) - self._id0, ptr(buf), ptr(gp), C.byref(n),
+                                                       _lib.current_stream()))
         return buf[:n.value].copy(), gp[0]
 
 

@@ -2,7 +2,7 @@
 
   MCTS(config).run(model, observation, legal_actions, to_play, add_exploration_noise, override_root_with=None)
       -> (root Node, {"max_tree_depth", "root_predicted_value"})                       self_play.py:261-362
-  Node / MinMaxStats / GameHistory                                                     :434-568
+  Node / GameHistory (MinMaxStats lives per game in the device tree store)             :434-568
   SelfPlay(initial_checkpoint, Game, config, seed)  .play_game(...) -> GameHistory     :11-246
   SelfPlay.play_games(...)                          G games in lock-step per GPU (the B200 path)
 
@@ -18,23 +18,6 @@ import torch
 from . import models
 from .envs import VectorEnv, game_kind
 from .search import BatchedMCTS
-
-
-class MinMaxStats:
-    """Min-max of the Q values seen in one search (self_play.py:551-568); the device keeps these per game."""
-
-    def __init__(self):
-        self.maximum = -float("inf")
-        self.minimum = float("inf")
-
-    def update(self, value):
-        self.maximum = max(self.maximum, value)
-        self.minimum = min(self.minimum, value)
-
-    def normalize(self, value):
-        if self.maximum > self.minimum:
-            return (value - self.minimum) / (self.maximum - self.minimum)
-        return value
 
 
 class Node:
@@ -113,6 +96,7 @@ class MCTS:
     """`MCTS(config).run(...)`: one search, executed by the batched kernels with G = 1."""
 
     _cache = {}
+    _calls = 0          # searches started without an explicit RNG step: each draws fresh noise / tie-breaks
 
     def __init__(self, config):
         self.config = config
@@ -146,9 +130,14 @@ class MCTS:
         if noise is not None:
             nz = torch.zeros((1, A), dtype=torch.float64, device=device)
             nz[0, list(legal_actions)] = torch.as_tensor(numpy.asarray(noise, dtype=numpy.float64), device=device)
+        if step is None:
+            # the reference draws from numpy's advancing global stream: a call without counters must not repeat the
+            # previous call's Dirichlet sample and tie-breaks, so the call number becomes the RNG step
+            step = MCTS._calls & 0x7FFFFFFF
+            MCTS._calls += 1
         out = eng.run(model, obs, legal, torch.tensor([to_play], dtype=torch.int8, device=device), add_exploration_noise,
                       noise=nz, slot=None if slot is None else torch.tensor([slot], dtype=torch.int32, device=device),
-                      step=None if step is None else torch.tensor([step], dtype=torch.int32, device=device))
+                      step=torch.tensor([step], dtype=torch.int32, device=device))
         root = self._materialise(eng, 0, list(legal_actions), to_play)
         info = {"max_tree_depth": int(out["max_depth"][0]), "root_predicted_value": float(out["root_predicted_value"][0])}
         return root, info
@@ -170,8 +159,11 @@ class MCTS:
             nz = torch.zeros((1, A), dtype=torch.float64, device=device)
             nz[0, actions] = torch.as_tensor(numpy.asarray(noise, dtype=numpy.float64), device=device)
         frac = float(cfg.root_exploration_fraction) if add_exploration_noise else 0.0
+        step = torch.tensor([MCTS._calls & 0x7FFFFFFF], dtype=torch.int32, device=device)
+        MCTS._calls += 1
         tree.root_init(torch.tensor([float(root.reward)], device=device), pri, False, legal,
-                       torch.tensor([to_play], dtype=torch.int8, device=device), nz, cfg.root_dirichlet_alpha, frac)
+                       torch.tensor([to_play], dtype=torch.int8, device=device), nz, cfg.root_dirichlet_alpha, frac,
+                       None, step)
         hs = root.hidden_state.to(device).float()
         hidden = torch.empty((1, cfg.num_simulations + 1, hs.numel()), device=device)
         hidden[0, 0] = hs.reshape(-1)
@@ -255,7 +247,12 @@ def decode_export(env):
 
 class SelfPlay:
     """Self-play worker.  `play_games` advances G games in lock-step on one GPU; `play_game` keeps the
-    reference's one-game signature (self_play.py:110-184) on top of it."""
+    reference's one-game signature (self_play.py:110-184) on top of it.
+
+    `Game` is honoured as in the reference: the built-in `games/<name>.Game` classes (they carry a `KIND`) and
+    `Game=None` select the vectorised device environment of the config's game; any OTHER `AbstractGame` subclass is
+    instantiated as `Game(seed)` and played on the host through the step / legal_actions / to_play contract, one
+    move at a time, with every search on the device kernels (G = 1)."""
 
     def __init__(self, initial_checkpoint, Game, config, seed, n_games=None, device=None, first_slot=0):
         self.config = config
@@ -275,8 +272,24 @@ class SelfPlay:
         self.first_slot = first_slot
         self._env = None
         self._mcts = None
+        self._solo = None
+        self._game = None
         self.num_played_games = 0
         self.num_played_steps = 0
+        self.host_game = Game is not None and getattr(Game, "KIND", None) is None
+        if self.host_game and n_games not in (None, 1):
+            raise NotImplementedError("a caller-supplied Game class is played one game at a time on the host "
+                                      "(n_games = 1); the vectorised path runs the built-in device environments")
+
+    @property
+    def game(self):
+        """The host `Game(seed)` object (reference: self.game), created on first use."""
+        if self._game is None:
+            if self.Game is None:
+                import importlib
+                self.Game = importlib.import_module(f"{__package__}.games.{game_kind(self.config)}").Game
+            self._game = self.Game(self.seed)
+        return self._game
 
     # -- batched device loop
     def _setup(self):
@@ -323,10 +336,9 @@ class SelfPlay:
         replay buffer, respect self_play_delay / ratio.  `shared_storage` is anything with get_info / set_info (plain
         methods or Ray-style `.remote`); a replay buffer with `ingest` (the device store, replay_buffer.ReplayBuffer)
         receives the games device to device, any other through `save_game(game_history, shared_storage)`.
-        test_mode (greedy play against an opponent, :54-88) is a host-side evaluation mode and not on this path.
-        `max_moves` bounds the loop for callers without a trainer (None: until training_steps / terminate)."""
-        if test_mode:
-            raise NotImplementedError("test_mode evaluation is not on the device self-play path")
+        test_mode (:54-88): greedy games, one at a time, against config.opponent; their statistics go to the shared
+        storage.  `max_moves` bounds the loop for callers without a trainer (None: until training_steps / terminate):
+        moves of the lock-step games, or whole games in test mode."""
         import time
 
         def call(method, *args):
@@ -338,29 +350,45 @@ class SelfPlay:
             return ray.get(out) if method.__name__.startswith("get") else out
 
         cfg = self.config
-        env, _ = self._setup()
         moves = 0
         while (call(shared_storage.get_info, "training_step") < cfg.training_steps
                and not call(shared_storage.get_info, "terminate")):
             weights = call(shared_storage.get_info, "weights")
             if weights is not None:
                 self.model.set_weights(weights)
-            T = cfg.visit_softmax_temperature_fn(trained_steps=call(shared_storage.get_info, "training_step"))
-            self.step(T, cfg.temperature_threshold)
-            if hasattr(replay_buffer, "ingest"):
-                n = replay_buffer.ingest(env)
-                if n:
-                    call(shared_storage.set_info, "num_played_games", replay_buffer.num_played_games)
-                    call(shared_storage.set_info, "num_played_steps", replay_buffer.num_played_steps)
+            if test_mode:
+                gh = self.play_game(0, cfg.temperature_threshold, False,
+                                    "self" if len(cfg.players) == 1 else cfg.opponent, cfg.muzero_player)
+                call(shared_storage.set_info, {"episode_length": len(gh.action_history) - 1,
+                                               "total_reward": sum(gh.reward_history),
+                                               "mean_value": numpy.mean([v for v in gh.root_values if v])})
+                if 1 < len(cfg.players):
+                    mine = [gh.to_play_history[i - 1] == cfg.muzero_player for i in range(len(gh.reward_history))]
+                    call(shared_storage.set_info,
+                         {"muzero_reward": sum(r for r, m in zip(gh.reward_history, mine) if m),
+                          "opponent_reward": sum(r for r, m in zip(gh.reward_history, mine) if not m)})
+            elif self.host_game:
+                gh = self.play_game(cfg.visit_softmax_temperature_fn(trained_steps=call(shared_storage.get_info, "training_step")),
+                                    cfg.temperature_threshold, False, "self", 0)
+                call(replay_buffer.save_game, gh, shared_storage)
             else:
-                for game_history in self.drain():
-                    call(replay_buffer.save_game, game_history, shared_storage)
+                env, _ = self._setup()
+                T = cfg.visit_softmax_temperature_fn(trained_steps=call(shared_storage.get_info, "training_step"))
+                self.step(T, cfg.temperature_threshold)
+                if hasattr(replay_buffer, "ingest"):
+                    n = replay_buffer.ingest(env)
+                    if n:
+                        call(shared_storage.set_info, "num_played_games", replay_buffer.num_played_games)
+                        call(shared_storage.set_info, "num_played_steps", replay_buffer.num_played_steps)
+                else:
+                    for game_history in self.drain():
+                        call(replay_buffer.save_game, game_history, shared_storage)
             moves += 1
             if max_moves is not None and moves >= max_moves:
                 break
-            if cfg.self_play_delay:
+            if not test_mode and cfg.self_play_delay:
                 time.sleep(cfg.self_play_delay)
-            if cfg.ratio:
+            if not test_mode and cfg.ratio:
                 while (call(shared_storage.get_info, "training_step") / max(1, call(shared_storage.get_info, "num_played_steps")) < cfg.ratio
                        and call(shared_storage.get_info, "training_step") < cfg.training_steps
                        and not call(shared_storage.get_info, "terminate")):
@@ -369,22 +397,89 @@ class SelfPlay:
 
     # -- reference-compatible single game
     def play_game(self, temperature, temperature_threshold, render, opponent, muzero_player):
-        """One complete game with G = 1 (self_play.py:110-184); `opponent` other than "self" is not on the
-        device path."""
-        if opponent != "self" and len(self.config.players) > 1:
-            raise NotImplementedError('device self-play implements opponent="self"')
-        solo = SelfPlay({"weights": self.model.get_weights()}, self.Game, self.config, self.seed, n_games=1,
-                        device=self.device, first_slot=self.first_slot)
-        for _ in range(self.config.max_moves + 1):
+        """One complete game (self_play.py:110-184).  Self-play of a built-in game runs entirely on the device
+        (G = 1: environment, search, action selection and history stay on the GPU); a caller-supplied Game class,
+        an opponent ("human" / "expert" / "random"), rendering or stacked observations take the host loop, whose
+        searches are `MCTS.run` on the same kernels."""
+        cfg = self.config
+        if (self.host_game or render or int(getattr(cfg, "stacked_observations", 0)) != 0
+                or (opponent != "self" and len(cfg.players) > 1)):
+            return self._play_game_host(temperature, temperature_threshold, render, opponent, muzero_player)
+        if self._solo is None:
+            # kept across calls: its environment step counter (the RNG stream position) keeps advancing, so repeated
+            # games with unchanged weights differ like the reference's do under numpy's advancing global stream
+            self._solo = SelfPlay(None, self.Game, cfg, self.seed, n_games=1, device=self.device, first_slot=self.first_slot)
+            self._solo.model = self.model
+        solo = self._solo
+        for _ in range(cfg.max_moves + 1):
             solo.step(float(temperature), temperature_threshold)
             games = solo.drain()
             if games:
                 return games[0]
         raise RuntimeError("game did not finish within max_moves")
 
+    def _play_game_host(self, temperature, temperature_threshold, render, opponent, muzero_player):
+        """play_game over the AbstractGame contract on the host (any Game class, any opponent)."""
+        cfg, game = self.config, self.game
+        gh = GameHistory()
+        observation = game.reset()
+        gh.action_history.append(0)
+        gh.observation_history.append(observation)
+        gh.reward_history.append(0)
+        gh.to_play_history.append(game.to_play())
+        done = False
+        if render:
+            game.render()
+        while not done and len(gh.action_history) <= cfg.max_moves:
+            shape = numpy.array(observation).shape
+            assert len(shape) == 3, f"Observation should be 3 dimensionnal instead of {len(shape)} dimensionnal. Got observation of shape: {shape}"
+            assert shape == tuple(cfg.observation_shape), f"Observation should match the observation_shape defined in MuZeroConfig. Expected {cfg.observation_shape} but got {shape}."
+            stacked = gh.get_stacked_observations(-1, cfg.stacked_observations)
+            if opponent == "self" or muzero_player == game.to_play():
+                root, info = MCTS(cfg).run(self.model, stacked, game.legal_actions(), game.to_play(), True)
+                greedy = temperature_threshold and len(gh.action_history) >= temperature_threshold
+                action = self.select_action(root, 0 if greedy else temperature)
+                if render:
+                    print(f'Tree depth: {info["max_tree_depth"]}')
+                    print(f"Root value for player {game.to_play()}: {root.value():.2f}")
+            else:
+                action, root = self.select_opponent_action(opponent, stacked)
+            observation, reward, done = game.step(action)
+            if render:
+                print(f"Played action: {game.action_to_string(action)}")
+                game.render()
+            gh.store_search_statistics(root, cfg.action_space)
+            gh.action_history.append(action)
+            gh.observation_history.append(observation)
+            gh.reward_history.append(reward)
+            gh.to_play_history.append(game.to_play())
+        return gh
+
+    def select_opponent_action(self, opponent, stacked_observations):
+        """The evaluation opponents (self_play.py:189-221)."""
+        game = self.game
+        if opponent == "human":
+            root, info = MCTS(self.config).run(self.model, stacked_observations, game.legal_actions(), game.to_play(), True)
+            print(f'Tree depth: {info["max_tree_depth"]}')
+            print(f"Root value for player {game.to_play()}: {root.value():.2f}")
+            print(f"Player {game.to_play()} turn. MuZero suggests {game.action_to_string(self.select_action(root, 0))}")
+            return game.human_to_action(), root
+        if opponent == "expert":
+            return game.expert_agent(), None
+        if opponent == "random":
+            legal = game.legal_actions()
+            assert legal, f"Legal actions should not be an empty array. Got {legal}."
+            assert set(legal).issubset(set(self.config.action_space)), "Legal actions should be a subset of the action space."
+            return numpy.random.choice(legal), None
+        raise NotImplementedError('Wrong argument: "opponent" argument should be "self", "human", "expert" or "random"')
+
     def close_game(self):
+        if self._game is not None and hasattr(self._game, "close"):
+            self._game.close()
         self._env = None
         self._mcts = None
+        self._solo = None
+        self._game = None
 
     @staticmethod
     def select_action(node, temperature):

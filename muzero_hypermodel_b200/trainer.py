@@ -212,6 +212,10 @@ class Trainer:
             r = self.model.representation_network.module             # torch.optim skips parameters without a gradient
             unused = {id(p) for p in list(r.conv.parameters()) + list(r.bn.parameters())}
         self.params = [p for p in self.model.parameters() if p.requires_grad and id(p) not in unused]
+        # torch.optim's state_dict numbers ALL model.parameters() (the unused ones keep their index and simply have no
+        # state): index in that numbering of every parameter the flat bucket holds
+        self.n_all_params = sum(1 for _ in self.model.parameters())
+        self.param_index = [i for i, p in enumerate(self.model.parameters()) if p.requires_grad and id(p) not in unused]
         total = sum(p.numel() for p in self.params)
         self.flat_param = torch.empty(total, dtype=torch.float32, device=self.device)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -235,7 +239,7 @@ class Trainer:
     # -- optimiser state in torch.optim's state_dict format (shared_storage / model.checkpoint compatibility)
     def optimizer_state(self):
         state, off = {}, 0
-        for i, p in enumerate(self.params):
+        for i, p in zip(self.param_index, self.params):
             n = p.numel()
             if self.opt_step > 0:
                 if self.config.optimizer == "Adam":
@@ -244,7 +248,7 @@ class Trainer:
                 else:
                     state[i] = {"momentum_buffer": self.state1[off:off + n].view_as(p).cpu().clone()}
             off += n
-        group = {"lr": self.lr, "weight_decay": self.config.weight_decay, "params": list(range(len(self.params)))}
+        group = {"lr": self.lr, "weight_decay": self.config.weight_decay, "params": list(range(self.n_all_params))}
         if self.config.optimizer == "Adam":
             group.update(betas=(0.9, 0.999), eps=1e-8, amsgrad=False)
         else:
@@ -253,7 +257,7 @@ class Trainer:
 
     def load_optimizer_state(self, st):
         off = 0
-        for i, p in enumerate(self.params):
+        for i, p in zip(self.param_index, self.params):
             n = p.numel()
             s = st["state"].get(i)
             if s:
@@ -283,6 +287,9 @@ class Trainer:
         loss, value_loss, reward_loss, policy_loss, priorities = self._forward_backward(tensors)
         self._step()
         self.training_step += 1
+        # a fresh tensor like the reference's numpy array: `priorities` aliases the CUDA graph's static output, which
+        # the next replay overwrites
+        priorities = priorities.clone()
         return priorities, loss.item(), value_loss.mean().item(), reward_loss.mean().item(), policy_loss.mean().item()
 
     def _forward_backward(self, tensors):

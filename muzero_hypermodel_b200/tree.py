@@ -14,6 +14,28 @@ from . import _lib
 from ._lib import check, ptr
 
 
+class _BlockedHidden:
+    """Index adaptor over the blocked hidden-state slots: h[game, slot] / h[game] without copying the store."""
+
+    def __init__(self, blocked, G):
+        self._b, self.G = blocked, G
+        self.shape = (G, blocked.shape[1], blocked.shape[3])
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple):
+            g, rest = idx[0], idx[1:]
+        else:
+            g, rest = idx, ()
+        if not isinstance(g, int):
+            raise TypeError("index the blocked hidden-state store by an integer game first")
+        v = self._b[g >> 5, :, g & 31]
+        return v[rest] if rest else v
+
+    def dense(self):
+        """A [G, S+1, H] copy in game-major order."""
+        return self._b.permute(0, 2, 1, 3).reshape(-1, self._b.shape[1], self._b.shape[3])[:self.G].contiguous()
+
+
 class BatchedTree:
     def __init__(self, n_games, n_actions, num_simulations, n_players, discount, pb_c_base, pb_c_init,
                  hidden_floats=0, seed=0, device=None):
@@ -83,13 +105,17 @@ class BatchedTree:
         return {"path_length_sum": int(c[0]), "simulations": int(c[1])}
 
     def hidden(self):
-        """fp32 view [G, S+1, H] of the hidden-state slots (inside the workspace)."""
+        """fp32 [G, S+1, H] view of the hidden-state slots.  The store keeps them blocked by 32 games and node-major
+        inside a block ([G/32][S+1][32][H], csrc/mzb_tree.cuh); the returned adaptor indexes that memory as
+        h[game, slot] without copying (h.dense() makes a game-major copy)."""
         p = _lib.lib.mzb_tree_hidden_ptr(self._h)
         if not p:
             return None
         off = (p - self.workspace.data_ptr())
-        n = self.G * (self.S + 1) * self.H
-        return self.workspace[off:off + 4 * n].view(torch.float32).view(self.G, self.S + 1, self.H)
+        nb = (self.G + 31) // 32
+        n = nb * (self.S + 1) * 32 * self.H
+        blocked = self.workspace[off:off + 4 * n].view(torch.float32).view(nb, self.S + 1, 32, self.H)
+        return _BlockedHidden(blocked, self.G)
 
     def export_game(self, game):
         S1, A = self.S + 1, self.A

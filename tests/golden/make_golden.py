@@ -753,7 +753,30 @@ def gen_trainer():
     print("trainer.npz", os.path.getsize(os.path.join(HERE, "trainer.npz")) // 1024, "KiB")
 
 
-FAMILIES = {"trainer": gen_trainer, "tree": gen_tree, "action": gen_action, "env": gen_env, "codec": gen_codec, "net": gen_net,
+def gen_stacked():
+    """GameHistory.get_stacked_observations (self_play.py:514-548) of the UNMODIFIED reference: every index (incl. the
+    -1 play_game uses and indices past the end, which wrap) for S in {0, 1, 2, 4} on three observation shapes."""
+    self_play = ref_loader.load("self_play")
+    rs = np.random.RandomState(SEED + 11)
+    out = {}
+    shapes = [((1, 1, 4), np.float32, 2), ((3, 3, 3), np.int32, 9), ((3, 6, 7), np.float64, 7)]
+    for si, (shape, dt, A) in enumerate(shapes):
+        n = 7
+        gh = self_play.GameHistory()
+        gh.observation_history = [(rs.randint(-1, 2, size=shape) if dt != np.float32 else rs.randn(*shape)).astype(dt)
+                                  for _ in range(n)]
+        gh.action_history = [0] + rs.randint(A, size=n - 1).tolist()
+        out[f"{si}/observations"] = np.stack(gh.observation_history)
+        out[f"{si}/actions"] = np.array(gh.action_history, dtype=np.int64)
+        for S in (0, 1, 2, 4):
+            for index in list(range(-1, n + 2)):
+                out[f"{si}/S{S}/i{index}"] = np.asarray(gh.get_stacked_observations(index, S))
+    out["n"] = np.array(len(shapes))
+    np.savez_compressed(os.path.join(HERE, "stacked.npz"), **out)
+    print("stacked.npz:", len(out), "arrays")
+
+
+FAMILIES = {"stacked": gen_stacked, "trainer": gen_trainer, "tree": gen_tree, "action": gen_action, "env": gen_env, "codec": gen_codec, "net": gen_net,
             "targets": gen_targets, "episode": gen_episode, "replay": gen_replay}
 
 if __name__ == "__main__":

@@ -273,3 +273,89 @@ def test_one_call_with_more_games_than_slots_equals_sequential_saves():
     ia, ba = rb_one.get_batch()
     ib, bb = rb_seq.get_batch()
     assert torch.equal(ia, ib) and all(torch.equal(x, y) for x, y in zip(ba, bb))
+
+
+def test_ingest_into_store_with_other_record_layout_goes_through_host_format():
+    """A store built with the reference's 3-argument constructor keeps decoded observations (27 floats for tictactoe)
+    while the environment's export ring holds packed records (3 floats): the C entry refuses the copy, `ingest` takes
+    the host GameHistory route, and both stores then hold the same games."""
+    import ctypes as C
+    from muzero_hypermodel_b200 import _lib, models
+    from muzero_hypermodel_b200.games.tictactoe import MuZeroConfig
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    from muzero_hypermodel_b200.self_play import SelfPlay
+    cfg = MuZeroConfig()
+    cfg.network, cfg.num_simulations, cfg.replay_buffer_size = "fullyconnected", 8, 512
+    ck = {"num_played_games": 0, "num_played_steps": 0}
+
+    def play():
+        torch.manual_seed(0)
+        sp = SelfPlay({"weights": None}, None, cfg, 3, n_games=64, device=DEV)
+        for _ in range(9):
+            sp.step()
+        return sp
+
+    sp = play()
+    plain = ReplayBuffer(ck, {}, cfg, device=DEV)                         # no record_env: decoded layout
+    n = C.c_int32(-1)
+    rc = _lib.lib.mzb_env_export_to_replay(sp._env._h, plain._h, C.byref(n), _lib.current_stream())
+    assert rc != 0 and b"floats per observation record" in _lib.lib.mzb_last_error()
+    assert len(plain) == 0                                                # nothing copied
+    got = plain.ingest(sp._env)                                           # host-format fallback
+    assert got >= 64 and len(plain) == got
+    sp2 = play()
+    packed = ReplayBuffer(ck, {}, cfg, device=DEV, record_env=sp2._env)
+    assert packed.ingest(sp2._env) == got
+    a, b = plain.get_buffer(), packed.get_buffer()
+    assert sorted(a) == sorted(b)
+    for k in a:
+        assert a[k].action_history == b[k].action_history and a[k].root_values == b[k].root_values
+        assert all(np.array_equal(x, y) for x, y in zip(a[k].observation_history, b[k].observation_history))
+        np.testing.assert_array_equal(a[k].priorities, b[k].priorities)
+
+
+def test_resume_keeps_checkpoint_counters_and_game_ids():
+    """replay_buffer.py:17-24: the counters come from the checkpoint (re-loading the buffer does not play its games
+    again) and the buffered games keep their ids; the next saved game continues the numbering."""
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    rb, cfg = make(1)
+    for gi in range(5):
+        rb.save_game(load_game(1, gi))
+    steps5 = rb.num_played_steps
+    buf = {7 + k: g for k, g in rb.get_buffer().items()}                  # as pickled by a run that had played 12 games
+    ck = {"num_played_games": 12, "num_played_steps": 345}
+    rb2 = ReplayBuffer(ck, buf, cfg, device=DEV)
+    assert rb2.num_played_games == 12 and rb2.num_played_steps == 345 and len(rb2) == 5
+    assert rb2.total_samples == steps5                                    # recomputed from the buffer (:22-24)
+    assert sorted(rb2.get_buffer()) == [7, 8, 9, 10, 11]
+    idx, batch = rb2.get_batch()
+    assert int(idx[:, 0].min()) >= 7 and int(idx[:, 0].max()) <= 11
+    rb2.update_priorities(torch.ones((idx.shape[0], cfg.num_unroll_steps + 1)), idx)   # public ids accepted back
+    g = load_game(1, 5)
+    rb2.save_game(g)
+    assert rb2.num_played_games == 13 and rb2.num_played_steps == 345 + len(g.root_values)
+    assert sorted(rb2.get_buffer())[-1] == 12
+    np.testing.assert_array_equal(rb.game_priorities(2)[0], ReplayBuffer(ck, buf, cfg, device=DEV).game_priorities(9)[0])
+
+
+def test_save_game_reports_to_plain_and_remote_storages():
+    """save_game(game_history, shared_storage) works with plain get_info / set_info objects (Trainer, tests) and
+    Ray-style handles (`.remote`)."""
+    rb, cfg = make(0)
+
+    class Plain:
+        def __init__(self): self.info = {}
+        def set_info(self, k, v): self.info[k] = v
+
+    class Remote:
+        def __init__(self):
+            self.info = {}
+            outer = self
+
+            class _M:
+                def remote(self, k, v): outer.info[k] = v
+            self.set_info = _M()
+
+    for st in (Plain(), Remote()):
+        rb.save_game(load_game(0, 0), st)
+        assert st.info["num_played_games"] == rb.num_played_games and st.info["num_played_steps"] == rb.num_played_steps

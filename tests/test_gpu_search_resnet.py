@@ -100,3 +100,23 @@ def test_mcts_run_dropin_materialises_node_graph():
     new_root.expand(cfg.action_space, 1, 0.0, pl, hs)
     root2, info2 = self_play.MCTS(cfg).run(net, None, cfg.action_space, 1, True, new_root)
     assert info2["root_predicted_value"] is None and root2.visit_count == cfg.num_simulations
+
+
+def test_reference_style_calls_draw_fresh_randomness():
+    """MCTS.run without RNG counters and repeated play_game calls must not replay the same noise / tie-breaks /
+    action samples (the reference draws from numpy's advancing global stream)."""
+    from muzero_hypermodel_b200 import models, self_play
+    from muzero_hypermodel_b200.games.cartpole import MuZeroConfig, Game
+    cfg = MuZeroConfig()
+    cfg.max_moves = 40
+    torch.manual_seed(1)
+    net = models.MuZeroNetwork(cfg).to(DEV).eval()
+    obs = np.zeros((1, 1, 4), dtype=np.float32)
+    priors = []
+    for _ in range(3):
+        root, _ = self_play.MCTS(cfg).run(net, obs, [0, 1], 0, True)
+        priors.append(tuple(root.children[a].prior for a in (0, 1)))
+    assert len(set(priors)) == 3, priors                  # three different Dirichlet samples mixed into the priors
+    sp = self_play.SelfPlay({"weights": net.get_weights()}, Game, cfg, 0, device=DEV)
+    games = [sp.play_game(1.0, None, False, "self", 0) for _ in range(3)]
+    assert len({(tuple(g.action_history), tuple(np.round(g.root_values, 12))) for g in games}) == 3

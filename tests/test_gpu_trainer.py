@@ -159,3 +159,48 @@ def test_self_play_replay_train_loop():
     sp2 = SelfPlay({"weights": None}, None, cfg, 1, n_games=128, device=DEV)
     sp2.continuous_self_play(st, rb, max_moves=2)           # refreshes the weights from the storage (self_play.py:37)
     assert any(not torch.equal(w_before[k], v) for k, v in sp2.model.get_weights().items())
+
+
+def test_optimizer_state_indices_follow_torch_optim_on_downsample_net():
+    """Breakout's DownSample representation never reaches conv/bn (models.py:338-345): torch.optim still NUMBERS those
+    parameters (they just have no state).  optimizer_state() must use the same numbering so a reference checkpoint's
+    optimizer_state loads into the right moments."""
+    from muzero_hypermodel_b200.games.breakout import MuZeroConfig
+    from muzero_hypermodel_b200.trainer import Trainer
+    cfg = MuZeroConfig()
+    cfg.batch_size, cfg.num_unroll_steps = 2, 2
+    torch.manual_seed(0)
+    tr = Trainer({"weights": None, "training_step": 0, "optimizer_state": None}, cfg, device=DEV)
+    B, K, A = 2, cfg.num_unroll_steps, len(cfg.action_space)
+    rs = np.random.RandomState(0)
+    batch = [rs.rand(B, 3, 96, 96).astype(np.float32), rs.randint(A, size=(B, K + 1)), rs.randn(B, K + 1), rs.randn(B, K + 1),
+             np.full((B, K + 1, A), 1.0 / A), np.ones(B, np.float32), np.ones((B, K + 1), np.float32)]
+    tr.use_cuda_graph = False
+    tr.update_lr(); tr.update_weights(batch)
+    ours = tr.optimizer_state()
+    # torch's own numbering: Adam over ALL model.parameters(), stepping with the same gradients present / absent
+    allp = list(tr.model.parameters())
+    opt = torch.optim.Adam(allp, lr=cfg.lr_init, weight_decay=cfg.weight_decay)
+    used = {id(p) for p in tr.params}
+    for p in allp:
+        p.grad = torch.zeros_like(p) if id(p) in used else None
+    opt.step()
+    ref = opt.state_dict()
+    assert ours["param_groups"][0]["params"] == ref["param_groups"][0]["params"]
+    assert sorted(ours["state"]) == sorted(ref["state"]) and len(ref["state"]) < len(allp)
+    for i in ref["state"]:
+        assert tuple(ours["state"][i]["exp_avg"].shape) == tuple(ref["state"][i]["exp_avg"].shape), i
+    # and a state in torch's numbering loads back into the same flat offsets
+    tr2 = Trainer({"weights": tr.model.get_weights(), "training_step": 1, "optimizer_state": ours}, cfg, device=DEV)
+    assert torch.equal(tr2.state1, tr.state1) and torch.equal(tr2.state2, tr.state2) and tr2.opt_step == tr.opt_step
+
+
+def test_update_weights_returns_fresh_priorities():
+    """The returned priorities must not alias the CUDA graph's static output (the reference returns a new array)."""
+    tr, cfg, batch, pre = setup_case(0)
+    outs = []
+    for _ in range(3):
+        tr.update_lr()
+        outs.append(tr.update_weights(batch)[0])
+    assert outs[1].data_ptr() != outs[2].data_ptr()
+    assert not torch.equal(outs[1], outs[2])          # weights moved between the steps; an alias would compare equal
