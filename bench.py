@@ -1,26 +1,28 @@
 #!/usr/bin/env python
 """bench.py - self-play hot path throughput: MCTS simulations/s (and env steps/s) per BASELINE.json.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cartpole|tictactoe|connect4|gomoku|breakout]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|cartpole|tictactoe|...]
                     [--games G]
 
-One "step" = one self-play move of every game on every GPU: observe -> MCTS.run (num_simulations
-simulations, network in the loop) -> select_action -> Game.step -> GameHistory append -> harvest/auto-reset.
-Workload (config.workload): BASELINE.json configs[0], "cartpole FC MuZero (games/cartpole.py defaults,
-num_simulations=50)" - the configuration the headline target (>=1e8 simulations/s on 8xB200) is quoted on.
-Weights: the reference's shipped cartpole checkpoint (tests/golden/net.npz "cartpole_shipped", 1,532
-parameters); observations come from the device CartPole-v1 environments (synthetic games, no dataset).
+Default (`--workload all`): the four other BASELINE configs run first and are nested under `workloads`
+(tictactoe-FC at 4,096 games/GPU, connect4 at 16,384 games/GPU, gomoku at 400 simulations, breakout on synthetic
+96x96 frames - each with its own value / e2e / roofline / cpu_baseline / parity / clocks), then the HEADLINE workload,
+BASELINE.json configs[0] "cartpole FC MuZero (games/cartpole.py defaults, num_simulations=50)" - the configuration the
+>= 1e8 simulations/s on 8xB200 target is quoted on - whose keys form the top level of the ONE JSON line printed last.
 
-JSON line keys: see the task contract; `value` = simulations/s over all GPUs with state resident in HBM,
-`e2e` = the same searches driven through the batched MCTS.run entry point with HOST observation /
-legal-action / to-play buffers (pinned H2D before, D2H of visit counts + root values after, every step),
-`roofline` = the dominant kernel alone, timed live with CUDA events: the whole-search kernel against the measured
-HBM copy peak (FC workloads; `traffic` = DRAM bytes per launch from the committed ncu capture), or the tower's
-C->C tcgen05 convolution replayed from a CUDA graph against the measured bf16 burst peak (resnet workloads;
-`roofline.whole_search` keeps the all-in figure), `cpu_baseline` = the oracle port of SelfPlay.play_game on the
-host cores (bounded sample), `collectives` (N > 1) = device time of the two learner-side collectives.
+One self-play MOVE = observe -> MCTS.run (num_simulations simulations, network in the loop) -> select_action ->
+Game.step -> GameHistory append -> harvest/auto-reset of every game on every GPU, with the finished games ingested by
+the device replay store every 4th move.  One bench STEP = `config.moves_per_step` consecutive moves (cartpole: 25, so
+that the driver's 20 steps time > 2 s of self-play and whole episodes, resets and replay ingests fall inside the timed
+region; the residual workloads: 1).  `value` = simulations/s over all GPUs with state resident in HBM; `e2e` = the
+same searches through the batched MCTS.run entry point with HOST observation / legal-action / to-play buffers (pinned
+H2D before, D2H of visit counts + root values after, every step); `roofline` = the dominant kernel: `frac` alone (timed
+live with CUDA events around the launch) and `in_step` (the same launches timed inside the timed region); `cpu_baseline`
+= the UNMODIFIED reference SelfPlay.play_game (oracle/_ref byte-code archive, kind "reference") on the host cores, with
+the oracle port beside it; `parity` = measured agreement of the benchmarked arithmetic with the exact path.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -32,16 +34,20 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+G_FULL_WAVES = 4 * 148 * 512        # cartpole: 4 full waves of the whole-search kernel's 148 SMs x 2 CTAs x 256 games
 WORKLOADS = {
-    # name: (golden weight tag, config module, games per GPU, (initial FLOP, recurrent FLOP) per BASELINE.md §3)
-    "cartpole": ("cartpole_shipped", "cartpole", 262144, (1312, 2752)),
-    "tictactoe": ("tictactoe_fc", "tictactoe", 4096 * 16, (3648, 5952)),
-    "connect4": ("connect4", "connect4", 16384, (37372160, 40396160)),
-    "gomoku": ("gomoku", "gomoku", 4096, (857557760, 892780160)),      # 51 GB bf16 hidden-state pool (401 slots x 31 KB x 4096)
-    "breakout": ("breakout", "breakout", 16384, (34192160, 1532480)),
+    # name: (golden weight tag, config module, games per GPU, (initial FLOP, recurrent FLOP) per BASELINE.md §3,
+    #        moves per bench step, default timed steps)
+    "cartpole": ("cartpole_shipped", "cartpole", G_FULL_WAVES, (1312, 2752), 25, 20),
+    "tictactoe": ("tictactoe_fc", "tictactoe", 4096, (3648, 5952), 9, 20),       # BASELINE configs[1]: 4096 games/GPU
+    "connect4": ("connect4", "connect4", 16384, (37372160, 40396160), 1, 3),
+    "gomoku": ("gomoku", "gomoku", 4096, (857557760, 892780160), 1, 2),          # 51 GB bf16 hidden-state pool
+    "breakout": ("breakout", "breakout", 16384, (34192160, 1532480), 1, 5),
 }
+NESTED = ("tictactoe", "connect4", "gomoku", "breakout")
 # committed `ncu --set full` captures of the dominant kernel at the bench shape (profiles/): DRAM bytes per launch
-NCU_CAPTURE = {"cartpole": "r01_ncu_k_search_fc_cartpole.csv", "connect4": "r01_ncu_k_conv_tc_connect4.csv"}
+NCU_CAPTURE = {"cartpole": "r02_ncu_k_search_fc_cartpole.csv", "connect4": "r02_ncu_k_conv_tc_connect4.csv",
+               "gomoku": "r02_ncu_k_conv_tc_gomoku.csv", "breakout": "r02_ncu_breakout.csv"}
 
 
 def ncu_traffic(workload):
@@ -95,8 +101,41 @@ def oracle_cfg(cfg):
                 downsample=cfg.downsample)
 
 
-def cpu_leg(workload, cfg, seconds):
-    """Oracle port of play_game on every host core for ~`seconds` (the bench's only use of oracle/)."""
+# searches per reference play_game call (config.max_moves cap): ~1-2 s of one core per call
+REF_SEARCH_CAP = {"cartpole": 24, "tictactoe": 9, "connect4": 2, "gomoku": 1}
+REF_OVERRIDES = {"tictactoe": {"network": "fullyconnected"}}
+
+
+def reference_leg(workload, cfg, calls=1, pool=None, cores=None, warm=True):
+    """The UNMODIFIED reference SelfPlay.play_game on every host core (oracle/ref_runner.py), or None if the byte-code
+    archive is missing / the game cannot run offline (breakout: ALE).  warm: one untimed call per process first
+    (imports torch, builds the reference model) so that start-up does not count against the CPU side."""
+    import multiprocessing as mp
+    from oracle import ref_runner
+    if not ref_runner.available(WORKLOADS[workload][1]):
+        return None
+    cores = cores or os.cpu_count() or 1
+    cap = REF_SEARCH_CAP[workload]
+    w = load_weights(WORKLOADS[workload][0])
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
+    game, over = WORKLOADS[workload][1], REF_OVERRIDES.get(workload, {})
+    if warm:
+        ref_runner.run_parallel(game, w, over, cores, cap, n_calls=1, pool=pool, seed0=cfg.seed)
+    sims, steps, wall = ref_runner.run_parallel(game, w, over, cores, cap, n_calls=calls, pool=pool, seed0=cfg.seed)
+    if own:
+        pool.close()
+        pool.join()
+    return {"value": sims / wall, "unit": "simulations/s", "cores": cores, "kind": "reference",
+            "env_steps_per_s": steps / wall, "wall_s": wall, "simulations": sims,
+            "sample": f"{cores} processes (torch.set_num_threads(1) each) x {calls} call(s) of the unmodified reference "
+                      f"SelfPlay.play_game capped at max_moves={cap} ({steps} searches of {cfg.num_simulations} "
+                      f"simulations, batch-1 torch modules, same weights/config; Ray RPC omitted; one untimed warm-up call per process)"}
+
+
+def port_leg(workload, cfg, seconds):
+    """Oracle port of play_game on every host core for ~`seconds`."""
     from oracle import cpu_baseline
     cores = os.cpu_count() or 1
     w = load_weights(WORKLOADS[workload][0])
@@ -107,38 +146,58 @@ def cpu_leg(workload, cfg, seconds):
                       f"{cfg.num_simulations} simulations, batch-1 numpy network, same weights/config)"}
 
 
+def cpu_legs(workload, cfg, seconds):
+    """cpu_baseline = the reference when it can run here, with the (faster) numpy port kept beside it."""
+    port = port_leg(workload, cfg, min(seconds, 6.0))
+    ref = reference_leg(workload, cfg, calls={"cartpole": 4, "tictactoe": 8}.get(workload, 1))
+    if ref is None:
+        return port, None
+    return ref, port
+
+
 def reference_arm(args):
-    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores - the UNMODIFIED
+    SelfPlay.play_game from the byte-code archive (kind "reference"), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    from oracle import cpu_baseline
-    cfg = make_config(args.workload)
+    workload = "cartpole" if args.workload == "all" else args.workload
+    cfg = make_config(workload)
     cores = os.cpu_count() or 1
-    w = load_weights(WORKLOADS[args.workload][0])
-    ocfg = oracle_cfg(cfg)
-    searches = 24 if cfg.network == "fullyconnected" else 1      # searches per process per step (bounded sample)
+    from oracle import ref_runner
+    use_ref = ref_runner.available(WORKLOADS[workload][1])
     pool = mp.get_context("fork").Pool(cores)
-    times, sims_total = [], 0
-    for i in range(args.warmup + args.steps):
-        sims, steps, wall = cpu_baseline.run_parallel(WORKLOADS[args.workload][1], w, dict(ocfg, seed=ocfg["seed"] + i),
-                                                      cores, max_searches=searches, pool=pool)
-        if i >= args.warmup:
-            times.append(wall)
-            sims_total += sims
+    times, sims_total, sample = [], 0, ""
+    if use_ref:
+        for i in range(args.warmup + args.steps):
+            leg = reference_leg(workload, cfg, calls=1, pool=pool, cores=cores, warm=False)
+            if i >= args.warmup:
+                times.append(leg["wall_s"]); sims_total += leg["simulations"]
+            sample = "each step = " + leg["sample"]
+    else:
+        from oracle import cpu_baseline
+        w = load_weights(WORKLOADS[workload][0])
+        ocfg = oracle_cfg(cfg)
+        searches = 24 if cfg.network == "fullyconnected" else 1
+        for i in range(args.warmup + args.steps):
+            sims, steps, wall = cpu_baseline.run_parallel(WORKLOADS[workload][1], w, dict(ocfg, seed=ocfg["seed"] + i), cores,
+                                                          max_searches=searches, pool=pool)
+            if i >= args.warmup:
+                times.append(wall); sims_total += sims
+        sample = (f"each step = {cores} processes x {searches} searches x {cfg.num_simulations} simulations of the oracle "
+                  f"port of SelfPlay.play_game (batch-1 numpy network)")
     pool.close()
     pool.join()
     total = sum(times)
     value = sims_total / total
-    sample = (f"each step = {cores} processes x {searches} searches x {cfg.num_simulations} simulations of the oracle "
-              f"port of SelfPlay.play_game (batch-1 numpy network)")
     line = {"impl": "reference", "metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, cfg), "games_per_gpu": cores,
+            "config": {"workload": workload_name(workload, cfg), "games_per_gpu": cores,
                        "num_simulations": cfg.num_simulations},
-            "cpu_baseline": {"value": value, "unit": "simulations/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "simulations/s", "cores": cores, "kind": "reference" if use_ref else "port",
+                             "sample": sample},
             "e2e": {"value": value, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -146,8 +205,8 @@ def reference_arm(args):
 
 def workload_name(workload, cfg):
     return {"cartpole": "cartpole FC MuZero (games/cartpole.py defaults, num_simulations=50)",
-            "tictactoe": "tictactoe FC MuZero, two-player, network=fullyconnected, num_simulations=25",
-            "connect4": "connect4 residual-network MuZero (games/connect4.py defaults, 3 blocks x 64 ch, num_simulations=200)",
+            "tictactoe": "tictactoe FC MuZero, two-player, network=fullyconnected, 4096 parallel games/GPU, num_simulations=25",
+            "connect4": "connect4 residual-network MuZero (games/connect4.py defaults, 3 blocks x 64 ch, num_simulations=200), 16384 parallel games/GPU",
             "gomoku": "gomoku residual MuZero (games/gomoku.py defaults, 6 blocks x 128 ch, A=121, num_simulations=400)",
             "breakout": "Atari Breakout residual MuZero on synthetic 96x96 frames (games/breakout.py defaults, num_simulations=30)"}[workload]
 
@@ -204,52 +263,128 @@ class ClockSampler:
         return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 50 for FC workloads, 3 for resnets)")
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cartpole", choices=list(WORKLOADS))
-    ap.add_argument("--games", type=int, default=0, help="games per GPU (default: workload's)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--modular", action="store_true", help="force the modular kernels instead of the whole-search kernel")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.steps <= 0:
-        args.steps = 50 if args.workload in ("cartpole", "tictactoe") else 3
-        if args.impl == "reference":
-            args.steps = 10
-
-    if args.impl == "reference":
-        return reference_arm(args)
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    cfg = make_config(args.workload)
-
-    # CPU baseline first (rank 0, N=1 only): forked workers must not inherit a CUDA context
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_leg(args.workload, cfg, args.cpu_seconds)
-
+def fc_parity(workload, cfg, sp, mcts, n_games=48):
+    """Network in the loop: the whole-search kernel against the oracle MCTS driven by the numpy restatement of the
+    reference network (oracle as the CHECKER).  Tree arithmetic is bit-exact given equal network outputs; float32
+    decode conditioning makes some searches diverge at a near-tie - this reports how many."""
     import numpy as np
     import torch
-    import torch.distributed as dist
+    from muzero_hypermodel_b200.parity import visit_agreement
+    from muzero_hypermodel_b200.search import BatchedMCTS
+    from oracle import mcts as omcts, networks as onet, rng
+    dev, A, S = sp.device, len(cfg.action_space), cfg.support_size
+    rs = np.random.RandomState(9)
+    if workload == "cartpole":
+        obs = rs.uniform(-0.2, 0.2, (n_games, 1, 1, 4)).astype(np.float32)
+        legal = np.ones((n_games, A), dtype=bool)
+        to_play = np.zeros(n_games, dtype=np.int8)
+    else:
+        stones = rs.randint(-1, 2, (n_games, 3, 3))
+        tp = rs.choice([-1, 1], size=(n_games, 1, 1))
+        obs = np.stack([(stones == 1), (stones == -1), np.broadcast_to(tp, stones.shape)], axis=1).astype(np.float32)
+        legal = stones.reshape(n_games, -1) == 0
+        legal[np.arange(n_games), rs.randint(A, size=n_games)] |= ~legal.any(1)
+        to_play = (tp.reshape(-1) == -1).astype(np.int8)
+    noise = np.zeros((n_games, A))
+    for g in range(n_games):
+        noise[g, legal[g]] = rs.dirichlet([cfg.root_dirichlet_alpha] * int(legal[g].sum()))
+    slot = rs.randint(1 << 20, size=n_games).astype(np.int32)
+    step = rs.randint(400, size=n_games).astype(np.int32)
+    seed = 1234
+    eng = BatchedMCTS(cfg, n_games, device=dev, seed=seed)
+    out = eng.run(sp.model, torch.tensor(obs, device=dev), torch.tensor(legal, device=dev), torch.tensor(to_play, device=dev),
+                  True, noise=torch.tensor(noise, device=dev), slot=torch.tensor(slot, device=dev),
+                  step=torch.tensor(step, device=dev))
+    onn = onet.FullyConnected({k: v.numpy() for k, v in sp.model.get_weights().items()}, A, S)
+    ov, orv = [], []
+    for g in range(n_games):
+        la = np.nonzero(legal[g])[0].tolist()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v, r, p, s = onn.initial_inference(obs[g:g + 1])
+        root = (float(onet.support_to_scalar(v, S)[0, 0]), float(onet.support_to_scalar(r, S)[0, 0]),
+                [float(x) for x in omcts.softmax_f32(p[0][la])], s)
+
+        def rec(hidden, action):
+            v, r, p, s = onn.recurrent_inference(hidden, np.array([action]))
+            return (float(onet.support_to_scalar(v, S)[0, 0]), float(onet.support_to_scalar(r, S)[0, 0]),
+                    [float(x) for x in omcts.softmax_f32(p[0])], s)
+
+        res = omcts.search(rec, root, la, int(to_play[g]), n_actions=A, n_players=len(cfg.players),
+                           num_simulations=cfg.num_simulations, discount=cfg.discount, pb_c_base=cfg.pb_c_base,
+                           pb_c_init=cfg.pb_c_init, noise=[float(noise[g, a]) for a in la],
+                           exploration_fraction=cfg.root_exploration_fraction,
+                           tie=lambda n, sim, depth: rng.tie_index(seed, int(slot[g]), int(step[g]), sim, depth, n))
+        vv = np.zeros(A, dtype=np.int64)
+        vv[la] = res.visits
+        ov.append(vv); orv.append(res.root_value())
+    m = visit_agreement(out["visits"], np.array(ov), out["root_value"], np.array(orv))
+    m["against"] = "oracle MCTS + numpy restatement of the reference network (network in the loop), same noise and tie-break draws"
+    return m
+
+
+def resnet_parity(workload, cfg, weights, dev, n_games):
+    """bf16 tcgen05 search against the fp32 search over the same roots, injected noise and tie-break counters."""
+    import numpy as np
+    import torch
+    from muzero_hypermodel_b200 import models
+    from muzero_hypermodel_b200.parity import visit_agreement
+    from muzero_hypermodel_b200.search import BatchedMCTS
+    from muzero_hypermodel_b200.envs import VectorEnv, game_kind
+    A = len(cfg.action_space)
+    env = VectorEnv(game_kind(cfg), n_games, cfg.max_moves, seed=99, device=dev)
+    # a few random opening moves so the roots are not all the empty board
+    rs = np.random.RandomState(4)
+    for _ in range(4 if len(cfg.players) == 2 else 1):
+        obs, legal, to_play = env.observe()
+        lg = legal.cpu().numpy().astype(bool)
+        act = np.array([rs.choice(np.nonzero(lg[g])[0]) for g in range(n_games)], dtype=np.int32)
+        env.act_step(None, None, forced_action=torch.tensor(act, device=dev))
+        env.harvest(False)
+    obs, legal, to_play = env.observe()
+    lg = legal.cpu().numpy().astype(bool)
+    noise = np.zeros((n_games, A))
+    for g in range(n_games):
+        noise[g, lg[g]] = rs.dirichlet([cfg.root_dirichlet_alpha] * int(lg[g].sum()))
+    nz = torch.tensor(noise, device=dev)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        net = models.MuZeroNetwork(cfg)
+        net.set_weights(weights)
+        net.set_precision(prec)
+        net.to(dev).eval()
+        eng = BatchedMCTS(cfg, n_games, device=dev, seed=77)
+        o = eng.run(net, obs, legal, to_play, True, noise=nz, slot=env.slot, step=env.step_count)
+        torch.cuda.synchronize()
+        res[prec] = {k: v.clone() for k, v in o.items()}
+        del eng, net
+    m = visit_agreement(res["bf16"]["visits"], res["fp32"]["visits"], res["bf16"]["root_value"], res["fp32"]["root_value"])
+    m["against"] = "the fp32 CUDA-core path of the same library (<= 2e-4 of the reference network), same roots / noise / tie-breaks"
+    m["num_simulations"] = int(cfg.num_simulations)
+    return m
+
+
+def run_workload(args, workload, steps, warmup, cpu_seconds, want_cpu, want_collectives):
+    """One BASELINE config on this rank's GPU (all ranks in lock-step); returns the result dict on rank 0."""
+    import torch
     from muzero_hypermodel_b200 import _lib
     from muzero_hypermodel_b200 import dist as mdist
     from muzero_hypermodel_b200.self_play import SelfPlay
 
-    torch.cuda.set_device(local_rank)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = make_config(workload)
     dev = torch.device("cuda", local_rank)
-    mdist.init(backend="nccl", device=dev)
     barrier = mdist.barrier
 
-    G = args.games or WORKLOADS[args.workload][2]
+    cpu, cpu_port = (None, None)
+    if want_cpu:
+        cpu, cpu_port = cpu_legs(workload, cfg, cpu_seconds)
+
+    tag, _, G_default, flops, moves_per_step, _ = WORKLOADS[workload]
+    G = args.games or G_default
     S = cfg.num_simulations
-    weights = {k: torch.tensor(v) for k, v in load_weights(WORKLOADS[args.workload][0]).items()}
+    weights = {k: torch.tensor(v) for k, v in load_weights(tag).items()}
     sp = SelfPlay({"weights": weights}, None, cfg, cfg.seed, n_games=G, device=dev, first_slot=mdist.first_slot(rank, G))
     env, mcts = sp._setup()
     is_fc = cfg.network == "fullyconnected"
@@ -263,15 +398,26 @@ def main():
     except NotImplementedError:                    # synthetic frames are regenerated, not stored
         rb = None
     moves = [0]
+    search_events = []                             # (start, end) CUDA events around the search launch of timed moves
 
-    def step():
-        sp.step(temperature=1.0, temperature_threshold=None, add_exploration_noise=True, export=True,
-                allow_fused=not args.modular)
+    def move(timed=False):
+        if timed and is_fc and len(search_events) < 512:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sp.step(temperature=1.0, temperature_threshold=None, add_exploration_noise=True, export=True,
+                    allow_fused=not args.modular, search_events=(a, b))
+            search_events.append((a, b))
+        else:
+            sp.step(temperature=1.0, temperature_threshold=None, add_exploration_noise=True, export=True,
+                    allow_fused=not args.modular)
         moves[0] += 1
         if rb is not None and moves[0] % 4 == 0:
             rb.ingest(env)
 
-    for _ in range(args.warmup):
+    def step(timed=False):
+        for _ in range(moves_per_step):
+            move(timed)
+
+    for _ in range(warmup):
         step()
     if rb is not None:
         rb.ingest(env)
@@ -281,15 +427,15 @@ def main():
     mcts.tree.counters(reset=True)
     barrier()
 
-    # ---------------- timed region: K whole self-play steps, CUDA events on the launching stream
+    # ---------------- timed region: K steps (K x moves_per_step whole self-play moves), CUDA events on the launching stream
     sampler = ClockSampler(local_rank) if rank == 0 else None
     c0 = env.counters()
     _lib.lib.mzb_reset_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     ev[0].record()
-    for _ in range(args.steps):
-        step()
+    for _ in range(steps):
+        step(timed=True)
     ev[1].record()
     barrier()
     ms = ev[0].elapsed_time(ev[1])
@@ -297,23 +443,27 @@ def main():
     c1 = env.counters()
     tc = mcts.tree.counters()
     ingested_end = rb.num_played_games if rb is not None else 0
-    # a timed region shorter than a few 50 ms sampling periods (breakout: 3 steps of 19 ms) would leave the clocks
-    # line empty: keep the same load running, untimed, until the sampler has seen it
+    # a timed region shorter than a few 50 ms sampling periods would leave the clocks line empty: keep the same load
+    # running, untimed, until the sampler has seen it
     extra = 0
     if sampler is not None and sampler.p is not None:
         t_end = time.time() + 3.0
         while sampler.count() < 3 and time.time() < t_end:
-            step()
+            move()
             torch.cuda.synchronize()
             extra += 1
     clocks = sampler.stop() if sampler else None
     if clocks is not None and extra:
-        clocks["untimed_load_steps_for_sampling"] = extra
+        clocks["untimed_load_moves_for_sampling"] = extra
     ms = mdist.max_over_ranks(ms, dev)
-    sims_total = args.steps * G * S * world
+    n_moves = steps * moves_per_step
+    sims_total = n_moves * G * S * world
     value = sims_total / (ms * 1e-3)
-    env_steps = args.steps * G * world / (ms * 1e-3)
+    env_steps = n_moves * G * world / (ms * 1e-3)
     mean_path = tc["path_length_sum"] / max(1, tc["simulations"])
+    in_step_ms = None
+    if search_events:
+        in_step_ms = sum(a.elapsed_time(b) for a, b in search_events) / len(search_events)
     if rb is not None:
         rb.ingest(env)
         ingested = ingested_end - ingested0
@@ -346,21 +496,31 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_per_sim * G * S / (k_ms * 1e-3) / 1e9
-    flops = WORKLOADS[args.workload][3]
     tflops = (flops[1] * S + flops[0]) * G / (k_ms * 1e-3) / 1e12
+    parity = None
     if is_fc:
+        in_step = None
+        if in_step_ms:
+            a_in = bytes_per_sim * G * S / (in_step_ms * 1e-3) / 1e9
+            in_step = {"achieved": a_in, "frac": a_in / peak, "kernel_ms": in_step_ms, "launches_timed": len(search_events),
+                       "note": "the same launch timed with CUDA events inside the timed region (after the env kernels of the move)"}
         roofline = {"bound": "hbm", "kernel": "k_search_fc (whole-search, fused)" if fused else "modular: k_select+k_fc_recurrent+k_expand_backup",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic(args.workload) if (fused and G == WORKLOADS[args.workload][2]) else None,
-                    "traffic_source": ("profiles/" + NCU_CAPTURE[args.workload]) if args.workload in NCU_CAPTURE else None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "in_step": in_step,
+                    "traffic": ncu_traffic(workload) if fused else None,
+                    "traffic_source": ("profiles/" + NCU_CAPTURE[workload]) if workload in NCU_CAPTURE else None,
                     "algorithmic_bytes_per_launch": bytes_per_sim * G * S,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                    "nominal_hbm_frac": achieved / 8000.0,
                     "kernel_ms": k_ms, "bytes_per_sim": bytes_per_sim, "mean_path_nodes": L, "fp32_tflops": tflops,
-                    "kernel_share_of_step": k_ms * args.steps / ms if world == 1 else None}
+                    "kernel_share_of_step": k_ms * n_moves / ms if world == 1 else None}
+        if rank == 0 and world == 1:
+            try:
+                parity = fc_parity(workload, cfg, sp, mcts)
+            except Exception as e:                    # noqa: BLE001 - a checker failure must not lose the measurement
+                parity = {"error": repr(e)}
     else:
         # the dominant kernel alone: the tower's C -> C convolution at the bench batch, timed live with CUDA events
         # (activation buffers 3 x B x rows x C bf16 rotate through HBM; connect4: 3 x 132 MB > L2)
-        import ctypes as C
         C_lat, H_lat, W_lat = (int(x) for x in sp.model.latent_shape)
         ws = sp.model._workspace(G, dev)
         iters = 20
@@ -379,6 +539,7 @@ def main():
         a.record(); graph.replay(); b.record()
         torch.cuda.synchronize()
         conv_ms = a.elapsed_time(b) / iters
+        del graph
         conv_flop = 2.0 * G * H_lat * W_lat * C_lat * C_lat * 9
         conv_tflops = conv_flop / (conv_ms * 1e-3) / 1e12
         # the same launch against the other roof: it reads every row of the padded NHWC layout ((H+1)(W+1) rows per
@@ -387,10 +548,16 @@ def main():
         conv_gbs = conv_bytes / (conv_ms * 1e-3) / 1e9
         tpeak = float(peaks.get("bf16_tflops", 1650.0))
         tpeak_s = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        in_ms = ms / n_moves                              # a whole move inside the timed region
+        tflops_in = (flops[1] * S + flops[0]) * G / (in_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": f"k_conv_tc (tcgen05 implicit-GEMM 3x3 conv, {C_lat}->{C_lat} ch, {H_lat}x{W_lat}, batch {G})",
                     "achieved": conv_tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": conv_tflops / tpeak,
-                    "traffic": ncu_traffic(args.workload),
-                    "traffic_source": ("profiles/" + NCU_CAPTURE[args.workload]) if args.workload in NCU_CAPTURE else None,
+                    "in_step": {"achieved": tflops_in, "peak": tpeak_s, "frac": tflops_in / tpeak_s,
+                                "note": "every FLOP of the move (BASELINE flop/sim x sims + initial inference) / move time inside the timed "
+                                        "region, tree / head / env kernels included, against the SUSTAINED bf16 peak: a lower bound of the "
+                                        "convolution's in-step fraction (it carries ~100 % of the FLOPs in < 100 % of the time)"},
+                    "traffic": ncu_traffic(workload),
+                    "traffic_source": ("profiles/" + NCU_CAPTURE[workload]) if workload in NCU_CAPTURE else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if peaks else "fallback 1650 TFLOP/s",
                     "kernel_us": conv_ms * 1e3, "flop_per_launch": conv_flop,
                     "hbm_side": {"algorithmic_bytes_per_launch": conv_bytes, "achieved": conv_gbs, "peak": peak, "unit": "GB/s",
@@ -398,7 +565,7 @@ def main():
                     "whole_search": {"achieved": tflops, "peak": tpeak_s, "frac": tflops / tpeak_s,
                                      "note": "all FLOPs of the search (BASELINE flop/sim) / search time, helper and tree kernels included; sustained peak"},
                     "search_ms": k_ms, "flop_per_sim": flops[1], "tree_bytes_per_sim": bytes_per_sim, "mean_path_nodes": L,
-                    "tree_hbm_gbs": achieved, "search_share_of_step": k_ms * args.steps / ms if world == 1 else None}
+                    "tree_hbm_gbs": achieved, "search_share_of_step": k_ms * n_moves / ms if world == 1 else None}
 
     # ---------------- e2e: batched MCTS.run entry point with HOST buffers, copies inside the timed region
     h_obs = torch.empty((G, env.obs_dim), dtype=torch.float32).pin_memory()
@@ -408,7 +575,7 @@ def main():
     h_vis = torch.empty((G, A), dtype=torch.int32).pin_memory()
     h_rv = torch.empty(G, dtype=torch.float64).pin_memory()
     d_obs, d_legal, d_tp = torch.empty_like(obs), torch.empty_like(legal), torch.empty_like(to_play)
-    e2e_steps = max(3, min(args.steps, 10)) if is_fc else 2
+    e2e_steps = max(3, min(steps * moves_per_step, 20)) if is_fc else 2
 
     def e2e_step():
         d_obs.copy_(h_obs, non_blocking=True); d_legal.copy_(h_legal, non_blocking=True); d_tp.copy_(h_tp, non_blocking=True)
@@ -431,12 +598,15 @@ def main():
     e2e = {"value": e2e_steps * G * S * world / (e2e_ms * 1e-3), "unit": "simulations/s",
            "h2d_bytes_per_step": (h_obs.numel() * 4 + h_legal.numel() + h_tp.numel()) * world,
            "d2h_bytes_per_step": (h_vis.numel() * 4 + h_rv.numel() * 8) * world,
-           "api": "BatchedMCTS.run == mzb_search_fc (G x MCTS.run) with pinned host buffers"}
+           "searches_timed": e2e_steps,
+           "api": ("BatchedMCTS.run == mzb_search_fc" if is_fc else "BatchedMCTS.run == mzb_search_resnet")
+                  + " (G x MCTS.run) with pinned host buffers; one search per e2e step"}
 
     # ---------------- learner-side collectives (off the self-play path): weight refresh + gradient all-reduce of this
     # workload's parameter count, device-timed, max over ranks
     collectives = None
-    if world > 1:
+    if world > 1 and want_collectives:
+        import torch.distributed as dist  # noqa: F401
         n_param = sum(int(v.numel()) for v in weights.values())
         sd = {k: v.to(dev) for k, v in weights.items()}
         grads = [torch.ones(n_param, device=dev)]
@@ -455,26 +625,114 @@ def main():
             res[name] = mdist.max_over_ranks(a.elapsed_time(b) / 20, dev)
         collectives = dict(res, parameters=n_param, backend="nccl", note="not on the self-play path (games are sharded, no data-path collective)")
 
+    tree_gib = mcts.tree.nbytes / 2**30
+    if not is_fc and rank == 0 and world == 1:
+        # free the big search state before the fp32 comparison model is built
+        del sp, env, mcts, rb
+        gc.collect(); torch.cuda.empty_cache()
+        try:
+            parity = resnet_parity(workload, cfg, weights, dev, {"connect4": 64, "gomoku": 16, "breakout": 64}.get(workload, 64))
+        except Exception as e:                        # noqa: BLE001
+            parity = {"error": repr(e)}
+        sp = env = mcts = rb = None
+
+    line = None
     if rank == 0:
         line = {"metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 network / f64 tree statistics" if is_fc else "bf16 conv operands, f32 accumulate / f64 tree statistics",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.workload, cfg), "games_per_gpu": G,
-                           "num_simulations": S, "weights": WORKLOADS[args.workload][0],
-                           "l2_policy": f"working set {mcts.tree.nbytes / 2**30:.1f} GiB tree store per GPU >> 126 MB L2",
+                "config": {"workload": workload_name(workload, cfg), "games_per_gpu": G,
+                           "num_simulations": S, "weights": tag, "moves_per_step": moves_per_step,
+                           "l2_policy": f"working set {tree_gib:.1f} GiB tree store per GPU >> 126 MB L2",
                            "path": ("fused whole-search kernel" if fused else "modular kernels") if is_fc else "tree kernels + tcgen05 resnet per simulation",
                            "parallelism": f"games sharded x{world}, no collective"},
                 "env_steps_per_sec": env_steps, "e2e": e2e, "roofline": roofline, "gpu_launches": launches,
-                "clocks": clocks, "mean_search_path_nodes": L,
+                "clocks": clocks, "mean_search_path_nodes": L, "timed_region_s": ms * 1e-3,
                 "games_finished_in_timed_region": c1["games"] - c0["games"],
                 "games_dropped": c1["dropped_games"] - c0["dropped_games"],
                 "games_ingested_by_replay_store": ingested}
+        if parity is not None:
+            line["parity"] = parity
         if collectives is not None:
             line["collectives"] = collectives
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if cpu_port is not None:
+            line["cpu_baseline_port"] = cpu_port
+    del sp, env, mcts, rb
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps of the headline workload (default 20)")
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all"] + list(WORKLOADS))
+    ap.add_argument("--games", type=int, default=0, help="games per GPU (default: workload's; single-workload runs only)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-nested", action="store_true", help="headline only (skip the other four BASELINE configs)")
+    ap.add_argument("--modular", action="store_true", help="force the modular kernels instead of the whole-search kernel")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    head = "cartpole" if args.workload == "all" else args.workload
+    if args.steps <= 0:
+        args.steps = WORKLOADS[head][5] if args.impl == "ours" else 10
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+
+    # CPU legs of the nested workloads first: forked workers must not inherit a CUDA context
+    nested = list(NESTED) if (args.workload == "all" and not args.no_nested) else []
+    if args.games and nested:
+        args.games = 0
+    pre_cpu = {}
+    if want_cpu:
+        for w in nested + [head]:
+            try:
+                pre_cpu[w] = cpu_legs(w, make_config(w), args.cpu_seconds if w == head else 5.0)
+            except Exception as e:                    # noqa: BLE001
+                pre_cpu[w] = ({"error": repr(e)}, None)
+
+    import torch
+    import torch.distributed as dist
+    from muzero_hypermodel_b200 import dist as mdist
+    torch.cuda.set_device(local_rank)
+    mdist.init(backend="nccl", device=torch.device("cuda", local_rank))
+
+    results = {}
+    for w in nested:
+        try:
+            line = run_workload(args, w, WORKLOADS[w][5], 3, 0.0, False, False)
+        except Exception as e:                        # noqa: BLE001 - one config failing must not lose the headline
+            import traceback
+            line = {"error": repr(e), "traceback": traceback.format_exc()[-1500:]}
+            gc.collect(); torch.cuda.empty_cache()
+        if rank == 0:
+            if isinstance(line, dict) and w in pre_cpu and "error" not in line:
+                line["cpu_baseline"], port = pre_cpu[w]
+                if port is not None:
+                    line["cpu_baseline_port"] = port
+            results[w] = line
+    line = run_workload(args, head, args.steps, args.warmup, 0.0, False, True)
+    if rank == 0:
+        if head in pre_cpu:
+            line["cpu_baseline"], port = pre_cpu[head]
+            if port is not None:
+                line["cpu_baseline_port"] = port
+        if results:
+            line["workloads"] = results
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -33,8 +33,11 @@ struct mzb_fc_model {
 };
 
 __device__ __forceinline__ float elu_f32(float x) {
-  // ATen's ELU evaluates exp(x) - 1 for x <= 0 (alpha = 1)
-  return x > 0.0f ? x : __fsub_rn(expf(x), 1.0f);
+  // ATen's ELU evaluates exp(x) - 1 for x <= 0 (alpha = 1).  Evaluated unconditionally on min(x, 0) and selected:
+  // a thread-per-game warp diverges on the sign of every hidden unit, and a branch around expf costs more than the
+  // eight instructions it skips (same value bit for bit: exp(0) - 1 = 0 is never selected for x > 0).
+  const float e = __fsub_rn(expf(fminf(x, 0.0f)), 1.0f);
+  return x > 0.0f ? x : e;
 }
 
 // Inverse of the value transform h(x) (models.py:656-661), in torch's float32 operation order.

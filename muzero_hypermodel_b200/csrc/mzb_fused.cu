@@ -13,7 +13,7 @@
 #include "mzb_fc.cuh"
 #include "mzb_tree.cuh"
 
-#define MZB_FUSED_DEFAULT_EXP 1
+#define MZB_FUSED_DEFAULT_EXP 7      // FFMA2 network, root record in registers, search path in shared memory
 
 namespace {
 
@@ -258,8 +258,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   const uint32_t my_step = io.step ? io.step[g] : 0u;
   const uint8_t* legal = io.legal ? io.legal + (size_t)g * A : nullptr;
   const int gm = (EXP & X_ALIAS) ? (g & 8191) : g;
-  auto rec_of = [&](int n) -> uint8_t* { return t.rec(gm, n); };
-  auto hid_of = [&](int n) -> float* { return t.hidden + t.rec_index(gm, n) * ENC; };
+  // per-thread bases of the blocked store (mzb_tree.cuh): node n of this game lives n * 32 records further on, so
+  // an address is one IMAD with a compile-time stride instead of a 64-bit multiply by runtime sizes
+  constexpr size_t RB = 24 * (size_t)A;
+  uint8_t* const rec_base = t.nodes + t.rec_index(gm, 0) * RB;
+  float* const hid_base = t.hidden + t.rec_index(gm, 0) * ENC;
+  auto rec_of = [&](int n) -> uint8_t* { return rec_base + (size_t)n * (32 * RB); };
+  auto hid_of = [&](int n) -> float* { return hid_base + (size_t)n * (32 * ENC); };
 
   // ---------------- initial inference (models.py:172-190) + root expansion (self_play.py:292-314)
   double rp[A];                       // root priors, float64 after the noise mix
@@ -335,71 +340,84 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   constexpr int LP = PB_LUT ? 64 : 1;
   uint32_t lp_edge[LP]; double lp_vs[LP]; int lp_vi[LP]; float lp_rw[LP];
 
-  for (int sim = 0; sim < io.num_sims; ++sim) {
-    // ---------------- select walk (self_play.py:326-335, 364-405)
-    int node = 0, N = root_visit, depth = 0, action = 0;
-    while (active) {
-      double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
-      {
-        Rec<A> rr;
-        bool from_regs = false;
-        if constexpr (ROOTREG) {
-          if (node == 0) {
-            from_regs = true;
+  // One level of the select walk (self_play.py:364-405) on the record `rr` of `node`: scores, arg-max with the
+  // reference's tie rule, path entry; returns the chosen child (< 0: leaf reached) and leaves the action in `action`.
+  int action = 0, N = 0;
+  auto walk_level = [&](const Rec<A>& rr, const bool root_level, const int node, const int depth, const int sim) -> int {
+    double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
 #pragma unroll
-            for (int i = 0; i < Rec<A>::WORDS; ++i) rr.w[i] = root.w[i];
-          }
-        }
-        if (!from_regs) rr.load(rec_of(node));
+    for (int a = 0; a < A; ++a) { vs[a] = rr.vs(a); pr[a] = rr.pr(a); vi[a] = rr.vi(a); rw[a] = rr.rw(a); ch[a] = rr.ch(a); }
+    const double pbc0 = PB_LUT ? 0.0 : lut[N];
+    const double sqrtN = PB_LUT ? 0.0 : __dsqrt_rn((double)N);
+    const double* pbrow = pbt + N * S1;
+    double sc[A];
+    double best = -CUDART_INF;
+    int n_best = 0;
+    action = -1;
 #pragma unroll
-        for (int a = 0; a < A; ++a) { vs[a] = rr.vs(a); pr[a] = rr.pr(a); vi[a] = rr.vi(a); rw[a] = rr.rw(a); ch[a] = rr.ch(a); }
-      }
-      const double pbc0 = PB_LUT ? 0.0 : lut[N];
-      const double sqrtN = PB_LUT ? 0.0 : __dsqrt_rn((double)N);
-      const double* pbrow = pbt + N * S1;
-      double sc[A];
-      double best = -CUDART_INF;
-      int n_best = 0;
-      action = -1;
+    for (int a = 0; a < A; ++a) {
+      if (ch[a] == MZB_CHILD_ILLEGAL) { sc[a] = -CUDART_INF; continue; }
+      const double p = root_level ? rp[a] : (double)pr[a];
+      const double pb = PB_LUT ? pbrow[vi[a]] : ucb_pb(pbc0, sqrtN, vi[a]);
+      sc[a] = ucb_score_pb(pb, vi[a], p, vs[a], (double)rw[a], t.discount, two, vmin, vmax);
+      if (sc[a] > best || action < 0) { best = sc[a]; n_best = 1; action = a; }
+      else if (sc[a] == best) ++n_best;
+    }
+    if (n_best > 1) {
+      int pick = (int)rng_tie_index(t.key, my_slot, my_step, (uint32_t)sim, (uint32_t)depth, (uint32_t)n_best);
 #pragma unroll
       for (int a = 0; a < A; ++a) {
-        if (ch[a] == MZB_CHILD_ILLEGAL) { sc[a] = -CUDART_INF; continue; }
-        const double p = node == 0 ? rp[a] : (double)pr[a];
-        const double pb = PB_LUT ? pbrow[vi[a]] : ucb_pb(pbc0, sqrtN, vi[a]);
-        sc[a] = ucb_score_pb(pb, vi[a], p, vs[a], (double)rw[a], t.discount, two, vmin, vmax);
-        if (sc[a] > best || action < 0) { best = sc[a]; n_best = 1; action = a; }
-        else if (sc[a] == best) ++n_best;
-      }
-      if (n_best > 1) {
-        int pick = (int)rng_tie_index(t.key, my_slot, my_step, (uint32_t)sim, (uint32_t)depth, (uint32_t)n_best);
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-          if (ch[a] != MZB_CHILD_ILLEGAL && sc[a] == best) {
-            if (pick == 0) action = a;
-            --pick;
-          }
+        if (ch[a] != MZB_CHILD_ILLEGAL && sc[a] == best) {
+          if (pick == 0) action = a;
+          --pick;
         }
       }
-      int next = MZB_CHILD_NONE, nv = 0;
-      double nvs = 0.0; float nrw = 0.0f;
+    }
+    int next = MZB_CHILD_NONE, nv = 0;
+    double nvs = 0.0; float nrw = 0.0f;
 #pragma unroll
-      for (int a = 0; a < A; ++a) if (a == action) { next = ch[a]; nv = vi[a]; nvs = vs[a]; nrw = rw[a]; }
-      if (PB_LUT) {
-        // node <= 63 and action < 2^8 here (PB_LUT: num_simulations <= 63): edge and visit count share one word
-        if (PD > 0 && depth < PD) {
-          sp_ev[depth * THREADS + threadIdx.x] = ((uint32_t)node << 24) | ((uint32_t)action << 16) | (uint32_t)nv;
-          sp_vs[depth * THREADS + threadIdx.x] = nvs; sp_rw[depth * THREADS + threadIdx.x] = nrw;
-        } else {
-          lp_edge[depth] = ((uint32_t)node << 16) | (uint32_t)action; lp_vs[depth] = nvs; lp_vi[depth] = nv; lp_rw[depth] = nrw;
-        }
+    for (int a = 0; a < A; ++a) if (a == action) { next = ch[a]; nv = vi[a]; nvs = vs[a]; nrw = rw[a]; }
+    if (PB_LUT) {
+      // node <= 63 and action < 2^8 here (PB_LUT: num_simulations <= 63): edge and visit count share one word
+      if (PD > 0 && depth < PD) {
+        sp_ev[depth * THREADS + threadIdx.x] = ((uint32_t)node << 24) | ((uint32_t)action << 16) | (uint32_t)nv;
+        sp_vs[depth * THREADS + threadIdx.x] = nvs; sp_rw[depth * THREADS + threadIdx.x] = nrw;
       } else {
-        path[(size_t)depth * G] = ((uint32_t)node << 16) | (uint32_t)action;
+        lp_edge[depth] = ((uint32_t)node << 16) | (uint32_t)action; lp_vs[depth] = nvs; lp_vi[depth] = nv; lp_rw[depth] = nrw;
       }
-      ++depth;
-      if (next < 0) break;
-      if ((EXP & X_NOWALK) && depth >= 1) break;
-      N = nv;
-      node = next;
+    } else {
+      path[(size_t)depth * G] = ((uint32_t)node << 16) | (uint32_t)action;
+    }
+    N = nv;
+    return next;
+  };
+
+  for (int sim = 0; sim < io.num_sims; ++sim) {
+    // ---------------- select walk (self_play.py:326-335): the root level straight from registers (ROOTREG), then
+    // one dependent record load per level
+    int node = 0, depth = 0;
+    N = root_visit;
+    if (active) {
+      int next;
+      if constexpr (ROOTREG) {
+        Rec<A> rr;
+#pragma unroll
+        for (int i = 0; i < Rec<A>::WORDS; ++i) rr.w[i] = root.w[i];
+        next = walk_level(rr, true, 0, 0, sim);
+      } else {
+        Rec<A> rr;
+        rr.load(rec_of(0));
+        next = walk_level(rr, true, 0, 0, sim);
+      }
+      depth = 1;
+      if (EXP & X_NOWALK) next = -1;
+      while (next >= 0) {
+        node = next;
+        Rec<A> rr;
+        rr.load(rec_of(node));
+        next = walk_level(rr, false, node, depth, sim);
+        ++depth;
+      }
     }
     const int L = depth, fresh = sim + 1;
     if (PHASE_SYNC) __syncthreads();          // warps of the block enter the unrolled network code together
@@ -567,6 +585,8 @@ template <class SH, bool TUNE>
 int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
   const bool lut = io.num_sims <= 63;                 // (S+1)^2 doubles must fit next to the weights
   if (!lut) return launch_variant<SH, false, MZB_FUSED_DEFAULT_EXP>(t, m, io, s);
+  // small batches (tictactoe at 4,096 games = 16 CTAs of 256): one warp per CTA spreads the games over all SMs
+  if (t->v.G < 148 * 128) return launch_variant<SH, true, MZB_FUSED_DEFAULT_EXP, 32, false, 2>(t, m, io, s);
   if constexpr (TUNE) {
     switch (fused_exp()) {
       case 0: return launch_variant<SH, true, 0>(t, m, io, s);

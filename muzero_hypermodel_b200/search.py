@@ -73,7 +73,8 @@ class BatchedMCTS:
             pool = getattr(self, "_pool", None)
             if pool is None or pool.dtype != dt:
                 pool = self._pool = torch.empty((G, cfg.num_simulations + 1, state), dtype=dt, device=dev)
-            obs4 = observations.to(device=dev, dtype=torch.float32).reshape((G,) + tuple(model.observation_shape)).contiguous()
+            # [G, C(S+1)+S, H, W]: the stacked planes of get_stacked_observations ride in the channel axis
+            obs4 = observations.to(device=dev, dtype=torch.float32).reshape((G, -1) + tuple(model.observation_shape[1:])).contiguous()
             with torch.cuda.device(dev):
                 ws = model._workspace(G, dev)
                 check(_lib.lib.mzb_search_resnet(self.tree._h, h, ptr(obs4), ptr(lg), ptr(tp), ptr(nz),

@@ -301,12 +301,17 @@ class SelfPlay:
         return self._env, self._mcts
 
     def step(self, temperature=1.0, temperature_threshold=None, add_exploration_noise=True, export=True,
-             allow_fused=True):
-        """One move of every game: observe -> search -> select_action + Game.step + record -> harvest."""
+             allow_fused=True, search_events=None):
+        """One move of every game: observe -> search -> select_action + Game.step + record -> harvest.
+        search_events: optional (start, end) CUDA events recorded around the search launch (bench: in-step timing)."""
         env, mcts = self._setup()
         obs, legal, to_play = env.observe()
+        if search_events is not None:
+            search_events[0].record()
         out = mcts.run(self.model, obs, legal, to_play, add_exploration_noise, slot=env.slot, step=env.step_count,
                        allow_fused=allow_fused, out=getattr(self, "_out", None))
+        if search_events is not None:
+            search_events[1].record()
         self._out = out
         env.act_step(out["visits"], out["root_value"], legal, temperature, temperature_threshold)
         env.harvest(export)

@@ -48,6 +48,9 @@ def _worker(args):
     game, weights, overrides, seed, searches_cap, n_calls = args
     import torch
     torch.set_num_threads(1)
+    # the CPU arm: the reference picks "cuda" whenever torch sees a GPU (self_play.py:27); a forked worker of a process
+    # that has touched the CUDA driver cannot initialise it anyway - keep the reference on the host cores
+    torch.cuda.is_available = lambda: False
     key = (game, tuple(sorted(overrides.items())))
     if _state.get("key") != key:
         sp, gm = _load(game)

@@ -142,3 +142,46 @@ def test_more_than_two_players_rejected():
     from muzero_hypermodel_b200.tree import BatchedTree
     with pytest.raises(NotImplementedError):
         BatchedTree(4, 3, 5, 3, 1.0, 19652, 1.25)
+
+
+@pytest.mark.parametrize("A,k_legal,alpha", [(2, 2, 0.25), (7, 7, 0.3), (9, 5, 0.1), (121, 121, 0.3), (121, 40, 0.3)])
+def test_device_dirichlet_matches_numpy_dirichlet(A, k_legal, alpha):
+    """Device-generated exploration noise (Marsaglia-Tsang Gamma from Philox, the mode every bench run uses) against
+    `numpy.random.dirichlet([alpha] * k)` (self_play.py:472-477): exact Beta(alpha, (k-1) alpha) marginals by a
+    one-sample Kolmogorov-Smirnov test, a two-sample KS test against numpy's own draws, and the first two moments
+    incl. the negative covariance between components."""
+    from scipy import stats
+    from muzero_hypermodel_b200.tree import BatchedTree
+    dev = torch.device("cuda:0")
+    G = 40000
+    legal = np.zeros((G, A), dtype=np.uint8)
+    legal[:, np.sort(np.random.RandomState(A).permutation(A)[:k_legal])] = 1
+    cols = np.nonzero(legal[0])[0]
+    tree = BatchedTree(G, A, 4, 1, 0.997, T.PB_C_BASE, T.PB_C_INIT, seed=77, device=dev)
+    pri = torch.full((G, A), 1.0 / A, device=dev)
+    tree.root_init(torch.zeros(G, device=dev), pri, False, torch.tensor(legal, device=dev), None, None, alpha, 1.0)
+    noise = tree.root_stats(full=True)["child_prior"].cpu().numpy()          # frac = 1: the root priors ARE the noise
+    assert (noise[:, legal[0] == 0] == 0).all() and np.allclose(noise.sum(1), 1.0, atol=1e-12)
+    x = noise[:, cols]
+    k = k_legal
+    ref = np.random.RandomState(5).dirichlet([alpha] * k, size=G)
+    # moments of Dirichlet(alpha 1_k): mean 1/k, var (k-1)/(k^2 (k alpha + 1)), cov -1/(k^2 (k alpha + 1))
+    var = (k - 1) / (k * k * (k * alpha + 1))
+    se_mean = np.sqrt(var / G)
+    assert np.abs(x.mean(0) - 1.0 / k).max() < 5 * se_mean + 1e-12
+    assert abs(x.var(0).mean() - var) < 0.05 * var
+    if k > 1:
+        cov01 = np.cov(x[:, 0], x[:, 1])[0, 1]
+        assert abs(cov01 + 1 / (k * k * (k * alpha + 1))) < 0.15 / (k * k * (k * alpha + 1)) + 4 * var / np.sqrt(G)
+    for j in (0, k // 2, k - 1):
+        # tiny components underflow towards 0 in both generators; compare on the resolvable range
+        p1 = stats.kstest(x[:, j], stats.beta(alpha, (k - 1) * alpha).cdf).pvalue if k > 1 else 1.0
+        p2 = stats.ks_2samp(x[:, j], ref[:, j]).pvalue
+        assert p1 > 1e-4 and p2 > 1e-4, (j, p1, p2)
+    # different (slot, step) counters give different samples; the same counters reproduce them
+    tree.root_init(torch.zeros(G, device=dev), pri, False, torch.tensor(legal, device=dev), None, None, alpha, 1.0)
+    again = tree.root_stats(full=True)["child_prior"].cpu().numpy()
+    assert again.tobytes() == noise.tobytes()
+    step = torch.full((G,), 3, dtype=torch.int32, device=dev)
+    tree.root_init(torch.zeros(G, device=dev), pri, False, torch.tensor(legal, device=dev), None, None, alpha, 1.0, None, step)
+    assert not np.array_equal(tree.root_stats(full=True)["child_prior"].cpu().numpy(), noise)
