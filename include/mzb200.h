@@ -174,6 +174,12 @@ int mzb_fc_recurrent(mzb_fc_model* m, int64_t B, const float* d_state_in, int64_
                      int64_t out_row_stride, int64_t out_offset, float* d_value_logits, float* d_reward_logits,
                      float* d_policy_logits, float* d_value, float* d_reward, float* d_priors, void* stream);
 
+/* uint8 image observations -> the float32 frames the reference's Atari wrapper builds on the host
+ * (games/breakout.py:141-159: `numpy.asarray(frame, dtype="float32") / 255.0`): out[i] = (float)in[i] / 255.0f, one
+ * correctly rounded float32 division per element, so a caller that ships the emulator's uint8 frames (4x fewer bytes
+ * over PCIe) feeds the network the same values bit for bit. */
+int mzb_u8_to_unit_float(const uint8_t* d_in, int64_t n, float* d_out, void* stream);
+
 /* models.support_to_scalar (models.py:641-662): d_logits [B, 2S+1] -> d_out [B]. */
 int mzb_support_to_scalar(const float* d_logits, int64_t B, int support_size, float* d_out, void* stream);
 /* models.scalar_to_support (models.py:665-685): d_x [n] -> d_out [n, 2S+1]. */
@@ -232,6 +238,12 @@ int mzb_env_reset(mzb_env* e, void* stream);
  * d_slot [G] u32 (global game id), d_step [G] u32 (env steps the slot has taken).  NULL = skip. */
 int mzb_env_observe(mzb_env* e, float* d_obs, uint8_t* d_legal, int8_t* d_to_play, uint32_t* d_slot, uint32_t* d_step,
                     void* stream);
+/* GameHistory.get_stacked_observations(-1, stacked_observations) (self_play.py:514-548) of every running game, built
+ * from the history the environment keeps on the device: d_obs [G][(C (S + 1) + S) * H * W] float32 - the current
+ * observation, then for k = 1..S the observation k moves ago and a plane filled with the action played from it (zeros
+ * before the start of the game).  S = 0 is mzb_env_observe's observation.  Not available for synthetic frames. */
+int mzb_env_observe_stacked(mzb_env* env, int32_t stacked_observations, float* d_obs, void* stream);
+
 /* One move for every running game: select_action from the root visit counts at `temperature`
  * (0 past temperature_threshold, <=0 disables the threshold), Game.step, GameHistory appends.
  *  d_uniforms [G] f64 injects the random draw (NULL = Philox(slot, step, STREAM_ACTION));
@@ -294,6 +306,9 @@ typedef struct {
 int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* cfg);
 /* Test hook: 0 makes the bf16 path run the CUDA-core direct convolution instead of the tcgen05 kernel. */
 void mzb_conv_tc_enable(int on);
+/* Test hook: 0 makes narrow networks (16 channels, <= 48 latent positions: Breakout) run recurrent inference layer by
+ * layer instead of the one-kernel warp-per-image path (csrc/mzb_tower16.cu, models.py:363-404, 447-456, 551-595). */
+void mzb_tower16_enable(int on);
 int mzb_resnet_destroy(mzb_resnet_model* m);
 int mzb_resnet_num_tensors(const mzb_resnet_model* m);
 int mzb_resnet_latent_dims(const mzb_resnet_model* m, int32_t* C, int32_t* H, int32_t* W);

@@ -217,6 +217,41 @@ __global__ void k_env_observe(EnvView e, float* __restrict__ obs, uint8_t* __res
   if (step) step[g] = e.steps[g];
 }
 
+// GameHistory.get_stacked_observations(-1, S) (self_play.py:514-548) for every game, from the running history on the
+// device: planes of the current observation, then for k = 1..S the observation k moves ago followed by a plane holding
+// the action that was played from it (action_history[index - k + 1], NOT normalised, as in the reference), or
+// all-zero planes before the start of the game.  Layout [G][(C (S + 1) + S) * H * W], C planes of H*W per observation.
+__global__ void k_env_observe_stacked(EnvView e, int S, int C, float* __restrict__ obs) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= e.G) return;
+  const int hw = e.obs_dim / C, len = e.h_len[g];
+  float* o = obs + (size_t)g * ((size_t)(C * (S + 1) + S) * hw);
+  for (int k = 0; k <= S; ++k) {
+    const int idx = len - k;
+    float* dst = o + (k == 0 ? 0 : (size_t)C * hw + (size_t)(k - 1) * (C + 1) * hw);
+    if (idx < 0) {
+      for (int i = 0; i < (C + 1) * hw; ++i) dst[i] = 0.0f;
+      continue;
+    }
+    const float* rec = e.h_obs + ((size_t)g * e.hist_cap + idx) * e.rec_floats;
+    if (e.kind == MZB_ENV_CARTPOLE) {
+      for (int i = 0; i < hw; ++i) dst[i] = rec[i];
+    } else {
+      const int8_t* b = reinterpret_cast<const int8_t*>(rec);
+      const float pl = (float)b[e.cells];
+      for (int i = 0; i < e.cells; ++i) {
+        dst[i] = b[i] == 1 ? 1.0f : 0.0f;
+        dst[e.cells + i] = b[i] == -1 ? 1.0f : 0.0f;
+        dst[2 * e.cells + i] = pl;
+      }
+    }
+    if (k > 0) {
+      const float act = (float)e.h_action[(size_t)g * e.hist_cap + idx + 1];
+      for (int i = 0; i < hw; ++i) dst[(size_t)C * hw + i] = act;
+    }
+  }
+}
+
 // Synthetic 3x96x96 frames U[0,1) (BASELINE.json: breakout on synthetic frames), a pure function of
 // (seed, slot, step, pixel): four pixels per Philox call, coalesced float4 stores.
 __global__ void k_synthetic_frames(EnvView e, float* __restrict__ obs) {
@@ -528,6 +563,19 @@ int mzb_env_observe(mzb_env* e, float* d_obs, uint8_t* d_legal, int8_t* d_to_pla
     k_synthetic_frames<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->v, d_obs);
     MZB_LAUNCH_CHECK();
   }
+  return MZB_OK;
+}
+
+int mzb_env_observe_stacked(mzb_env* e, int32_t stacked_observations, float* d_obs, void* stream) {
+  MZB_CHECK_ARG(e && d_obs, "NULL argument");
+  MZB_CHECK_ARG(stacked_observations >= 0 && stacked_observations <= e->v.max_moves, "stacked_observations out of range: %d", stacked_observations);
+  if (e->v.kind == MZB_ENV_SYNTHETIC_FRAMES) {
+    mzb_set_error("stacked observations of regenerated synthetic frames are not kept on the device");
+    return MZB_EUNSUPPORTED;
+  }
+  const int C = e->v.kind == MZB_ENV_CARTPOLE ? 1 : 3;
+  k_env_observe_stacked<<<blocks(e->v.G, 128), 128, 0, (cudaStream_t)stream>>>(e->v, stacked_observations, C, d_obs);
+  MZB_LAUNCH_CHECK();
   return MZB_OK;
 }
 

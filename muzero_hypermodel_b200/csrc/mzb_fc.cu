@@ -344,6 +344,29 @@ int mzb_fc_recurrent(mzb_fc_model* m, int64_t B, const float* d_state_in, int64_
   return MZB_OK;
 }
 
+__global__ void k_u8_to_unit_float(const uint8_t* __restrict__ in, long long n, float* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i + 16 <= n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(in + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      reinterpret_cast<float4*>(out + i)[k] = make_float4(__fdiv_rn((float)(w[k] & 255u), 255.0f), __fdiv_rn((float)((w[k] >> 8) & 255u), 255.0f),
+                                                          __fdiv_rn((float)((w[k] >> 16) & 255u), 255.0f), __fdiv_rn((float)(w[k] >> 24), 255.0f));
+  } else {
+    for (long long k = i; k < n; ++k) out[k] = __fdiv_rn((float)in[k], 255.0f);
+  }
+}
+
+int mzb_u8_to_unit_float(const uint8_t* d_in, int64_t n, float* d_out, void* stream) {
+  MZB_CHECK_ARG(d_in && d_out && n > 0, "bad argument");
+  MZB_CHECK_ARG(((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_out & 15) == 0, "buffers must be 16-byte aligned");
+  const long long threads = (n + 15) / 16;
+  k_u8_to_unit_float<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, n, d_out);
+  MZB_LAUNCH_CHECK();
+  return MZB_OK;
+}
+
 }  // extern "C"
 
 // Internal (mzb_search_fc's modular path): hidden states read from / written to the tree store's blocked slots

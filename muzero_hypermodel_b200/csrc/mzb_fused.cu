@@ -223,6 +223,9 @@ struct SearchIO {
 // 4 = the search path's edge statistics in shared memory for the first 12 levels (deeper levels: local memory).
 enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32 };
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm) { return blocks_per_sm >= 3 ? 8 : 12; }
+__host__ __device__ constexpr int smem_path_depth(int blocks_per_sm, int threads) {
+  return threads * blocks_per_sm > 512 ? 8 : 12;        // 48 KB (12 levels) per 256 threads fit twice per SM, not three times
+}
 
 template <class SH, int THREADS, bool PHASE_SYNC, bool PB_LUT, int EXP, int MINB = 512 / THREADS>
 __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const float* __restrict__ gpack, SearchIO io) {
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   const int S1 = io.num_sims + 1;
   double* pbt = lut + ((S1 + 1) & ~1);                     // [S1][S1] when PB_LUT
   // SPATH: [PD][THREADS] value sums f64 | rewards f32 | (node << 16 | action << 8... ) see path_put
-  constexpr int PD = ((EXP & X_SPATH) != 0 && PB_LUT) ? smem_path_depth(MINB) : 0;
+  constexpr int PD = ((EXP & X_SPATH) != 0 && PB_LUT) ? smem_path_depth(MINB, THREADS) : 0;
   double* sp_vs = pbt + (PB_LUT ? S1 * S1 : 0);
   float* sp_rw = reinterpret_cast<float*>(sp_vs + PD * THREADS);
   uint32_t* sp_ev = reinterpret_cast<uint32_t*>(sp_rw + PD * THREADS);
@@ -558,7 +561,7 @@ template <class SH, bool PB_LUT, int EXP, int THREADS = 256, bool PHASE_SYNC = t
 int launch_variant(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
   const int S1 = io.num_sims + 1;
   const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? S1 * S1 : 0)) +
-                      (((EXP & X_SPATH) != 0 && PB_LUT) ? (size_t)smem_path_depth(MINB) * THREADS * 16 : 0);
+                      (((EXP & X_SPATH) != 0 && PB_LUT) ? (size_t)smem_path_depth(MINB, THREADS) * THREADS * 16 : 0);
   static bool configured = false;
   if (!configured) {
     MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT, EXP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -590,12 +593,11 @@ int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t 
   if constexpr (TUNE) {
     switch (fused_exp()) {
       case 0: return launch_variant<SH, true, 0>(t, m, io, s);
-      case 1: return launch_variant<SH, true, 1>(t, m, io, s);
-      case 3: return launch_variant<SH, true, 3>(t, m, io, s);
       case 7: return launch_variant<SH, true, 7>(t, m, io, s);
       case 23: return launch_variant<SH, true, 23>(t, m, io, s);
-      case 1003: return launch_variant<SH, true, 3, 256, true, 3>(t, m, io, s);     // 1000 + flags: 3 blocks per SM (<= 85 registers)
-      case 1007: return launch_variant<SH, true, 7, 256, true, 3>(t, m, io, s);
+      case 1007: return launch_variant<SH, true, 7, 256, true, 3>(t, m, io, s);     // 3 x 256 threads per SM (<= 85 registers)
+      case 2007: return launch_variant<SH, true, 7, 128, true, 5>(t, m, io, s);     // 5 x 128 threads per SM (<= 102 registers)
+      case 3007: return launch_variant<SH, true, 7, 128, true, 4>(t, m, io, s);     // 4 x 128 threads per SM (128 registers)
       case 19: return launch_variant<SH, true, 19>(t, m, io, s);
       case 35: return launch_variant<SH, true, 35>(t, m, io, s);
       default: break;

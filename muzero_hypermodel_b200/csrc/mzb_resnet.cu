@@ -1249,6 +1249,24 @@ int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_r
   mzb_resnet_model* m = r.m;
   const int B = r.B, C = m->C;
   const Geo gl = latent_geo<T>(m);
+  if (sizeof(T) == 2 && mzb_tower16_supported(m, in_layout, o.layout)) {
+    // narrow network (Breakout: 16 x 6 x 6): the whole recurrent inference is one warp-per-image kernel; only the
+    // head mlps remain, fed by its projection rows
+    const int hw = gl.H * gl.W, rr = m->reward.r, rvp = m->value.r + m->policy.r;
+    float* pr = r.proj();
+    float* pvp = pr + (size_t)r.cap_B * rr * hw;
+    const bool want_reward = o.reward_logits || o.reward;
+    const bool want_pred = o.value_logits || o.policy_logits || o.value || o.priors;
+    r.rc = mzb_tower16_recurrent(m, B, state_in, in_layout, in_row_stride, in_slot, slot_stride, action, o.state, o.layout,
+                                 o.row_stride, o.off, want_reward ? pr : nullptr, want_pred ? pvp : nullptr, r.s);
+    if (r.rc) return r.rc;
+    head<T>(r, r.buf<T>(0), gl, m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr, pr, (long long)rr * hw, 0);
+    if (want_pred) {
+      head<T>(r, r.buf<T>(0), gl, m->value, 0, nullptr, o.value_logits, o.value, nullptr, pvp, (long long)rvp * hw, 0);
+      head<T>(r, r.buf<T>(0), gl, m->policy, 1, nullptr, o.policy_logits, nullptr, o.priors, pvp, (long long)rvp * hw, m->value.r * hw);
+    }
+    return r.rc;
+  }
   const long long n = (long long)B * gl.H * gl.W * C;
   if (in_layout == 0) {
     k_nchw_to_nhwc<T><<<nblk(n, 256), 256, 0, r.s>>>((const float*)state_in, in_row_stride, in_slot, slot_stride, B, gl, r.buf<T>(0));
@@ -1296,7 +1314,9 @@ size_t act_bytes_for(const mzb_resnet_model* m, long long B) {
 }
 
 size_t ws_bytes_for(const mzb_resnet_model* m, long long B) {
-  const size_t proj_rows = (size_t)std::max(m->reward.r, m->value.r + m->policy.r) * m->Hl * m->Wl;
+  // projection rows of the heads' 1x1 convolutions: reward AND value|policy regions (the one-kernel recurrent
+  // inference of narrow networks fills both before any head runs)
+  const size_t proj_rows = (size_t)(m->reward.r + m->value.r + m->policy.r) * m->Hl * m->Wl;
   return 3 * act_bytes_for(m, B) + mzb_align_up((size_t)B * 4, 256) + mzb_align_up((size_t)B * proj_rows * 4, 256) + 1024;
 }
 

@@ -34,3 +34,9 @@ bool mzb_head_mma_pack(mzb_resnet_model* m, const HeadParams& hp, const std::vec
 void mzb_head_mma_free(void* opaque);
 int mzb_head_mma_launch(void* opaque, const float* proj, long long proj_stride, int proj_off, int B, int S, int mode,
                         const uint8_t* legal, float* logits, float* scalar, float* priors, cudaStream_t stream);
+
+// whole recurrent inference of a 16-channel network as one kernel (mzb_tower16.cu); projections feed the head kernels
+bool mzb_tower16_supported(const mzb_resnet_model* m, int in_layout, int out_layout);
+int mzb_tower16_recurrent(mzb_resnet_model* m, int B, const void* state_in, int in_layout, long long in_row_stride,
+                          const int* in_slot, long long slot_stride, const int* action, void* state_out, int out_layout,
+                          long long out_row_stride, long long out_off, float* proj_r, float* proj_vp, cudaStream_t s);

@@ -1,0 +1,335 @@
+// K7n: recurrent inference of a NARROW residual MuZero network (16 channels, latent <= 48 positions - Breakout's
+// 16 x 6 x 6 hidden state) as ONE kernel: dynamics convolution with the action plane, the dynamics tower, the reward
+// head's 1x1 projection, per-channel min-max scaling + hidden-state store, the prediction tower and the value / policy
+// 1x1 projections (models.py:363-404, 447-456, 551-595, 612-619).  Only the head mlps stay separate launches.
+//
+// Why not the tcgen05 kernel per layer (mzb_conv_tc.cu): a 16-channel 3x3 convolution is a 128 x 16 x 144 GEMM tile whose
+// MMA needs 8 cycles of math and 41-57 of operand fetch (tests/ubench_umma*.cu), every layer is a latency-bound launch
+// (9 convolutions + 3 heads + min-max + gather = 14 launches of 20-40 us per simulation for 16,384 games) and the whole
+// activation set of an image is 1.1 KB.  Here a WARP owns an image: its activations live in shared memory in the padded
+// layout of mzb_resnet.cuh (so a tap is a row shift), all layers' weights are resident in shared memory (9 x 4.6 KB),
+// and each convolution is 3 m-tiles x 2 n-tiles x 9 taps of mma.sync.m16n8k16 (bf16 operands, fp32 accumulate) fed by
+// ldmatrix - the warp-level MMA is the right size for a 36 x 16 x 144 product; nothing but the input state, the output
+// state and the projection rows touches global memory.  Arithmetic per layer is the bf16 path's: fp32 accumulate,
+// folded batch-norm, residual, ReLU, one bf16 rounding of the stored activation.
+#include <cuda_bf16.h>
+
+#include "mzb_resnet_model.h"
+
+namespace {
+
+constexpr int kRowB = 48;              // bytes per shared-memory row: 16 bf16 + 16 B pad -> conflict-free ldmatrix / 4-byte stores
+constexpr int kTapB = 16 * kRowB;      // one tap of one convolution: 16 output channels x 16 input channels
+constexpr int kConvB = 9 * kTapB;
+constexpr int kMaxBlocks = 4;
+constexpr int kWarps = 16;
+constexpr int MT = 3;                  // m-tiles of 16 positions
+
+struct T16Conv { const __nv_bfloat16* w; const float* scale; const float* shift; };
+struct T16Args {
+  int B, H, W, A, n_dyn, n_pred, n_conv;
+  T16Conv conv[1 + 4 * kMaxBlocks];            // dyn_conv, dyn blocks (c1, c2)..., pred blocks (c1, c2)...
+  const float* plane_table;                    // [H*W][16]
+  const float* w_r; int r_r;                   // reward 1x1 [r_r][16]
+  const float* w_vp; int r_vp;                 // value | policy 1x1 [r_vp][16]
+  const void* state_in; int in_layout; long long in_row_stride; const int* in_slot; long long slot_stride;
+  const int* action;
+  void* state_out; int out_layout; long long out_row_stride, out_off;
+  float* proj_r; float* proj_vp;               // [B][r * H*W] fp32, bias added by the head kernels
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  // not volatile: the compiler may issue a tap's loads ahead of the previous tap's MMAs; the memory clobber keeps them
+  // behind the __syncwarp() that publishes the previous layer's stores
+  asm("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+struct Lane {
+  int a_row[MT];            // A fragment: padded row of the position this lane addresses, per m-tile
+  int a_koff;               // byte offset of the k half it addresses
+  int o_row[MT][2], o_pos[MT][2];
+  bool o_ok[MT][2];
+  uint32_t b_off;           // B fragment: byte offset of the weight row this lane addresses inside a tap
+};
+
+// One 3x3 convolution (16 -> 16 channels) over the warp's image: in -> out, both padded shared-memory buffers.
+template <bool PLANE, bool RES>
+__device__ __forceinline__ void conv16(uint32_t in_u32, uint8_t* out, const uint8_t* res, uint32_t w_u32, const float* sc,
+                                       const float* sh, float pl, const float* ptab, const Lane& L, int pitch, int lane) {
+  float acc[MT][2][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.0f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int shift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
+    uint32_t bf[4];
+    ldsm_x4(w_u32 + (uint32_t)tap * kTapB + L.b_off, bf);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      uint32_t af[4];
+      ldsm_x4(in_u32 + (uint32_t)((L.a_row[mt] + shift) * kRowB + L.a_koff), af);
+      mma16816(acc[mt][0], af, bf[0], bf[1]);
+      mma16816(acc[mt][1], af, bf[2], bf[3]);
+    }
+  }
+  const int cq = (lane & 3) * 2;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!L.o_ok[mt][h]) continue;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = 8 * j + cq;
+        float v0 = acc[mt][j][2 * h], v1 = acc[mt][j][2 * h + 1];
+        if (PLANE) {
+          v0 = fmaf(pl, ptab[L.o_pos[mt][h] * 16 + c], v0);
+          v1 = fmaf(pl, ptab[L.o_pos[mt][h] * 16 + c + 1], v1);
+        }
+        v0 = fmaf(v0, sc[c], sh[c]);
+        v1 = fmaf(v1, sc[c + 1], sh[c + 1]);
+        if (RES) {
+          const uint32_t rw = *reinterpret_cast<const uint32_t*>(res + L.o_row[mt][h] * kRowB + c * 2);
+          v0 += bf_lo(rw); v1 += bf_hi(rw);
+        }
+        v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f);
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+        *reinterpret_cast<uint32_t*>(out + L.o_row[mt][h] * kRowB + c * 2) = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// 1x1 projection of the warp's image (bf16 activations in `buf`) onto r rows: out[r][p] = sum_c x[p][c] * w[r][c]
+__device__ __forceinline__ void project(const uint8_t* buf, const float* w, int r, float* out, int HW, const int* s_row, int lane) {
+  for (int p = lane; p < HW; p += 32) {
+    const int row = s_row[p];
+    const uint4 lo = *reinterpret_cast<const uint4*>(buf + row * kRowB), hi = *reinterpret_cast<const uint4*>(buf + row * kRowB + 16);
+    const uint32_t x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    for (int k = 0; k < r; ++k) {
+      float s = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s = fmaf(bf_lo(x[i]), w[k * 16 + 2 * i], s);
+        s = fmaf(bf_hi(x[i]), w[k * 16 + 2 * i + 1], s);
+      }
+      out[(long long)k * HW + p] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = a.H, W = a.W, HW = H * W, pitch = geo_pitch(W), halo = geo_halo(W);
+  const int rows = halo + geo_rows_per_image(H, W) + halo;
+  uint8_t* s_w = smem;                                              // [n_conv][9][16][kRowB]
+  float* s_sc = reinterpret_cast<float*>(s_w + (size_t)a.n_conv * kConvB);       // [n_conv][32]: scale | shift
+  float* s_ptab = s_sc + a.n_conv * 32;                             // [HW][16]
+  float* s_wr = s_ptab + HW * 16;                                   // [r_r][16]
+  float* s_wvp = s_wr + a.r_r * 16;                                 // [r_vp][16]
+  int* s_row = reinterpret_cast<int*>(s_wvp + a.r_vp * 16);          // [HW]: padded row of position p (no divisions in the loops)
+  uint8_t* s_act = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_row + HW) + 127) & ~(uintptr_t)127);
+  const size_t buf_bytes = (size_t)rows * kRowB;
+  // ---- stage the weights: w_bf16 [16 cout][9 taps][16 cin] -> [tap][cout] rows of kRowB bytes
+  for (int i = threadIdx.x; i < a.n_conv * 9 * 16 * 2; i += blockDim.x) {
+    const int half = i & 1, n = (i >> 1) & 15, tap = (i >> 5) % 9, ci = i / (9 * 32);
+    const uint4 v = *reinterpret_cast<const uint4*>(a.conv[ci].w + (size_t)n * 144 + tap * 16 + half * 8);
+    *reinterpret_cast<uint4*>(s_w + (size_t)ci * kConvB + tap * kTapB + n * kRowB + half * 16) = v;
+  }
+  for (int i = threadIdx.x; i < a.n_conv * 32; i += blockDim.x) {
+    const int ci = i >> 5, k = i & 31;
+    s_sc[i] = k < 16 ? a.conv[ci].scale[k] : a.conv[ci].shift[k - 16];
+  }
+  for (int i = threadIdx.x; i < HW * 16; i += blockDim.x) s_ptab[i] = a.plane_table[i];
+  for (int i = threadIdx.x; i < a.r_r * 16; i += blockDim.x) s_wr[i] = a.w_r[i];
+  for (int i = threadIdx.x; i < a.r_vp * 16; i += blockDim.x) s_wvp[i] = a.w_vp[i];
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) s_row[p] = halo + (p / W + 1) * pitch + p % W;
+  for (size_t i = threadIdx.x; i < kWarps * 3 * buf_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0u, 0u, 0u, 0u);       // pad rows stay zero for the whole kernel
+  __syncthreads();
+
+  uint8_t* bufs[3] = {s_act + (size_t)(warp * 3 + 0) * buf_bytes, s_act + (size_t)(warp * 3 + 1) * buf_bytes,
+                      s_act + (size_t)(warp * 3 + 2) * buf_bytes};
+  Lane L;
+  {
+    const int r = (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int p = 16 * mt + r;
+      L.a_row[mt] = p < HW ? halo + (p / W + 1) * pitch + p % W : halo;          // out-of-image rows read a zero line
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int q = 16 * mt + (lane >> 2) + 8 * h;
+        L.o_ok[mt][h] = q < HW;
+        L.o_pos[mt][h] = q < HW ? q : 0;
+        L.o_row[mt][h] = q < HW ? halo + (q / W + 1) * pitch + q % W : halo;
+      }
+    }
+    L.a_koff = (lane >> 4) * 16;
+    L.b_off = (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * kRowB + ((lane >> 3) & 1) * 16);
+  }
+  const uint32_t w_u32 = smem_u32(s_w);
+
+  for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
+    // ---- hidden state of the parent node -> buffer 0
+    const long long in_off = (long long)b * a.in_row_stride + (a.in_slot ? (long long)a.in_slot[b] * a.slot_stride : 0);
+    if (a.in_layout == 2) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.state_in) + in_off);
+      for (int i = lane; i < 2 * HW; i += 32) {
+        const int p = i >> 1;
+        *reinterpret_cast<uint4*>(bufs[0] + s_row[p] * kRowB + (i & 1) * 16) = src[i];
+      }
+    } else {                                                        // fp32 NCHW rows (per-row API)
+      const float* src = reinterpret_cast<const float*>(a.state_in) + in_off;
+      for (int i = lane; i < 16 * HW; i += 32) {
+        const int c = i / HW, p = i - c * HW;
+        *reinterpret_cast<__nv_bfloat16*>(bufs[0] + s_row[p] * kRowB + c * 2) = __float2bfloat16_rn(src[i]);
+      }
+    }
+    const float pl = __fdiv_rn((float)a.action[b], (float)a.A);     // action * ones / action_space_size (:553-568)
+    __syncwarp();
+    // ---- dynamics: conv + action plane, residual tower (models.py:377-387)
+    int ci = 0;
+    conv16<true, false>(smem_u32(bufs[0]), bufs[1], nullptr, w_u32, s_sc, s_sc + 16, pl, s_ptab, L, pitch, lane);
+    ci = 1;
+    int cur = 1;
+    for (int k = 0; k < a.n_dyn; ++k, ci += 2) {
+      const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+      conv16<false, false>(smem_u32(bufs[cur]), bufs[t], nullptr, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32, s_sc + ci * 32 + 16, 0.0f,
+                           nullptr, L, pitch, lane);
+      conv16<false, true>(smem_u32(bufs[t]), bufs[o], bufs[cur], w_u32 + (uint32_t)(ci + 1) * kConvB, s_sc + (ci + 1) * 32,
+                          s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane);
+      cur = o;
+    }
+    // ---- reward head projection on the UN-normalised next state (:388-391)
+    if (a.proj_r) project(bufs[cur], s_wr, a.r_r, a.proj_r + (long long)b * a.r_r * HW, HW, s_row, lane);
+    // ---- per-channel min-max scaling (:571-586) -> next buffer + the caller's hidden-state slot
+    const int nx = (cur + 1) % 3;
+    {
+      const int cp = lane & 7, pg = lane >> 3;                      // channel pair, position group (p = 4 i + pg)
+      float lo0 = CUDART_INF_F, hi0 = -CUDART_INF_F, lo1 = CUDART_INF_F, hi1 = -CUDART_INF_F;
+      for (int p = pg; p < HW; p += 4) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(bufs[cur] + s_row[p] * kRowB + cp * 4);
+        lo0 = fminf(lo0, bf_lo(v)); hi0 = fmaxf(hi0, bf_lo(v)); lo1 = fminf(lo1, bf_hi(v)); hi1 = fmaxf(hi1, bf_hi(v));
+      }
+#pragma unroll
+      for (int o = 8; o < 32; o <<= 1) {
+        lo0 = fminf(lo0, __shfl_xor_sync(0xFFFFFFFFu, lo0, o)); hi0 = fmaxf(hi0, __shfl_xor_sync(0xFFFFFFFFu, hi0, o));
+        lo1 = fminf(lo1, __shfl_xor_sync(0xFFFFFFFFu, lo1, o)); hi1 = fmaxf(hi1, __shfl_xor_sync(0xFFFFFFFFu, hi1, o));
+      }
+      float s0 = __fsub_rn(hi0, lo0), s1 = __fsub_rn(hi1, lo1);
+      if (s0 < 1e-5f) s0 = __fadd_rn(s0, 1e-5f);
+      if (s1 < 1e-5f) s1 = __fadd_rn(s1, 1e-5f);
+      const float i0 = 1.0f / s0, i1 = 1.0f / s1;                   // one reciprocal per channel (as k_minmax_store_bf16)
+      const long long out_base = (long long)b * a.out_row_stride + a.out_off;
+      for (int p = pg; p < HW; p += 4) {
+        const int row = s_row[p];
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(bufs[cur] + row * kRowB + cp * 4);
+        const __nv_bfloat162 pk = __floats2bfloat162_rn((bf_lo(v) - lo0) * i0, (bf_hi(v) - lo1) * i1);
+        const uint32_t pw = *reinterpret_cast<const uint32_t*>(&pk);
+        *reinterpret_cast<uint32_t*>(bufs[nx] + row * kRowB + cp * 4) = pw;
+        if (a.state_out) {
+          if (a.out_layout == 2) {
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.state_out) + out_base + (long long)p * 16 + cp * 2) = pw;
+          } else {                                                  // fp32 NCHW
+            float* o = reinterpret_cast<float*>(a.state_out) + out_base;
+            o[(long long)(cp * 2) * HW + p] = bf_lo(pw);
+            o[(long long)(cp * 2 + 1) * HW + p] = bf_hi(pw);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- prediction tower + value / policy projections (:447-456)
+    cur = nx;
+    if (a.proj_vp) {
+      for (int k = 0; k < a.n_pred; ++k, ci += 2) {
+        const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+        conv16<false, false>(smem_u32(bufs[cur]), bufs[t], nullptr, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32, s_sc + ci * 32 + 16,
+                             0.0f, nullptr, L, pitch, lane);
+        conv16<false, true>(smem_u32(bufs[t]), bufs[o], bufs[cur], w_u32 + (uint32_t)(ci + 1) * kConvB, s_sc + (ci + 1) * 32,
+                            s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane);
+        cur = o;
+      }
+      project(bufs[cur], s_wvp, a.r_vp, a.proj_vp + (long long)b * a.r_vp * HW, HW, s_row, lane);
+    }
+    __syncwarp();
+  }
+}
+
+size_t tower16_smem(const mzb_resnet_model* m) {
+  const int n_conv = 1 + 2 * (int)m->dyn_blocks.size() + 2 * (int)m->pred_blocks.size();
+  const int HW = m->Hl * m->Wl, rows = 2 * geo_halo(m->Wl) + geo_rows_per_image(m->Hl, m->Wl);
+  return 128 + (size_t)n_conv * kConvB + sizeof(float) * ((size_t)n_conv * 32 + (size_t)HW * 17 + (size_t)(m->reward.r + m->value.r + m->policy.r) * 16) +
+         128 + (size_t)kWarps * 3 * rows * kRowB;
+}
+
+}  // namespace
+
+static bool g_tower16_enabled = true;
+extern "C" void mzb_tower16_enable(int on) { g_tower16_enabled = on != 0; }     // comparison / bring-up knob
+
+bool mzb_tower16_supported(const mzb_resnet_model* m, int in_layout, int out_layout) {
+  if (!g_tower16_enabled || !mzb_conv_tc_enabled() || m->precision != 1 || m->C != 16 || m->Hl * m->Wl > 16 * MT) return false;
+  if (m->dyn_blocks.size() > kMaxBlocks || m->pred_blocks.size() > kMaxBlocks) return false;
+  if ((in_layout != 0 && in_layout != 2) || (out_layout != 0 && out_layout != 2)) return false;
+  if (!m->dyn_conv.w_bf16 || !m->dyn_conv.plane_table || m->dyn_conv.cin != 16 || !m->pv_w) return false;
+  for (const auto* blocks : {&m->dyn_blocks, &m->pred_blocks})
+    for (const Block& b : *blocks)
+      if (!b.c1.w_bf16 || !b.c2.w_bf16 || b.c1.cin != 16 || b.c2.cin != 16) return false;
+  return tower16_smem(m) <= 227 * 1024;
+}
+
+int mzb_tower16_recurrent(mzb_resnet_model* m, int B, const void* state_in, int in_layout, long long in_row_stride,
+                          const int* in_slot, long long slot_stride, const int* action, void* state_out, int out_layout,
+                          long long out_row_stride, long long out_off, float* proj_r, float* proj_vp, cudaStream_t s) {
+  T16Args a{};
+  a.B = B; a.H = m->Hl; a.W = m->Wl; a.A = m->A;
+  a.n_dyn = (int)m->dyn_blocks.size(); a.n_pred = (int)m->pred_blocks.size();
+  int k = 0;
+  auto put = [&](const ConvParams& c) { a.conv[k++] = T16Conv{c.w_bf16, c.scale, c.shift}; };
+  put(m->dyn_conv);
+  for (const Block& b : m->dyn_blocks) { put(b.c1); put(b.c2); }
+  for (const Block& b : m->pred_blocks) { put(b.c1); put(b.c2); }
+  a.n_conv = k;
+  a.plane_table = m->dyn_conv.plane_table;
+  a.w_r = m->reward.w1x1; a.r_r = m->reward.r;
+  a.w_vp = m->pv_w; a.r_vp = m->value.r + m->policy.r;
+  a.state_in = state_in; a.in_layout = in_layout; a.in_row_stride = in_row_stride; a.in_slot = in_slot; a.slot_stride = slot_stride;
+  a.action = action;
+  a.state_out = state_out; a.out_layout = out_layout; a.out_row_stride = out_row_stride; a.out_off = out_off;
+  a.proj_r = proj_r; a.proj_vp = proj_vp;
+  const size_t smem = tower16_smem(m);
+  static bool configured = false;
+  if (!configured) {
+    MZB_CUDA(cudaFuncSetAttribute(k_recurrent16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  int grid = (B + kWarps - 1) / kWarps;
+  if (grid > n_sm) grid = n_sm;                      // persistent: the weights are staged once per CTA
+  k_recurrent16<<<grid, kWarps * 32, smem, s>>>(a);
+  MZB_LAUNCH_CHECK();
+  return MZB_OK;
+}

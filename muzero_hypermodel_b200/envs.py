@@ -31,6 +31,7 @@ _lib.bind("mzb_env_destroy", C.c_int, [_vp])
 _lib.bind("mzb_env_info", C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)])
 _lib.bind("mzb_env_reset", C.c_int, [_vp, _vp])
 _lib.bind("mzb_env_observe", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp])
+_lib.bind("mzb_env_observe_stacked", C.c_int, [_vp, _i32, _vp, _vp])
 _lib.bind("mzb_env_act_step", C.c_int, [_vp, _vp, _vp, _vp, C.c_double, _i32, _vp, _vp, _vp, _vp, _vp, _vp])
 _lib.bind("mzb_env_harvest", C.c_int, [_vp, C.c_int, _vp])
 _lib.bind("mzb_env_counters_sync", C.c_int, [_vp, C.POINTER(C.c_uint64), _vp])
@@ -97,6 +98,20 @@ class VectorEnv:
         check(_lib.lib.mzb_env_observe(self._h, ptr(self.obs), ptr(self.legal), ptr(self.to_play), ptr(self.slot),
                                        ptr(self.step_count), _lib.current_stream()))
         return self.obs, self.legal, self.to_play
+
+    def observe_stacked(self, stacked_observations):
+        """observe() with GameHistory.get_stacked_observations(-1, S) (self_play.py:514-548) as the observation:
+        [G, C (S + 1) + S, H, W] float32, assembled on the device from the running histories."""
+        S = int(stacked_observations)
+        _, legal, to_play = self.observe()
+        if S == 0:
+            return self.obs, legal, to_play
+        c, h, w = self.obs_shape
+        buf = getattr(self, "_stacked", None)
+        if buf is None or buf.shape[1] != c * (S + 1) + S:
+            buf = self._stacked = torch.empty((self.G, c * (S + 1) + S, h, w), dtype=torch.float32, device=self.device)
+        check(_lib.lib.mzb_env_observe_stacked(self._h, S, ptr(buf), _lib.current_stream()))
+        return buf, legal, to_play
 
     def act_step(self, visits, root_value, legal=None, temperature=1.0, temperature_threshold=None, uniforms=None,
                  forced_action=None, want_outputs=False):

@@ -18,6 +18,7 @@ _vp = C.c_void_p
 _lib.bind("mzb_search_fc", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, C.c_int32, C.c_int,
                                      _vp, _vp, _vp, _vp, _vp])
 _lib.bind("mzb_search_fc_is_fused", C.c_int, [_vp])
+_lib.bind("mzb_u8_to_unit_float", C.c_int, [_vp, C.c_int64, _vp, _vp])
 _lib.bind("mzb_search_resnet", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, C.c_int32, _vp, _vp,
                                          C.c_size_t, _vp, _vp, _vp, _vp, _vp])
 
@@ -46,6 +47,16 @@ class BatchedMCTS:
         dev = self.device
         G, A = self.G, self.A
         S = cfg.num_simulations if num_simulations is None else num_simulations
+        if observations.dtype == torch.uint8:
+            # emulator frames: normalised on the device exactly as the reference's wrapper does on the host
+            # (games/breakout.py:141-159, float32(frame) / 255), so uint8 crosses PCIe instead of float32
+            src = observations.to(device=dev).contiguous()
+            buf = getattr(self, "_frames_f32", None)
+            if buf is None or buf.shape != src.shape:
+                buf = self._frames_f32 = torch.empty(src.shape, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                check(_lib.lib.mzb_u8_to_unit_float(ptr(src), src.numel(), ptr(buf), _lib.current_stream()))
+            observations = buf
         obs = observations.to(device=dev, dtype=torch.float32).reshape(G, -1).contiguous()
         lg = None if legal_mask is None else legal_mask.to(device=dev, dtype=torch.uint8).contiguous()
         tp = None if to_play is None else to_play.to(device=dev, dtype=torch.int8).contiguous()

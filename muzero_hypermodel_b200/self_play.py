@@ -305,7 +305,7 @@ class SelfPlay:
         """One move of every game: observe -> search -> select_action + Game.step + record -> harvest.
         search_events: optional (start, end) CUDA events recorded around the search launch (bench: in-step timing)."""
         env, mcts = self._setup()
-        obs, legal, to_play = env.observe()
+        obs, legal, to_play = env.observe_stacked(int(getattr(self.config, "stacked_observations", 0) or 0))
         if search_events is not None:
             search_events[0].record()
         out = mcts.run(self.model, obs, legal, to_play, add_exploration_noise, slot=env.slot, step=env.step_count,
@@ -404,11 +404,10 @@ class SelfPlay:
     def play_game(self, temperature, temperature_threshold, render, opponent, muzero_player):
         """One complete game (self_play.py:110-184).  Self-play of a built-in game runs entirely on the device
         (G = 1: environment, search, action selection and history stay on the GPU); a caller-supplied Game class,
-        an opponent ("human" / "expert" / "random"), rendering or stacked observations take the host loop, whose
-        searches are `MCTS.run` on the same kernels."""
+        an opponent ("human" / "expert" / "random") or rendering take the host loop, whose searches are `MCTS.run` on
+        the same kernels.  stacked_observations > 0 is assembled on the device from the running histories."""
         cfg = self.config
-        if (self.host_game or render or int(getattr(cfg, "stacked_observations", 0)) != 0
-                or (opponent != "self" and len(cfg.players) > 1)):
+        if self.host_game or render or (opponent != "self" and len(cfg.players) > 1):
             return self._play_game_host(temperature, temperature_threshold, render, opponent, muzero_player)
         if self._solo is None:
             # kept across calls: its environment step counter (the RNG stream position) keeps advancing, so repeated

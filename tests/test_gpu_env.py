@@ -253,3 +253,39 @@ def test_synthetic_frames_env_matches_oracle():
         o.step(np.zeros(3))
         assert not r.any() and not d.any()
     assert 0.45 < float(obs.mean()) < 0.55
+
+
+@pytest.mark.parametrize("kind,S", [("tictactoe", 2), ("connect4", 4), ("cartpole", 3)])
+def test_device_stacked_observations_equal_game_history(kind, S):
+    """mzb_env_observe_stacked against GameHistory.get_stacked_observations(-1, S) (pinned to the reference by
+    tests/golden/stacked.npz) applied to the same running games: at every move of random play, incl. the zero planes
+    before the start of a game and across an auto-reset."""
+    from muzero_hypermodel_b200.envs import VectorEnv
+    from muzero_hypermodel_b200.self_play import GameHistory
+    G, moves = 6, 14
+    env = VectorEnv(kind, G, 500 if kind == "cartpole" else 60, seed=3, device=DEV)
+    rs = np.random.RandomState(1)
+    hist = [GameHistory() for _ in range(G)]
+    obs, legal, _ = env.observe()
+    for g in range(G):
+        hist[g].observation_history.append(obs[g].cpu().numpy().reshape(env.obs_shape).copy())
+        hist[g].action_history.append(0)
+    for mv in range(moves):
+        st, legal, _ = env.observe_stacked(S)
+        st = st.cpu().numpy()
+        for g in range(G):
+            want = np.asarray(hist[g].get_stacked_observations(-1, S), dtype=np.float32)
+            assert st[g].shape == want.shape and np.array_equal(st[g], want), (mv, g)
+        lg = legal.cpu().numpy().astype(bool)
+        act = np.array([rs.choice(np.nonzero(lg[g])[0]) for g in range(G)], dtype=np.int32)
+        _, _, done = env.act_step(None, None, forced_action=torch.tensor(act, device=DEV), want_outputs=True)
+        done = done.cpu().numpy().astype(bool)
+        env.harvest(False)
+        obs, _, _ = env.observe()
+        for g in range(G):
+            if done[g]:
+                hist[g] = GameHistory()
+                hist[g].action_history.append(0)
+            else:
+                hist[g].action_history.append(int(act[g]))
+            hist[g].observation_history.append(obs[g].cpu().numpy().reshape(env.obs_shape).copy())

