@@ -122,6 +122,12 @@ int mzb_tree_root_stats(mzb_tree* t, int32_t* d_visits, double* d_root_value, in
 /* h_counters2 = {sum of search-path lengths (nodes below the root), simulations} since creation / last reset. */
 int mzb_tree_counters_sync(mzb_tree* t, uint64_t* h_counters2, int reset, void* stream);
 
+/* Test hook: d_fast[i] = a[i] / b[i] through the whole-search kernel's hoisted-reciprocal float64 division
+ * (csrc/mzb_common.cuh ddiv_rcp: the compiler's own div.rn.f64 sequence with the refinement of 1/b computed once per
+ * divisor), d_ref[i] = the compiler's division.  Python's float division (self_play.py:393-404, 563-568) is the
+ * correctly rounded quotient; the two must agree bit for bit. */
+int mzb_debug_ddiv_rcp(const double* d_a, const double* d_b, int64_t n, double* d_fast, double* d_ref, void* stream);
+
 /* Copy one game's complete tree to the host (synchronises `stream`): used to materialise the
  * reference's Node graph for callers that walk it (diagnose_model.py:161-252).
  * Arrays are [num_simulations+1][A] unless noted; h_root_prior [A] f64; h_scalars[4] =

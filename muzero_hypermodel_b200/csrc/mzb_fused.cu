@@ -13,7 +13,7 @@
 #include "mzb_fc.cuh"
 #include "mzb_tree.cuh"
 
-#define MZB_FUSED_DEFAULT_EXP 7      // FFMA2 network, root record in registers, search path in shared memory
+#define MZB_FUSED_DEFAULT_EXP 135    // FFMA2 network, root record in registers, search path in shared memory, barrier per 4 warps
 
 namespace {
 
@@ -221,7 +221,7 @@ struct SearchIO {
 // EXP: experiment / tuning flags (MZB_FUSED_EXP): 1 = packed FFMA2 network, 2 = root record in registers (A <= 4),
 // 4/8/16/32 = timing-only diagnostics (blocked layout, aliased trees, no network, no walk) - results are NOT valid.
 // 4 = the search path's edge statistics in shared memory for the first 12 levels (deeper levels: local memory).
-enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32 };
+enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32, X_SYNC2 = 64, X_HALFBAR = 128, X_RCP = 256 };
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm) { return blocks_per_sm >= 3 ? 8 : 12; }
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm, int threads) {
   return threads * blocks_per_sm > 512 ? 8 : 12;        // 48 KB (12 levels) per 256 threads fit twice per SM, not three times
@@ -242,6 +242,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   double* sp_vs = pbt + (PB_LUT ? S1 * S1 : 0);
   float* sp_rw = reinterpret_cast<float*>(sp_vs + PD * THREADS);
   uint32_t* sp_ev = reinterpret_cast<uint32_t*>(sp_rw + PD * THREADS);
+  // RCP: refined reciprocals of the visit counts 1..S (the divisor of value_sum / visit_count)
+  constexpr bool RCP = (EXP & X_RCP) != 0 && PB_LUT;
+  double* rcpn = reinterpret_cast<double*>(sp_ev + PD * THREADS);
+  if (RCP) for (int i = threadIdx.x; i < S1; i += THREADS) rcpn[i] = i > 0 ? rcp_refined((double)i) : 0.0;
   for (int i = threadIdx.x; i < SH::PACK / 4; i += THREADS) smem4[i] = reinterpret_cast<const float4*>(gpack)[i];
   for (int i = threadIdx.x; i < S1; i += THREADS) lut[i] = t.log_lut[i];
   if (PB_LUT) {
@@ -346,6 +350,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   // One level of the select walk (self_play.py:364-405) on the record `rr` of `node`: scores, arg-max with the
   // reference's tie rule, path entry; returns the chosen child (< 0: leaf reached) and leaves the action in `action`.
   int action = 0, N = 0;
+  double mm_den = 0.0, mm_y = 0.0;          // RCP: vmax - vmin of this simulation and its refined reciprocal
+  bool mm_ok = false;
   auto walk_level = [&](const Rec<A>& rr, const bool root_level, const int node, const int depth, const int sim) -> int {
     double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
 #pragma unroll
@@ -362,7 +368,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
       if (ch[a] == MZB_CHILD_ILLEGAL) { sc[a] = -CUDART_INF; continue; }
       const double p = root_level ? rp[a] : (double)pr[a];
       const double pb = PB_LUT ? pbrow[vi[a]] : ucb_pb(pbc0, sqrtN, vi[a]);
-      sc[a] = ucb_score_pb(pb, vi[a], p, vs[a], (double)rw[a], t.discount, two, vmin, vmax);
+      if constexpr (RCP)
+        sc[a] = ucb_score_pb_rcp(pb, vi[a], p, vs[a], (double)rw[a], t.discount, two, vmin, vmax, rcpn[vi[a]], mm_den, mm_y, mm_ok);
+      else
+        sc[a] = ucb_score_pb(pb, vi[a], p, vs[a], (double)rw[a], t.discount, two, vmin, vmax);
       if (sc[a] > best || action < 0) { best = sc[a]; n_best = 1; action = a; }
       else if (sc[a] == best) ++n_best;
     }
@@ -400,6 +409,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     // one dependent record load per level
     int node = 0, depth = 0;
     N = root_visit;
+    if (RCP && vmax > vmin) {
+      mm_den = __dsub_rn(vmax, vmin);
+      mm_ok = rcp_divisor_ok(mm_den);
+      mm_y = mm_ok ? rcp_refined(mm_den) : 0.0;
+    }
     if (active) {
       int next;
       if constexpr (ROOTREG) {
@@ -423,7 +437,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
       }
     }
     const int L = depth, fresh = sim + 1;
-    if (PHASE_SYNC) __syncthreads();          // warps of the block enter the unrolled network code together
+    if (PHASE_SYNC) {                         // warps of the block enter the unrolled network code together
+      if constexpr ((EXP & X_HALFBAR) != 0) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");      // per group of four warps
+      } else if constexpr ((EXP & X_SYNC2) != 0) {
+        if (sim & 1) __syncthreads();
+      } else {
+        __syncthreads();
+      }
+    }
     if (!active) continue;
 
     // ---------------- recurrent inference on the parent's hidden state (models.py:192-195)
@@ -561,7 +583,8 @@ template <class SH, bool PB_LUT, int EXP, int THREADS = 256, bool PHASE_SYNC = t
 int launch_variant(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
   const int S1 = io.num_sims + 1;
   const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? S1 * S1 : 0)) +
-                      (((EXP & X_SPATH) != 0 && PB_LUT) ? (size_t)smem_path_depth(MINB, THREADS) * THREADS * 16 : 0);
+                      (((EXP & X_SPATH) != 0 && PB_LUT) ? (size_t)smem_path_depth(MINB, THREADS) * THREADS * 16 : 0) +
+                      (((EXP & X_RCP) != 0 && PB_LUT) ? sizeof(double) * (size_t)S1 : 0);
   static bool configured = false;
   if (!configured) {
     MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT, EXP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -595,9 +618,9 @@ int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t 
       case 0: return launch_variant<SH, true, 0>(t, m, io, s);
       case 7: return launch_variant<SH, true, 7>(t, m, io, s);
       case 23: return launch_variant<SH, true, 23>(t, m, io, s);
-      case 1007: return launch_variant<SH, true, 7, 256, true, 3>(t, m, io, s);     // 3 x 256 threads per SM (<= 85 registers)
-      case 2007: return launch_variant<SH, true, 7, 128, true, 5>(t, m, io, s);     // 5 x 128 threads per SM (<= 102 registers)
-      case 3007: return launch_variant<SH, true, 7, 128, true, 4>(t, m, io, s);     // 4 x 128 threads per SM (128 registers)
+      case 263: return launch_variant<SH, true, 263>(t, m, io, s);
+      case 135: return launch_variant<SH, true, 135>(t, m, io, s);
+      case 2007: return launch_variant<SH, true, 7, 128, true, 5>(t, m, io, s);     // 5 x 128 threads per SM (96 registers, no spills): slower
       case 19: return launch_variant<SH, true, 19>(t, m, io, s);
       case 35: return launch_variant<SH, true, 35>(t, m, io, s);
       default: break;

@@ -163,8 +163,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0u, 0u, 0u, 0u);       // pad rows stay zero for the whole kernel
   __syncthreads();
 
-  uint8_t* bufs[3] = {s_act + (size_t)(warp * 3 + 0) * buf_bytes, s_act + (size_t)(warp * 3 + 1) * buf_bytes,
-                      s_act + (size_t)(warp * 3 + 2) * buf_bytes};
+  // the warp's three rotating buffers: buf(i) by arithmetic (an indexed pointer array would live in local memory)
+  uint8_t* const buf0 = s_act + (size_t)(warp * 3) * buf_bytes;
+  auto buf = [&](int i) -> uint8_t* { return buf0 + (size_t)i * buf_bytes; };
   Lane L;
   {
     const int r = (lane & 7) + 8 * ((lane >> 3) & 1);
@@ -192,39 +193,39 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
       const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.state_in) + in_off);
       for (int i = lane; i < 2 * HW; i += 32) {
         const int p = i >> 1;
-        *reinterpret_cast<uint4*>(bufs[0] + s_row[p] * kRowB + (i & 1) * 16) = src[i];
+        *reinterpret_cast<uint4*>(buf(0) + s_row[p] * kRowB + (i & 1) * 16) = src[i];
       }
     } else {                                                        // fp32 NCHW rows (per-row API)
       const float* src = reinterpret_cast<const float*>(a.state_in) + in_off;
       for (int i = lane; i < 16 * HW; i += 32) {
         const int c = i / HW, p = i - c * HW;
-        *reinterpret_cast<__nv_bfloat16*>(bufs[0] + s_row[p] * kRowB + c * 2) = __float2bfloat16_rn(src[i]);
+        *reinterpret_cast<__nv_bfloat16*>(buf(0) + s_row[p] * kRowB + c * 2) = __float2bfloat16_rn(src[i]);
       }
     }
     const float pl = __fdiv_rn((float)a.action[b], (float)a.A);     // action * ones / action_space_size (:553-568)
     __syncwarp();
     // ---- dynamics: conv + action plane, residual tower (models.py:377-387)
     int ci = 0;
-    conv16<true, false>(smem_u32(bufs[0]), bufs[1], nullptr, w_u32, s_sc, s_sc + 16, pl, s_ptab, L, pitch, lane);
+    conv16<true, false>(smem_u32(buf(0)), buf(1), nullptr, w_u32, s_sc, s_sc + 16, pl, s_ptab, L, pitch, lane);
     ci = 1;
     int cur = 1;
     for (int k = 0; k < a.n_dyn; ++k, ci += 2) {
       const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-      conv16<false, false>(smem_u32(bufs[cur]), bufs[t], nullptr, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32, s_sc + ci * 32 + 16, 0.0f,
+      conv16<false, false>(smem_u32(buf(cur)), buf(t), nullptr, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32, s_sc + ci * 32 + 16, 0.0f,
                            nullptr, L, pitch, lane);
-      conv16<false, true>(smem_u32(bufs[t]), bufs[o], bufs[cur], w_u32 + (uint32_t)(ci + 1) * kConvB, s_sc + (ci + 1) * 32,
+      conv16<false, true>(smem_u32(buf(t)), buf(o), buf(cur), w_u32 + (uint32_t)(ci + 1) * kConvB, s_sc + (ci + 1) * 32,
                           s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane);
       cur = o;
     }
     // ---- reward head projection on the UN-normalised next state (:388-391)
-    if (a.proj_r) project(bufs[cur], s_wr, a.r_r, a.proj_r + (long long)b * a.r_r * HW, HW, s_row, lane);
+    if (a.proj_r) project(buf(cur), s_wr, a.r_r, a.proj_r + (long long)b * a.r_r * HW, HW, s_row, lane);
     // ---- per-channel min-max scaling (:571-586) -> next buffer + the caller's hidden-state slot
     const int nx = (cur + 1) % 3;
     {
       const int cp = lane & 7, pg = lane >> 3;                      // channel pair, position group (p = 4 i + pg)
       float lo0 = CUDART_INF_F, hi0 = -CUDART_INF_F, lo1 = CUDART_INF_F, hi1 = -CUDART_INF_F;
       for (int p = pg; p < HW; p += 4) {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(bufs[cur] + s_row[p] * kRowB + cp * 4);
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(buf(cur) + s_row[p] * kRowB + cp * 4);
         lo0 = fminf(lo0, bf_lo(v)); hi0 = fmaxf(hi0, bf_lo(v)); lo1 = fminf(lo1, bf_hi(v)); hi1 = fmaxf(hi1, bf_hi(v));
       }
 #pragma unroll
@@ -239,10 +240,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
       const long long out_base = (long long)b * a.out_row_stride + a.out_off;
       for (int p = pg; p < HW; p += 4) {
         const int row = s_row[p];
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(bufs[cur] + row * kRowB + cp * 4);
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(buf(cur) + row * kRowB + cp * 4);
         const __nv_bfloat162 pk = __floats2bfloat162_rn((bf_lo(v) - lo0) * i0, (bf_hi(v) - lo1) * i1);
         const uint32_t pw = *reinterpret_cast<const uint32_t*>(&pk);
-        *reinterpret_cast<uint32_t*>(bufs[nx] + row * kRowB + cp * 4) = pw;
+        *reinterpret_cast<uint32_t*>(buf(nx) + row * kRowB + cp * 4) = pw;
         if (a.state_out) {
           if (a.out_layout == 2) {
             *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.state_out) + out_base + (long long)p * 16 + cp * 2) = pw;
@@ -260,13 +261,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     if (a.proj_vp) {
       for (int k = 0; k < a.n_pred; ++k, ci += 2) {
         const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-        conv16<false, false>(smem_u32(bufs[cur]), bufs[t], nullptr, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32, s_sc + ci * 32 + 16,
+        conv16<false, false>(smem_u32(buf(cur)), buf(t), nullptr, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32, s_sc + ci * 32 + 16,
                              0.0f, nullptr, L, pitch, lane);
-        conv16<false, true>(smem_u32(bufs[t]), bufs[o], bufs[cur], w_u32 + (uint32_t)(ci + 1) * kConvB, s_sc + (ci + 1) * 32,
+        conv16<false, true>(smem_u32(buf(t)), buf(o), buf(cur), w_u32 + (uint32_t)(ci + 1) * kConvB, s_sc + (ci + 1) * 32,
                             s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane);
         cur = o;
       }
-      project(bufs[cur], s_wvp, a.r_vp, a.proj_vp + (long long)b * a.r_vp * HW, HW, s_row, lane);
+      project(buf(cur), s_wvp, a.r_vp, a.proj_vp + (long long)b * a.r_vp * HW, HW, s_row, lane);
     }
     __syncwarp();
   }

@@ -524,6 +524,23 @@ int mzb_tree_counters_sync(mzb_tree* t, uint64_t* h_counters2, int reset, void* 
   return MZB_OK;
 }
 
+// Test hook: the hoisted-reciprocal division of mzb_common.cuh against the compiler's div.rn.f64, element-wise.
+static __global__ void k_debug_ddiv_rcp(const double* __restrict__ a, const double* __restrict__ b, long long n,
+                                        double* __restrict__ fast, double* __restrict__ ref) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double y = rcp_divisor_ok(b[i]) ? rcp_refined(b[i]) : 0.0;
+  fast[i] = rcp_divisor_ok(b[i]) ? ddiv_rcp(a[i], b[i], y) : __ddiv_rn(a[i], b[i]);
+  ref[i] = __ddiv_rn(a[i], b[i]);
+}
+
+int mzb_debug_ddiv_rcp(const double* d_a, const double* d_b, int64_t n, double* d_fast, double* d_ref, void* stream) {
+  MZB_CHECK_ARG(d_a && d_b && d_fast && d_ref && n > 0, "bad argument");
+  k_debug_ddiv_rcp<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_a, d_b, n, d_fast, d_ref);
+  MZB_LAUNCH_CHECK();
+  return MZB_OK;
+}
+
 int mzb_tree_export_game_sync(mzb_tree* t, int32_t game, double* h_value_sum, float* h_prior, int32_t* h_visit,
                               float* h_reward, int32_t* h_child, double* h_root_prior, double* h_scalars,
                               void* stream) {

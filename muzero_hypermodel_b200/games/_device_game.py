@@ -55,6 +55,22 @@ def make_game_class(kind, max_moves):
         def render(self):
             print(self._observation())
 
+        def expert_agent(self):
+            """The hard-coded evaluation opponents (games/tictactoe.py:217-225, connect4.py:196-204, gomoku.py) are
+            host heuristics over the reference's board objects and never influence training.  SelfPlay honours any
+            caller-supplied Game class: pass the reference's own `games.<name>.Game` to play against its expert."""
+            raise NotImplementedError(
+                f"the device {kind} Game has no expert agent: pass a host Game class with expert_agent() to SelfPlay "
+                "(it is played through the AbstractGame contract, searches stay on the device)")
+
+        def human_to_action(self):
+            legal = self.legal_actions()
+            while True:
+                choice = input(f"Enter the action to play for player {self.to_play()} {legal}: ")
+                if choice.strip().lstrip("-").isdigit() and int(choice) in legal:
+                    return int(choice)
+                print("Wrong input, try again")
+
         def action_to_string(self, action_number):
             if kind == "tictactoe":
                 return f"Play row {action_number // 3 + 1}, column {action_number % 3 + 1}"

@@ -289,3 +289,55 @@ def test_device_stacked_observations_equal_game_history(kind, S):
             else:
                 hist[g].action_history.append(int(act[g]))
             hist[g].observation_history.append(obs[g].cpu().numpy().reshape(env.obs_shape).copy())
+
+
+def test_caller_supplied_game_class_and_opponents():
+    """SelfPlay honours the `Game` argument (self_play.py:16-19): a host AbstractGame subclass is played through
+    step / legal_actions / to_play with every search on the device kernels, incl. the evaluation opponents
+    ("random", "expert") and test mode of continuous_self_play (:54-88)."""
+    from muzero_hypermodel_b200.games.abstract_game import AbstractGame
+    from muzero_hypermodel_b200.games.tictactoe import MuZeroConfig
+    from muzero_hypermodel_b200.self_play import SelfPlay
+    from muzero_hypermodel_b200.shared_storage import SharedStorage, new_checkpoint
+
+    class Nim(AbstractGame):
+        """3x3x3-shaped toy: players alternately take 1-3 of 9 stones; taking the last stone wins."""
+        def __init__(self, seed=None): self.reset()
+        def reset(self):
+            self.left, self.player = 9, 0
+            return self._obs()
+        def _obs(self):
+            o = np.zeros((3, 3, 3), dtype=np.int32)
+            o[0].flat[:self.left] = 1
+            o[2][:] = 1 if self.player == 0 else -1
+            return o
+        def step(self, action):
+            take = action % 3 + 1
+            self.left -= min(take, self.left)
+            done = self.left == 0
+            reward = 1 if done else 0
+            self.player = 1 - self.player
+            return self._obs(), reward, done
+        def to_play(self): return self.player
+        def legal_actions(self): return [a for a in range(9) if a % 3 + 1 <= self.left]
+        def expert_agent(self): return (self.left % 4 or 1) - 1
+        def close(self): pass
+        def render(self): pass
+        def action_to_string(self, a): return f"take {a % 3 + 1}"
+
+    cfg = MuZeroConfig()
+    cfg.network, cfg.num_simulations, cfg.opponent, cfg.muzero_player = "fullyconnected", 12, "expert", 0
+    torch.manual_seed(0)
+    sp = SelfPlay({"weights": None}, Nim, cfg, 0, device=DEV)
+    assert sp.host_game
+    gh = sp.play_game(1.0, None, False, "self", 0)
+    assert len(gh.root_values) == len(gh.action_history) - 1 >= 3 and all(v is not None for v in gh.root_values)
+    assert sum(gh.reward_history) == 1 and all(len(cv) == 9 and abs(sum(cv) - 1) < 1e-12 for cv in gh.child_visits)
+    for opp in ("random", "expert"):
+        g = sp.play_game(0, None, False, opp, 0)
+        assert any(v is None for v in g.root_values) and any(v is not None for v in g.root_values)      # opponent moves carry no search
+    st = SharedStorage(new_checkpoint(sp.model.get_weights()), cfg)
+    sp.continuous_self_play(st, None, test_mode=True, max_moves=2)
+    assert st.get_info("episode_length") >= 3 and st.get_info("muzero_reward") + st.get_info("opponent_reward") == 1
+    with pytest.raises(NotImplementedError):
+        SelfPlay({"weights": None}, Nim, cfg, 0, n_games=64, device=DEV)

@@ -185,3 +185,38 @@ def test_device_dirichlet_matches_numpy_dirichlet(A, k_legal, alpha):
     step = torch.full((G,), 3, dtype=torch.int32, device=dev)
     tree.root_init(torch.zeros(G, device=dev), pri, False, torch.tensor(legal, device=dev), None, None, alpha, 1.0, None, step)
     assert not np.array_equal(tree.root_stats(full=True)["child_prior"].cpu().numpy(), noise)
+
+
+def test_ddiv_rcp_equals_ddiv_rn():
+    """The whole-search kernel divides value_sum by visit counts and Q values by the MinMaxStats range through a
+    hoisted reciprocal (csrc/mzb_common.cuh).  It must be the IEEE quotient bit for bit - also at zeros, signed
+    values, tiny / huge magnitudes (where it defers to the full division) and for every visit count up to 400."""
+    import ctypes as C
+    from muzero_hypermodel_b200 import _lib
+    from muzero_hypermodel_b200._lib import check, ptr
+    _lib.bind("mzb_debug_ddiv_rcp", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(12)
+    n = 1 << 22
+    parts_a, parts_b = [], []
+    # value sums / visit counts
+    parts_a.append(rs.standard_normal(n) * 10.0 ** rs.uniform(-3, 3, n)); parts_b.append(rs.randint(1, 401, n).astype(np.float64))
+    # (q - min) / (max - min): both arbitrary positive / signed doubles over a wide exponent range
+    parts_a.append(rs.standard_normal(n) * 10.0 ** rs.uniform(-8, 8, n)); parts_b.append(np.abs(rs.standard_normal(n)) * 10.0 ** rs.uniform(-8, 8, n) + 1e-300)
+    # mantissa patterns that stress the last rounding step: a = k * b +- 1 ulp
+    b3 = rs.uniform(0.5, 2.0, n); k3 = rs.randint(1, 1 << 20, n).astype(np.float64)
+    parts_a.append(np.nextafter(k3 * b3, np.where(rs.rand(n) < 0.5, np.inf, -np.inf))); parts_b.append(b3)
+    # edge cases: zeros, signed zeros, subnormal / tiny / huge numerators and divisors
+    edge_a = np.array([0.0, -0.0, 5e-324, -5e-324, 1e-310, 1e-200, 1e200, 1.7e308, -1.7e308, 1.0, 3.0, 1e-130, 1e130])
+    edge_b = np.array([1.0, 3.0, 7.0, 50.0, 1e-310, 1e-200, 1e-130, 1e130, 1e200, 1.7e308, 0.1])
+    ea, eb = np.meshgrid(edge_a, edge_b)
+    parts_a.append(ea.ravel()); parts_b.append(eb.ravel())
+    a = torch.tensor(np.concatenate(parts_a), device=dev)
+    b = torch.tensor(np.concatenate(parts_b), device=dev)
+    fast, ref = torch.empty_like(a), torch.empty_like(a)
+    check(_lib.lib.mzb_debug_ddiv_rcp(ptr(a), ptr(b), a.numel(), ptr(fast), ptr(ref), _lib.current_stream()))
+    torch.cuda.synchronize()
+    fa, re = fast.cpu().numpy(), ref.cpu().numpy()
+    assert fa.tobytes() == re.tobytes(), int((fa.view(np.uint64) != re.view(np.uint64)).sum())
+    host = (a.cpu().numpy() / b.cpu().numpy())                        # numpy float64 division = Python's
+    assert re.tobytes() == host.tobytes()
