@@ -385,6 +385,9 @@ typedef struct {
   int32_t td_steps;          /* config.td_steps                                               */
   int32_t per;               /* config.PER                                                    */
   int32_t max_batch;         /* largest batch get_batch / update_priorities will see          */
+  int32_t stacked_observations; /* config.stacked_observations: get_batch / game_observations return
+                              * GameHistory.get_stacked_observations(position, S) (self_play.py:514-548)          */
+  int32_t obs_channels;      /* C of the observation (planes of H*W); used for the action planes when S > 0  */
   double per_alpha;          /* config.PER_alpha                                              */
   uint64_t seed;             /* Philox key                                                    */
 } mzb_replay_config;

@@ -125,7 +125,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 // compile-time count so the dot products are straight-line code) are separate instantiations, so the common layer
 // keeps its register allocation.  RES: weights resident in shared memory (true) or streamed through the ring (false) -
 // compile-time because the MMA stream is issue-bound and every instruction between two bursts of MMAs shows.
-template <int KC, bool ZP, int PR, int kEpiWarps, bool RES>
+// NC: compile-time channel-chunk count of the streamed-weights path (0 = runtime).  With NC = 2 (gomoku: 128 input
+// channels) the 18 k-blocks of a super-tile are fully unrolled and the ring is 3 deep - a depth that divides 18 - so a
+// block's ring slot (kb % 3) and barrier parity ((kb / 3) & 1) are compile-time constants: the slot counter, the
+// divisions and the R2UR moves that sat between two bursts of MMAs (99 cycles per MMA in situ against 64 for the
+// instruction stream alone) disappear.
+template <int KC, bool ZP, int PR, int kEpiWarps, bool RES, int NC = 0>
 __global__ void __launch_bounds__(64 + kEpiWarps * 32, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAtail,
           const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -136,13 +141,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // warp index / TMEM base are broadcast through a shuffle so the compiler knows they are warp-uniform and keeps the
   // role loops (addresses, descriptors, barrier phases) in uniform registers
   const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr int RING = NC == 2 ? 3 : kStages;
+  const int n_chunks = NC > 0 ? NC : a.n_chunks;
   const int MT = a.mt, N = a.Cout, halo = geo_halo(a.W);
   const int a_rows = MT * 128 + a.tail_rows;
   const uint32_t a_chunk_bytes = (uint32_t)a_rows * ROWB;
-  const uint32_t a_stage_bytes = (uint32_t)a.n_chunks * a_chunk_bytes;
+  const uint32_t a_stage_bytes = (uint32_t)n_chunks * a_chunk_bytes;
   const uint32_t b_block_bytes = (uint32_t)N * ROWB;
-  const int NKB = 9 * a.n_chunks;
-  const int b_slots = RES ? NKB : kStages;
+  const int NKB = 9 * n_chunks;
+  const int b_slots = RES ? NKB : RING;
   uint8_t* sA = smem;
   uint8_t* sB = sA + 2 * (size_t)a_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)b_slots * b_block_bytes);
@@ -195,7 +202,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (RES) {
         if (leader) mbar_expect_tx(b_full, (uint32_t)NKB * b_block_bytes);
         for (int kb = 0; kb < NKB; ++kb) {
-          const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
+          const int tap = kb / n_chunks, j = kb % n_chunks;
           if (leader) tma_load_2d(smem_u32(sB + (size_t)kb * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full);
         }
       }
@@ -209,20 +216,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (it >= 2) mbar_wait(a_empty + s, ((it >> 1) - 1) & 1);
         if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (3 * 32 + it) * 4; d[0] = p0; d[1] = clock64(); }
         const long long m0 = tile0 * 128;
-        if (leader) mbar_expect_tx(a_full + s, (uint32_t)a.n_chunks * (uint32_t)(mt_cur * 128 + a.tail_rows) * ROWB);
-        for (int j = 0; j < a.n_chunks; ++j) {
+        if (leader) mbar_expect_tx(a_full + s, (uint32_t)n_chunks * (uint32_t)(mt_cur * 128 + a.tail_rows) * ROWB);
+        for (int j = 0; j < n_chunks; ++j) {
           uint8_t* dst = sA + (size_t)s * a_stage_bytes + (size_t)j * a_chunk_bytes;
           for (int box = 0; box < mt_cur; ++box)
             if (leader) tma_load_2d(smem_u32(dst + (size_t)box * 128 * ROWB), &tmA, j * KC, (int)(m0 + (long long)box * 128), a_full + s);
           if (leader) tma_load_2d(smem_u32(dst + (size_t)mt_cur * 128 * ROWB), &tmAtail, j * KC, (int)(m0 + (long long)mt_cur * 128), a_full + s);
         }
         if (!RES) {
-          for (int kb = 0; kb < NKB; ++kb, ++ring) {
-            const int rs = (int)(ring % kStages);
-            if (ring >= kStages) mbar_wait(b_empty + rs, (uint32_t)((ring / kStages) - 1) & 1);
-            if (leader) mbar_expect_tx(b_full + rs, b_block_bytes);
-            const int tap = kb / a.n_chunks, j = kb % a.n_chunks;
-            if (leader) tma_load_2d(smem_u32(sB + (size_t)rs * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full + rs);
+          if constexpr (NC == 2) {
+#pragma unroll
+            for (int kb = 0; kb < 9 * NC; ++kb) {
+              const int rs = kb % RING;                                   // 18 % 3 == 0: slot and parity do not depend on `it`
+              if (it > 0 || kb >= RING) mbar_wait(b_empty + rs, (uint32_t)((kb / RING) + 1) & 1);
+              if (leader) mbar_expect_tx(b_full + rs, b_block_bytes);
+              if (leader) tma_load_2d(smem_u32(sB + (size_t)rs * b_block_bytes), &tmB, (kb / NC) * a.Cin + (kb % NC) * KC, 0, b_full + rs);
+            }
+          } else {
+            for (int kb = 0; kb < NKB; ++kb, ++ring) {
+              const int rs = (int)(ring % kStages);
+              if (ring >= kStages) mbar_wait(b_empty + rs, (uint32_t)((ring / kStages) - 1) & 1);
+              if (leader) mbar_expect_tx(b_full + rs, b_block_bytes);
+              const int tap = kb / n_chunks, j = kb % n_chunks;
+              if (leader) tma_load_2d(smem_u32(sB + (size_t)rs * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full + rs);
+            }
           }
         }
       }
@@ -260,11 +277,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int tap = 0; tap < 9; ++tap) {
           const int shift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
           const uint64_t a_tap_desc = a_stage_desc + (uint64_t)(((uint32_t)(halo + shift) * ROWB) >> 4);
-          for (int j = 0; j < a.n_chunks; ++j, ++kb) {
+          auto k_block = [&](const int j) {
             uint64_t bd;
             int rs = 0;
             if (RES) {
               bd = b_base_desc + (uint64_t)((uint32_t)kb * blk16);
+            } else if constexpr (NC == 2) {
+              const int kbc = tap * NC + j;                               // compile-time after unrolling
+              rs = kbc % RING;
+              mbar_wait(b_full + rs, (uint32_t)(kbc / RING) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              bd = b_base_desc + (uint64_t)((uint32_t)rs * blk16);
             } else {
               rs = (int)(ring % kStages);
               mbar_wait(b_full + rs, (ring / kStages) & 1);
@@ -280,6 +303,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (leader) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
             if (!RES && leader) umma_commit(b_empty + rs);
+            ++kb;
+          };
+          if constexpr (NC > 0) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) k_block(j);
+          } else {
+            for (int j = 0; j < n_chunks; ++j) k_block(j);
           }
         }
         if (leader) {
@@ -506,6 +536,9 @@ int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
 
 struct TcPlan { int kc, n_chunks, mt, tail_rows, b_resident, ncols; size_t smem; };
 
+// ring depth of the streamed-weights path: 3 (divides the 18 k-blocks of a 128-channel layer: compile-time slots) or 4
+int ring_depth(int kc, int n_chunks) { return (kc == 64 && n_chunks == 2) ? 3 : kStages; }
+
 // Largest MT whose double-buffered activation stages, weights (resident if they fit, else a ring) and
 // 2 x MT x C_out TMEM columns fit in one SM.
 bool make_plan(int cin, int cout, int W, TcPlan* out) {
@@ -514,7 +547,7 @@ bool make_plan(int cin, int cout, int W, TcPlan* out) {
   p.n_chunks = cin / p.kc;
   p.tail_rows = 2 * geo_halo(W) <= 32 ? 32 : 128;
   const size_t rowb = (size_t)p.kc * 2, limit = 225 * 1024;
-  const size_t b_all = (size_t)9 * p.n_chunks * cout * rowb, b_ring = (size_t)kStages * cout * rowb;
+  const size_t b_all = (size_t)9 * p.n_chunks * cout * rowb, b_ring = (size_t)ring_depth(p.kc, p.n_chunks) * cout * rowb;
   const size_t misc = 1024 + 512 + 8 * (size_t)cout + 32 * (size_t)cout;      // barriers, scale/shift, <= 8 projection rows
   // narrow layers (C_out <= 32) are bound by per-super-tile latencies, not by the MMAs: give them more rows per step
   static int mt_narrow = -1;
@@ -590,11 +623,11 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   if (narrow_on < 0) { const char* e = getenv("MZB_TC_NARROW_EPI"); narrow_on = (e && atoi(e) == 0) ? 0 : 1; }
   const bool narrow = narrow_on && cp.cout <= 32;
   MZB_CHECK_ARG(!(zero_pads && pr), "pad zeroing and head projection are not combined");
-#define LAUNCH_RES(KCV, ZPV, PRV, EWV, RESV)                                                                             \
+#define LAUNCH_RES(KCV, ZPV, PRV, EWV, RESV, NCV)                                                                           \
   {                                                                                                                 \
     static bool configured = false;                                                                                 \
     if (!configured) {                                                                                              \
-      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV, ZPV, PRV, EWV, RESV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<KCV, ZPV, PRV, EWV, RESV, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       configured = true;                                                                                            \
     }                                                                                                               \
     cudaLaunchConfig_t lc = {};                                                                                     \
@@ -603,12 +636,13 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
     la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                  \
     la[0].val.programmaticStreamSerializationAllowed = 1;                                                           \
     lc.attrs = la; lc.numAttrs = pdl_enabled() ? 1 : 0;                                                             \
-    MZB_CUDA(cudaLaunchKernelEx(&lc, k_conv_tc<KCV, ZPV, PRV, EWV, RESV>, tmA, tmAtail, tmB, a));                         \
+    MZB_CUDA(cudaLaunchKernelEx(&lc, k_conv_tc<KCV, ZPV, PRV, EWV, RESV, NCV>, tmA, tmAtail, tmB, a));                    \
   }
 #define LAUNCH_EW(KCV, ZPV, PRV, EWV)                                                                               \
   {                                                                                                                 \
-    if (p.b_resident) LAUNCH_RES(KCV, ZPV, PRV, EWV, true)                                                          \
-    else LAUNCH_RES(KCV, ZPV, PRV, EWV, false)                                                                      \
+    if (p.b_resident) LAUNCH_RES(KCV, ZPV, PRV, EWV, true, 0)                                                       \
+    else if (KCV == 64 && p.n_chunks == 2 && !ZPV) LAUNCH_RES(KCV, ZPV, PRV, EWV, false, 2)                         \
+    else LAUNCH_RES(KCV, ZPV, PRV, EWV, false, 0)                                                                   \
   }
 #define LAUNCH_ONE(KCV, ZPV, PRV)                                                                                   \
   {                                                                                                                 \

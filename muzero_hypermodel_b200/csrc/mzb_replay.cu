@@ -39,8 +39,30 @@ struct ReplayView {
   double* discount_pow;
   int* b_slot; uint32_t* b_step; float* b_w;       // per batch element scratch [max_batch]
   int A, obs_floats, cap, stride, K, td, per, max_batch, decode, oh, ow;
+  int S, C;                    // stacked_observations, channels per observation
   double alpha; RngKey key;
+  // one observation as network input: `per` floats = C planes of hw; the stacked form adds S x (per + hw)
+  __host__ __device__ int hw() const { return decode ? oh * ow : obs_floats / C; }
+  __host__ __device__ int per_obs() const { return decode ? 3 * oh * ow : obs_floats; }
+  __host__ __device__ int out_floats() const { return per_obs() + S * (per_obs() + hw()); }
 };
+
+// Element i of GameHistory.get_stacked_observations(p, S) (self_play.py:514-548) of the game whose entries start at s:
+// the observation at p, then for k = 1..S the observation at p - k followed by a plane holding action_history[p - k + 1]
+// (not normalised, as in the reference), all zeros before the start of the game.  S = 0: the observation itself.
+__device__ __forceinline__ float replay_obs_value(const ReplayView& v, int s, int p, int i) {
+  const int hw = v.hw(), per = v.per_obs();
+  int k = 0, j = i;
+  if (i >= per) { const int r = i - per; k = 1 + r / (per + hw); j = r - (k - 1) * (per + hw); }
+  const int idx = p - k;
+  if (idx < 0) return 0.0f;
+  if (j >= per) return (float)v.action[s + idx + 1];
+  const float* src = v.obs + (long long)(s + idx) * v.obs_floats;
+  if (!v.decode) return src[j];
+  const int8_t* raw = reinterpret_cast<const int8_t*>(src);       // packed board record -> [own, other, to-play] planes
+  const int plane = j / hw, c = j - plane * hw;
+  return plane == 0 ? (raw[c] == 1 ? 1.0f : 0.0f) : (plane == 1 ? (raw[c] == -1 ? 1.0f : 0.0f) : (float)raw[hw]);
+}
 
 // compute_target_value (replay_buffer.py:222-254) on the store's arrays; s = first entry of the game, n = moves
 __device__ double target_value(const ReplayView& v, int s, int n, int cur) {
@@ -228,20 +250,8 @@ __global__ void __launch_bounds__(256) k_replay_assemble(ReplayView v, int B, co
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int slot = v.b_slot[b], s = v.g_start[slot], n = v.g_len[slot], p = pos[b];
     if (obs) {
-      const float* src = v.obs + (long long)(s + p) * v.obs_floats;
-      if (v.decode == 0) {
-        for (int i = threadIdx.x; i < v.obs_floats; i += blockDim.x) obs[(long long)b * v.obs_floats + i] = src[i];
-      } else {                                    // packed board record -> [board == 1, board == -1, player] planes
-        const int8_t* raw = reinterpret_cast<const int8_t*>(src);
-        const int cells = v.oh * v.ow;
-        const float player = (float)raw[cells];
-        float* o = obs + (long long)b * 3 * cells;
-        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-          o[i] = raw[i] == 1 ? 1.0f : 0.0f;
-          o[cells + i] = raw[i] == -1 ? 1.0f : 0.0f;
-          o[2 * cells + i] = player;
-        }
-      }
+      const int nf = v.out_floats();
+      for (int i = threadIdx.x; i < nf; i += blockDim.x) obs[(long long)b * nf + i] = replay_obs_value(v, s, p, i);
     }
     if (gscale) {
       const int gs = min(v.K, n + 1 - p);
@@ -254,15 +264,11 @@ __global__ void __launch_bounds__(256) k_replay_assemble(ReplayView v, int B, co
 // The observations of one stored game as network input [n, obs_out] (Reanalyse, replay_buffer.py:337-349).
 __global__ void k_replay_game_obs(ReplayView v, int slot, float* out) {
   const int s = v.g_start[slot], n = v.g_len[slot];
-  const int cells = v.oh * v.ow, per = v.decode ? 3 * cells : v.obs_floats;
+  const int nf = v.out_floats();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n * per) return;
-  const int e = (int)(i / per), k = (int)(i - (long long)e * per);
-  const float* src = v.obs + (long long)(s + e) * v.obs_floats;
-  if (!v.decode) { out[i] = src[k]; return; }
-  const int8_t* raw = reinterpret_cast<const int8_t*>(src);
-  const int plane = k / cells, c = k - plane * cells;
-  out[i] = plane == 0 ? (raw[c] == 1 ? 1.0f : 0.0f) : (plane == 1 ? (raw[c] == -1 ? 1.0f : 0.0f) : (float)raw[cells]);
+  if (i >= (long long)n * nf) return;
+  const int e = (int)(i / nf);
+  out[i] = replay_obs_value(v, s, e, (int)(i - (long long)e * nf));
 }
 
 __global__ void k_replay_set_reanalysed(ReplayView v, int slot, const float* values) {
@@ -343,7 +349,9 @@ Layout replay_layout(const mzb_replay_config& c) {
 bool config_ok(const mzb_replay_config* c) {
   return c && c->n_actions > 0 && c->n_actions <= 65535 && c->obs_floats > 0 && c->capacity_games > 0 && c->entry_stride > 1 &&
          c->num_unroll_steps >= 0 && c->td_steps > 0 && c->max_batch > 0 && (c->per == 0 || c->per == 1) && c->per_alpha >= 0.0 &&
-         (c->obs_decode == 0 || (c->obs_decode == 1 && c->obs_h > 0 && c->obs_w > 0 && c->obs_h * c->obs_w + 1 <= 4 * c->obs_floats));
+         (c->obs_decode == 0 || (c->obs_decode == 1 && c->obs_h > 0 && c->obs_w > 0 && c->obs_h * c->obs_w + 1 <= 4 * c->obs_floats)) &&
+         c->stacked_observations >= 0 && c->obs_channels >= 0 &&
+         (c->stacked_observations == 0 || c->obs_decode == 1 || (c->obs_channels > 0 && c->obs_floats % c->obs_channels == 0));
 }
 
 }  // namespace
@@ -373,6 +381,7 @@ int mzb_replay_create(mzb_replay** out, const mzb_replay_config* c, void* d_work
   v.A = c->n_actions; v.obs_floats = c->obs_floats; v.cap = c->capacity_games; v.stride = c->entry_stride;
   v.decode = c->obs_decode; v.oh = c->obs_h; v.ow = c->obs_w;
   v.K = c->num_unroll_steps; v.td = c->td_steps; v.per = c->per; v.max_batch = c->max_batch; v.alpha = c->per_alpha;
+  v.S = c->stacked_observations; v.C = c->obs_channels > 0 ? c->obs_channels : 1;
   v.key = rng_key(c->seed);
   r->d_meta = (int*)(w + L.meta);
   r->max_save = MZB_REPLAY_MAX_SAVE;
@@ -517,7 +526,7 @@ int mzb_replay_game_observations(mzb_replay* r, int64_t game_id, float* d_obs, i
   const int slot = (int)(game_id % r->cfg.capacity_games), n = r->h_len[slot];
   *h_len = n;
   if (d_obs) {
-    const long long per = r->v.decode ? 3ll * r->v.oh * r->v.ow : r->v.obs_floats;
+    const long long per = r->v.out_floats();
     k_replay_game_obs<<<(unsigned)((n * per + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r->v, slot, d_obs);
     MZB_LAUNCH_CHECK();
   }

@@ -25,6 +25,7 @@ class ReplayConfig(C.Structure):
     _fields_ = [("n_actions", _i32), ("obs_floats", _i32), ("obs_decode", _i32), ("obs_h", _i32), ("obs_w", _i32),
                 ("capacity_games", _i32), ("entry_stride", _i32),
                 ("num_unroll_steps", _i32), ("td_steps", _i32), ("per", _i32), ("max_batch", _i32),
+                ("stacked_observations", _i32), ("obs_channels", _i32),
                 ("per_alpha", C.c_double), ("seed", C.c_uint64)]
 
 
@@ -99,8 +100,9 @@ class ReplayBuffer:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if self.device.type != "cuda":
             raise RuntimeError("the replay store lives on a CUDA device (there is no CPU path)")
-        if int(getattr(config, "stacked_observations", 0)) != 0:
-            raise NotImplementedError("stacked_observations > 0 is not on the device path")
+        self.S = int(getattr(config, "stacked_observations", 0) or 0)
+        c, h, w = config.observation_shape
+        self.obs_out_shape = (c * (self.S + 1) + self.S, h, w)         # get_stacked_observations (self_play.py:514-548)
         self.A = len(config.action_space)
         self.obs_floats = int(np.prod(config.observation_shape))
         self.K, self.td = int(config.num_unroll_steps), int(config.td_steps)
@@ -114,7 +116,7 @@ class ReplayBuffer:
                 raise NotImplementedError(f"no record decoder for {record_env.kind!r} observations")
         self.decode, self.rec_floats, self.board = decode, rec, (oh, ow)
         self.cfg = ReplayConfig(self.A, rec, decode, oh, ow, int(config.replay_buffer_size), int(config.max_moves) + 2, self.K,
-                                self.td, int(bool(config.PER)), self.max_batch, float(config.PER_alpha),
+                                self.td, int(bool(config.PER)), self.max_batch, self.S, int(c), float(config.PER_alpha),
                                 int(config.seed) & 0xFFFFFFFFFFFFFFFF)
         nbytes = _lib.lib.mzb_replay_workspace_bytes(C.byref(self.cfg))
         if nbytes == 0:
@@ -235,7 +237,7 @@ class ReplayBuffer:
         dev, K, A = self.device, self.K, self.A
         gid = torch.empty(B, dtype=torch.int64, device=dev)
         pos = torch.empty(B, dtype=torch.int32, device=dev)
-        obs = torch.empty((B,) + tuple(self.config.observation_shape), dtype=torch.float32, device=dev)
+        obs = torch.empty((B,) + self.obs_out_shape, dtype=torch.float32, device=dev)
         act = torch.empty((B, K + 1), dtype=torch.int32, device=dev)
         val = torch.empty((B, K + 1), dtype=torch.float64, device=dev)
         rew = torch.empty((B, K + 1), dtype=torch.float64, device=dev)
@@ -278,7 +280,7 @@ class ReplayBuffer:
         n = _i32()
         game_id = int(game_id) - self._id0
         check(_lib.lib.mzb_replay_game_observations(self._h, int(game_id), None, C.byref(n), _lib.current_stream()))
-        obs = torch.empty((n.value,) + tuple(self.config.observation_shape), dtype=torch.float32, device=self.device)
+        obs = torch.empty((n.value,) + self.obs_out_shape, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(_lib.lib.mzb_replay_game_observations(self._h, int(game_id), ptr(obs), C.byref(n), _lib.current_stream()))
         return obs

@@ -359,3 +359,53 @@ def test_save_game_reports_to_plain_and_remote_storages():
     for st in (Plain(), Remote()):
         rb.save_game(load_game(0, 0), st)
         assert st.info["num_played_games"] == rb.num_played_games and st.info["num_played_steps"] == rb.num_played_steps
+
+
+@pytest.mark.parametrize("kind,S", [("tictactoe", 2), ("cartpole", 3)])
+def test_get_batch_stacks_observations_like_game_history(kind, S):
+    """stacked_observations > 0: get_batch and Reanalyse's game_observations return
+    GameHistory.get_stacked_observations(position, S) (self_play.py:514-548, pinned to the reference by
+    tests/golden/stacked.npz) of the stored games, from the packed records and from decoded host games alike."""
+    import importlib
+    from muzero_hypermodel_b200.replay_buffer import ReplayBuffer
+    from muzero_hypermodel_b200.self_play import SelfPlay, decode_export
+    cfg = importlib.import_module(f"muzero_hypermodel_b200.games.{kind}").MuZeroConfig()
+    if kind == "tictactoe":
+        cfg.network = "fullyconnected"
+    cfg.num_simulations, cfg.stacked_observations = 6, S
+    cfg.max_moves = min(cfg.max_moves, 12)
+    cfg.replay_buffer_size, cfg.batch_size, cfg.PER = 64, 48, False
+    torch.manual_seed(0)
+    stores = []
+    games = None
+    for mode in ("packed", "host"):
+        sp = SelfPlay({"weights": None}, None, cfg, 5, n_games=24, device=DEV)
+        env, _ = sp._setup()
+        rb = ReplayBuffer({"num_played_games": 0, "num_played_steps": 0}, {}, cfg, device=DEV,
+                          record_env=env if mode == "packed" else None)
+        got = []
+        for _ in range(cfg.max_moves + 1):
+            sp.step(1.0, None)
+            if mode == "packed":
+                rb.ingest(env)
+            else:
+                for gh in decode_export(env):
+                    rb.save_game(gh)
+                    got.append(gh)
+        stores.append(rb)
+        if mode == "host":
+            games = got
+    packed, host = stores
+    assert len(packed) == len(host) == len(games) > 8
+    for rb in stores:
+        idx, (obs, *_rest) = rb.get_batch()
+        idx, obs = idx.cpu().numpy(), obs.cpu().numpy()
+        c, h, w = cfg.observation_shape
+        assert obs.shape[1:] == (c * (S + 1) + S, h, w)
+        for b in range(idx.shape[0]):
+            gh = games[int(idx[b, 0])]
+            want = np.asarray(gh.get_stacked_observations(int(idx[b, 1]), S), dtype=np.float32)
+            assert np.array_equal(obs[b], want), (b, idx[b])
+        g0 = rb.game_observations(3).cpu().numpy()
+        want = np.stack([np.asarray(games[3].get_stacked_observations(i, S), dtype=np.float32) for i in range(len(games[3].root_values))])
+        assert np.array_equal(g0, want)
