@@ -548,6 +548,36 @@ def run_workload(args, workload, steps, warmup, cpu_seconds, want_cpu, want_coll
         conv_gbs = conv_bytes / (conv_ms * 1e-3) / 1e9
         tpeak = float(peaks.get("bf16_tflops", 1650.0))
         tpeak_s = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        narrow = None
+        if C_lat == 16 and getattr(mcts, "_pool", None) is not None:
+            # narrow network (breakout): the dominant kernel of a step is the ONE-KERNEL recurrent inference
+            # (k_recurrent16, csrc/mzb_tower16.cu) - time it alone on the search's own hidden-state pool (+ its three
+            # head-mlp launches), slot 0 -> slot 1 of every game
+            pool = mcts._pool
+            state = int(pool.shape[2])
+            zero_slot = torch.zeros(G, dtype=torch.int32, device=dev)
+            act = torch.zeros((G, 1), dtype=torch.int32, device=dev)
+            rec = lambda: sp.model.recurrent_inference_fused(pool, act, in_layout=2, in_slot=zero_slot,
+                                                            in_row_stride=int(pool.shape[1]) * state, slot_stride=state,
+                                                            state_out=pool, out_layout=2, out_row_stride=int(pool.shape[1]) * state,
+                                                            out_offset=state)
+            for _ in range(3):
+                rec()
+            torch.cuda.synchronize()
+            ra, rb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ra.record()
+            for _ in range(10):
+                rec()
+            rb_.record()
+            torch.cuda.synchronize()
+            rec_ms = ra.elapsed_time(rb_) / 10
+            rec_tf = flops[1] * G / (rec_ms * 1e-3) / 1e12
+            narrow = {"kernel": "k_recurrent16 (whole recurrent inference of the 16-channel network, warp per image, mma.sync on "
+                                "shared-memory activations) + 3 x k_head_mma", "us": rec_ms * 1e3, "achieved": rec_tf, "peak": tpeak,
+                      "unit": "TFLOP/s", "frac": rec_tf / tpeak, "flop_per_launch": flops[1] * G,
+                      "limiter": "shared-memory pipe 82 % busy (profiles/r02_ncu_breakout.csv): the implicit GEMM re-reads each "
+                                 "activation row once per tap; tensor pipe 27 %",
+                      "traffic": ncu_traffic(workload), "traffic_source": "profiles/" + NCU_CAPTURE[workload]}
         in_ms = ms / n_moves                              # a whole move inside the timed region
         tflops_in = (flops[1] * S + flops[0]) * G / (in_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": f"k_conv_tc (tcgen05 implicit-GEMM 3x3 conv, {C_lat}->{C_lat} ch, {H_lat}x{W_lat}, batch {G})",
@@ -556,8 +586,9 @@ def run_workload(args, workload, steps, warmup, cpu_seconds, want_cpu, want_coll
                                 "note": "every FLOP of the move (BASELINE flop/sim x sims + initial inference) / move time inside the timed "
                                         "region, tree / head / env kernels included, against the SUSTAINED bf16 peak: a lower bound of the "
                                         "convolution's in-step fraction (it carries ~100 % of the FLOPs in < 100 % of the time)"},
-                    "traffic": ncu_traffic(workload),
-                    "traffic_source": ("profiles/" + NCU_CAPTURE[workload]) if workload in NCU_CAPTURE else None,
+                    "traffic": ncu_traffic(workload) if narrow is None else None,
+                    "traffic_source": ("profiles/" + NCU_CAPTURE[workload]) if (workload in NCU_CAPTURE and narrow is None) else None,
+                    "recurrent_inference": narrow,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if peaks else "fallback 1650 TFLOP/s",
                     "kernel_us": conv_ms * 1e3, "flop_per_launch": conv_flop,
                     "hbm_side": {"algorithmic_bytes_per_launch": conv_bytes, "achieved": conv_gbs, "peak": peak, "unit": "GB/s",

@@ -457,6 +457,26 @@ int mzb_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* 
 int mzb_sgd_step(float* d_param, const float* d_grad, float* d_momentum_buffer, int64_t n, double lr, double momentum,
                  double weight_decay, int64_t step, double grad_scale, void* stream);
 
+/* Gradient all-reduce fused into the optimiser step over NVLink peer memory (single node, <= 8 ranks; trainer.py:35-53
+ * + the data-parallel mean).  Every rank keeps two flat gradient buckets (step parity) and a flag array of `world`
+ * uint32 in mzb_p2p_alloc'd memory, exports them (mzb_p2p_export -> 64-byte IPC handle, exchanged by the caller) and
+ * maps its peers' (mzb_p2p_import).  One launch per rank and step: barrier on the flags (release/acquire at system
+ * scope, bounded spin), then param[i] is updated from sum_r bucket_r[i] / world, summed in rank order on every rank so
+ * the replicas stay bit-identical.  h_peer_grads / h_peer_flags: HOST arrays of `world` device pointers valid on this
+ * rank (own buffers at index `rank`); `seq` = the step sequence number (starts at 1, the same on all ranks; selects
+ * nothing by itself - the caller passes the buckets of parity seq & 1). */
+int mzb_p2p_alloc(void** d_ptr, size_t bytes);
+int mzb_p2p_free(void* d_ptr);
+int mzb_p2p_export(void* d_ptr, uint8_t* handle64);
+int mzb_p2p_import(const uint8_t* handle64, void** d_ptr);
+int mzb_p2p_close(void* d_ptr);
+int mzb_adam_step_allreduce(float* d_param, const float* const* h_peer_grads, uint32_t* const* h_peer_flags, int32_t rank,
+                            int32_t world, uint32_t seq, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, double lr,
+                            double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
+int mzb_sgd_step_allreduce(float* d_param, const float* const* h_peer_grads, uint32_t* const* h_peer_flags, int32_t rank,
+                           int32_t world, uint32_t seq, float* d_momentum_buffer, int64_t n, double lr, double momentum,
+                           double weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,3 +110,74 @@ def allreduce_gradients(grads, average=True):
         n = g.numel()
         g.copy_(flat[off:off + n].reshape(g.shape))
         off += n
+
+
+# ---- gradient all-reduce fused into the optimiser step (csrc/mzb_optim.cu), over NVLink peer memory
+class PeerGradientBuckets:
+    """Every rank's flat gradient bucket in IPC-shared device memory, mapped by all ranks of the node, so that ONE
+    kernel per rank can sum the ranks' gradients over NVLink / NVSwitch and apply the optimiser update
+    (`mzb_adam_step_allreduce` / `mzb_sgd_step_allreduce`) - no NCCL call on the step.  torch.distributed only carries
+    the 64-byte IPC handles once, at construction.  Two buckets per rank (step parity), one flag word per peer."""
+
+    def __init__(self, n_floats, device):
+        import ctypes as C
+        from . import _lib
+        from ._lib import check
+        vp = C.c_void_p
+        for name, res, args in (("mzb_p2p_alloc", C.c_int, [C.POINTER(vp), C.c_size_t]), ("mzb_p2p_free", C.c_int, [vp]),
+                                ("mzb_p2p_export", C.c_int, [vp, C.c_char_p]), ("mzb_p2p_import", C.c_int, [C.c_char_p, C.POINTER(vp)]),
+                                ("mzb_p2p_close", C.c_int, [vp])):
+            _lib.bind(name, res, args)
+        self._C, self._lib, self._check = C, _lib, check
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world > 8:
+            raise NotImplementedError("fused gradient all-reduce: one node, at most 8 ranks")
+        self.n, self.device = int(n_floats), torch.device(device)
+        self._own, handles = [], []
+        with torch.cuda.device(self.device):
+            for nbytes in (4 * self.n, 4 * self.n, 4 * 64):            # bucket 0, bucket 1, flags
+                p = vp()
+                check(_lib.lib.mzb_p2p_alloc(C.byref(p), nbytes))
+                h = C.create_string_buffer(64)
+                check(_lib.lib.mzb_p2p_export(p, h))
+                self._own.append(p)
+                handles.append(bytes(h.raw))
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, handles)
+            self._peer = []                                             # [rank][bucket0, bucket1, flags] device pointers
+            for r, hs in enumerate(everyone):
+                if r == self.rank:
+                    self._peer.append([p.value for p in self._own])
+                    continue
+                ptrs = []
+                for h in hs:
+                    p = vp()
+                    check(_lib.lib.mzb_p2p_import(C.create_string_buffer(h, 64), C.byref(p)))
+                    ptrs.append(p.value)
+                self._peer.append(ptrs)
+        dist.barrier()
+
+    def bucket(self, seq):
+        """This rank's bucket of parity seq & 1 as a float32 tensor (to copy the step's flat gradients into)."""
+        ptr, n = self._own[seq & 1].value, self.n
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def pointers(self, seq):
+        """(host array of every rank's bucket pointer for this parity, host array of every rank's flag pointer)."""
+        C = self._C
+        grads = (C.c_void_p * self.world)(*[self._peer[r][seq & 1] for r in range(self.world)])
+        flags = (C.c_void_p * self.world)(*[self._peer[r][2] for r in range(self.world)])
+        return grads, flags
+
+    def close(self):
+        for r, ptrs in enumerate(getattr(self, "_peer", [])):
+            if r != self.rank:
+                for p in ptrs:
+                    self._lib.lib.mzb_p2p_close(self._C.c_void_p(p))
+        for p in getattr(self, "_own", []):
+            self._lib.lib.mzb_p2p_free(p)
+        self._peer, self._own = [], []

@@ -334,21 +334,48 @@ class Trainer:
         return out
 
     def _step(self):
-        """Gradient all-reduce over the ranks + one fused optimiser launch on the flat bucket."""
+        """Gradient all-reduce over the ranks + optimiser update of the flat bucket.  With more than one rank on the
+        node both happen in ONE kernel per rank: the ranks' gradient buckets are peer-mapped over NVLink and summed in
+        rank order inside the optimiser kernel (dist.PeerGradientBuckets, csrc/mzb_optim.cu); MZB_FUSED_ALLREDUCE=0
+        selects an NCCL all-reduce followed by the plain optimiser launch."""
+        import os
         world = tdist.get_world_size() if tdist.is_available() and tdist.is_initialized() else 1
-        if world > 1:
-            tdist.all_reduce(self.flat_grad, op=tdist.ReduceOp.SUM)
         self.opt_step += 1
         n, cfg = self.flat_param.numel(), self.config
+        fused = world > 1 and os.environ.get("MZB_FUSED_ALLREDUCE", "1") != "0"
         with torch.cuda.device(self.device):
-            if cfg.optimizer == "Adam":
-                check(_lib.lib.mzb_adam_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.state1), ptr(self.state2), n,
-                                             self.lr, 0.9, 0.999, 1e-8, float(cfg.weight_decay), self.opt_step, 1.0 / world,
-                                             _lib.current_stream()))
+            if fused:
+                from .dist import PeerGradientBuckets
+                if getattr(self, "_peers", None) is None:
+                    self._peers = PeerGradientBuckets(n, self.device)
+                    _lib.bind("mzb_adam_step_allreduce", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
+                                                                  C.c_void_p, C.c_void_p, C.c_int64] + [C.c_double] * 5 + [C.c_int64, C.c_void_p])
+                    _lib.bind("mzb_sgd_step_allreduce", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
+                                                                 C.c_void_p, C.c_int64] + [C.c_double] * 3 + [C.c_int64, C.c_void_p])
+                    self._seq = 0
+                self._seq += 1
+                pb = self._peers
+                pb.bucket(self._seq).copy_(self.flat_grad)                 # this step's gradients into the shared bucket
+                grads, flags = pb.pointers(self._seq)
+                if cfg.optimizer == "Adam":
+                    check(_lib.lib.mzb_adam_step_allreduce(ptr(self.flat_param), grads, flags, pb.rank, pb.world, self._seq,
+                                                           ptr(self.state1), ptr(self.state2), n, self.lr, 0.9, 0.999, 1e-8,
+                                                           float(cfg.weight_decay), self.opt_step, _lib.current_stream()))
+                else:
+                    check(_lib.lib.mzb_sgd_step_allreduce(ptr(self.flat_param), grads, flags, pb.rank, pb.world, self._seq,
+                                                          ptr(self.state1), n, self.lr, float(cfg.momentum),
+                                                          float(cfg.weight_decay), self.opt_step, _lib.current_stream()))
             else:
-                check(_lib.lib.mzb_sgd_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.state1), n, self.lr,
-                                            float(cfg.momentum), float(cfg.weight_decay), self.opt_step, 1.0 / world,
-                                            _lib.current_stream()))
+                if world > 1:
+                    tdist.all_reduce(self.flat_grad, op=tdist.ReduceOp.SUM)
+                if cfg.optimizer == "Adam":
+                    check(_lib.lib.mzb_adam_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.state1), ptr(self.state2), n,
+                                                 self.lr, 0.9, 0.999, 1e-8, float(cfg.weight_decay), self.opt_step, 1.0 / world,
+                                                 _lib.current_stream()))
+                else:
+                    check(_lib.lib.mzb_sgd_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.state1), n, self.lr,
+                                                float(cfg.momentum), float(cfg.weight_decay), self.opt_step, 1.0 / world,
+                                                _lib.current_stream()))
         self.model._synced = None          # the inference kernels re-pack the weights on their next call
 
     # -- trainer.py:55-122 over plain get_info / set_info objects
