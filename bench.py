@@ -564,13 +564,17 @@ def run_workload(args, workload, steps, warmup, cpu_seconds, want_cpu, want_coll
             for _ in range(3):
                 rec()
             torch.cuda.synchronize()
+            rgraph = torch.cuda.CUDAGraph()                 # replayed from a graph like the search itself (4 launches
+            with torch.cuda.graph(rgraph):                  # per call: eager ctypes launches would time the host)
+                for _ in range(10):
+                    rec()
+            rgraph.replay()
+            torch.cuda.synchronize()
             ra, rb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ra.record()
-            for _ in range(10):
-                rec()
-            rb_.record()
+            ra.record(); rgraph.replay(); rb_.record()
             torch.cuda.synchronize()
             rec_ms = ra.elapsed_time(rb_) / 10
+            del rgraph
             rec_tf = flops[1] * G / (rec_ms * 1e-3) / 1e12
             narrow = {"kernel": "k_recurrent16 (whole recurrent inference of the 16-channel network, warp per image, mma.sync on "
                                 "shared-memory activations) + 3 x k_head_mma", "us": rec_ms * 1e3, "achieved": rec_tf, "peak": tpeak,

@@ -224,7 +224,8 @@ struct SearchIO {
 enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32, X_SYNC2 = 64, X_HALFBAR = 128, X_RCP = 256 };
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm) { return blocks_per_sm >= 3 ? 8 : 12; }
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm, int threads) {
-  return threads * blocks_per_sm > 512 ? 8 : 12;        // 48 KB (12 levels) per 256 threads fit twice per SM, not three times
+  // 16 bytes per level and thread next to ~18 KB of weights + tables per CTA: 12 levels up to 640 threads per SM
+  return threads * blocks_per_sm > 768 ? 8 : (threads * blocks_per_sm > 640 ? 10 : 12);
 }
 
 template <class SH, int THREADS, bool PHASE_SYNC, bool PB_LUT, int EXP, int MINB = 512 / THREADS>
@@ -236,10 +237,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   float* pack = reinterpret_cast<float*>(smem4);
   double* lut = reinterpret_cast<double*>(pack + SH::PACK);
   const int S1 = io.num_sims + 1;
-  double* pbt = lut + ((S1 + 1) & ~1);                     // [S1][S1] when PB_LUT
+  // pb(N, n) only for n <= N (a child is never visited more often than its parent): triangular table, row N at
+  // N (N + 1) / 2 - half the shared memory of the square one
+  double* pbt = lut + ((S1 + 1) & ~1);
+  const int TRI = S1 * (S1 + 1) / 2;
   // SPATH: [PD][THREADS] value sums f64 | rewards f32 | (node << 16 | action << 8... ) see path_put
   constexpr int PD = ((EXP & X_SPATH) != 0 && PB_LUT) ? smem_path_depth(MINB, THREADS) : 0;
-  double* sp_vs = pbt + (PB_LUT ? S1 * S1 : 0);
+  double* sp_vs = pbt + (PB_LUT ? TRI : 0);
   float* sp_rw = reinterpret_cast<float*>(sp_vs + PD * THREADS);
   uint32_t* sp_ev = reinterpret_cast<uint32_t*>(sp_rw + PD * THREADS);
   // RCP: refined reciprocals of the visit counts 1..S (the divisor of value_sum / visit_count)
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   if (PB_LUT) {
     for (int i = threadIdx.x; i < S1 * S1; i += THREADS) {
       const int N = i / S1, n = i % S1;
-      pbt[i] = ucb_pb(t.log_lut[N], __dsqrt_rn((double)N), n);
+      if (n <= N) pbt[N * (N + 1) / 2 + n] = ucb_pb(t.log_lut[N], __dsqrt_rn((double)N), n);
     }
   }
   __syncthreads();
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     for (int a = 0; a < A; ++a) { vs[a] = rr.vs(a); pr[a] = rr.pr(a); vi[a] = rr.vi(a); rw[a] = rr.rw(a); ch[a] = rr.ch(a); }
     const double pbc0 = PB_LUT ? 0.0 : lut[N];
     const double sqrtN = PB_LUT ? 0.0 : __dsqrt_rn((double)N);
-    const double* pbrow = pbt + N * S1;
+    const double* pbrow = pbt + ((N * (N + 1)) >> 1);
     double sc[A];
     double best = -CUDART_INF;
     int n_best = 0;
@@ -582,7 +586,7 @@ using TicTacToeFcShape = Shape<27, 32, 9, 10, 0, 16, 16, 0, 0>;    // games/tict
 template <class SH, bool PB_LUT, int EXP, int THREADS = 256, bool PHASE_SYNC = true, int MINB = 512 / THREADS>
 int launch_variant(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
   const int S1 = io.num_sims + 1;
-  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? S1 * S1 : 0)) +
+  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? S1 * (S1 + 1) / 2 : 0)) +
                       (((EXP & X_SPATH) != 0 && PB_LUT) ? (size_t)smem_path_depth(MINB, THREADS) * THREADS * 16 : 0) +
                       (((EXP & X_RCP) != 0 && PB_LUT) ? sizeof(double) * (size_t)S1 : 0);
   static bool configured = false;
@@ -621,6 +625,10 @@ int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t 
       case 263: return launch_variant<SH, true, 263>(t, m, io, s);
       case 135: return launch_variant<SH, true, 135>(t, m, io, s);
       case 2007: return launch_variant<SH, true, 7, 128, true, 5>(t, m, io, s);     // 5 x 128 threads per SM (96 registers, no spills): slower
+      case 1135: return launch_variant<SH, true, 135, 256, true, 1>(t, m, io, s);   // 8 warps per SM: 6.22 ms
+      case 3135: return launch_variant<SH, true, 135, 128, true, 3>(t, m, io, s);   // 12 warps per SM: 5.22 ms (16: 4.23)
+      case 5135: return launch_variant<SH, true, 135, 128, true, 5>(t, m, io, s);   // 20 warps per SM (96 registers)
+      case 6135: return launch_variant<SH, true, 135, 128, true, 6>(t, m, io, s);   // 24 warps per SM (80 registers)
       case 19: return launch_variant<SH, true, 19>(t, m, io, s);
       case 35: return launch_variant<SH, true, 35>(t, m, io, s);
       default: break;
