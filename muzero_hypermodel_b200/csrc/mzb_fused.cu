@@ -13,7 +13,7 @@
 #include "mzb_fc.cuh"
 #include "mzb_tree.cuh"
 
-#define MZB_FUSED_DEFAULT_EXP 135    // FFMA2 network, root record in registers, search path in shared memory, barrier per 4 warps
+#define MZB_FUSED_DEFAULT_EXP 647    // FFMA2 network, root record in registers, search path in shared memory, barrier per 4 warps, branch-free scores
 
 namespace {
 
@@ -22,7 +22,8 @@ __host__ __device__ constexpr int pad4(int x) { return (x + 3) / 4 * 4; }
 // ---- one Linear layer, compile-time shape.  w: Wt [*][OUTP] in shared memory, b: [OUTP].
 // F2: the same fmaf chain per output, issued as packed FFMA2 (fma.rn.f32x2: two IEEE fp32 FMAs per instruction on
 // sm_100) over adjacent outputs - bit-identical to the scalar form, half the FMA instructions.
-template <int NIN, int OUT, int OUTP, bool F2 = false>
+// FE: ELU through ex2.approx (max(x, __expf(min(x, 0)) - 1): five instructions instead of eleven)
+template <int NIN, int OUT, int OUTP, bool F2 = false, bool FE = false>
 __device__ __forceinline__ void lin(const float* __restrict__ w, const float* __restrict__ b, const float (&x)[NIN],
                                     int hot, float (&y)[OUT], bool elu) {
   if constexpr (F2) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ void lin(const float* __restrict__ w, const float* __
   }
   if (elu) {
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) y[o] = elu_f32(y[o]);
+    for (int o = 0; o < OUT; ++o) y[o] = FE ? fmaxf(y[o], __fsub_rn(__expf(fminf(y[o], 0.0f)), 1.0f)) : elu_f32(y[o]);
   }
 }
 
@@ -67,15 +68,15 @@ struct Mlp {
   static constexpr int OUT0 = H > 0 ? H : OUT;
   static constexpr int SIZE0 = IN * pad4(OUT0) + pad4(OUT0);
   static constexpr int SIZE = SIZE0 + (H > 0 ? H * pad4(OUT) + pad4(OUT) : 0);
-  template <bool F2 = false>
+  template <bool F2 = false, bool FE = false>
   __device__ __forceinline__ static void run(const float* __restrict__ p, const float (&x)[NDIRECT], int hot,
                                              float (&y)[OUT]) {
     if constexpr (H > 0) {
       float h[H];
-      lin<NDIRECT, H, pad4(H), F2>(p, p + IN * pad4(H), x, hot, h, true);
-      lin<H, OUT, pad4(OUT), F2>(p + SIZE0, p + SIZE0 + H * pad4(OUT), h, -1, y, false);
+      lin<NDIRECT, H, pad4(H), F2, FE>(p, p + IN * pad4(H), x, hot, h, true);
+      lin<H, OUT, pad4(OUT), F2, FE>(p + SIZE0, p + SIZE0 + H * pad4(OUT), h, -1, y, false);
     } else {
-      lin<NDIRECT, OUT, pad4(OUT), F2>(p, p + IN * pad4(OUT), x, hot, y, false);
+      lin<NDIRECT, OUT, pad4(OUT), F2, FE>(p, p + IN * pad4(OUT), x, hot, y, false);
     }
   }
 };
@@ -221,7 +222,7 @@ struct SearchIO {
 // EXP: experiment / tuning flags (MZB_FUSED_EXP): 1 = packed FFMA2 network, 2 = root record in registers (A <= 4),
 // 4/8/16/32 = timing-only diagnostics (blocked layout, aliased trees, no network, no walk) - results are NOT valid.
 // 4 = the search path's edge statistics in shared memory for the first 12 levels (deeper levels: local memory).
-enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32, X_SYNC2 = 64, X_HALFBAR = 128, X_RCP = 256 };
+enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32, X_SYNC2 = 64, X_HALFBAR = 128, X_RCP = 256, X_BF = 512, X_FELU = 1024, X_SCHEDBAR = 2048, X_PF = 4096, X_P1 = 8192 };
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm) { return blocks_per_sm >= 3 ? 8 : 12; }
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm, int threads) {
   // 16 bytes per level and thread next to ~18 KB of weights + tables per CTA: 12 levels up to 640 threads per SM
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   constexpr int A = SH::A, ENC = SH::ENC, FULL = SH::FULL;
   constexpr bool F2 = (EXP & X_F2) != 0;
   constexpr bool ROOTREG = (EXP & X_ROOTREG) != 0 && A <= 4;
+  constexpr bool FE = (EXP & X_FELU) != 0;
   extern __shared__ float4 smem4[];
   float* pack = reinterpret_cast<float*>(smem4);
   double* lut = reinterpret_cast<double*>(pack + SH::PACK);
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   // pb(N, n) only for n <= N (a child is never visited more often than its parent): triangular table, row N at
   // N (N + 1) / 2 - half the shared memory of the square one
   double* pbt = lut + ((S1 + 1) & ~1);
-  const int TRI = S1 * (S1 + 1) / 2;
+  const int TRI = (S1 * (S1 + 1) / 2 + 1) & ~1;     // even: what follows stays 16-byte aligned
   // SPATH: [PD][THREADS] value sums f64 | rewards f32 | (node << 16 | action << 8... ) see path_put
   constexpr int PD = ((EXP & X_SPATH) != 0 && PB_LUT) ? smem_path_depth(MINB, THREADS) : 0;
   double* sp_vs = pbt + (PB_LUT ? TRI : 0);
@@ -248,8 +250,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   uint32_t* sp_ev = reinterpret_cast<uint32_t*>(sp_rw + PD * THREADS);
   // RCP: refined reciprocals of the visit counts 1..S (the divisor of value_sum / visit_count)
   constexpr bool RCP = (EXP & X_RCP) != 0 && PB_LUT;
+  // BF: branch-free scores - every division of a level goes through a hoisted reciprocal with the validity checks
+  // OR-ed into one flag (one rare branch per level to the exact form), so the children's float64 chains interleave
+  constexpr bool BF = (EXP & X_BF) != 0 && PB_LUT;
   double* rcpn = reinterpret_cast<double*>(sp_ev + PD * THREADS);
+  double2* rcpn2 = reinterpret_cast<double2*>(sp_ev + PD * THREADS);       // {refined 1 / n, (double)n}
   if (RCP) for (int i = threadIdx.x; i < S1; i += THREADS) rcpn[i] = i > 0 ? rcp_refined((double)i) : 0.0;
+  if (BF) for (int i = threadIdx.x; i <= S1; i += THREADS) rcpn2[i] = make_double2(i > 0 ? rcp_refined((double)i) : 0.0, (double)i);
   for (int i = threadIdx.x; i < SH::PACK / 4; i += THREADS) smem4[i] = reinterpret_cast<const float4*>(gpack)[i];
   for (int i = threadIdx.x; i < S1; i += THREADS) lut[i] = t.log_lut[i];
   if (PB_LUT) {
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   const bool active = g_raw < t.G;
   if (!PHASE_SYNC && !active) return;
   const int g = active ? g_raw : 0;                        // idle threads of the last block only take part in barriers
-  const bool two = t.P == 2;
+  const bool two = (EXP & X_P1) ? false : t.P == 2;        // X_P1: single-player instantiation (the launcher checks t.P)
   const size_t G = (size_t)t.G;
   const uint32_t my_slot = io.slot ? io.slot[g] : (uint32_t)g;
   const uint32_t my_step = io.step ? io.step[g] : 0u;
@@ -285,15 +292,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     float ob[SH::OBS];
     load_floats<SH::OBS>(io.obs + (size_t)g * SH::OBS, ob);
     float st[ENC];
-    SH::Rep::template run<F2>(pack + SH::OFF_REP, ob, -1, st);
+    SH::Rep::template run<F2, FE>(pack + SH::OFF_REP, ob, -1, st);
     minmax_regs(st);
     store_floats<ENC>(hid_of(0), st);
     float pl[A], pri[A];
-    SH::Pol::template run<F2>(pack + SH::OFF_POL, st, -1, pl);
+    SH::Pol::template run<F2, FE>(pack + SH::OFF_POL, st, -1, pl);
     priors_regs<A>(pl, legal, pri);
     if (io.root_pred_value) {
       float vl[FULL];
-      SH::Val::template run<F2>(pack + SH::OFF_VAL, st, -1, vl);
+      SH::Val::template run<F2, FE>(pack + SH::OFF_VAL, st, -1, vl);
       io.root_pred_value[g] = s2s_regs<SH::SUP>(vl);
     }
     float zl[FULL];
@@ -360,6 +367,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) { vs[a] = rr.vs(a); pr[a] = rr.pr(a); vi[a] = rr.vi(a); rw[a] = rr.rw(a); ch[a] = rr.ch(a); }
+    if constexpr ((EXP & X_PF) != 0) {
+#pragma unroll
+      for (int a = 0; a < A; ++a)
+        if (ch[a] > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec_of(ch[a])));
+    }
     const double pbc0 = PB_LUT ? 0.0 : lut[N];
     const double sqrtN = PB_LUT ? 0.0 : __dsqrt_rn((double)N);
     const double* pbrow = pbt + ((N * (N + 1)) >> 1);
@@ -367,9 +379,40 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     double best = -CUDART_INF;
     int n_best = 0;
     action = -1;
+    if constexpr (BF) {
+      const bool norm = vmax > vmin;
+      bool bad = norm && !mm_ok;
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        const int n = vi[a];
+        const double2 yn = rcpn2[n];
+        const double p = root_level ? rp[a] : (double)pr[a];
+        const double s = __dmul_rn(pbrow[n], p);
+        bool okv, okq;
+        double v = ddiv_rcp_nb(vs[a], yn.y, yn.x, okv);
+        if (two) v = -v;
+        const double q = __dadd_rn((double)rw[a], __dmul_rn(t.discount, v));
+        const double qn = __dsub_rn(q, vmin);
+        const double u = ddiv_rcp_nb(qn, mm_den, mm_y, okq);
+        okq = okq || qn == 0.0;
+        const bool has = n > 0;
+        sc[a] = has ? __dadd_rn(s, norm ? u : q) : s;
+        bad = bad || (has && !(okv && (!norm || okq)));
+      }
+      if (bad) {
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+          sc[a] = ucb_score_pb(pbrow[vi[a]], vi[a], root_level ? rp[a] : (double)pr[a], vs[a], (double)rw[a], t.discount, two, vmin, vmax);
+      }
+    }
 #pragma unroll
     for (int a = 0; a < A; ++a) {
-      if (ch[a] == MZB_CHILD_ILLEGAL) { sc[a] = -CUDART_INF; continue; }
+      if ((root_level || !BF) && ch[a] == MZB_CHILD_ILLEGAL) { sc[a] = -CUDART_INF; continue; }   // illegal edges exist at the root only
+      if constexpr (BF) {
+        if (sc[a] > best || action < 0) { best = sc[a]; n_best = 1; action = a; }
+        else if (sc[a] == best) ++n_best;
+        continue;
+      }
       const double p = root_level ? rp[a] : (double)pr[a];
       const double pb = PB_LUT ? pbrow[vi[a]] : ucb_pb(pbc0, sqrtN, vi[a]);
       if constexpr (RCP)
@@ -413,7 +456,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     // one dependent record load per level
     int node = 0, depth = 0;
     N = root_visit;
-    if (RCP && vmax > vmin) {
+    if ((RCP || BF) && vmax > vmin) {
       mm_den = __dsub_rn(vmax, vmin);
       mm_ok = rcp_divisor_ok(mm_den);
       mm_y = mm_ok ? rcp_refined(mm_den) : 0.0;
@@ -442,7 +485,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     }
     const int L = depth, fresh = sim + 1;
     if (PHASE_SYNC) {                         // warps of the block enter the unrolled network code together
-      if constexpr ((EXP & X_HALFBAR) != 0) {
+      if constexpr ((EXP & X_SCHEDBAR) != 0) {
+        // the warps that share a scheduler (warp id mod 4) and hence an L0 instruction cache enter the network together
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((threadIdx.x >> 5) & 3)), "n"(THREADS / 4) : "memory");
+      } else if constexpr ((EXP & X_HALFBAR) != 0) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");      // per group of four warps
       } else if constexpr ((EXP & X_SYNC2) != 0) {
         if (sim & 1) __syncthreads();
@@ -465,22 +511,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
       float st[ENC];
       load_floats<ENC>(hid_of(node), st);
       float nx[ENC];
-      SH::Dyn::template run<F2>(pack + SH::OFF_DYN, st, action, nx);
+      SH::Dyn::template run<F2, FE>(pack + SH::OFF_DYN, st, action, nx);
       {
         float rl[FULL];
-        SH::Rew::template run<F2>(pack + SH::OFF_REW, nx, -1, rl);
+        SH::Rew::template run<F2, FE>(pack + SH::OFF_REW, nx, -1, rl);
         reward = s2s_regs<SH::SUP>(rl);
       }
       minmax_regs(nx);
       store_floats<ENC>(hid_of(fresh), nx);
       {
         float pl[A];
-        SH::Pol::template run<F2>(pack + SH::OFF_POL, nx, -1, pl);
+        SH::Pol::template run<F2, FE>(pack + SH::OFF_POL, nx, -1, pl);
         priors_regs<A>(pl, nullptr, pri);
       }
       {
         float vl[FULL];
-        SH::Val::template run<F2>(pack + SH::OFF_VAL, nx, -1, vl);
+        SH::Val::template run<F2, FE>(pack + SH::OFF_VAL, nx, -1, vl);
         value = s2s_regs<SH::SUP>(vl);
       }
     }
@@ -523,7 +569,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
       uint8_t* er = rec_of(pn);
       if (!PB_LUT) { e_vs = t.value_sum(er)[pa]; e_vi = t.visit(er)[pa]; l_rw = t.reward(er)[pa]; }
       const double e_rw = (k == L - 1) ? (double)reward : (double)l_rw;
-      backup_step(e_vs, e_vi, e_rw, val, t.discount, two, ((L - (k + 1)) & 1) == 0, vmin, vmax);
+      if constexpr (BF) backup_step_rcp(e_vs, e_vi, e_rw, val, t.discount, two, ((L - (k + 1)) & 1) == 0, vmin, vmax, rcpn2);
+      else backup_step(e_vs, e_vi, e_rw, val, t.discount, two, ((L - (k + 1)) & 1) == 0, vmin, vmax);
       bool in_regs = false;
       if constexpr (ROOTREG) {
         if (pn == 0) {
@@ -541,7 +588,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
         t.visit(er)[pa] = e_vi;
       }
     }
-    backup_step(root_vs, root_visit, (double)root_reward, val, t.discount, two, (L & 1) == 0, vmin, vmax);
+    if constexpr (BF) backup_step_rcp(root_vs, root_visit, (double)root_reward, val, t.discount, two, (L & 1) == 0, vmin, vmax, rcpn2);
+    else backup_step(root_vs, root_visit, (double)root_reward, val, t.discount, two, (L & 1) == 0, vmin, vmax);
     max_depth = L > max_depth ? L : max_depth;
     depth_sum += (unsigned int)L;
   }
@@ -586,15 +634,16 @@ using TicTacToeFcShape = Shape<27, 32, 9, 10, 0, 16, 16, 0, 0>;    // games/tict
 template <class SH, bool PB_LUT, int EXP, int THREADS = 256, bool PHASE_SYNC = true, int MINB = 512 / THREADS>
 int launch_variant(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t s) {
   const int S1 = io.num_sims + 1;
-  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? S1 * (S1 + 1) / 2 : 0)) +
+  const size_t smem = sizeof(float) * SH::PACK + sizeof(double) * (size_t)(((S1 + 1) & ~1) + (PB_LUT ? ((S1 * (S1 + 1) / 2 + 1) & ~1) : 0)) +
                       (((EXP & X_SPATH) != 0 && PB_LUT) ? (size_t)smem_path_depth(MINB, THREADS) * THREADS * 16 : 0) +
-                      (((EXP & X_RCP) != 0 && PB_LUT) ? sizeof(double) * (size_t)S1 : 0);
+                      (((EXP & X_RCP) != 0 && PB_LUT) ? sizeof(double) * (size_t)S1 : 0) +
+                      (((EXP & X_BF) != 0 && PB_LUT) ? sizeof(double2) * (size_t)(S1 + 1) : 0);
   static bool configured = false;
   if (!configured) {
-    MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT, EXP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MZB_CUDA(cudaFuncSetAttribute(k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT, EXP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
-  MZB_CHECK_ARG(smem <= 96 * 1024, "fused search: shared memory %zu > 96 KiB", smem);
+  MZB_CHECK_ARG(smem <= 160 * 1024, "fused search: shared memory %zu > 160 KiB", smem);
   const int grid = (t->v.G + THREADS - 1) / THREADS;
   k_search_fc<SH, THREADS, PHASE_SYNC, PB_LUT, EXP, MINB><<<grid, THREADS, smem, s>>>(t->v, m->d_pack, io);
   MZB_LAUNCH_CHECK();
@@ -624,6 +673,10 @@ int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t 
       case 23: return launch_variant<SH, true, 23>(t, m, io, s);
       case 263: return launch_variant<SH, true, 263>(t, m, io, s);
       case 135: return launch_variant<SH, true, 135>(t, m, io, s);
+      case 647: return launch_variant<SH, true, 647>(t, m, io, s);                  // + branch-free scores: 4.20 -> 3.64 ms
+      // measured on top of 647 and dropped (303,104 games, 3.64 ms): ex2-based ELU 3.61 (-380 instructions per simulation
+      // buy 0.7 %: not issue-bound); barrier per scheduler (warps w, w+4) 3.72; one 512-thread CTA per SM 3.76;
+      // prefetch.global.L1 of both children's records 3.69; compile-time single player 3.67
       case 2007: return launch_variant<SH, true, 7, 128, true, 5>(t, m, io, s);     // 5 x 128 threads per SM (96 registers, no spills): slower
       case 1135: return launch_variant<SH, true, 135, 256, true, 1>(t, m, io, s);   // 8 warps per SM: 6.22 ms
       case 3135: return launch_variant<SH, true, 135, 128, true, 3>(t, m, io, s);   // 12 warps per SM: 5.22 ms (16: 4.23)

@@ -530,8 +530,17 @@ static __global__ void k_debug_ddiv_rcp(const double* __restrict__ a, const doub
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double y = rcp_divisor_ok(b[i]) ? rcp_refined(b[i]) : 0.0;
-  fast[i] = rcp_divisor_ok(b[i]) ? ddiv_rcp(a[i], b[i], y) : __ddiv_rn(a[i], b[i]);
-  ref[i] = __ddiv_rn(a[i], b[i]);
+  double f = rcp_divisor_ok(b[i]) ? ddiv_rcp(a[i], b[i], y) : __ddiv_rn(a[i], b[i]);
+  const double r = __ddiv_rn(a[i], b[i]);
+  // the branch-free form (ddiv_rcp_nb): wherever it declares its fast path valid the quotient must be the same bits;
+  // a mismatch is reported as a quotient that cannot equal the reference (bits flipped)
+  if (rcp_divisor_ok(b[i])) {
+    bool ok;
+    const double q = ddiv_rcp_nb(a[i], b[i], y, ok);
+    if (ok && __double_as_longlong(q) != __double_as_longlong(r)) f = __longlong_as_double(~__double_as_longlong(r));
+  }
+  fast[i] = f;
+  ref[i] = r;
 }
 
 int mzb_debug_ddiv_rcp(const double* d_a, const double* d_b, int64_t n, double* d_fast, double* d_ref, void* stream) {
