@@ -13,7 +13,7 @@
 #include "mzb_fc.cuh"
 #include "mzb_tree.cuh"
 
-#define MZB_FUSED_DEFAULT_EXP 647    // FFMA2 network, root record in registers, search path in shared memory, barrier per 4 warps, branch-free scores
+#define MZB_FUSED_DEFAULT_EXP 17031  // FFMA2 network, root record in registers, search path in shared memory, barrier per 4 warps, branch-free scores, reward/value heads share one copy of the code
 
 namespace {
 
@@ -111,7 +111,14 @@ __device__ __forceinline__ void minmax_regs(float (&s)[N]) {
   float scale = __fsub_rn(hi, lo);
   if (scale < 1e-5f) scale = __fadd_rn(scale, 1e-5f);
 #pragma unroll
-  for (int i = 0; i < N; ++i) s[i] = __fdiv_rn(__fsub_rn(s[i], lo), scale);
+  for (int i = 0; i < N; ++i) {
+    // the minimum itself gives 0 / scale: a zero numerator fails the division's fast-path check (FCHK) and some lane of
+    // a warp holds the minimum at almost every i, so the ~100-instruction slow path ran 2.5 times per simulation;
+    // divide scale / scale there instead and select the exact +0
+    const float d = __fsub_rn(s[i], lo);
+    const float q = __fdiv_rn(d == 0.0f ? scale : d, scale);
+    s[i] = d == 0.0f ? 0.0f : q;
+  }
 }
 
 template <int SUP>
@@ -222,7 +229,7 @@ struct SearchIO {
 // EXP: experiment / tuning flags (MZB_FUSED_EXP): 1 = packed FFMA2 network, 2 = root record in registers (A <= 4),
 // 4/8/16/32 = timing-only diagnostics (blocked layout, aliased trees, no network, no walk) - results are NOT valid.
 // 4 = the search path's edge statistics in shared memory for the first 12 levels (deeper levels: local memory).
-enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32, X_SYNC2 = 64, X_HALFBAR = 128, X_RCP = 256, X_BF = 512, X_FELU = 1024, X_SCHEDBAR = 2048, X_PF = 4096, X_P1 = 8192 };
+enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32, X_SYNC2 = 64, X_HALFBAR = 128, X_RCP = 256, X_BF = 512, X_FELU = 1024, X_SCHEDBAR = 2048, X_BAR2 = 4096, X_P1 = 8192, X_HEADLOOP = 16384, X_UNPEEL = 32768 };
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm) { return blocks_per_sm >= 3 ? 8 : 12; }
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm, int threads) {
   // 16 bytes per level and thread next to ~18 KB of weights + tables per CTA: 12 levels up to 640 threads per SM
@@ -367,11 +374,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     double vs[A]; float pr[A], rw[A]; int vi[A], ch[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) { vs[a] = rr.vs(a); pr[a] = rr.pr(a); vi[a] = rr.vi(a); rw[a] = rr.rw(a); ch[a] = rr.ch(a); }
-    if constexpr ((EXP & X_PF) != 0) {
-#pragma unroll
-      for (int a = 0; a < A; ++a)
-        if (ch[a] > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec_of(ch[a])));
-    }
     const double pbc0 = PB_LUT ? 0.0 : lut[N];
     const double sqrtN = PB_LUT ? 0.0 : __dsqrt_rn((double)N);
     const double* pbrow = pbt + ((N * (N + 1)) >> 1);
@@ -463,7 +465,21 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     }
     if (active) {
       int next;
-      if constexpr (ROOTREG) {
+      if constexpr (ROOTREG && (EXP & X_UNPEEL) != 0) {
+        // one copy of the level code: the root's record comes from registers, the others from the store
+        Rec<A> rr;
+#pragma unroll
+        for (int i = 0; i < Rec<A>::WORDS; ++i) rr.w[i] = root.w[i];
+        bool at_root = true;
+        for (;;) {
+          next = walk_level(rr, at_root, node, depth, sim);
+          ++depth;
+          if (next < 0) break;
+          node = next;
+          rr.load(rec_of(node));
+          at_root = false;
+        }
+      } else if constexpr (ROOTREG) {
         Rec<A> rr;
 #pragma unroll
         for (int i = 0; i < Rec<A>::WORDS; ++i) rr.w[i] = root.w[i];
@@ -473,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
         rr.load(rec_of(0));
         next = walk_level(rr, true, 0, 0, sim);
       }
-      depth = 1;
+      if constexpr (!(ROOTREG && (EXP & X_UNPEEL) != 0)) depth = 1;
       if (EXP & X_NOWALK) next = -1;
       while (next >= 0) {
         node = next;
@@ -484,8 +500,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
       }
     }
     const int L = depth, fresh = sim + 1;
+    // the parent's hidden state is requested before the phase barrier, so its latency overlaps the wait
+    float st[ENC];
+    if (active) load_floats<ENC>(hid_of(node), st);
     if (PHASE_SYNC) {                         // warps of the block enter the unrolled network code together
-      if constexpr ((EXP & X_SCHEDBAR) != 0) {
+      if constexpr ((EXP & X_BAR2) != 0) {
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory");       // per pair of consecutive warps
+      } else if constexpr ((EXP & X_SCHEDBAR) != 0) {
         // the warps that share a scheduler (warp id mod 4) and hence an L0 instruction cache enter the network together
         asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)((threadIdx.x >> 5) & 3)), "n"(THREADS / 4) : "memory");
       } else if constexpr ((EXP & X_HALFBAR) != 0) {
@@ -501,17 +522,33 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     // ---------------- recurrent inference on the parent's hidden state (models.py:192-195)
     float value, reward, pri[A];
     if constexpr ((EXP & X_NONET) != 0) {
-      float st[ENC];
-      load_floats<ENC>(hid_of(node), st);
       value = st[0] + 0.5f; reward = 1.0f;
 #pragma unroll
       for (int a = 0; a < A; ++a) pri[a] = 1.0f / A;
       store_floats<ENC>(hid_of(fresh), st);
     } else {
-      float st[ENC];
-      load_floats<ENC>(hid_of(node), st);
       float nx[ENC];
       SH::Dyn::template run<F2, FE>(pack + SH::OFF_DYN, st, action, nx);
+      if constexpr ((EXP & X_HEADLOOP) != 0 && SH::Rew::SIZE == SH::Val::SIZE) {
+        // reward head (on the raw next state) and value head (on the normalised one) share one copy of the code
+        reward = 0.0f; value = 0.0f;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          float hl[FULL];
+          SH::Rew::template run<F2, FE>(pack + (h ? SH::OFF_VAL : SH::OFF_REW), nx, -1, hl);
+          const float o = s2s_regs<SH::SUP>(hl);
+          if (h == 0) {
+            reward = o;
+            minmax_regs(nx);
+            store_floats<ENC>(hid_of(fresh), nx);
+            float pl[A];
+            SH::Pol::template run<F2, FE>(pack + SH::OFF_POL, nx, -1, pl);
+            priors_regs<A>(pl, nullptr, pri);
+          } else {
+            value = o;
+          }
+        }
+      } else {
       {
         float rl[FULL];
         SH::Rew::template run<F2, FE>(pack + SH::OFF_REW, nx, -1, rl);
@@ -528,6 +565,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
         float vl[FULL];
         SH::Val::template run<F2, FE>(pack + SH::OFF_VAL, nx, -1, vl);
         value = s2s_regs<SH::SUP>(vl);
+      }
       }
     }
 
@@ -555,6 +593,41 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
 
     // ---------------- backup (self_play.py:407-431), leaf first
     double val = (double)value;
+    if constexpr (BF && ROOTREG && PD > 0) {
+      // Levels L-1 .. 1 are edges of non-root nodes (always in the HBM store), level 0 is the root's edge (always in
+      // registers): peeled, so neither carries the other's branch; field offsets are compile-time.
+      for (int k = L - 1; k >= 1; --k) {
+        int pn, pa, e_vi; double e_vs; float l_rw;
+        if (k < PD) {
+          const uint32_t ev = sp_ev[k * THREADS + threadIdx.x];
+          pn = (int)(ev >> 24); pa = (int)((ev >> 16) & 0xFFu); e_vi = (int)(ev & 0xFFFFu);
+          e_vs = sp_vs[k * THREADS + threadIdx.x]; l_rw = sp_rw[k * THREADS + threadIdx.x];
+        } else {
+          const uint32_t pe = lp_edge[k];
+          pn = (int)(pe >> 16); pa = (int)(pe & 0xFFFFu);
+          e_vs = lp_vs[k]; e_vi = lp_vi[k]; l_rw = lp_rw[k];
+        }
+        const double e_rw = (k == L - 1) ? (double)reward : (double)l_rw;
+        backup_step_rcp(e_vs, e_vi, e_rw, val, t.discount, two, ((L - (k + 1)) & 1) == 0, vmin, vmax, rcpn2);
+        uint8_t* er = rec_of(pn);
+        reinterpret_cast<double*>(er)[pa] = e_vs;
+        reinterpret_cast<int*>(er + 12 * A)[pa] = e_vi;
+      }
+      {
+        const uint32_t ev = sp_ev[threadIdx.x];
+        const int pa = (int)((ev >> 16) & 0xFFu);
+        int e_vi = (int)(ev & 0xFFFFu);
+        double e_vs = sp_vs[threadIdx.x];
+        const double e_rw = (L == 1) ? (double)reward : (double)sp_rw[threadIdx.x];
+        backup_step_rcp(e_vs, e_vi, e_rw, val, t.discount, two, ((L - 1) & 1) == 0, vmin, vmax, rcpn2);
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+          if (a == pa) {
+            root.w[2 * a] = (uint32_t)__double2loint(e_vs); root.w[2 * a + 1] = (uint32_t)__double2hiint(e_vs);
+            root.w[3 * A + a] = (uint32_t)e_vi;
+          }
+      }
+    } else
     for (int k = L - 1; k >= 0; --k) {
       int pn, pa, e_vi; double e_vs; float l_rw = 0.0f;
       if (PD > 0 && k < PD) {
@@ -674,6 +747,10 @@ int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t 
       case 263: return launch_variant<SH, true, 263>(t, m, io, s);
       case 135: return launch_variant<SH, true, 135>(t, m, io, s);
       case 647: return launch_variant<SH, true, 647>(t, m, io, s);                  // + branch-free scores: 4.20 -> 3.64 ms
+      case 17031: return launch_variant<SH, true, 17031>(t, m, io, s);              // reward and value heads as one two-trip loop: 3.57 -> 3.46 ms
+      // (the loop body is ~47 KB of SASS against a 32 KB L1.5 instruction cache: code size shows).  On top of it: root
+      // level not peeled 3.48; ex2-based ELU 3.40 (not adopted: changes the network's rounding); barrier per pair of
+      // consecutive warps 3.68 (on 647); parent's hidden state requested before the barrier: no change
       // measured on top of 647 and dropped (303,104 games, 3.64 ms): ex2-based ELU 3.61 (-380 instructions per simulation
       // buy 0.7 %: not issue-bound); barrier per scheduler (warps w, w+4) 3.72; one 512-thread CTA per SM 3.76;
       // prefetch.global.L1 of both children's records 3.69; compile-time single player 3.67
