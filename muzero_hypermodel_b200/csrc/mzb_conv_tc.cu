@@ -32,7 +32,7 @@ constexpr int kEpiWarpsWide = 8;                   // two epilogue warpgroups: l
 constexpr int kEpiWarpsNarrow = 16;                // four for narrow layers, whose pace the per-tile epilogue latency sets
 
 struct TcArgs {
-  int B, H, W, Cin, Cout, R_img, mt, n_chunks, relu, ncols, tail_rows, b_resident, zero_pads;
+  int B, H, W, Cin, Cout, R_img, mt, n_chunks, relu, ncols, tail_rows, b_resident, zero_pads, plane_classes;
   long long rows_valid;                 // B * R_img
   long long rows_cover;                 // rows the super-tiles cover: rows_valid (+ the trailing halo when zero_pads)
   const float* scale; const float* shift; const float* plane; const float* plane_table;
@@ -162,7 +162,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kStages);
   float* s_scale = reinterpret_cast<float*>(bars + 10 + 2 * kStages);
   float* s_shift = s_scale + N;
-  float* s_proj = s_shift + N;             // [proj_r][N]
+  float* s_proj = s_shift + N;             // [PR][N]
+  // The action plane's term acc += plane[b] * table[position][channel] (DynamicsNetwork's first convolution) from shared
+  // memory.  Read from global memory, a warp's 32 rows (32 positions) made every float4 of the table an uncoalesced
+  // request - 16 per row, each touching up to 32 lines: the layer took 110 us against 67 us for a plain one.  The table
+  // only depends on which taps fall outside the board, i.e. on the border class of the position (top / inner / bottom
+  // line x left / inner / right column): nine rows when the board has an interior, else one row per position.
+  float* s_ptab = s_proj + PR * N;
   // Work split: every CTA owns one CONTIGUOUS range of 128-row tiles (sizes differ by at most one tile) and walks it in
   // super-tiles of up to MT tiles; only the range's last super-tile may be short.  A strided split in whole super-tiles
   // would leave a tail wave in which most SMs idle (connect4: 12.1 waves of work took 13).
@@ -189,6 +195,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   for (int i = threadIdx.x; i < N; i += kThreads) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
   if (PR > 0) for (int i = threadIdx.x; i < PR * N; i += kThreads) s_proj[i] = i < a.proj_r * N ? a.proj_w[i] : 0.0f;
+  if (a.plane) {                           // weights, not activations: safe before griddepcontrol.wait
+    const int rows = a.plane_classes ? 9 : a.H * a.W;
+    for (int i = threadIdx.x; i < rows * N; i += kThreads) {
+      const int r = i / N, c = i - r * N;
+      int pos = r;
+      if (a.plane_classes) {
+        const int cy = r / 3, cx = r - cy * 3;
+        pos = (cy == 0 ? 0 : (cy == 2 ? a.H - 1 : 1)) * a.W + (cx == 0 ? 0 : (cx == 2 ? a.W - 1 : 1));
+      }
+      s_ptab[i] = a.plane_table[(size_t)pos * N + c];
+    }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -328,9 +346,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int q = warp & 3, group = (warp - 2) >> 2;
     const int ncg = (N + 63) / 64;
     constexpr int NG = kEpiWarps / 4;
-    const uint32_t s_scale_u32 = smem_u32(s_scale), s_shift_u32 = smem_u32(s_shift), s_proj_u32 = smem_u32(s_proj);
+    const uint32_t s_scale_u32 = smem_u32(s_scale), s_shift_u32 = smem_u32(s_shift), s_proj_u32 = smem_u32(s_proj), s_ptab_u32 = smem_u32(s_ptab);
     const uint32_t R_img = (uint32_t)a.R_img, Wp = (uint32_t)geo_pitch(a.W);
-    struct Item { long long row_off; int b, pos, t, g0, gw; uint32_t m; bool valid; };
+    struct Item { long long row_off; int b, pos, cls, t, g0, gw; uint32_t m; bool valid; };
     auto get_item = [&](uint32_t m0, int item, Item& I) {
       I.t = item / ncg;
       I.g0 = (item - I.t * ncg) * 64;
@@ -342,13 +360,29 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       I.valid = (long long)I.m < a.rows_valid && geo_is_pixel((int)yy, (int)xx, a.W);
       I.row_off = ((long long)I.m + halo) * (long long)N;
       I.pos = (int)((yy - 1) * (uint32_t)a.W + xx);
+      I.cls = a.plane_classes ? (int)((yy == 1u ? 0u : (yy == (uint32_t)a.H ? 2u : 1u)) * 3u + (xx == 0u ? 0u : (xx == (uint32_t)a.W - 1u ? 2u : 1u)))
+                              : I.pos;
     };
+    // 256-bit global accesses for the wide layers (measured: connect4 64 -> 64 channels 79.6 -> 71.6 us per layer in step,
+    // gomoku 162 -> 154); the 16-channel stem layers of breakout were 10 % slower with them and keep the 128-bit form
+    const bool wide_ls = N >= 64;
     auto load_res = [&](const Item& I, int hh, uint4 (&r)[4]) {
       if (I.valid && a.residual) {
         const uint4* rp = reinterpret_cast<const uint4*>(a.residual + I.row_off + I.g0 + hh * 32);
         const int cw = I.gw - hh * 32;
+        // 32-byte requests (LDG.256): half the load instructions of the 16-byte form; a row-per-lane access touches 32
+        // lines per instruction whatever its width, and every such wavefront is taken from the MMA's operand fetch
+        if (!wide_ls) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) if (i * 8 < cw) r[i] = __ldg(rp + i);
+          for (int i = 0; i < 4; ++i) if (i * 8 < cw) r[i] = __ldg(rp + i);
+          return;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i += 2)
+          if (i * 8 < cw)
+            asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[i].x), "=r"(r[i].y), "=r"(r[i].z), "=r"(r[i].w), "=r"(r[i + 1].x), "=r"(r[i + 1].y),
+                           "=r"(r[i + 1].z), "=r"(r[i + 1].w) : "l"(rp + i));
       }
     };
     asm volatile("griddepcontrol.wait;" ::: "memory");        // residual / plane reads below: earlier kernels' outputs
@@ -373,7 +407,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       while (have) {
         const float pl = (cur.valid && a.plane) ? a.plane[cur.b] : 0.0f;
-        const float* ptab = (cur.valid && a.plane) ? a.plane_table + (size_t)cur.pos * N : nullptr;
+        const bool ptab = cur.valid && a.plane;
+        const uint32_t ptab_u32 = s_ptab_u32 + (uint32_t)(cur.cls * N) * 4;
         float pacc[PR > 0 ? PR : 1];
 #pragma unroll
         for (int r = 0; r < PR; ++r) pacc[r] = 0.0f;
@@ -414,7 +449,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w)
                              : "r"(s_shift_u32 + (uint32_t)(c0 + c * 16 + i4 * 4) * 4));
                 float4 pt = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (ptab) pt = __ldg(reinterpret_cast<const float4*>(ptab + c0 + c * 16 + i4 * 4));
+                if (ptab)
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pt.x), "=f"(pt.y), "=f"(pt.z), "=f"(pt.w)
+                               : "r"(ptab_u32 + (uint32_t)(c0 + c * 16 + i4 * 4) * 4));
                 const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
                 const float ptv[4] = {pt.x, pt.y, pt.z, pt.w};
 #pragma unroll
@@ -443,9 +480,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 o[i] = *reinterpret_cast<const uint32_t*>(&pk);
                 if (PR > 0) { f[2 * i] = __uint_as_float(o[i] << 16); f[2 * i + 1] = __uint_as_float(o[i] & 0xFFFF0000u); }
               }
-              uint4* op = reinterpret_cast<uint4*>(a.y + cur.row_off + c0 + c * 16);
-              op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-              op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+              if (wide_ls) {
+                // one 32-byte store (STG.256) per 16 columns: a complete sector, half the store instructions
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(a.y + cur.row_off + c0 + c * 16),
+                             "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+              } else {
+                uint4* op = reinterpret_cast<uint4*>(a.y + cur.row_off + c0 + c * 16);
+                op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+              }
               if (PR > 0) {
 #pragma unroll
                 for (int r = 0; r < PR; ++r) {
@@ -541,14 +584,15 @@ int ring_depth(int kc, int n_chunks) { return (kc == 64 && n_chunks == 2) ? 3 : 
 
 // Largest MT whose double-buffered activation stages, weights (resident if they fit, else a ring) and
 // 2 x MT x C_out TMEM columns fit in one SM.
-bool make_plan(int cin, int cout, int W, TcPlan* out) {
+bool make_plan(int cin, int cout, int W, int plane_rows, TcPlan* out) {
   TcPlan p{};
   p.kc = pick_kc(cin);
   p.n_chunks = cin / p.kc;
   p.tail_rows = 2 * geo_halo(W) <= 32 ? 32 : 128;
   const size_t rowb = (size_t)p.kc * 2, limit = 225 * 1024;
   const size_t b_all = (size_t)9 * p.n_chunks * cout * rowb, b_ring = (size_t)ring_depth(p.kc, p.n_chunks) * cout * rowb;
-  const size_t misc = 1024 + 512 + 8 * (size_t)cout + 32 * (size_t)cout;      // barriers, scale/shift, <= 8 projection rows
+  // barriers, scale/shift, <= 8 projection rows, the action plane's table (9 border classes or H*W positions)
+  const size_t misc = 1024 + 512 + 8 * (size_t)cout + 32 * (size_t)cout + 4 * (size_t)cout * plane_rows;
   // narrow layers (C_out <= 32) are bound by per-super-tile latencies, not by the MMAs: give them more rows per step
   static int mt_narrow = -1;
   if (mt_narrow < 0) { const char* e = getenv("MZB_TC_MT_NARROW"); mt_narrow = e ? atoi(e) : 8; }
@@ -575,14 +619,14 @@ bool mzb_conv_tc_enabled() { return g_tc_enabled && encode_fn() != nullptr; }
 
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
   return g_tc_enabled && cp.stride == 1 && cp.cin == cin_stride && cp.cin % 16 == 0 && cp.cout % 16 == 0 && cp.cout >= 16 &&
-         cp.cout <= 256 && W <= 61 && cp.w_bf16 != nullptr && encode_fn() != nullptr && make_plan(cp.cin, cp.cout, W, nullptr);
+         cp.cout <= 256 && W <= 61 && cp.w_bf16 != nullptr && encode_fn() != nullptr && make_plan(cp.cin, cp.cout, W, cp.extra_plane ? ((H >= 3 && W >= 3) ? 9 : H * W) : 0, nullptr);
 }
 
 int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
                        const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t stream, int zero_pads,
                        const TcProj* proj) {
   TcPlan p;
-  MZB_CHECK_ARG(make_plan(cp.cin, cp.cout, W, &p), "tensor-core convolution: no tile configuration fits");
+  MZB_CHECK_ARG(make_plan(cp.cin, cp.cout, W, cp.extra_plane ? ((H >= 3 && W >= 3) ? 9 : H * W) : 0, &p), "tensor-core convolution: no tile configuration fits");
   const Geo g{H, W, cp.cin, 1};
   const long long rows_total = geo_rows_total(g, B);
   CUtensorMap tmA, tmAtail, tmB;
@@ -603,6 +647,7 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   MZB_CHECK_ARG(a.rows_cover + 4 * 128 < (1ll << 31), "tensor-core convolution: %lld rows exceed the 32-bit row index", a.rows_cover);
   a.scale = cp.scale; a.shift = cp.shift; a.plane = cp.extra_plane ? plane : nullptr; a.plane_table = cp.plane_table;
   a.residual = residual; a.y = y;
+  a.plane_classes = (H >= 3 && W >= 3) ? 1 : 0;
   a.debug = g_tc_debug;
   if (proj && proj->r > 0) {
     MZB_CHECK_ARG(proj->r <= 8 && proj->w && proj->out, "fused head projection: at most 8 rows");

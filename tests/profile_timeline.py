@@ -38,3 +38,10 @@ print(f"{wl} G={G} sims={sims}: {len(ev)} kernels, span {span/1e3:.2f} ms, busy 
 print(f"{'kernel':50s} {'n':>5s} {'avg us':>8s} {'total ms':>9s} {'gap before, avg us':>18s}")
 for k, (n, t, g) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:50s} {n:5d} {t/n:8.1f} {t/1e3:9.2f} {g/n:18.1f}")
+if len(sys.argv) > 4 and sys.argv[4] == "seq":
+    # launch-by-launch durations of one simulation in the middle of the search (between two k_select launches)
+    sel = [i for i, e in enumerate(ev) if "k_select" in e.name]
+    if len(sel) > 11:
+        print("one simulation, launch by launch (us):")
+        for e in ev[sel[10]:sel[11]]:
+            print(f"  {e.name.replace('void ', '').replace('(anonymous namespace)::', '')[:60]:60s} {e.time_range.end - e.time_range.start:8.1f}")
