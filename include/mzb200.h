@@ -447,6 +447,36 @@ int mzb_replay_game_priorities_sync(mzb_replay* r, int64_t game_id, float* h_pri
                                     int32_t* h_len, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training step of the fully-connected network as ONE kernel: unrolled forward, categorical
+ * cross-entropies, backward through time, batch reduction into the flat gradient bucket.  Replaces the autograd graph
+ * of Trainer.update_weights (trainer.py:124-255; loss_function :267-284) for MuZeroFullyConnectedNetwork
+ * (models.py:80-195): gradient hooks (0.5 into the dynamics function, 1 / gradient_scale on the losses of the unrolled
+ * steps), value loss weight, PER importance weights, priorities |support_to_scalar(value) - target| ** PER_alpha.
+ * The layer table indexes the trainer's flat parameter bucket (model.parameters() order: weight [out][in], bias [out]);
+ * networks in the order representation, dynamics, reward, policy, value; layer l of a network with n_layers layers is
+ * followed by ELU unless it is the last (models.py:626-638).  Deterministic: no atomics on the gradients. */
+typedef struct {
+  int32_t obs_dim, encoding_size, n_actions, support_size;
+  int32_t n_layers[5];
+  int32_t in[5][4], out[5][4];
+  int64_t w_off[5][4], b_off[5][4];
+} mzb_fc_train_desc;
+/* Bytes of device scratch mzb_fc_train_grad needs (zero-initialised ONCE by the caller), or -1 for a bad table. */
+int64_t mzb_fc_train_workspace_bytes(const mzb_fc_train_desc* desc, int32_t batch, int32_t unroll_plus_1);
+/* 1 when weights + per-sample activations of the unrolled steps fit the kernel's shared memory, else 0. */
+int mzb_fc_train_fits(const mzb_fc_train_desc* desc, int32_t batch, int32_t unroll_plus_1);
+/* d_obs [B][obs_dim] f32, d_action [B][K+1] i64 (column 0 unused), target supports [B][K+1][2S+1], target policy
+ * [B][K+1][A], target value scalars [B][K+1], PER weights [B] or NULL, gradient scale [B][K+1].
+ * Outputs: d_grad [n_params] (overwritten), d_losses [3][B] = per-sample value / reward / policy loss sums,
+ * d_priorities [B][K+1], d_loss [1] = the batch objective. */
+int mzb_fc_train_grad(const mzb_fc_train_desc* desc, const float* d_params, int64_t n_params, int32_t batch, int32_t unroll_plus_1,
+                      const float* d_obs, const int64_t* d_action, const float* d_target_value_support,
+                      const float* d_target_reward_support, const float* d_target_policy, const float* d_target_value_scalar,
+                      const float* d_weight, const float* d_gradient_scale, double value_loss_weight, double per_alpha,
+                      float* d_grad, float* d_losses, float* d_priorities, float* d_loss, void* d_workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimiser step on one flat float32 bucket: the trainer keeps all parameters and all
  * gradients as views into two flat buffers, all-reduces the gradient bucket (NCCL) and applies ONE of these launches.
  * Replaces torch.optim.Adam / SGD as configured in trainer.py:35-52 (L2 weight decay added to the gradient; Adam

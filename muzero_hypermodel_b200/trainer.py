@@ -28,6 +28,18 @@ _vp, _i64, _f64 = C.c_void_p, C.c_int64, C.c_double
 _lib.bind("mzb_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _f64, _vp])
 _lib.bind("mzb_sgd_step", C.c_int, [_vp, _vp, _vp, _i64, _f64, _f64, _f64, _i64, _f64, _vp])
 
+
+
+class FcTrainDesc(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("encoding_size", C.c_int32), ("n_actions", C.c_int32), ("support_size", C.c_int32),
+                ("n_layers", C.c_int32 * 5), ("in_", (C.c_int32 * 4) * 5), ("out", (C.c_int32 * 4) * 5),
+                ("w_off", (C.c_int64 * 4) * 5), ("b_off", (C.c_int64 * 4) * 5)]
+
+
+_lib.bind("mzb_fc_train_workspace_bytes", C.c_int64, [C.POINTER(FcTrainDesc), C.c_int32, C.c_int32])
+_lib.bind("mzb_fc_train_fits", C.c_int, [C.POINTER(FcTrainDesc), C.c_int32, C.c_int32])
+_lib.bind("mzb_fc_train_grad", C.c_int, [C.POINTER(FcTrainDesc), _vp, _i64, C.c_int32, C.c_int32] + [_vp] * 8 + [_f64, _f64] + [_vp] * 5 + [_i64, _vp])
+
 F = torch.nn.functional
 
 
@@ -292,7 +304,74 @@ class Trainer:
         priorities = priorities.clone()
         return priorities, loss.item(), value_loss.mean().item(), reward_loss.mean().item(), policy_loss.mean().item()
 
+    # -- one-kernel training step of the fully-connected family (csrc/mzb_fc_train.cu)
+    def _fc_desc(self):
+        """Layer table of the FC network over the flat parameter bucket, or None (residual family / frozen parameters)."""
+        if getattr(self, "_fc_desc_cache", 0) != 0:
+            return self._fc_desc_cache
+        self._fc_desc_cache = None
+        m = self.model
+        if self.config.network != "fullyconnected" or len(self.params) != sum(1 for _ in m.parameters()):
+            return None
+        offset, off = {}, 0
+        for p in self.params:
+            offset[id(p)] = off
+            off += p.numel()
+        d = FcTrainDesc()
+        d.obs_dim, d.encoding_size, d.n_actions, d.support_size = m.obs_dim, m.encoding_size, m.action_space_size, m.support_size
+        nets = (m.representation_network, m.dynamics_encoded_state_network, m.dynamics_reward_network,
+                m.prediction_policy_network, m.prediction_value_network)
+        for k, net in enumerate(nets):
+            layers = [x for x in net.module if isinstance(x, torch.nn.Linear)]
+            if not 1 <= len(layers) <= 4:
+                return None
+            d.n_layers[k] = len(layers)
+            for l, lin in enumerate(layers):
+                d.in_[k][l], d.out[k][l] = lin.in_features, lin.out_features
+                d.w_off[k][l], d.b_off[k][l] = offset[id(lin.weight)], offset[id(lin.bias)]
+        self._fc_desc_cache = d
+        return d
+
+    def _fc_kernel_step(self, tensors):
+        """Forward + backward of one batch in ONE launch; returns None when the shape is outside the kernel's reach."""
+        import os
+        if os.environ.get("MZB_TRAIN_KERNEL", "1") == "0":
+            return None
+        d = self._fc_desc()
+        obs, action, tv, tr_, tp, weight, gscale = tensors
+        if d is None:
+            return None
+        B, K1 = int(action.shape[0]), int(action.shape[1])
+        if not _lib.lib.mzb_fc_train_fits(C.byref(d), B, K1):
+            return None
+        cfg, S = self.config, self.config.support_size
+        key = (B, K1)
+        ws = getattr(self, "_fc_ws", {}).get(key)
+        if ws is None:
+            nbytes = int(_lib.lib.mzb_fc_train_workspace_bytes(C.byref(d), B, K1))
+            ws = (torch.zeros(nbytes, dtype=torch.uint8, device=self.device), torch.empty(3, B, device=self.device),
+                  torch.empty(B, K1, device=self.device), torch.empty(1, device=self.device))
+            self._fc_ws = dict(getattr(self, "_fc_ws", {}))
+            self._fc_ws[key] = ws
+        work, losses, priorities, loss = ws
+        tv_sup = models.scalar_to_support(tv, S).contiguous()
+        tr_sup = models.scalar_to_support(tr_, S).contiguous()
+        obs2 = obs.reshape(B, -1).contiguous()
+        with torch.cuda.device(self.device):
+            check(_lib.lib.mzb_fc_train_grad(C.byref(d), ptr(self.flat_param), self.flat_param.numel(), B, K1, ptr(obs2),
+                                             ptr(action.contiguous()), ptr(tv_sup), ptr(tr_sup), ptr(tp.contiguous()), ptr(tv.contiguous()),
+                                             ptr(weight.contiguous()) if weight is not None else None, ptr(gscale.contiguous()),
+                                             float(cfg.value_loss_weight), float(cfg.PER_alpha), ptr(self.flat_grad), ptr(losses),
+                                             ptr(priorities), ptr(loss), ptr(work), work.numel(), _lib.current_stream()))
+        return loss[0], losses[0], losses[1], losses[2], priorities
+
     def _forward_backward(self, tensors):
+        out = self._fc_kernel_step(tensors)
+        if out is not None:
+            return out
+        return self._forward_backward_autograd(tensors)
+
+    def _forward_backward_autograd(self, tensors):
         """Gradients of one batch into the flat bucket.  The unrolled graph is hundreds of small kernels (launch-bound:
         13 ms per cartpole step eagerly), so from the second batch of a given shape on it is replayed from a CUDA graph
         captured over static input buffers; the optimiser launch stays outside (its step count and learning rate

@@ -204,3 +204,47 @@ def test_update_weights_returns_fresh_priorities():
         outs.append(tr.update_weights(batch)[0])
     assert outs[1].data_ptr() != outs[2].data_ptr()
     assert not torch.equal(outs[1], outs[2])          # weights moved between the steps; an alias would compare equal
+
+
+@pytest.mark.parametrize("game,B", [("cartpole", 128), ("cartpole", 7), ("tictactoe", 33)])
+def test_one_kernel_fc_training_step_equals_autograd(game, B):
+    """The one-kernel forward / backward of the fully-connected family (csrc/mzb_fc_train.cu) against PyTorch autograd
+    over the same parameters (the path pinned to the reference by tests/golden/trainer.npz and tests/test_trainer_graph.py):
+    every gradient, the per-sample losses, the batch objective and the priorities; twice, to show it is deterministic."""
+    from muzero_hypermodel_b200.trainer import Trainer
+    cfg = importlib.import_module(f"muzero_hypermodel_b200.games.{game}").MuZeroConfig()
+    cfg.network = "fullyconnected"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    tr = Trainer({"weights": None, "training_step": 0, "optimizer_state": None}, cfg, device=DEV)
+    rs = np.random.RandomState(5)
+    K1, A = cfg.num_unroll_steps + 1, len(cfg.action_space)
+    obs = torch.tensor(rs.uniform(-1, 1, (B,) + tuple(cfg.observation_shape)).astype(np.float32), device=DEV)
+    action = torch.tensor(rs.randint(0, A, (B, K1)), device=DEV)
+    tv = torch.tensor(rs.uniform(-3, 30, (B, K1)).astype(np.float32), device=DEV)
+    trw = torch.tensor(rs.uniform(-1, 1, (B, K1)).astype(np.float32), device=DEV)
+    tp = torch.tensor(rs.dirichlet([0.5] * A, (B, K1)).astype(np.float32), device=DEV)
+    tp[:, -1] = 0.0                                        # an absorbing tail with an all-zero policy target
+    w = torch.tensor(rs.uniform(0.2, 1.0, B).astype(np.float32), device=DEV)
+    gs = torch.tensor(np.repeat(rs.randint(1, K1 + 1, (B, 1)), K1, 1).astype(np.float32), device=DEV)
+    tensors = (obs, action, tv, trw, tp, w if cfg.PER else None, gs)
+    assert tr._fc_desc() is not None
+    out = tr._fc_kernel_step(tensors)
+    assert out is not None, "the one-kernel step must take this shape"
+    g1 = tr.flat_grad.clone()
+    k = [x.clone() for x in out]
+    out2 = tr._fc_kernel_step(tensors)
+    assert torch.equal(tr.flat_grad, g1) and all(torch.equal(a, b) for a, b in zip(out2, k)), "not deterministic"
+    tr.use_cuda_graph = False
+    ref = tr._forward_backward_autograd(tensors)
+    g0 = tr.flat_grad.clone()
+    scale = float(g0.abs().max())
+    assert scale > 0
+    err = float((g1 - g0).abs().max())
+    assert err <= 2e-5 * scale + 1e-7, (err, scale)
+    np.testing.assert_allclose(float(k[0]), float(ref[0]), rtol=2e-5)
+    for a, b in zip(k[1:4], ref[1:4]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.detach().cpu().numpy(), rtol=2e-5, atol=1e-5)
+    # priorities through the ill-conditioned decode (DESIGN.md §7): compare the value errors, not their roots
+    al = cfg.PER_alpha
+    d = np.abs(k[4].cpu().numpy().astype(np.float64) ** (1 / al) - ref[4].detach().cpu().numpy().astype(np.float64) ** (1 / al))
+    assert d.max() <= 5e-3, float(d.max())
