@@ -46,8 +46,11 @@ WORKLOADS = {
 }
 NESTED = ("tictactoe", "connect4", "gomoku", "breakout")
 # committed `ncu --set full` captures of the dominant kernel at the bench shape (profiles/): DRAM bytes per launch
-NCU_CAPTURE = {"cartpole": "r02_ncu_k_search_fc_cartpole.csv", "connect4": "r02_ncu_k_conv_tc_connect4.csv",
-               "gomoku": "r02_ncu_k_conv_tc_gomoku.csv", "breakout": "r02_ncu_breakout.csv"}
+NCU_CAPTURE = {"cartpole": "r03_ncu_k_search_fc_cartpole.csv", "connect4": "r03_ncu_k_conv_tc_connect4.csv",
+               "gomoku": "r03_ncu_k_conv_tc_gomoku.csv", "breakout": "r02_ncu_breakout.csv"}
+# column of the capture that holds the probed layer (a plain tower layer, no residual input): the connect4 capture is of
+# four consecutive launches (residual, plain, residual, plain)
+NCU_COLUMN = {"connect4": 1}
 
 
 def ncu_traffic(workload):
@@ -60,8 +63,9 @@ def ncu_traffic(workload):
     try:
         for ln in open(os.path.join(ROOT, "profiles", name)):
             c = ln.strip().split(",")
-            if len(c) >= 3 and c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and c[1] in unit:
-                total += float(c[2]) * unit[c[1]]
+            col = 2 + NCU_COLUMN.get(workload, 0)
+            if len(c) > col and c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and c[1] in unit:
+                total += float(c[col]) * unit[c[1]]
                 seen += 1
     except (OSError, ValueError):
         return None

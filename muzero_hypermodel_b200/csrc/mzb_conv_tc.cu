@@ -204,7 +204,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int cy = r / 3, cx = r - cy * 3;
         pos = (cy == 0 ? 0 : (cy == 2 ? a.H - 1 : 1)) * a.W + (cx == 0 ? 0 : (cx == 2 ? a.W - 1 : 1));
       }
-      s_ptab[i] = a.plane_table[(size_t)pos * N + c];
+      s_ptab[i] = a.plane_table[(size_t)pos * N + c] * a.scale[c];        // the scale is folded into the weights, so into this term too
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -443,23 +443,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               float f[16];
 #pragma unroll
               for (int i4 = 0; i4 < 4; ++i4) {
-                float4 sc, sh;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w)
-                             : "r"(s_scale_u32 + (uint32_t)(c0 + c * 16 + i4 * 4) * 4));
+                float4 sh;                                    // the batch-norm scale is folded into the bf16 weights (w_tc)
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w)
                              : "r"(s_shift_u32 + (uint32_t)(c0 + c * 16 + i4 * 4) * 4));
                 float4 pt = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (ptab)
                   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pt.x), "=f"(pt.y), "=f"(pt.z), "=f"(pt.w)
                                : "r"(ptab_u32 + (uint32_t)(c0 + c * 16 + i4 * 4) * 4));
-                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                const float shv[4] = {sh.x, sh.y, sh.z, sh.w};
                 const float ptv[4] = {pt.x, pt.y, pt.z, pt.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const int i = i4 * 4 + j;
                   float acc = __uint_as_float(v[c * 16 + i]);
                   if (ptab) acc = fmaf(pl, ptv[j], acc);
-                  f[i] = fmaf(acc, scv[j], shv[j]);
+                  f[i] = acc + shv[j];
                 }
               }
               if (a.residual) {
@@ -619,7 +617,7 @@ bool mzb_conv_tc_enabled() { return g_tc_enabled && encode_fn() != nullptr; }
 
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
   return g_tc_enabled && cp.stride == 1 && cp.cin == cin_stride && cp.cin % 16 == 0 && cp.cout % 16 == 0 && cp.cout >= 16 &&
-         cp.cout <= 256 && W <= 61 && cp.w_bf16 != nullptr && encode_fn() != nullptr && make_plan(cp.cin, cp.cout, W, cp.extra_plane ? ((H >= 3 && W >= 3) ? 9 : H * W) : 0, nullptr);
+         cp.cout <= 256 && W <= 61 && cp.w_tc != nullptr && encode_fn() != nullptr && make_plan(cp.cin, cp.cout, W, cp.extra_plane ? ((H >= 3 && W >= 3) ? 9 : H * W) : 0, nullptr);
 }
 
 int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfloat16* x, const float* plane,
@@ -633,7 +631,7 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   if (!make_map_2d(&tmA, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)p.kc, 128, p.kc) ||
       !make_map_2d(&tmAtail, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)p.kc,
                    (uint32_t)p.tail_rows, p.kc) ||
-      !make_map_2d(&tmB, cp.w_bf16, (uint64_t)9 * cp.cin, (uint64_t)cp.cout, (uint64_t)9 * cp.cin * 2, (uint32_t)p.kc,
+      !make_map_2d(&tmB, cp.w_tc, (uint64_t)9 * cp.cin, (uint64_t)cp.cout, (uint64_t)9 * cp.cin * 2, (uint32_t)p.kc,
                    (uint32_t)cp.cout, p.kc)) {
     mzb_set_error("cuTensorMapEncodeTiled failed (C_in=%d C_out=%d rows=%lld)", cp.cin, cp.cout, rows_total);
     return MZB_ECUDA;

@@ -736,8 +736,9 @@ static bool init_conv(mzb_resnet_model* m, ConvParams& c, int cin, int cout, int
   c.scale = (float*)dev_alloc(m, sizeof(float) * cout);
   c.shift = (float*)dev_alloc(m, sizeof(float) * cout);
   c.w_bf16 = (__nv_bfloat16*)dev_alloc(m, sizeof(__nv_bfloat16) * 9 * (size_t)cin * cout);
+  c.w_tc = (__nv_bfloat16*)dev_alloc(m, sizeof(__nv_bfloat16) * 9 * (size_t)cin * cout);
   c.plane_table = extra ? (float*)dev_alloc(m, sizeof(float) * (size_t)hw * cout) : nullptr;
-  return c.w && c.scale && c.shift && c.w_bf16 && (!extra || c.plane_table);
+  return c.w && c.scale && c.shift && c.w_bf16 && c.w_tc && (!extra || c.plane_table);
 }
 
 static bool init_head(mzb_resnet_model* m, HeadParams& h, int cin, int r, int hw, const int32_t* hidden, int n_hidden, int out) {
@@ -864,16 +865,19 @@ bool pack_conv(ConvParams& c, const float* w, int src_cin, int src_cout, const s
   std::vector<float> scale(c.cout, 0.0f), shift(c.cout, 0.0f);
   for (int o = 0; o < src_cout; ++o) { scale[o] = scale_src[o]; shift[o] = shift_src[o]; }
   std::vector<float> wp((size_t)9 * cw * c.cout, 0.0f);
-  std::vector<__nv_bfloat16> wb((size_t)9 * c.cin * c.cout, __float2bfloat16(0.0f));
+  std::vector<__nv_bfloat16> wb((size_t)9 * c.cin * c.cout, __float2bfloat16(0.0f)), wt(wb);
   for (int o = 0; o < src_cout; ++o)
     for (int ci = 0; ci < src_cw; ++ci)
       for (int tap = 0; tap < 9; ++tap) {
         const float v = w[((size_t)o * src_cw + ci) * 9 + tap];
         const int cd = ci < src_cin ? ci : c.cin;                  // the extra plane stays the last input channel
         wp[((size_t)tap * cw + cd) * c.cout + o] = v;
-        if (ci < src_cin) wb[((size_t)o * 9 + tap) * c.cin + ci] = __float2bfloat16(v);
+        if (ci < src_cin) {
+          wb[((size_t)o * 9 + tap) * c.cin + ci] = __float2bfloat16(v);
+          wt[((size_t)o * 9 + tap) * c.cin + ci] = __float2bfloat16(v * scale[o]);
+        }
       }
-  bool ok = upload(c.w, wp.data(), wp.size() * 4) && upload(c.w_bf16, wb.data(), wb.size() * 2) &&
+  bool ok = upload(c.w, wp.data(), wp.size() * 4) && upload(c.w_bf16, wb.data(), wb.size() * 2) && upload(c.w_tc, wt.data(), wt.size() * 2) &&
             upload(c.scale, scale.data(), scale.size() * 4) && upload(c.shift, shift.data(), shift.size() * 4);
   if (c.extra_plane) {
     std::vector<float> tab((size_t)Hl * Wl * c.cout, 0.0f);
@@ -898,7 +902,7 @@ bool pack_conv_pair(ConvParams& c, const float* w, int src, const std::vector<fl
   for (int po = 0; po < 2; ++po)
     for (int o = 0; o < src; ++o) { scale[po * src + o] = scale_src[o]; shift[po * src + o] = shift_src[o]; }
   std::vector<float> wp((size_t)9 * C2 * C2, 0.0f);
-  std::vector<__nv_bfloat16> wb((size_t)9 * C2 * C2, __float2bfloat16(0.0f));
+  std::vector<__nv_bfloat16> wb((size_t)9 * C2 * C2, __float2bfloat16(0.0f)), wt(wb);
   for (int po = 0; po < 2; ++po)
     for (int pi = 0; pi < 2; ++pi)
       for (int kxp = 0; kxp < 3; ++kxp) {
@@ -911,9 +915,10 @@ bool pack_conv_pair(ConvParams& c, const float* w, int src, const std::vector<fl
               const int tap = ky * 3 + kxp, oc = po * src + o, ic = pi * src + ci;
               wp[((size_t)tap * C2 + ic) * C2 + oc] = v;
               wb[((size_t)oc * 9 + tap) * C2 + ic] = __float2bfloat16(v);
+              wt[((size_t)oc * 9 + tap) * C2 + ic] = __float2bfloat16(v * scale[oc]);
             }
       }
-  return upload(c.w, wp.data(), wp.size() * 4) && upload(c.w_bf16, wb.data(), wb.size() * 2) &&
+  return upload(c.w, wp.data(), wp.size() * 4) && upload(c.w_bf16, wb.data(), wb.size() * 2) && upload(c.w_tc, wt.data(), wt.size() * 2) &&
          upload(c.scale, scale.data(), scale.size() * 4) && upload(c.shift, shift.data(), shift.size() * 4);
 }
 

@@ -43,6 +43,8 @@ struct ConvParams {
   int extra_plane;                // 1: one more input channel, constant per image (the action plane :553-568)
   float* w;                       // fp32 [9][cin + extra_plane][cout]
   __nv_bfloat16* w_bf16;          // bf16 [cout][9][cin]   (K-major B operand of the implicit GEMM), or NULL
+  __nv_bfloat16* w_tc;            // bf16 [cout][9][cin] with the folded batch-norm SCALE multiplied in (fp32 product, one bf16
+                                  // rounding): B operand of k_conv_tc, whose epilogue then only adds `shift`
   float* plane_table;             // fp32 [H*W][cout]: sum over in-bounds taps of the extra-plane weights
   float* scale;                   // folded batch-norm: y = conv * scale + shift   (identity when no bn)
   float* shift;

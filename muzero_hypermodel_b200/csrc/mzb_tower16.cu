@@ -98,8 +98,8 @@ __device__ __forceinline__ void conv16(uint32_t in_u32, uint8_t* out, const uint
           v0 = fmaf(pl, ptab[L.o_pos[mt][h] * 16 + c], v0);
           v1 = fmaf(pl, ptab[L.o_pos[mt][h] * 16 + c + 1], v1);
         }
-        v0 = fmaf(v0, sc[c], sh[c]);
-        v1 = fmaf(v1, sc[c + 1], sh[c + 1]);
+        v0 += sh[c];                       // the batch-norm scale is folded into the bf16 weights (ConvParams::w_tc), as in k_conv_tc
+        v1 += sh[c + 1];
         if (RES) {
           const uint32_t rw = *reinterpret_cast<const uint32_t*>(res + L.o_row[mt][h] * kRowB + c * 2);
           v0 += bf_lo(rw); v1 += bf_hi(rw);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
   int* s_row = reinterpret_cast<int*>(s_wvp + a.r_vp * 16);          // [HW]: padded row of position p (no divisions in the loops)
   uint8_t* s_act = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_row + HW) + 127) & ~(uintptr_t)127);
   const size_t buf_bytes = (size_t)rows * kRowB;
-  // ---- stage the weights: w_bf16 [16 cout][9 taps][16 cin] -> [tap][cout] rows of kRowB bytes
+  // ---- stage the weights: w_tc (scale folded in) [16 cout][9 taps][16 cin] -> [tap][cout] rows of kRowB bytes
   for (int i = threadIdx.x; i < a.n_conv * 9 * 16 * 2; i += blockDim.x) {
     const int half = i & 1, n = (i >> 1) & 15, tap = (i >> 5) % 9, ci = i / (9 * 32);
     const uint4 v = *reinterpret_cast<const uint4*>(a.conv[ci].w + (size_t)n * 144 + tap * 16 + half * 8);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     const int ci = i >> 5, k = i & 31;
     s_sc[i] = k < 16 ? a.conv[ci].scale[k] : a.conv[ci].shift[k - 16];
   }
-  for (int i = threadIdx.x; i < HW * 16; i += blockDim.x) s_ptab[i] = a.plane_table[i];
+  for (int i = threadIdx.x; i < HW * 16; i += blockDim.x) s_ptab[i] = a.plane_table[i] * a.conv[0].scale[i & 15];   // conv[0] = the dynamics convolution
   for (int i = threadIdx.x; i < a.r_r * 16; i += blockDim.x) s_wr[i] = a.w_r[i];
   for (int i = threadIdx.x; i < a.r_vp * 16; i += blockDim.x) s_wvp[i] = a.w_vp[i];
   for (int p = threadIdx.x; p < HW; p += blockDim.x) s_row[p] = halo + (p / W + 1) * pitch + p % W;
@@ -303,7 +303,7 @@ int mzb_tower16_recurrent(mzb_resnet_model* m, int B, const void* state_in, int 
   a.B = B; a.H = m->Hl; a.W = m->Wl; a.A = m->A;
   a.n_dyn = (int)m->dyn_blocks.size(); a.n_pred = (int)m->pred_blocks.size();
   int k = 0;
-  auto put = [&](const ConvParams& c) { a.conv[k++] = T16Conv{c.w_bf16, c.scale, c.shift}; };
+  auto put = [&](const ConvParams& c) { a.conv[k++] = T16Conv{c.w_tc, c.scale, c.shift}; };
   put(m->dyn_conv);
   for (const Block& b : m->dyn_blocks) { put(b.c1); put(b.c2); }
   for (const Block& b : m->pred_blocks) { put(b.c1); put(b.c2); }
