@@ -670,6 +670,33 @@ def run_workload(args, workload, steps, warmup, cpu_seconds, want_cpu, want_coll
             res[name] = mdist.max_over_ranks(a.elapsed_time(b) / 20, dev)
         collectives = dict(res, parameters=n_param, backend="nccl", note="not on the self-play path (games are sharded, no data-path collective)")
 
+    # the learner's step on the games this run just produced (off the self-play path, reported beside it):
+    # batch from the device replay store -> forward + backward + optimiser -> priorities written back.  FC family: the
+    # one-kernel training step (csrc/mzb_fc_train.cu) against the autograd graph replayed from a CUDA graph.
+    trainer_probe = None
+    if is_fc and rb is not None and world == 1 and len(rb) >= 16:
+        try:
+            from muzero_hypermodel_b200.trainer import Trainer
+            trainer_probe = {}
+            for key, env_val in (("ms_per_step", "1"), ("ms_per_step_autograd_cuda_graph", "0")):
+                os.environ["MZB_TRAIN_KERNEL"] = env_val
+                tr = Trainer({"weights": weights, "training_step": 0, "optimizer_state": None}, cfg, device=dev)
+                for _ in range(4):
+                    idx, batch = rb.get_batch(); tr.update_lr(); out = tr.update_weights(batch); rb.update_priorities(out[0], idx)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(20):
+                    idx, batch = rb.get_batch(); tr.update_lr(); out = tr.update_weights(batch); rb.update_priorities(out[0], idx)
+                b.record(); torch.cuda.synchronize()
+                trainer_probe[key] = a.elapsed_time(b) / 20
+                del tr
+            os.environ.pop("MZB_TRAIN_KERNEL", None)
+            trainer_probe.update(batch_size=cfg.batch_size, unroll_steps=cfg.num_unroll_steps, optimizer=cfg.optimizer,
+                                 samples_per_s=cfg.batch_size / (trainer_probe["ms_per_step"] * 1e-3),
+                                 path="ReplayBuffer.get_batch (device) -> k_fc_train (forward + backward, one launch) -> k_adam_flat -> update_priorities")
+        except Exception as e:                        # noqa: BLE001
+            trainer_probe = {"error": repr(e)}
+
     tree_gib = mcts.tree.nbytes / 2**30
     if not is_fc and rank == 0 and world == 1:
         # free the big search state before the fp32 comparison model is built
@@ -700,6 +727,8 @@ def run_workload(args, workload, steps, warmup, cpu_seconds, want_cpu, want_coll
                 "games_ingested_by_replay_store": ingested}
         if parity is not None:
             line["parity"] = parity
+        if trainer_probe is not None:
+            line["trainer"] = trainer_probe
         if collectives is not None:
             line["collectives"] = collectives
         if cpu is not None:

@@ -11,8 +11,8 @@
 // memory, TRANSPOSED with an odd row length ([in + 1][out | 1], the last row is the bias), so that "lane = output"
 // (forward, weight gradients) and "lane = input" (data gradients) are both conflict-free.  Every warp keeps the
 // activations of all K+1 steps and a PRIVATE gradient image of the whole network in shared memory - no atomics.  When a
-// CTA's warps are done their images are summed in warp order; the last CTA to finish sums the per-CTA partial sums in
-// CTA order: the result does not depend on scheduling (deterministic, run to run and rank to rank).
+// CTA's warps are done their images are summed in warp order; a second, tiny launch sums the per-CTA partial sums in CTA
+// order: the result does not depend on scheduling (deterministic, run to run and rank to rank).
 //
 // Gradient flow, as autograd sees the reference's graph:
 //   total = mean_b w_b * (value_loss_weight * sum_i CE(value_i) + sum_{i>=1} CE(reward_i) + sum_i CE(policy_i));
@@ -52,7 +52,8 @@ __device__ __forceinline__ void lin_fwd(const float* __restrict__ Wt, const Lyr&
   const float* w = Wt + L.wt;
   for (int o = lane; o < L.out; o += 32) {
     float acc = w[L.in * L.outp + o];
-    for (int i = 0; i < n_dense; ++i) acc = fmaf(x[i], w[i * L.outp + o], acc);
+#pragma unroll 8
+    for (int i = 0; i < n_dense; ++i) acc = fmaf(x[i], w[i * L.outp + o], acc);      // unrolled: the loads of 8 terms in flight
     if (hot >= 0) acc += w[(n_dense + hot) * L.outp + o];
     y[o] = elu ? elu_train(acc) : acc;
   }
@@ -65,6 +66,7 @@ __device__ __forceinline__ void lin_bwd(const float* __restrict__ Wt, float* gW,
   float* g = gW + L.wt;
   for (int o = lane; o < L.out; o += 32) {
     const float d = dy[o];
+#pragma unroll 8
     for (int i = 0; i < n_dense; ++i) g[i * L.outp + o] = fmaf(x[i], d, g[i * L.outp + o]);
     if (hot >= 0) g[(n_dense + hot) * L.outp + o] += d;
     g[L.in * L.outp + o] += d;
@@ -73,6 +75,7 @@ __device__ __forceinline__ void lin_bwd(const float* __restrict__ Wt, float* gW,
     const float* w = Wt + L.wt;
     for (int i = lane; i < n_dense; i += 32) {
       float acc = 0.0f;
+#pragma unroll 8
       for (int o = 0; o < L.out; ++o) acc = fmaf(w[i * L.outp + o], dy[o], acc);
       dx[i] = acc;
     }
@@ -151,7 +154,7 @@ __device__ __forceinline__ float support_scalar(const float* z, int S, int lane)
 struct TrainIO {
   const float* params; const float* obs; const long long* action; const float* tv_sup; const float* tr_sup; const float* tp;
   const float* tv_scalar; const float* weight; const float* gscale;
-  float* grad; float* losses; float* priorities; float* loss; float* partial; unsigned int* counter;
+  float* grad; float* losses; float* priorities; float* loss; float* partial; unsigned int* unused;
 };
 
 template <int WARPS>
@@ -300,23 +303,28 @@ __global__ void __launch_bounds__(WARPS * 32) k_fc_train(const TD d, const Train
         part[dst] = acc;
       }
     }
-  // ---------------- the last CTA to arrive sums the partials in CTA order (deterministic) and forms the batch loss
-  __shared__ unsigned int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicInc(io.counter, gridDim.x - 1) == gridDim.x - 1 ? 1u : 0u;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (long long p = threadIdx.x; p < d.P; p += WARPS * 32) {
+}
+
+// Second (tiny) launch: gradient element p = sum over the CTAs' partial sums IN CTA ORDER (deterministic), eight loads in
+// flight at a time; thread 0 forms the batch objective.  A "last CTA reduces" epilogue in the first kernel serialised
+// 32 dependent L2 round trips per element on one CTA and took longer than the training step itself.
+__global__ void k_fc_train_reduce(const TD d, const TrainIO io, int n_cta) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < d.P) {
     float acc = 0.0f;
-    for (unsigned int c = 0; c < gridDim.x; ++c) acc += __ldcg(io.partial + (size_t)c * d.P + p);
+    for (int c0 = 0; c0 < n_cta; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = c0 + j < n_cta ? io.partial[(size_t)(c0 + j) * d.P + p] : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
     io.grad[p] = acc;
   }
-  if (threadIdx.x == 0) {
+  if (p == 0) {
     float total = 0.0f;
     for (int i = 0; i < d.B; ++i) {
-      float l = __ldcg(io.losses + i) * d.vlw + __ldcg(io.losses + d.B + i) + __ldcg(io.losses + 2 * d.B + i);
+      float l = io.losses[i] * d.vlw + io.losses[d.B + i] + io.losses[2 * d.B + i];
       if (io.weight) l *= io.weight[i];
       total += l;
     }
@@ -414,6 +422,8 @@ int mzb_fc_train_grad(const mzb_fc_train_desc* desc, const float* d_params, int6
              d_target_value_scalar, d_weight, d_gradient_scale, d_grad, d_losses, d_priorities, d_loss,
              reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_workspace) + 256), reinterpret_cast<unsigned int*>(d_workspace)};
   k_fc_train<kTrainWarps><<<ctas, kTrainWarps * 32, smem, (cudaStream_t)stream>>>(d, io);
+  MZB_LAUNCH_CHECK();
+  k_fc_train_reduce<<<(unsigned)((d.P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, io, ctas);
   MZB_LAUNCH_CHECK();
   return MZB_OK;
 }

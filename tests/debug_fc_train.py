@@ -30,3 +30,11 @@ print("vl", float((k[1] - r[1]).abs().max()), "rl", float((k[2] - r[2]).abs().ma
 bad = (g1 - g0).abs() > 1e-4 * g0.abs().max()
 print("bad grads", int(bad.sum()), "of", bad.numel(), "first", bad.nonzero()[:10].flatten().tolist())
 print("tp row sums", tp.sum(-1).min().item() if torch.is_tensor(tp) else None)
+# in-situ time of the one-kernel step (warm caches, back to back) against the autograd path replayed from a CUDA graph
+for name, fn in (("k_fc_train + reduce (+ 2 codec launches)", lambda: tr._fc_kernel_step(tensors)),):
+    for _ in range(5): fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(100): fn()
+    b.record(); torch.cuda.synchronize()
+    print(f"{name}: {a.elapsed_time(b) * 10:.1f} us per call")
