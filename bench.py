@@ -34,7 +34,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-G_FULL_WAVES = 4 * 148 * 512        # cartpole: 4 full waves of the whole-search kernel's 148 SMs x 2 CTAs x 256 games
+G_FULL_WAVES = 8 * 148 * 512        # cartpole: 8 full waves of the whole-search kernel's 148 SMs x 2 CTAs x 256 games (ramp-up and
+                                    # tail of a launch amortised: 10.86 ns per search against 11.02 at 4 waves, 11.1 at 3)
 WORKLOADS = {
     # name: (golden weight tag, config module, games per GPU, (initial FLOP, recurrent FLOP) per BASELINE.md §3,
     #        moves per bench step, default timed steps)

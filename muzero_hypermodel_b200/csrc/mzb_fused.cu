@@ -13,7 +13,7 @@
 #include "mzb_fc.cuh"
 #include "mzb_tree.cuh"
 
-#define MZB_FUSED_DEFAULT_EXP 17031  // FFMA2 network, root record in registers, search path in shared memory, barrier per 4 warps, branch-free scores, reward/value heads share one copy of the code
+#define MZB_FUSED_DEFAULT_EXP 213639 // FFMA2 network, root record in registers, search path in shared memory, barrier per 4 warps, branch-free scores, reward/value heads share one copy of the code, L2 policies (records evict_last, hidden states evict_first)
 
 namespace {
 
@@ -170,6 +170,21 @@ struct Rec {
       for (int i = 0; i < WORDS / 2; ++i) { const uint2 q = p[i]; w[2 * i] = q.x; w[2 * i + 1] = q.y; }
     }
   }
+  // same, with an L2 cache policy (createpolicy): the records are what the walk re-reads, so they are kept (evict_last)
+  // against the hidden states, which are read at most A times and are written / read with evict_first
+  __device__ __forceinline__ void load_hint(const uint8_t* r, uint64_t pol) {
+    static_assert(A % 2 == 0, "vector form");
+#pragma unroll
+    for (int i = 0; i < WORDS / 4; ++i)
+      asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                   : "=r"(w[4 * i]), "=r"(w[4 * i + 1]), "=r"(w[4 * i + 2]), "=r"(w[4 * i + 3]) : "l"(r + 16 * i), "l"(pol));
+  }
+  __device__ __forceinline__ void store_hint(uint8_t* r, uint64_t pol) const {
+#pragma unroll
+    for (int i = 0; i < WORDS / 4; ++i)
+      asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(r + 16 * i), "r"(w[4 * i]), "r"(w[4 * i + 1]),
+                   "r"(w[4 * i + 2]), "r"(w[4 * i + 3]), "l"(pol) : "memory");
+  }
   __device__ __forceinline__ void store(uint8_t* r) const {
     if constexpr (A % 2 == 0) {
       uint4* p = reinterpret_cast<uint4*>(r);
@@ -204,6 +219,22 @@ __device__ __forceinline__ void load_floats(const float* __restrict__ p, float (
   }
 }
 template <int N>
+__device__ __forceinline__ void load_floats_hint(const float* __restrict__ p, float (&x)[N], uint64_t pol) {
+  static_assert(N % 4 == 0, "vector form");
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i)
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(x[4 * i]), "=f"(x[4 * i + 1]), "=f"(x[4 * i + 2]), "=f"(x[4 * i + 3]) : "l"(p + 4 * i), "l"(pol));
+}
+template <int N>
+__device__ __forceinline__ void store_floats_hint(float* __restrict__ p, const float (&x)[N], uint64_t pol) {
+  static_assert(N % 4 == 0, "vector form");
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i)
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p + 4 * i), "f"(x[4 * i]), "f"(x[4 * i + 1]),
+                 "f"(x[4 * i + 2]), "f"(x[4 * i + 3]), "l"(pol) : "memory");
+}
+template <int N>
 __device__ __forceinline__ void store_floats(float* __restrict__ p, const float (&x)[N]) {
   if constexpr (N % 4 == 0) {
 #pragma unroll
@@ -229,7 +260,7 @@ struct SearchIO {
 // EXP: experiment / tuning flags (MZB_FUSED_EXP): 1 = packed FFMA2 network, 2 = root record in registers (A <= 4),
 // 4/8/16/32 = timing-only diagnostics (blocked layout, aliased trees, no network, no walk) - results are NOT valid.
 // 4 = the search path's edge statistics in shared memory for the first 12 levels (deeper levels: local memory).
-enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32, X_SYNC2 = 64, X_HALFBAR = 128, X_RCP = 256, X_BF = 512, X_FELU = 1024, X_SCHEDBAR = 2048, X_BAR2 = 4096, X_P1 = 8192, X_HEADLOOP = 16384, X_UNPEEL = 32768 };
+enum { X_F2 = 1, X_ROOTREG = 2, X_SPATH = 4, X_ALIAS = 8, X_NONET = 16, X_NOWALK = 32, X_SYNC2 = 64, X_HALFBAR = 128, X_RCP = 256, X_BF = 512, X_FELU = 1024, X_SCHEDBAR = 2048, X_BAR2 = 4096, X_P1 = 8192, X_HEADLOOP = 16384, X_UNPEEL = 32768, X_L2HINT = 65536, X_L2HINT2 = 131072 };
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm) { return blocks_per_sm >= 3 ? 8 : 12; }
 __host__ __device__ constexpr int smem_path_depth(int blocks_per_sm, int threads) {
   // 16 bytes per level and thread next to ~18 KB of weights + tables per CTA: 12 levels up to 640 threads per SM
@@ -242,6 +273,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
   constexpr bool F2 = (EXP & X_F2) != 0;
   constexpr bool ROOTREG = (EXP & X_ROOTREG) != 0 && A <= 4;
   constexpr bool FE = (EXP & X_FELU) != 0;
+  constexpr bool L2H = (EXP & X_L2HINT) != 0 && A % 2 == 0 && ENC % 4 == 0;
+  uint64_t pol_keep = 0, pol_stream = 0;
+  if (L2H) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  }
   extern __shared__ float4 smem4[];
   float* pack = reinterpret_cast<float*>(smem4);
   double* lut = reinterpret_cast<double*>(pack + SH::PACK);
@@ -494,7 +531,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
       while (next >= 0) {
         node = next;
         Rec<A> rr;
-        rr.load(rec_of(node));
+        if constexpr (L2H) rr.load_hint(rec_of(node), pol_keep); else rr.load(rec_of(node));
         next = walk_level(rr, false, node, depth, sim);
         ++depth;
       }
@@ -502,7 +539,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
     const int L = depth, fresh = sim + 1;
     // the parent's hidden state is requested before the phase barrier, so its latency overlaps the wait
     float st[ENC];
-    if (active) load_floats<ENC>(hid_of(node), st);
+    if (active) { if constexpr (L2H) load_floats_hint<ENC>(hid_of(node), st, pol_stream); else load_floats<ENC>(hid_of(node), st); }
     if (PHASE_SYNC) {                         // warps of the block enter the unrolled network code together
       if constexpr ((EXP & X_BAR2) != 0) {
         asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory");       // per pair of consecutive warps
@@ -540,7 +577,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
           if (h == 0) {
             reward = o;
             minmax_regs(nx);
-            store_floats<ENC>(hid_of(fresh), nx);
+            if constexpr (L2H) store_floats_hint<ENC>(hid_of(fresh), nx, pol_stream); else store_floats<ENC>(hid_of(fresh), nx);
             float pl[A];
             SH::Pol::template run<F2, FE>(pack + SH::OFF_POL, nx, -1, pl);
             priors_regs<A>(pl, nullptr, pri);
@@ -574,7 +611,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
       Rec<A> rr;
 #pragma unroll
       for (int a = 0; a < A; ++a) rr.set(a, 0.0, pri[a], 0, 0.0f, MZB_CHILD_NONE);
-      rr.store(rec_of(fresh));
+      if constexpr (L2H) rr.store_hint(rec_of(fresh), pol_keep); else rr.store(rec_of(fresh));
       bool in_regs = false;
       if constexpr (ROOTREG) {
         if (node == 0) {
@@ -586,8 +623,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
       }
       if (!in_regs) {
         uint8_t* pr_ = rec_of(node);
-        t.reward(pr_)[action] = reward;
-        t.child(pr_)[action] = fresh;
+        if constexpr (L2H && (EXP & X_L2HINT2) != 0) {
+          asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(pr_ + 16 * A + 4 * action), "f"(reward), "l"(pol_keep) : "memory");
+          asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(pr_ + 20 * A + 4 * action), "r"(fresh), "l"(pol_keep) : "memory");
+        } else {
+          t.reward(pr_)[action] = reward;
+          t.child(pr_)[action] = fresh;
+        }
       }
     }
 
@@ -610,8 +652,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_fc(TreeView t, const f
         const double e_rw = (k == L - 1) ? (double)reward : (double)l_rw;
         backup_step_rcp(e_vs, e_vi, e_rw, val, t.discount, two, ((L - (k + 1)) & 1) == 0, vmin, vmax, rcpn2);
         uint8_t* er = rec_of(pn);
-        reinterpret_cast<double*>(er)[pa] = e_vs;
-        reinterpret_cast<int*>(er + 12 * A)[pa] = e_vi;
+        if constexpr (L2H && (EXP & X_L2HINT2) != 0) {
+          asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(er + 8 * pa), "d"(e_vs), "l"(pol_keep) : "memory");
+          asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(er + 12 * A + 4 * pa), "r"(e_vi), "l"(pol_keep) : "memory");
+        } else {
+          reinterpret_cast<double*>(er)[pa] = e_vs;
+          reinterpret_cast<int*>(er + 12 * A)[pa] = e_vi;
+        }
       }
       {
         const uint32_t ev = sp_ev[threadIdx.x];
@@ -738,6 +785,9 @@ int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t 
   const bool lut = io.num_sims <= 63;                 // (S+1)^2 doubles must fit next to the weights
   if (!lut) return launch_variant<SH, false, MZB_FUSED_DEFAULT_EXP>(t, m, io, s);
   // small batches (tictactoe at 4,096 games = 16 CTAs of 256): one warp per CTA spreads the games over all SMs
+  // (fewer games per warp - 16 / 8 / 4 active lanes, i.e. 256 / 512 / 1,024 one-warp CTAs for 4,096 games - is slower:
+  // 0.45 / 0.59 / 1.10 ms against 0.47 ms per tictactoe search; several unsynchronised warps per SM thrash the
+  // instruction caches on the unrolled network code, like the kernel without its phase barrier)
   if (t->v.G < 148 * 128) return launch_variant<SH, true, MZB_FUSED_DEFAULT_EXP, 32, false, 2>(t, m, io, s);
   if constexpr (TUNE) {
     switch (fused_exp()) {
@@ -748,6 +798,8 @@ int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t 
       case 135: return launch_variant<SH, true, 135>(t, m, io, s);
       case 647: return launch_variant<SH, true, 647>(t, m, io, s);                  // + branch-free scores: 4.20 -> 3.64 ms
       case 17031: return launch_variant<SH, true, 17031>(t, m, io, s);              // reward and value heads as one two-trip loop: 3.57 -> 3.46 ms
+      case 82567: return launch_variant<SH, true, 82567>(t, m, io, s);              // + L2 policies: records evict_last, hidden states evict_first
+      case 213639: return launch_variant<SH, true, 213639>(t, m, io, s);            // + the backup's / expand's partial record stores evict_last too: 3.46 -> 3.34 ms
       // (the loop body is ~47 KB of SASS against a 32 KB L1.5 instruction cache: code size shows).  On top of it: root
       // level not peeled 3.48; ex2-based ELU 3.40 (not adopted: changes the network's rounding); barrier per pair of
       // consecutive warps 3.68 (on 647); parent's hidden state requested before the barrier: no change
