@@ -206,14 +206,15 @@ def test_update_weights_returns_fresh_priorities():
     assert not torch.equal(outs[1], outs[2])          # weights moved between the steps; an alias would compare equal
 
 
-@pytest.mark.parametrize("game,B", [("cartpole", 128), ("cartpole", 7), ("tictactoe", 33)])
-def test_one_kernel_fc_training_step_equals_autograd(game, B):
+@pytest.mark.parametrize("game,B,per", [("cartpole", 128, True), ("cartpole", 7, False), ("tictactoe", 33, True)])
+def test_one_kernel_fc_training_step_equals_autograd(game, B, per):
     """The one-kernel forward / backward of the fully-connected family (csrc/mzb_fc_train.cu) against PyTorch autograd
     over the same parameters (the path pinned to the reference by tests/golden/trainer.npz and tests/test_trainer_graph.py):
     every gradient, the per-sample losses, the batch objective and the priorities; twice, to show it is deterministic."""
     from muzero_hypermodel_b200.trainer import Trainer
     cfg = importlib.import_module(f"muzero_hypermodel_b200.games.{game}").MuZeroConfig()
     cfg.network = "fullyconnected"
+    cfg.PER = per                                          # without PER the batch carries no importance weights
     torch.backends.cuda.matmul.allow_tf32 = False
     tr = Trainer({"weights": None, "training_step": 0, "optimizer_state": None}, cfg, device=DEV)
     rs = np.random.RandomState(5)
