@@ -800,6 +800,8 @@ int launch_fused(mzb_tree* t, mzb_fc_model* m, const SearchIO& io, cudaStream_t 
       case 17031: return launch_variant<SH, true, 17031>(t, m, io, s);              // reward and value heads as one two-trip loop: 3.57 -> 3.46 ms
       case 82567: return launch_variant<SH, true, 82567>(t, m, io, s);              // + L2 policies: records evict_last, hidden states evict_first
       case 213639: return launch_variant<SH, true, 213639>(t, m, io, s);            // + the backup's / expand's partial record stores evict_last too: 3.46 -> 3.34 ms
+      // (swept at 606,208 games, 6.58 ms: evict_last fraction 1.0 / 0.75 / 0.5 / 0.25 makes no difference; hidden states
+      // evict_normal or evict_unchanged instead of evict_first: 6.67 - the streaming of the hidden states is what pays)
       // (the loop body is ~47 KB of SASS against a 32 KB L1.5 instruction cache: code size shows).  On top of it: root
       // level not peeled 3.48; ex2-based ELU 3.40 (not adopted: changes the network's rounding); barrier per pair of
       // consecutive warps 3.68 (on 647); parent's hidden state requested before the barrier: no change
