@@ -82,6 +82,33 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// cta_group::2: ONE instruction issued by the leader CTA of a pair multiplies both CTAs' 128-row A tiles (M = 256) by a
+// B tile of which each CTA's shared memory holds half the rows; the accumulators land in both CTAs' TMEM.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all MMAs issued so far -> the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -130,7 +157,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
 // block's ring slot (kb % 3) and barrier parity ((kb / 3) & 1) are compile-time constants: the slot counter, the
 // divisions and the R2UR moves that sat between two bursts of MMAs (99 cycles per MMA in situ against 64 for the
 // instruction stream alone) disappear.
-template <int KC, bool ZP, int PR, int kEpiWarps, bool RES, int NC = 0>
+// PAIR: two CTAs on one TPC form a cluster and share every MMA (cta_group::2, M = 256): each CTA loads its own
+// super-tile of activations but only HALF the rows of every weight block, so an MMA fetches 128 + N/2 instead of
+// 128 + N operand rows from each SM's shared memory - the fetch, not the math, bounds an N = 64 MMA (tests/ubench_umma2.cu:
+// 43 against 53 cycles per 128 x 64 x 16 MMA per SM).  The leader CTA (cluster rank 0) issues; the peer's "activations
+// landed" and both CTAs' "accumulator stage drained" events reach the leader's barriers through cluster-scope arrives,
+// the MMA completion is committed to both CTAs' barriers by multicast.  Resident weights only (RES).
+template <int KC, bool ZP, int PR, int kEpiWarps, bool RES, int NC = 0, bool PAIR = false>
 __global__ void __launch_bounds__(64 + kEpiWarps * 32, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAtail,
           const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -147,7 +180,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int a_rows = MT * 128 + a.tail_rows;
   const uint32_t a_chunk_bytes = (uint32_t)a_rows * ROWB;
   const uint32_t a_stage_bytes = (uint32_t)n_chunks * a_chunk_bytes;
-  const uint32_t b_block_bytes = (uint32_t)N * ROWB;
+  uint32_t rank = 0;                                                     // cluster rank (PAIR): 0 = leader
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int NB = PAIR ? N / 2 : N;                                       // weight rows this CTA holds of every k-block
+  const uint32_t b_block_bytes = (uint32_t)NB * ROWB;
   const int NKB = 9 * n_chunks;
   const int b_slots = RES ? NKB : RING;
   uint8_t* sA = smem;
@@ -160,7 +196,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* b_full = bars + 8;             // [kStages] (ring) / [0] = resident weights landed
   uint64_t* b_empty = bars + 8 + kStages;  // [kStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kStages);
-  float* s_scale = reinterpret_cast<float*>(bars + 10 + 2 * kStages);
+  uint64_t* peer_a_full = bars + 10 + 2 * kStages;   // [2] (PAIR, leader): the peer CTA's activations of stage s landed
+  float* s_scale = reinterpret_cast<float*>(bars + 12 + 2 * kStages);
   float* s_shift = s_scale + N;
   float* s_proj = s_shift + N;             // [PR][N]
   // The action plane's term acc += plane[b] * table[position][channel] (DynamicsNetwork's first convolution) from shared
@@ -172,10 +209,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // Work split: every CTA owns one CONTIGUOUS range of 128-row tiles (sizes differ by at most one tile) and walks it in
   // super-tiles of up to MT tiles; only the range's last super-tile may be short.  A strided split in whole super-tiles
   // would leave a tail wave in which most SMs idle (connect4: 12.1 waves of work took 13).
+  // PAIR: the range belongs to the cluster; per iteration the leader takes MT tiles and the peer the next MT (the peer
+  // may get fewer, or none, in the last iteration - it still takes part in every barrier).
   const long long total_tiles = (a.rows_cover + 127) / 128;
-  const long long t_base = total_tiles / gridDim.x, t_rem = total_tiles % gridDim.x;
-  const long long tile_begin = (long long)blockIdx.x * t_base + ((long long)blockIdx.x < t_rem ? (long long)blockIdx.x : t_rem);
-  const long long tile_end = tile_begin + t_base + ((long long)blockIdx.x < t_rem ? 1 : 0);
+  const long long n_owner = PAIR ? gridDim.x / 2 : gridDim.x, owner = PAIR ? blockIdx.x / 2 : blockIdx.x;
+  const long long t_base = total_tiles / n_owner, t_rem = total_tiles % n_owner;
+  const long long tile_begin = owner * t_base + (owner < t_rem ? owner : t_rem);
+  const long long tile_end = tile_begin + t_base + (owner < t_rem ? 1 : 0);
+  const int it_stride = PAIR ? 2 * MT : MT;
+  const int n_it = (int)((tile_end - tile_begin + it_stride - 1) / it_stride);
+  const long long tile_first = tile_begin + (long long)rank * MT;
+  auto mt_of = [&](long long tile0) -> int { const long long r = tile_end - tile0; return r <= 0 ? 0 : (r < MT ? (int)r : MT); };
 
   // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as this grid's CTAs free
   // their SMs (its prologue - barrier setup, TMEM allocation, weight loads - then overlaps this grid's tail); every
@@ -183,15 +227,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps);
+      mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, PAIR ? 2 * kEpiWarps : kEpiWarps);         // PAIR (leader): both CTAs' epilogue warps arrive here
+      mbar_init(peer_a_full + i, 1);
     }
     for (int s = 0; s < kStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.ncols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.ncols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = threadIdx.x; i < N; i += kThreads) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
   if (PR > 0) for (int i = threadIdx.x; i < PR * N; i += kThreads) s_proj[i] = i < a.proj_r * N ? a.proj_w[i] : 0.0f;
@@ -209,6 +260,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();                // both CTAs' barriers are initialised before any remote arrive / multicast
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);
 
@@ -221,21 +273,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (leader) mbar_expect_tx(b_full, (uint32_t)NKB * b_block_bytes);
         for (int kb = 0; kb < NKB; ++kb) {
           const int tap = kb / n_chunks, j = kb % n_chunks;
-          if (leader) tma_load_2d(smem_u32(sB + (size_t)kb * b_block_bytes), &tmB, tap * a.Cin + j * KC, 0, b_full);
+          if (leader) tma_load_2d(smem_u32(sB + (size_t)kb * b_block_bytes), &tmB, tap * a.Cin + j * KC, (int)rank * NB, b_full);
         }
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");      // the activations come from the preceding kernel
       long long ring = 0;
       int it = 0;
-      for (long long tile0 = tile_begin; tile0 < tile_end; tile0 += MT, ++it) {
+      for (; it < n_it; ++it) {
+        const long long tile0 = tile_first + (long long)it * it_stride;
         const int s = it & 1;
-        const int mt_cur = tile_end - tile0 < MT ? (int)(tile_end - tile0) : MT;
+        const int mt_cur = mt_of(tile0);
         const long long p0 = clock64();
         if (it >= 2) mbar_wait(a_empty + s, ((it >> 1) - 1) & 1);
         if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (3 * 32 + it) * 4; d[0] = p0; d[1] = clock64(); }
         const long long m0 = tile0 * 128;
-        if (leader) mbar_expect_tx(a_full + s, (uint32_t)n_chunks * (uint32_t)(mt_cur * 128 + a.tail_rows) * ROWB);
-        for (int j = 0; j < n_chunks; ++j) {
+        if (leader) mbar_expect_tx(a_full + s, mt_cur > 0 ? (uint32_t)n_chunks * (uint32_t)(mt_cur * 128 + a.tail_rows) * ROWB : 0u);
+        for (int j = 0; j < n_chunks && mt_cur > 0; ++j) {
           uint8_t* dst = sA + (size_t)s * a_stage_bytes + (size_t)j * a_chunk_bytes;
           for (int box = 0; box < mt_cur; ++box)
             if (leader) tma_load_2d(smem_u32(dst + (size_t)box * 128 * ROWB), &tmA, j * KC, (int)(m0 + (long long)box * 128), a_full + s);
@@ -262,21 +315,34 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }
     }
+  } else if (warp == 1 && PAIR && rank != 0) {
+    // ---------------- peer CTA of a pair: forward "my activations of stage s (and my half of the weights) landed" to
+    // the leader, which issues the MMAs for both CTAs
+    if (elect_one_sync()) {
+      if (RES) mbar_wait(b_full, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        mbar_wait(a_full + s, (it >> 1) & 1);
+        mbar_arrive_cluster(peer_a_full + s, 0);
+      }
+    }
   } else if (warp == 1) {
     // ---------------- MMA issuer: warp-uniform loop, tcgen05.mma / commit issued by one elected lane
     if (elect_one_sync()) {
       const bool leader = true;
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
       const uint64_t desc_hi = make_desc<KC>(0);
       const uint64_t b_base_desc = desc_hi | (uint64_t)((smem_u32(sB) >> 4) & 0x3FFF);
       if (RES) mbar_wait(b_full, 0);
       uint32_t ring = 0;
       int it = 0;
-      for (long long tile0 = tile_begin; tile0 < tile_end; tile0 += MT, ++it) {
+      for (; it < n_it; ++it) {
+        const long long tile0 = tile_first + (long long)it * it_stride;
         const int s = it & 1;
-        const int mt_cur = tile_end - tile0 < MT ? (int)(tile_end - tile0) : MT;
+        const int mt_cur = mt_of(tile0);                    // the leader's count; the peer's is never larger
         const long long c0 = clock64();
         mbar_wait(a_full + s, (it >> 1) & 1);
+        if (PAIR) mbar_wait(peer_a_full + s, (it >> 1) & 1);
         const long long c1 = clock64();
         if (it >= 2) mbar_wait(acc_empty + s, ((it >> 1) - 1) & 1);
         const long long c2 = clock64();
@@ -318,7 +384,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int t = 0; t < mt_cur; ++t, ad += (128 * ROWB) >> 4, d += (uint32_t)N) {
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k)
-                if (leader) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                if (leader) {
+                  if (PAIR) umma_bf16_pair(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                  else umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
             }
             if (!RES && leader) umma_commit(b_empty + rs);
             ++kb;
@@ -331,8 +400,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
         if (leader) {
-          umma_commit(a_empty + s);            // activation stage reusable once these MMAs retire
-          umma_commit(acc_full + s);           // accumulators of this super-tile complete
+          if (PAIR) { umma_commit_pair(a_empty + s); umma_commit_pair(acc_full + s); }      // both CTAs' barriers
+          else {
+            umma_commit(a_empty + s);            // activation stage reusable once these MMAs retire
+            umma_commit(acc_full + s);           // accumulators of this super-tile complete
+          }
         }
         if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (0 * 32 + it) * 4; d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64(); }
       }
@@ -387,9 +459,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     };
     asm volatile("griddepcontrol.wait;" ::: "memory");        // residual / plane reads below: earlier kernels' outputs
     int it = 0, item_base = 0;
-    for (long long tile0 = tile_begin; tile0 < tile_end; tile0 += MT, ++it) {
+    for (; it < n_it; ++it) {
+      const long long tile0 = tile_first + (long long)it * it_stride;
       const int s = it & 1;
-      const int n_items = (tile_end - tile0 < MT ? (int)(tile_end - tile0) : MT) * ncg;
+      const int n_items = mt_of(tile0) * ncg;
       const uint32_t m0 = (uint32_t)(tile0 * 128);
       // items are dealt round-robin over ALL super-tiles (not restarted per super-tile)
       int item = (((group - item_base) % NG) + NG) % NG;
@@ -522,15 +595,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // this warp is done reading the TMEM stage: release it to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + s)) : "memory");
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(acc_empty + s, 0);          // the leader's barrier counts both CTAs' epilogue warps
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + s)) : "memory");
+      }
       if (a.debug && blockIdx.x == 0 && it < 32 && lane == 0 && q == 2) { long long* d = a.debug + ((1 + group) * 32 + it) * 4; d[0] = e0; d[1] = e1; d[2] = clock64(); d[3] = 0; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();                // no CTA of the pair leaves (or frees TMEM) while the other still works
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.ncols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.ncols) : "memory");
   }
 }
 
@@ -607,12 +685,47 @@ bool make_plan(int cin, int cout, int W, int plane_rows, TcPlan* out) {
   return true;
 }
 
+// The pair form is OFF by default: parity-green (bit-identical to the single-CTA form) but slower in situ - connect4
+// plain layers 85 us against 66 us in step.  The issue-loop micro-benchmark (tests/ubench_umma2.cu) gives 43 cycles per
+// M = 256 instruction against 53.5 for M = 128; inside the kernel, with TMA writes and the epilogue's LSU traffic on BOTH
+// SMs' shared-memory data paths and every instruction waiting for the slower of the two, the leader's issue loop takes
+// 69 cycles per instruction (clock64 timeline: 9.9 k cycles per 144 MMAs = 8 tiles, period 10.5 k; the single-CTA form
+// does 8 tiles on two SMs in 9.5 k).  MZB_TC_PAIR=1 or mzb_conv_tc_pair_enable(1) selects it.
+bool g_tc_pair = false;
+bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MZB_TC_PAIR"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v == 1 || g_tc_pair;
+}
+
+// cta_group::2 form: clusters of two CTAs (64 -> 64 channel layers with resident weights)
+template <int PRV>
+int launch_pair(unsigned grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmAtail,
+                const CUtensorMap& tmB, const TcArgs& a) {
+  static bool configured = false;
+  if (!configured) {
+    MZB_CUDA(cudaFuncSetAttribute(k_conv_tc<64, false, PRV, kEpiWarpsWide, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(64 + kEpiWarpsWide * 32); lc.dynamicSmemBytes = smem; lc.stream = stream;
+  cudaLaunchAttribute la[2];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  la[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[1].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = la; lc.numAttrs = pdl_enabled() ? 2 : 1;
+  MZB_CUDA(cudaLaunchKernelEx(&lc, k_conv_tc<64, false, PRV, kEpiWarpsWide, true, 0, true>, tmA, tmAtail, tmB, a));
+  return MZB_OK;
+}
+
 }  // namespace
 
 static bool g_tc_enabled = true;
 static long long* g_tc_debug = nullptr;
 extern "C" void mzb_conv_tc_debug_buffer(long long* d_buf) { g_tc_debug = d_buf; }   // bring-up: 4*32*4 int64
 extern "C" void mzb_conv_tc_enable(int on) { g_tc_enabled = on != 0; }
+extern "C" void mzb_conv_tc_pair_enable(int on) { g_tc_pair = on != 0; }
 bool mzb_conv_tc_enabled() { return g_tc_enabled && encode_fn() != nullptr; }
 
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
@@ -627,12 +740,23 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   MZB_CHECK_ARG(make_plan(cp.cin, cp.cout, W, cp.extra_plane ? ((H >= 3 && W >= 3) ? 9 : H * W) : 0, &p), "tensor-core convolution: no tile configuration fits");
   const Geo g{H, W, cp.cin, 1};
   const long long rows_total = geo_rows_total(g, B);
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const long long total_tiles_h = (geo_rows_per_image(H, W) * (long long)B + (zero_pads ? geo_halo(W) : 0) + 127) / 128;
+  // the pair form: 64 -> 64 channels, one 64-channel chunk, resident weights, enough tiles for every CTA of an even grid
+  const bool pair = pair_enabled() && p.kc == 64 && p.n_chunks == 1 && cp.cout == 64 && p.b_resident && !zero_pads &&
+                    n_sm % 2 == 0 && total_tiles_h >= 2ll * n_sm;
   CUtensorMap tmA, tmAtail, tmB;
   if (!make_map_2d(&tmA, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)p.kc, 128, p.kc) ||
       !make_map_2d(&tmAtail, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)p.kc,
                    (uint32_t)p.tail_rows, p.kc) ||
       !make_map_2d(&tmB, cp.w_tc, (uint64_t)9 * cp.cin, (uint64_t)cp.cout, (uint64_t)9 * cp.cin * 2, (uint32_t)p.kc,
-                   (uint32_t)cp.cout, p.kc)) {
+                   (uint32_t)(pair ? cp.cout / 2 : cp.cout), p.kc)) {
     mzb_set_error("cuTensorMapEncodeTiled failed (C_in=%d C_out=%d rows=%lld)", cp.cin, cp.cout, rows_total);
     return MZB_ECUDA;
   }
@@ -652,13 +776,6 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
     a.proj_w = proj->w; a.proj_out = proj->out; a.proj_r = proj->r; a.proj_hw = H * W;
     if (cp.cout > 64) MZB_CUDA(cudaMemsetAsync(proj->out, 0, sizeof(float) * (size_t)B * proj->r * H * W, stream));
   }
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
   const long long total_tiles = (a.rows_cover + 127) / 128;
   const unsigned grid = (unsigned)(total_tiles < n_sm ? total_tiles : n_sm);   // persistent: one CTA per SM
   const int pr = (a.proj_r + 1) / 2 * 2;              // instantiated projection heights: 2, 4, 6, 8
@@ -666,6 +783,19 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   if (narrow_on < 0) { const char* e = getenv("MZB_TC_NARROW_EPI"); narrow_on = (e && atoi(e) == 0) ? 0 : 1; }
   const bool narrow = narrow_on && cp.cout <= 32;
   MZB_CHECK_ARG(!(zero_pads && pr), "pad zeroing and head projection are not combined");
+  if (pair) {
+    int rc;
+    switch (pr) {
+      case 0: rc = launch_pair<0>(grid, p.smem, stream, tmA, tmAtail, tmB, a); break;
+      case 2: rc = launch_pair<2>(grid, p.smem, stream, tmA, tmAtail, tmB, a); break;
+      case 4: rc = launch_pair<4>(grid, p.smem, stream, tmA, tmAtail, tmB, a); break;
+      case 6: rc = launch_pair<6>(grid, p.smem, stream, tmA, tmAtail, tmB, a); break;
+      default: rc = launch_pair<8>(grid, p.smem, stream, tmA, tmAtail, tmB, a); break;
+    }
+    if (rc) return rc;
+    MZB_LAUNCH_CHECK();
+    return MZB_OK;
+  }
 #define LAUNCH_RES(KCV, ZPV, PRV, EWV, RESV, NCV)                                                                           \
   {                                                                                                                 \
     static bool configured = false;                                                                                 \

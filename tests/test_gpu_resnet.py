@@ -160,3 +160,31 @@ def test_one_kernel_recurrent_inference_equals_layer_by_layer():
         # lands on the other side of a bf16 rounding boundary (0.4 %) is then amplified by the per-channel min-max
         # scaling; measured 94.4 - 96 % of the second step's elements inside the band, median 2e-3
         assert a.shape == b.shape and np.mean(d <= 1e-2 * np.abs(b) + 1e-2) > 0.93 and np.median(d) < 4e-3, (k, float(d.max()))
+
+
+def test_cta_pair_convolution_equals_single_cta_form():
+    """The cta_group::2 form of the tensor-core convolution (clusters of two CTAs sharing every MMA, each holding half of
+    the weight rows; csrc/mzb_conv_tc.cu, PAIR) against the single-CTA form on a batch large enough to take it
+    (connect4: 64 -> 64 channels, 1,500 boards = 657 tiles): same operands, same K order, fp32 accumulation in TMEM ->
+    bit-identical hidden states and logits, with the residual / action-plane / head-projection epilogues in play."""
+    import ctypes as C
+    from muzero_hypermodel_b200 import _lib
+    _lib.bind("mzb_conv_tc_pair_enable", None, [C.c_int])
+    net, cfg, z = _model("connect4", precision="bf16")
+    rs = np.random.RandomState(11)
+    B = 1500                                              # not a multiple of anything: short last super-tiles, a peer with no tile
+    obs = torch.tensor(rs.randint(-1, 2, (B, 3, 6, 7)).astype(np.float32), device=DEV)
+    act = torch.tensor(rs.randint(7, size=(B, 1)), device=DEV)
+    outs = {}
+    for mode in (1, 0):
+        _lib.lib.mzb_conv_tc_pair_enable(mode)
+        try:
+            v0, r0, p0, s0 = net.initial_inference(obs)
+            v1, r1, p1, s1 = net.recurrent_inference(s0, act)
+            v2, r2, p2, s2 = net.recurrent_inference(s1, act)
+            torch.cuda.synchronize()
+            outs[mode] = [t.float().cpu().numpy() for t in (v0, p0, s0, v1, r1, p1, s1, v2, r2, p2, s2)]
+        finally:
+            _lib.lib.mzb_conv_tc_pair_enable(0)              # the library's default
+    for a, b in zip(outs[1], outs[0]):
+        assert a.shape == b.shape and np.array_equal(a, b), float(np.abs(a - b).max())
