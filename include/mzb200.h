@@ -312,10 +312,11 @@ typedef struct {
 int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* cfg);
 /* Test hook: 0 makes the bf16 path run the CUDA-core direct convolution instead of the tcgen05 kernel. */
 void mzb_conv_tc_enable(int on);
-/* 1 runs the 64 -> 64 channel layers with resident weights as CTA pairs (tcgen05.mma cta_group::2, each CTA holding half
- * of the weight rows) on batches that give every CTA of the grid at least two tiles; default 0 (the pair form is
- * bit-identical but slower in situ).  Also MZB_TC_PAIR=1. */
-void mzb_conv_tc_pair_enable(int on);
+/* Which 64 -> 64 channel layers with resident weights run as CTA pairs (tcgen05.mma cta_group::2, each CTA holding half of
+ * the weight rows) on batches that give every CTA of the grid at least two tiles: 0 none, 1 plain layers (no residual /
+ * action plane / head projection; the default), 2 every eligible layer, -1 back to the MZB_TC_PAIR environment value.
+ * The forms are bit-identical. */
+void mzb_conv_tc_pair_enable(int mode);
 /* Test hook: 0 makes narrow networks (16 channels, <= 48 latent positions: Breakout) run recurrent inference layer by
  * layer instead of the one-kernel warp-per-image path (csrc/mzb_tower16.cu, models.py:363-404, 447-456, 551-595). */
 void mzb_tower16_enable(int on);

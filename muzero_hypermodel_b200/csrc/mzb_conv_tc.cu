@@ -181,7 +181,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t a_chunk_bytes = (uint32_t)a_rows * ROWB;
   const uint32_t a_stage_bytes = (uint32_t)n_chunks * a_chunk_bytes;
   uint32_t rank = 0;                                                     // cluster rank (PAIR): 0 = leader
-  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (PAIR) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    // broadcast through a shuffle: the compiler then knows the rank is warp-uniform.  Without it the role branch on the
+    // rank counts as divergent and ptxas wraps EVERY tcgen05.mma of the issue loop in an ELECT / BRA.U.ANY loop (7
+    // instructions per MMA instead of back-to-back UTCHMMA)
+    rank = __shfl_sync(0xFFFFFFFFu, rank, 0);
+  }
   const int NB = PAIR ? N / 2 : N;                                       // weight rows this CTA holds of every k-block
   const uint32_t b_block_bytes = (uint32_t)NB * ROWB;
   const int NKB = 9 * n_chunks;
@@ -315,20 +321,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }
     }
-  } else if (warp == 1 && PAIR && rank != 0) {
-    // ---------------- peer CTA of a pair: forward "my activations of stage s (and my half of the weights) landed" to
-    // the leader, which issues the MMAs for both CTAs
-    if (elect_one_sync()) {
-      if (RES) mbar_wait(b_full, 0);
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it & 1;
-        mbar_wait(a_full + s, (it >> 1) & 1);
-        mbar_arrive_cluster(peer_a_full + s, 0);
-      }
-    }
   } else if (warp == 1) {
     // ---------------- MMA issuer: warp-uniform loop, tcgen05.mma / commit issued by one elected lane
     if (elect_one_sync()) {
+      if (PAIR && rank != 0) {
+        // peer CTA of a pair: forward "my activations of stage s (and my half of the weights) landed" to the leader,
+        // which issues the MMAs for both CTAs
+        if (RES) mbar_wait(b_full, 0);
+        for (int it = 0; it < n_it; ++it) {
+          const int s = it & 1;
+          mbar_wait(a_full + s, (it >> 1) & 1);
+          mbar_arrive_cluster(peer_a_full + s, 0);
+        }
+      } else {
       const bool leader = true;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
       const uint64_t desc_hi = make_desc<KC>(0);
@@ -407,6 +412,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
         if (a.debug && blockIdx.x == 0 && it < 32 && leader) { long long* d = a.debug + (0 * 32 + it) * 4; d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64(); }
+      }
       }
     }
   } else {
@@ -685,17 +691,17 @@ bool make_plan(int cin, int cout, int W, int plane_rows, TcPlan* out) {
   return true;
 }
 
-// The pair form is OFF by default: parity-green (bit-identical to the single-CTA form) but slower in situ - connect4
-// plain layers 85 us against 66 us in step.  The issue-loop micro-benchmark (tests/ubench_umma2.cu) gives 43 cycles per
-// M = 256 instruction against 53.5 for M = 128; inside the kernel, with TMA writes and the epilogue's LSU traffic on BOTH
-// SMs' shared-memory data paths and every instruction waiting for the slower of the two, the leader's issue loop takes
-// 69 cycles per instruction (clock64 timeline: 9.9 k cycles per 144 MMAs = 8 tiles, period 10.5 k; the single-CTA form
-// does 8 tiles on two SMs in 9.5 k).  MZB_TC_PAIR=1 or mzb_conv_tc_pair_enable(1) selects it.
-bool g_tc_pair = false;
-bool pair_enabled() {
+// Which layers run as CTA pairs.  The pair form is bit-identical to the single-CTA form; in step (connect4, 16,384 boards)
+// it takes 60-62 us against 64-67 us for a PLAIN layer (the MMA stream is bound by its operand fetch, and a pair fetches
+// 128 + 32 instead of 128 + 64 rows per SM and instruction), but 88 against 81 us with a residual input, 80 against 70 with
+// the action plane and 96 / 111 against 90 / 107 with a head projection: those layers are paced by their epilogue, and a
+// pair moves at the pace of the slower of its two epilogues.  Mode 1 (default) = plain layers only, 2 = every eligible
+// layer, 0 = never (MZB_TC_PAIR; mzb_conv_tc_pair_enable() overrides: the tests compare the forms in one process).
+int g_tc_pair = -1;                    // -1: follow MZB_TC_PAIR
+int pair_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MZB_TC_PAIR"); v = (e && atoi(e) != 0) ? 1 : 0; }
-  return v == 1 || g_tc_pair;
+  if (v < 0) { const char* e = getenv("MZB_TC_PAIR"); v = e ? atoi(e) : 1; }
+  return g_tc_pair >= 0 ? g_tc_pair : v;
 }
 
 // cta_group::2 form: clusters of two CTAs (64 -> 64 channel layers with resident weights)
@@ -725,7 +731,7 @@ static bool g_tc_enabled = true;
 static long long* g_tc_debug = nullptr;
 extern "C" void mzb_conv_tc_debug_buffer(long long* d_buf) { g_tc_debug = d_buf; }   // bring-up: 4*32*4 int64
 extern "C" void mzb_conv_tc_enable(int on) { g_tc_enabled = on != 0; }
-extern "C" void mzb_conv_tc_pair_enable(int on) { g_tc_pair = on != 0; }
+extern "C" void mzb_conv_tc_pair_enable(int mode) { g_tc_pair = mode; }
 bool mzb_conv_tc_enabled() { return g_tc_enabled && encode_fn() != nullptr; }
 
 bool mzb_conv_tc_supported(const ConvParams& cp, int H, int W, int cin_stride) {
@@ -749,7 +755,9 @@ int mzb_conv_tc_launch(int B, int H, int W, const ConvParams& cp, const __nv_bfl
   }
   const long long total_tiles_h = (geo_rows_per_image(H, W) * (long long)B + (zero_pads ? geo_halo(W) : 0) + 127) / 128;
   // the pair form: 64 -> 64 channels, one 64-channel chunk, resident weights, enough tiles for every CTA of an even grid
-  const bool pair = pair_enabled() && p.kc == 64 && p.n_chunks == 1 && cp.cout == 64 && p.b_resident && !zero_pads &&
+  const int pmode = pair_mode();
+  const bool plain_layer = residual == nullptr && !cp.extra_plane && !(proj && proj->r > 0);
+  const bool pair = (pmode == 2 || (pmode == 1 && plain_layer)) && p.kc == 64 && p.n_chunks == 1 && cp.cout == 64 && p.b_resident && !zero_pads &&
                     n_sm % 2 == 0 && total_tiles_h >= 2ll * n_sm;
   CUtensorMap tmA, tmAtail, tmB;
   if (!make_map_2d(&tmA, x, (uint64_t)cp.cin, (uint64_t)rows_total, (uint64_t)cp.cin * 2, (uint32_t)p.kc, 128, p.kc) ||

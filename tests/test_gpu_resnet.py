@@ -176,7 +176,7 @@ def test_cta_pair_convolution_equals_single_cta_form():
     obs = torch.tensor(rs.randint(-1, 2, (B, 3, 6, 7)).astype(np.float32), device=DEV)
     act = torch.tensor(rs.randint(7, size=(B, 1)), device=DEV)
     outs = {}
-    for mode in (1, 0):
+    for mode in (2, 0):                                   # 2: every eligible layer as a pair, 0: none
         _lib.lib.mzb_conv_tc_pair_enable(mode)
         try:
             v0, r0, p0, s0 = net.initial_inference(obs)
@@ -185,6 +185,6 @@ def test_cta_pair_convolution_equals_single_cta_form():
             torch.cuda.synchronize()
             outs[mode] = [t.float().cpu().numpy() for t in (v0, p0, s0, v1, r1, p1, s1, v2, r2, p2, s2)]
         finally:
-            _lib.lib.mzb_conv_tc_pair_enable(0)              # the library's default
-    for a, b in zip(outs[1], outs[0]):
+            _lib.lib.mzb_conv_tc_pair_enable(-1)             # back to the library's default (plain layers only)
+    for a, b in zip(outs[2], outs[0]):
         assert a.shape == b.shape and np.array_equal(a, b), float(np.abs(a - b).max())
