@@ -249,3 +249,37 @@ def test_one_kernel_fc_training_step_equals_autograd(game, B, per):
     al = cfg.PER_alpha
     d = np.abs(k[4].cpu().numpy().astype(np.float64) ** (1 / al) - ref[4].detach().cpu().numpy().astype(np.float64) ** (1 / al))
     assert d.max() <= 5e-3, float(d.max())
+
+
+def test_one_kernel_fc_training_step_argument_checks():
+    """mzb_fc_train_grad refuses what it cannot run instead of computing garbage: a layer table that does not cover the
+    parameter bucket, a workspace that is too small, an unroll too long for the kernel's shared memory (the trainer then
+    falls back to autograd)."""
+    import ctypes as C
+    from muzero_hypermodel_b200 import _lib
+    from muzero_hypermodel_b200.trainer import Trainer
+    cfg = importlib.import_module("muzero_hypermodel_b200.games.cartpole").MuZeroConfig()
+    tr = Trainer({"weights": None, "training_step": 0, "optimizer_state": None}, cfg, device=DEV)
+    d = tr._fc_desc()
+    B, K1 = 8, cfg.num_unroll_steps + 1
+    assert _lib.lib.mzb_fc_train_fits(C.byref(d), B, K1) == 1
+    assert _lib.lib.mzb_fc_train_fits(C.byref(d), B, 4000) == 0                     # activations of 4,000 steps do not fit
+    need = int(_lib.lib.mzb_fc_train_workspace_bytes(C.byref(d), B, K1))
+    assert need > 0
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=DEV)
+    full, A = 2 * cfg.support_size + 1, len(cfg.action_space)
+    # the tensors stay referenced for the whole test: a temporary's block would be handed to the next allocation
+    t = dict(obs=z(B, 4), action=z(B, K1, dt=torch.int64), tv=z(B, K1, full), tr=z(B, K1, full), tp=z(B, K1, A), tvs=z(B, K1),
+             gs=torch.ones(B, K1, device=DEV), losses=z(3, B), prio=z(B, K1), loss=z(1))
+    args = lambda n_params, ws: (C.byref(d), _lib.ptr(tr.flat_param), n_params, B, K1, _lib.ptr(t["obs"]), _lib.ptr(t["action"]),
+                                 _lib.ptr(t["tv"]), _lib.ptr(t["tr"]), _lib.ptr(t["tp"]), _lib.ptr(t["tvs"]), None,
+                                 _lib.ptr(t["gs"]), 0.25, 0.5, _lib.ptr(tr.flat_grad), _lib.ptr(t["losses"]),
+                                 _lib.ptr(t["prio"]), _lib.ptr(t["loss"]), _lib.ptr(ws), ws.numel(), _lib.current_stream())
+    ws = torch.zeros(need, dtype=torch.uint8, device=DEV)
+    assert _lib.lib.mzb_fc_train_grad(*args(tr.flat_param.numel(), ws)) == 0
+    torch.cuda.synchronize()
+    assert _lib.lib.mzb_fc_train_grad(*args(tr.flat_param.numel() - 1, ws)) != 0      # table / bucket mismatch
+    assert b"parameters" in _lib.lib.mzb_last_error()
+    small = torch.zeros(16, dtype=torch.uint8, device=DEV)
+    assert _lib.lib.mzb_fc_train_grad(*args(tr.flat_param.numel(), small)) != 0       # workspace too small
+    assert b"workspace" in _lib.lib.mzb_last_error()
