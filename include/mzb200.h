@@ -320,6 +320,9 @@ void mzb_conv_tc_pair_enable(int mode);
 /* Test hook: 0 makes narrow networks (16 channels, <= 48 latent positions: Breakout) run recurrent inference layer by
  * layer instead of the one-kernel warp-per-image path (csrc/mzb_tower16.cu, models.py:363-404, 447-456, 551-595). */
 void mzb_tower16_enable(int on);
+/* Test hook: 0 makes the bf16 DownSample stem (models.py:226-275) run its residual blocks layer by layer on the tcgen05
+ * convolution instead of one launch per resolution with the image resident in shared memory (csrc/mzb_stem16.cu). */
+void mzb_stem16_enable(int on);
 int mzb_resnet_destroy(mzb_resnet_model* m);
 int mzb_resnet_num_tensors(const mzb_resnet_model* m);
 int mzb_resnet_latent_dims(const mzb_resnet_model* m, int32_t* C, int32_t* H, int32_t* W);

@@ -1155,6 +1155,11 @@ int stem_tc(Runner& r, const float* obs) {
   const size_t sm1 = sizeof(float) * ((size_t)9 * m->Cobs * (C / 2) + C), sm2 = sizeof(float) * ((size_t)9 * (C / 2) * C + 2 * C);
   if (sm1 > 96 * 1024 || sm2 > 96 * 1024) { mzb_set_error("bf16 stem: stride-2 weights exceed 96 KiB of shared memory"); r.rc = MZB_EUNSUPPORTED; return 0; }
   r.zero_pads = 1;
+  // The leading halo is never written by a layer, and the buffers change geometry (halo g1 >= g2 >= g3 >= latent): rows that
+  // are halo at this call's first resolutions held image rows of the previous call's later ones, and the (-1, -1) tap of image
+  // 0's first pixel reads the halo's last row.  Clear it once per call (found by the run-to-run determinism test).
+  { const size_t lead = (size_t)std::max(geo_halo(g1.W) * g1.C, geo_halo(g2.W) * g2.C) * sizeof(T);
+    for (int i = 0; i < 3; ++i) cudaMemsetAsync(r.buf<T>(i), 0, lead, r.s); }
   if (g0.W % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0)
     k_stem_conv1_pair<<<nblk(out_rows(g1), 128), 128, sm1, r.s>>>(obs, B, g0, m->Cobs, m->ds_conv1.w, m->ds_conv1.scale,
                                                                 m->ds_conv1.shift, C / 2, g1, r.buf<T>(1));
@@ -1162,16 +1167,22 @@ int stem_tc(Runner& r, const float* obs) {
     k_conv_s2<true><<<nblk(2 * out_rows(g1), 128), 128, sm1, r.s>>>(obs, B, g0, m->Cobs, 0, m->ds_conv1.w, m->ds_conv1.scale,
                                                                   m->ds_conv1.shift, C / 2, g1, 1, r.buf<T>(1));
   mzb_count_launch();
-  int cur = tower<T>(r, m->ds1_tc, g1, 1);
+  // a stage's blocks: one launch with the image resident in shared memory (mzb_stem16.cu, in place), else layer by layer
+  auto stage = [&](std::vector<Block>& blocks, const Geo& g, int at) {
+    if (r.rc || !mzb_stem16_supported(blocks, g.H, g.W, g.C)) return tower<T>(r, blocks, g, at);
+    r.rc = mzb_stem16_tower(blocks, B, g.H, g.W, r.buf<T>(at), r.s);
+    return at;
+  };
+  int cur = stage(m->ds1_tc, g1, 1);
   { const int nx = (cur + 1) % 3;
     k_conv_s2<false><<<nblk(out_rows(g2), 128), 128, sm2, r.s>>>(r.buf<T>(cur), B, g1, C / 2, 1, m->ds_conv2.w, m->ds_conv2.scale,
                                                                m->ds_conv2.shift, C, g2, 0, r.buf<T>(nx));
     mzb_count_launch(); cur = nx; }
-  cur = tower<T>(r, m->ds2, g2, cur);
+  cur = stage(m->ds2, g2, cur);
   { const int nx = (cur + 1) % 3;
     k_avgpool_pad<<<nblk(out_rows(g3) * (C / 8), 256), 256, 0, r.s>>>(r.buf<T>(cur), B, g2, g3, r.buf<T>(nx));
     mzb_count_launch(); cur = nx; }
-  cur = tower<T>(r, m->ds3, g3, cur);
+  cur = stage(m->ds3, g3, cur);
   { const int nx = (cur + 1) % 3;
     k_avgpool_pad<<<nblk(out_rows(gl) * (C / 8), 256), 256, 0, r.s>>>(r.buf<T>(cur), B, g3, gl, r.buf<T>(nx));
     mzb_count_launch(); cur = nx; }

@@ -40,3 +40,7 @@ bool mzb_tower16_supported(const mzb_resnet_model* m, int in_layout, int out_lay
 int mzb_tower16_recurrent(mzb_resnet_model* m, int B, const void* state_in, int in_layout, long long in_row_stride,
                           const int* in_slot, long long slot_stride, const int* action, void* state_out, int out_layout,
                           long long out_row_stride, long long out_off, float* proj_r, float* proj_vp, cudaStream_t s);
+
+// a stem stage's residual tower with the image resident in shared memory (mzb_stem16.cu), in place on a padded buffer
+bool mzb_stem16_supported(const std::vector<Block>& blocks, int H, int W, int C);
+int mzb_stem16_tower(const std::vector<Block>& blocks, int B, int H, int W, __nv_bfloat16* x, cudaStream_t s);

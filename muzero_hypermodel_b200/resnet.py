@@ -30,6 +30,7 @@ _lib.bind("mzb_resnet_set_weights", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i6
 _lib.bind("mzb_resnet_workspace_bytes", C.c_size_t, [_vp, _i64])
 _lib.bind("mzb_conv_tc_enable", None, [C.c_int])
 _lib.bind("mzb_tower16_enable", None, [C.c_int])
+_lib.bind("mzb_stem16_enable", None, [C.c_int])
 _lib.bind("mzb_resnet_workspace_init", C.c_int, [_vp, _vp, C.c_size_t, _vp])
 _lib.bind("mzb_resnet_initial", C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_size_t, _vp, C.c_int, _i64, _i64] + [_vp] * 7)
 _lib.bind("mzb_resnet_conv_probe", C.c_int, [_vp, _i64, _vp, C.c_size_t, C.c_int32, _vp])

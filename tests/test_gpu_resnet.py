@@ -162,6 +162,39 @@ def test_one_kernel_recurrent_inference_equals_layer_by_layer():
         assert a.shape == b.shape and np.mean(d <= 1e-2 * np.abs(b) + 1e-2) > 0.93 and np.median(d) < 4e-3, (k, float(d.max()))
 
 
+def test_stem_towers_in_shared_memory_equal_layer_by_layer():
+    """Breakout's DownSample stem: the residual blocks of each resolution as ONE launch with the image resident in shared
+    memory (csrc/mzb_stem16.cu: mma.sync convolutions, weights as register-resident A fragments, stmatrix epilogue) against
+    the same blocks layer by layer on the tcgen05 convolution.  Same bf16 weights (scale folded in), same rounding points;
+    only the fp32 summation order inside the MMAs differs.  333 frames: more images than CTAs x groups, so the persistent
+    loop, the prefetch of the next image and a ragged last round are in play."""
+    from muzero_hypermodel_b200 import _lib
+    net, cfg, z = _model("breakout", precision="bf16")
+    rs = np.random.RandomState(5)
+    B = 333
+    obs = torch.tensor(rs.randint(0, 256, size=(B,) + tuple(z["breakout/obs"].shape[1:])).astype(np.float32) / 255.0, device=DEV)
+    outs = {}
+    for mode in (1, 0):
+        _lib.lib.mzb_stem16_enable(mode)
+        try:
+            v0, r0, p0, s0 = net.initial_inference(obs)
+            outs[mode] = dict(v0=v0.float().cpu().numpy(), p0=p0.float().cpu().numpy(), s0=s0.float().cpu().numpy())
+        finally:
+            _lib.lib.mzb_stem16_enable(1)
+    again = net.initial_inference(obs)[3].float().cpu().numpy()
+    np.testing.assert_array_equal(again, outs[1]["s0"])                  # deterministic, no state left behind in the buffers
+    for k in ("v0", "p0"):
+        a, b = outs[1][k], outs[0][k]
+        np.testing.assert_allclose(a, b, rtol=3e-2, atol=3e-2, err_msg=k)
+        assert np.median(np.abs(a - b)) < 3e-3, (k, float(np.median(np.abs(a - b))))
+    a, b = outs[1]["s0"], outs[0]["s0"]
+    d = np.abs(a - b)
+    assert a.shape == b.shape and np.mean(d <= 1e-2 * np.abs(b) + 1e-2) > 0.93 and np.median(d) < 4e-3, (float(d.max()), float(np.mean(d <= 1e-2 * np.abs(b) + 1e-2)))
+    # every image went through the same program: image i alone gives image i of the batch
+    one = net.initial_inference(obs[200:201])[3].float().cpu().numpy()
+    np.testing.assert_array_equal(one[0], outs[1]["s0"][200])
+
+
 def test_cta_pair_convolution_equals_single_cta_form():
     """The cta_group::2 form of the tensor-core convolution (clusters of two CTAs sharing every MMA, each holding half of
     the weight rows; csrc/mzb_conv_tc.cu, PAIR) against the single-CTA form on a batch large enough to take it
