@@ -8,10 +8,18 @@
 // (9 convolutions + 3 heads + min-max + gather = 14 launches of 20-40 us per simulation for 16,384 games) and the whole
 // activation set of an image is 1.1 KB.  Here a WARP owns an image: its activations live in shared memory in the padded
 // layout of mzb_resnet.cuh (so a tap is a row shift), all layers' weights are resident in shared memory (9 x 4.6 KB),
-// and each convolution is 3 m-tiles x 2 n-tiles x 9 taps of mma.sync.m16n8k16 (bf16 operands, fp32 accumulate) fed by
-// ldmatrix - the warp-level MMA is the right size for a 36 x 16 x 144 product; nothing but the input state, the output
-// state and the projection rows touches global memory.  Arithmetic per layer is the bf16 path's: fp32 accumulate,
-// folded batch-norm, residual, ReLU, one bf16 rounding of the stored activation.
+// and each convolution is 9 taps x ceil(HW / 8) n-tiles of mma.sync.m16n8k16 (bf16 operands, fp32 accumulate) with the roles
+// of mzb_stem16.cu: A = a tap's weights [cout][cin], the nine A fragments of a layer held in registers; B = 8 positions x 16
+// input channels, one ldmatrix.x4 feeds two n-tiles; D = [cout][position], stored through stmatrix.trans, the residual read
+// through ldmatrix.trans.  An n-tile is 8 CONSECUTIVE PADDED ROWS starting at the first pixel line (6 n-tiles span the 42
+// rows of a 6 x 6 image; the zero-column rows inside are computed and stored as zeros): with 48-byte rows any 8 consecutive
+// rows are conflict-free, whereas 8 consecutive POSITIONS are 8 of 9 consecutive rows and rows r and r + 8 share a bank
+// group - every ldmatrix of the position-mapped form took 2 wavefronts per 8 x 8 matrix (ncu: 2,400 shared-memory load
+// wavefronts per image where 1,300 were expected).  The kernel is bound by shared-memory bandwidth, so wavefronts per
+// layer and image are what counts: 108 (activations) + 36 (weights) + 24 (epilogue).
+// The warp-level MMA is the right size for a 36 x 16 x 144 product; nothing but the input state, the output state and
+// the projection rows touches global memory.  Arithmetic per layer is the bf16 path's: fp32 accumulate, folded
+// batch-norm, residual, ReLU, one bf16 rounding of the stored activation.
 #include <cuda_bf16.h>
 
 #include "mzb_resnet_model.h"
@@ -23,7 +31,9 @@ constexpr int kTapB = 16 * kRowB;      // one tap of one convolution: 16 output 
 constexpr int kConvB = 9 * kTapB;
 constexpr int kMaxBlocks = 4;
 constexpr int kWarps = 16;
-constexpr int MT = 3;                  // m-tiles of 16 positions
+constexpr int NP = 3;                  // pairs of n-tiles: up to 48 positions
+constexpr int kTabP = 72;              // row length of the transposed action-plane table: 72 / 2 = 4 (mod 16) -> the 8-byte
+                                       // loads of a half-warp (4 channels x 4 position pairs) hit 16 distinct bank pairs
 
 struct T16Conv { const __nv_bfloat16* w; const float* scale; const float* shift; };
 struct T16Args {
@@ -45,6 +55,14 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void stsm_x4_t(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+               :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -52,63 +70,65 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// Per-lane addressing of one pair of n-tiles (16 padded rows): matrix lane >> 3 of an ldmatrix / stmatrix .x4 is
+// (n-tile (lane >> 4), channel half (lane >> 3) & 1), its row is lane & 7.
 struct Lane {
-  int a_row[MT];            // A fragment: padded row of the position this lane addresses, per m-tile
-  int a_koff;               // byte offset of the k half it addresses
-  int o_row[MT][2], o_pos[MT][2];
-  bool o_ok[MT][2];
-  uint32_t b_off;           // B fragment: byte offset of the weight row this lane addresses inside a tap
+  uint32_t b_off[NP];       // byte offset of the row this lane addresses; rows past the last pixel line: a row of the zero
+                            // line (reads give zeros or discarded sums, the masked stores write zeros onto zeros)
+  uint32_t ok;              // bit 2 nt + e: row 8 nt + 2 (lane & 3) + e of the span is a pixel (else stored as zero)
+  uint32_t a_off;           // weights: row (cout) and channel half inside a tap
 };
 
 // One 3x3 convolution (16 -> 16 channels) over the warp's image: in -> out, both padded shared-memory buffers.
 template <bool PLANE, bool RES>
-__device__ __forceinline__ void conv16(uint32_t in_u32, uint8_t* out, const uint8_t* res, uint32_t w_u32, const float* sc,
-                                       const float* sh, float pl, const float* ptab, const Lane& L, int pitch, int lane) {
-  float acc[MT][2][4];
+__device__ __forceinline__ void conv16(uint32_t in_u32, uint32_t out_u32, uint32_t res_u32, uint32_t w_u32, const float* sh, float pl,
+                                       const float* ptab, const Lane& L, int pitch, int lane, int HP) {
+  uint32_t af[9][4];
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+  for (int tap = 0; tap < 9; ++tap) ldsm_x4(w_u32 + (uint32_t)tap * kTapB + L.a_off, af[tap]);
+  float acc[2 * NP][4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+  for (int j = 0; j < 2 * NP; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.0f;
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    const int shift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
-    uint32_t bf[4];
-    ldsm_x4(w_u32 + (uint32_t)tap * kTapB + L.b_off, bf);
+    const uint32_t shift = (uint32_t)(((tap / 3 - 1) * pitch + (tap % 3 - 1)) * kRowB);
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      uint32_t af[4];
-      ldsm_x4(in_u32 + (uint32_t)((L.a_row[mt] + shift) * kRowB + L.a_koff), af);
-      mma16816(acc[mt][0], af, bf[0], bf[1]);
-      mma16816(acc[mt][1], af, bf[2], bf[3]);
+    for (int p = 0; p < NP; ++p) {
+      if (16 * p >= HP) continue;                      // warp-uniform: HP = H * pitch rows from the first to the last pixel
+      uint32_t bf[4];
+      ldsm_x4(in_u32 + L.b_off[p] + shift, bf);
+      mma16816(acc[2 * p], af[tap], bf[0], bf[1]);
+      if (16 * p + 8 < HP) mma16816(acc[2 * p + 1], af[tap], bf[2], bf[3]);
     }
   }
-  const int cq = (lane & 3) * 2;
+  const int c_lo = lane >> 2, q2 = (lane & 3) * 2;
+  const float sh_lo = sh[c_lo], sh_hi = sh[c_lo + 8];  // the batch-norm scale is folded into the bf16 weights (ConvParams::w_tc), as in k_conv_tc
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
+  for (int p = 0; p < NP; ++p) {
+    if (16 * p >= HP) continue;
+    uint32_t rs[4] = {0u, 0u, 0u, 0u}, pk[4];
+    if (RES) ldsm_x4_t(res_u32 + L.b_off[p], rs);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (!L.o_ok[mt][h]) continue;
+    for (int jj = 0; jj < 2; ++jj) {
+      const int nt = 2 * p + jj;
+      const bool k0 = (L.ok >> (2 * nt)) & 1u, k1 = (L.ok >> (2 * nt + 1)) & 1u;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = 8 * j + cq;
-        float v0 = acc[mt][j][2 * h], v1 = acc[mt][j][2 * h + 1];
+      for (int h = 0; h < 2; ++h) {
+        float v0 = acc[nt][2 * h], v1 = acc[nt][2 * h + 1];
         if (PLANE) {
-          v0 = fmaf(pl, ptab[L.o_pos[mt][h] * 16 + c], v0);
-          v1 = fmaf(pl, ptab[L.o_pos[mt][h] * 16 + c + 1], v1);
+          const float2 t = *reinterpret_cast<const float2*>(ptab + (c_lo + 8 * h) * kTabP + 8 * nt + q2);
+          v0 = fmaf(pl, t.x, v0); v1 = fmaf(pl, t.y, v1);
         }
-        v0 += sh[c];                       // the batch-norm scale is folded into the bf16 weights (ConvParams::w_tc), as in k_conv_tc
-        v1 += sh[c + 1];
-        if (RES) {
-          const uint32_t rw = *reinterpret_cast<const uint32_t*>(res + L.o_row[mt][h] * kRowB + c * 2);
-          v0 += bf_lo(rw); v1 += bf_hi(rw);
-        }
-        v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f);
-        const __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
-        *reinterpret_cast<uint32_t*>(out + L.o_row[mt][h] * kRowB + c * 2) = *reinterpret_cast<const uint32_t*>(&pk);
+        v0 += h ? sh_hi : sh_lo; v1 += h ? sh_hi : sh_lo;
+        if (RES) { v0 += bf_lo(rs[2 * jj + h]); v1 += bf_hi(rs[2 * jj + h]); }
+        v0 = k0 ? fmaxf(v0, 0.0f) : 0.0f; v1 = k1 ? fmaxf(v1, 0.0f) : 0.0f;
+        const __nv_bfloat162 pr = __floats2bfloat162_rn(v0, v1);
+        pk[2 * jj + h] = *reinterpret_cast<const uint32_t*>(&pr);
       }
     }
+    stsm_x4_t(out_u32 + L.b_off[p], pk);
   }
   __syncwarp();
 }
@@ -139,11 +159,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
   const int rows = halo + geo_rows_per_image(H, W) + halo;
   uint8_t* s_w = smem;                                              // [n_conv][9][16][kRowB]
   float* s_sc = reinterpret_cast<float*>(s_w + (size_t)a.n_conv * kConvB);       // [n_conv][32]: scale | shift
-  float* s_ptab = s_sc + a.n_conv * 32;                             // [HW][16]
-  float* s_wr = s_ptab + HW * 16;                                   // [r_r][16]
+  float* s_ptab = s_sc + a.n_conv * 32;                             // [16][kTabP]: action-plane table, channel-major
+  float* s_wr = s_ptab + 16 * kTabP;                                // [r_r][16]
   float* s_wvp = s_wr + a.r_r * 16;                                 // [r_vp][16]
   int* s_row = reinterpret_cast<int*>(s_wvp + a.r_vp * 16);          // [HW]: padded row of position p (no divisions in the loops)
   uint8_t* s_act = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_row + HW) + 127) & ~(uintptr_t)127);
+  const int HP = H * pitch;                                           // padded rows from the first pixel to the end of the last line
   const size_t buf_bytes = (size_t)rows * kRowB;
   // ---- stage the weights: w_tc (scale folded in) [16 cout][9 taps][16 cin] -> [tap][cout] rows of kRowB bytes
   for (int i = threadIdx.x; i < a.n_conv * 9 * 16 * 2; i += blockDim.x) {
@@ -155,7 +176,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     const int ci = i >> 5, k = i & 31;
     s_sc[i] = k < 16 ? a.conv[ci].scale[k] : a.conv[ci].shift[k - 16];
   }
-  for (int i = threadIdx.x; i < HW * 16; i += blockDim.x) s_ptab[i] = a.plane_table[i] * a.conv[0].scale[i & 15];   // conv[0] = the dynamics convolution
+  for (int i = threadIdx.x; i < 16 * kTabP; i += blockDim.x) {       // conv[0] = the dynamics convolution
+    const int c = i / kTabP, rel = i - c * kTabP, y = rel / pitch, x = rel - y * pitch;       // indexed by the row of the span
+    s_ptab[i] = (rel < HP && x < W) ? a.plane_table[(y * W + x) * 16 + c] * a.conv[0].scale[c] : 0.0f;
+  }
   for (int i = threadIdx.x; i < a.r_r * 16; i += blockDim.x) s_wr[i] = a.w_r[i];
   for (int i = threadIdx.x; i < a.r_vp * 16; i += blockDim.x) s_wvp[i] = a.w_vp[i];
   for (int p = threadIdx.x; p < HW; p += blockDim.x) s_row[p] = halo + (p / W + 1) * pitch + p % W;
@@ -168,21 +192,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
   auto buf = [&](int i) -> uint8_t* { return buf0 + (size_t)i * buf_bytes; };
   Lane L;
   {
-    const int r = (lane & 7) + 8 * ((lane >> 3) & 1);
+    L.ok = 0u;
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const int p = 16 * mt + r;
-      L.a_row[mt] = p < HW ? halo + (p / W + 1) * pitch + p % W : halo;          // out-of-image rows read a zero line
+    for (int p = 0; p < NP; ++p) {
+      const int rel = 16 * p + 8 * (lane >> 4) + (lane & 7);
+      L.b_off[p] = (uint32_t)((rel < HP ? halo + pitch + rel : halo) * kRowB + ((lane >> 3) & 1) * 16);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int q = 16 * mt + (lane >> 2) + 8 * h;
-        L.o_ok[mt][h] = q < HW;
-        L.o_pos[mt][h] = q < HW ? q : 0;
-        L.o_row[mt][h] = q < HW ? halo + (q / W + 1) * pitch + q % W : halo;
+      for (int e = 0; e < 4; ++e) {
+        const int r2 = 16 * p + 8 * (e >> 1) + (lane & 3) * 2 + (e & 1);
+        if (r2 < HP && r2 % pitch < W) L.ok |= 1u << (4 * p + e);
       }
     }
-    L.a_koff = (lane >> 4) * 16;
-    L.b_off = (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * kRowB + ((lane >> 3) & 1) * 16);
+    L.a_off = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * kRowB + (lane >> 4) * 16);
   }
   const uint32_t w_u32 = smem_u32(s_w);
 
@@ -206,15 +227,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     __syncwarp();
     // ---- dynamics: conv + action plane, residual tower (models.py:377-387)
     int ci = 0;
-    conv16<true, false>(smem_u32(buf(0)), buf(1), nullptr, w_u32, s_sc, s_sc + 16, pl, s_ptab, L, pitch, lane);
+    conv16<true, false>(smem_u32(buf(0)), smem_u32(buf(1)), 0u, w_u32, s_sc + 16, pl, s_ptab, L, pitch, lane, HP);
     ci = 1;
     int cur = 1;
     for (int k = 0; k < a.n_dyn; ++k, ci += 2) {
       const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-      conv16<false, false>(smem_u32(buf(cur)), buf(t), nullptr, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32, s_sc + ci * 32 + 16, 0.0f,
-                           nullptr, L, pitch, lane);
-      conv16<false, true>(smem_u32(buf(t)), buf(o), buf(cur), w_u32 + (uint32_t)(ci + 1) * kConvB, s_sc + (ci + 1) * 32,
-                          s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane);
+      conv16<false, false>(smem_u32(buf(cur)), smem_u32(buf(t)), 0u, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32 + 16, 0.0f,
+                           nullptr, L, pitch, lane, HP);
+      conv16<false, true>(smem_u32(buf(t)), smem_u32(buf(o)), smem_u32(buf(cur)), w_u32 + (uint32_t)(ci + 1) * kConvB,
+                          s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane, HP);
       cur = o;
     }
     // ---- reward head projection on the UN-normalised next state (:388-391)
@@ -261,10 +282,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     if (a.proj_vp) {
       for (int k = 0; k < a.n_pred; ++k, ci += 2) {
         const int t = (cur + 1) % 3, o = (cur + 2) % 3;
-        conv16<false, false>(smem_u32(buf(cur)), buf(t), nullptr, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32, s_sc + ci * 32 + 16,
-                             0.0f, nullptr, L, pitch, lane);
-        conv16<false, true>(smem_u32(buf(t)), buf(o), buf(cur), w_u32 + (uint32_t)(ci + 1) * kConvB, s_sc + (ci + 1) * 32,
-                            s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane);
+        conv16<false, false>(smem_u32(buf(cur)), smem_u32(buf(t)), 0u, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32 + 16,
+                             0.0f, nullptr, L, pitch, lane, HP);
+        conv16<false, true>(smem_u32(buf(t)), smem_u32(buf(o)), smem_u32(buf(cur)), w_u32 + (uint32_t)(ci + 1) * kConvB,
+                            s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane, HP);
         cur = o;
       }
       project(buf(cur), s_wvp, a.r_vp, a.proj_vp + (long long)b * a.r_vp * HW, HW, s_row, lane);
@@ -276,7 +297,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
 size_t tower16_smem(const mzb_resnet_model* m) {
   const int n_conv = 1 + 2 * (int)m->dyn_blocks.size() + 2 * (int)m->pred_blocks.size();
   const int HW = m->Hl * m->Wl, rows = 2 * geo_halo(m->Wl) + geo_rows_per_image(m->Hl, m->Wl);
-  return 128 + (size_t)n_conv * kConvB + sizeof(float) * ((size_t)n_conv * 32 + (size_t)HW * 17 + (size_t)(m->reward.r + m->value.r + m->policy.r) * 16) +
+  return 128 + (size_t)n_conv * kConvB + sizeof(float) * ((size_t)n_conv * 32 + (size_t)16 * kTabP + HW + (size_t)(m->reward.r + m->value.r + m->policy.r) * 16) +
          128 + (size_t)kWarps * 3 * rows * kRowB;
 }
 
@@ -286,7 +307,7 @@ static bool g_tower16_enabled = true;
 extern "C" void mzb_tower16_enable(int on) { g_tower16_enabled = on != 0; }     // comparison / bring-up knob
 
 bool mzb_tower16_supported(const mzb_resnet_model* m, int in_layout, int out_layout) {
-  if (!g_tower16_enabled || !mzb_conv_tc_enabled() || m->precision != 1 || m->C != 16 || m->Hl * m->Wl > 16 * MT) return false;
+  if (!g_tower16_enabled || !mzb_conv_tc_enabled() || m->precision != 1 || m->C != 16 || m->Hl * (m->Wl + 1) > 16 * NP) return false;
   if (m->dyn_blocks.size() > kMaxBlocks || m->pred_blocks.size() > kMaxBlocks) return false;
   if ((in_layout != 0 && in_layout != 2) || (out_layout != 0 && out_layout != 2)) return false;
   if (!m->dyn_conv.w_bf16 || !m->dyn_conv.plane_table || m->dyn_conv.cin != 16 || !m->pv_w) return false;
