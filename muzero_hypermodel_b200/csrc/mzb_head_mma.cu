@@ -39,13 +39,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&p);
 }
 
+// One head's work: blockIdx.y selects it, so the reward / value / policy heads of one inference are ONE launch (each was a
+// ~10 us latency-bound launch: 30 us of a 230 us Breakout simulation).
+struct HeadJob {
+  const float* proj; long long proj_stride; int proj_off; int mode;
+  const uint8_t* legal; float* logits; float* scalar; float* priors;
+  MmaHead hp;
+};
+constexpr int kMaxJobs = 3;
+struct HeadJobs { HeadJob j[kMaxJobs]; };
+
 // MAXN: widest layer output (64 or 128): bounds the accumulator / fragment register arrays
 template <int MAXN>
-__global__ void __launch_bounds__(256) k_head_mma(const float* __restrict__ proj, long long proj_stride, int proj_off, int B,
-                                                  MmaHead hp, int S, int mode, const uint8_t* __restrict__ legal,
-                                                  float* __restrict__ logits_out, float* __restrict__ scalar_out,
-                                                  float* __restrict__ priors_out) {
+__global__ void __launch_bounds__(256) k_head_mma(const __grid_constant__ HeadJobs jobs, int B, int S) {
   extern __shared__ __align__(16) uint8_t smem[];
+  const HeadJob& job = jobs.j[blockIdx.y];
+  const MmaHead& hp = job.hp;
+  const float* __restrict__ proj = job.proj;
+  const long long proj_stride = job.proj_stride;
+  const int proj_off = job.proj_off, mode = job.mode;
+  const uint8_t* __restrict__ legal = job.legal;
+  float* __restrict__ logits_out = job.logits;
+  float* __restrict__ scalar_out = job.scalar;
+  float* __restrict__ priors_out = job.priors;
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---- stage weights (bf16, padded rows) and biases
   {
@@ -220,24 +236,37 @@ bool mzb_head_mma_pack(mzb_resnet_model* m, const HeadParams& hp, const std::vec
 
 void mzb_head_mma_free(void* opaque) { delete static_cast<MmaHeadPack*>(opaque); }
 
-int mzb_head_mma_launch(void* opaque, const float* proj, long long proj_stride, int proj_off, int B, int S, int mode,
-                        const uint8_t* legal, float* logits, float* scalar, float* priors, cudaStream_t stream) {
-  auto* pk = static_cast<MmaHeadPack*>(opaque);
-  if (!pk || !pk->ok) { mzb_set_error("tensor-core head: shape not packed"); return MZB_EUNSUPPORTED; }
-  const MmaHead& h = pk->h;
+int mzb_head_mma_launch_n(int n, const MmaHeadCall* calls, int B, int S, cudaStream_t stream) {
+  if (n < 1 || n > kMaxJobs) { mzb_set_error("tensor-core head: %d jobs in one launch", n); return MZB_EINVAL; }
+  HeadJobs jobs{};
   int maxn = 0;
-  for (int l = 0; l < h.n_fc; ++l) maxn = maxn > h.l[l].Np ? maxn : h.l[l].Np;
-  const size_t smem = (size_t)h.smem_w_bytes + (size_t)8 * 16 * h.logit_stride * 4;
+  size_t smem = 0;
+  for (int i = 0; i < n; ++i) {
+    auto* pk = static_cast<MmaHeadPack*>(calls[i].opaque);
+    if (!pk || !pk->ok) { mzb_set_error("tensor-core head: shape not packed"); return MZB_EUNSUPPORTED; }
+    const MmaHead& h = pk->h;
+    for (int l = 0; l < h.n_fc; ++l) maxn = maxn > h.l[l].Np ? maxn : h.l[l].Np;
+    smem = std::max(smem, (size_t)h.smem_w_bytes + (size_t)8 * 16 * h.logit_stride * 4);
+    jobs.j[i] = HeadJob{calls[i].proj, calls[i].proj_stride, calls[i].proj_off, calls[i].mode, calls[i].legal,
+                        calls[i].logits, calls[i].scalar, calls[i].priors, h};
+  }
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_head_mma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_head_mma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
-  int grid = (B + 8 * 16 - 1) / (8 * 16);
-  if (grid > 148 * 2) grid = 148 * 2;
-  if (maxn <= 64) k_head_mma<64><<<grid, 256, smem, stream>>>(proj, proj_stride, proj_off, B, h, S, mode, legal, logits, scalar, priors);
-  else k_head_mma<128><<<grid, 256, smem, stream>>>(proj, proj_stride, proj_off, B, h, S, mode, legal, logits, scalar, priors);
+  int gx = (B + 8 * 16 - 1) / (8 * 16);
+  if (gx > 148 * 2) gx = 148 * 2;
+  const dim3 grid(gx, n);
+  if (maxn <= 64) k_head_mma<64><<<grid, 256, smem, stream>>>(jobs, B, S);
+  else k_head_mma<128><<<grid, 256, smem, stream>>>(jobs, B, S);
   MZB_LAUNCH_CHECK();
   return MZB_OK;
+}
+
+int mzb_head_mma_launch(void* opaque, const float* proj, long long proj_stride, int proj_off, int B, int S, int mode,
+                        const uint8_t* legal, float* logits, float* scalar, float* priors, cudaStream_t stream) {
+  const MmaHeadCall c{opaque, proj, proj_stride, proj_off, mode, legal, logits, scalar, priors};
+  return mzb_head_mma_launch_n(1, &c, B, S, stream);
 }

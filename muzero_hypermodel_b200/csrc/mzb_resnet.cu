@@ -802,6 +802,10 @@ int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* c) {
       m->ds1_tc.resize(2);
       for (auto& b : m->ds1_tc)
         ok = ok && init_conv(m, b.c1, m->stem_cp1, m->stem_cp1, 1, 0, 0) && init_conv(m, b.c2, m->stem_cp1, m->stem_cp1, 1, 0, 0);
+      if (C == 16) {
+        m->ds_conv2_mma = (__nv_bfloat16*)dev_alloc(m, sizeof(__nv_bfloat16) * 6 * C * 16);
+        ok = ok && m->ds_conv2_mma;
+      }
     }
   }
   ok = ok && init_conv(m, m->rep_conv, m->Cobs, C, 1, 0, 0) && init_conv(m, m->dyn_conv, C, C, 1, 1, hw);
@@ -922,7 +926,23 @@ bool pack_conv_pair(ConvParams& c, const float* w, int src, const std::vector<fl
          upload(c.scale, scale.data(), scale.size() * 4) && upload(c.shift, shift.data(), shift.size() * 4);
 }
 
-bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl, ConvParams* wide = nullptr) {
+// DownSample.conv2 on pixel-pair input rows (16 = 2 pixels x 8 channels) as six K = 16 taps: tap 2 ky + 0 reads the pair
+// row LEFT of the output pixel (its second pixel is input column 2 ox - 1: kx = 0; its first pixel is not a tap), tap
+// 2 ky + 1 the pair row AT the output pixel (columns 2 ox, 2 ox + 1: kx = 1, 2).  [6][cout][16] bf16, scale folded in.
+bool pack_s2_mma(__nv_bfloat16* dst, const float* w, int cin, int cout, const std::vector<float>& scale) {
+  std::vector<__nv_bfloat16> wb((size_t)6 * cout * 2 * cin, __float2bfloat16(0.0f));
+  for (int ky = 0; ky < 3; ++ky)
+    for (int o = 0; o < cout; ++o)
+      for (int ci = 0; ci < cin; ++ci) {
+        auto src = [&](int kx) { return w[((size_t)o * cin + ci) * 9 + ky * 3 + kx] * scale[o]; };
+        wb[((size_t)(2 * ky) * cout + o) * 2 * cin + cin + ci] = __float2bfloat16(src(0));
+        wb[((size_t)(2 * ky + 1) * cout + o) * 2 * cin + ci] = __float2bfloat16(src(1));
+        wb[((size_t)(2 * ky + 1) * cout + o) * 2 * cin + cin + ci] = __float2bfloat16(src(2));
+      }
+  return upload(dst, wb.data(), wb.size() * 2);
+}
+
+bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl, ConvParams* wide = nullptr, __nv_bfloat16* s2_mma = nullptr) {
   const int cw = c.cin + c.extra_plane;
   const float* w = cur.take((int64_t)c.cout * cw * 9);
   std::vector<float> scale(c.cout, 1.0f), shift(c.cout, 0.0f);
@@ -936,7 +956,8 @@ bool load_conv(Cursor& cur, ConvParams& c, bool with_bn, int Hl, int Wl, ConvPar
     }
   }
   if (cur.bad) return false;
-  return pack_conv(c, w, c.cin, c.cout, scale, shift, Hl, Wl) && (!wide || pack_conv_pair(*wide, w, c.cin, scale, shift));
+  return pack_conv(c, w, c.cin, c.cout, scale, shift, Hl, Wl) && (!wide || pack_conv_pair(*wide, w, c.cin, scale, shift)) &&
+         (!s2_mma || pack_s2_mma(s2_mma, w, c.cin, c.cout, scale));
 }
 
 bool load_block(Cursor& cur, Block& b) { return load_conv(cur, b.c1, true, 0, 0) && load_conv(cur, b.c2, true, 0, 0); }
@@ -983,7 +1004,7 @@ extern "C" int mzb_resnet_set_weights(mzb_resnet_model* m, const float* const* h
       ok = ok && load_conv(cur, m->ds1[i].c1, true, 0, 0, wide ? &wide->c1 : nullptr) &&
            load_conv(cur, m->ds1[i].c2, true, 0, 0, wide ? &wide->c2 : nullptr);
     }
-    ok = ok && load_conv(cur, m->ds_conv2, false, 0, 0);
+    ok = ok && load_conv(cur, m->ds_conv2, false, 0, 0, nullptr, m->ds_conv2_mma);
     for (auto& b : m->ds2) ok = ok && load_block(cur, b);
     for (auto& b : m->ds3) ok = ok && load_block(cur, b);
   }
@@ -1123,6 +1144,13 @@ void prediction_and_state(Runner& r, int cur, Geo g, const Outputs& o, const uin
     // narrow layers (C < 64) are epilogue-bound: there the heads keep their own (cheap) 1x1 convolution
     const int p = tower<T>(r, m->pred_blocks, g, cur, (sizeof(T) == 2 && m->pv_w && rv + rp <= 8 && m->C >= 64) ? &pj : nullptr);
     const float* pr = r.proj_fused ? r.proj() : nullptr;
+    if (sizeof(T) == 2 && pr && m->value.mma && m->policy.mma && mzb_conv_tc_enabled() && !r.rc) {   // both head mlps as one launch
+      const MmaHeadCall calls[2] = {
+          {m->value.mma, pr, (long long)(rv + rp) * hw, 0, 0, nullptr, o.value_logits, o.value, nullptr},
+          {m->policy.mma, pr, (long long)(rv + rp) * hw, rv * hw, 1, legal, o.policy_logits, nullptr, o.priors}};
+      r.rc = mzb_head_mma_launch_n(2, calls, r.B, m->S, r.s);
+      return;
+    }
     head<T>(r, r.buf<T>(p), g, m->value, 0, nullptr, o.value_logits, o.value, nullptr, pr, (long long)(rv + rp) * hw, 0);
     head<T>(r, r.buf<T>(p), g, m->policy, 1, legal, o.policy_logits, nullptr, o.priors, pr, (long long)(rv + rp) * hw, rv * hw);
   }
@@ -1173,8 +1201,15 @@ int stem_tc(Runner& r, const float* obs) {
     r.rc = mzb_stem16_tower(blocks, B, g.H, g.W, r.buf<T>(at), r.s);
     return at;
   };
-  int cur = stage(m->ds1_tc, g1, 1);
-  { const int nx = (cur + 1) % 3;
+  int cur = 1;
+  if (!r.rc && m->ds_conv2_mma && mzb_stem16_supported(m->ds1_tc, g1.H, g1.W, g1.C) && g2.H * 2 == g1.H && g2.W == g1.W && C == 16) {
+    // resblocks1 AND DownSample.conv2 on the image while it is resident in shared memory: its 604 MB (16,384 frames) are
+    // neither written nor read back
+    r.rc = mzb_stem16_tower(m->ds1_tc, B, g1.H, g1.W, r.buf<T>(1), r.s, m->ds_conv2_mma, m->ds_conv2.shift, r.buf<T>(2));
+    cur = 2;
+  } else {
+    cur = stage(m->ds1_tc, g1, 1);
+    const int nx = (cur + 1) % 3;
     k_conv_s2<false><<<nblk(out_rows(g2), 128), 128, sm2, r.s>>>(r.buf<T>(cur), B, g1, C / 2, 1, m->ds_conv2.w, m->ds_conv2.scale,
                                                                m->ds_conv2.shift, C, g2, 0, r.buf<T>(nx));
     mzb_count_launch(); cur = nx; }
@@ -1276,6 +1311,13 @@ int run_recurrent(Runner& r, const void* state_in, int in_layout, long long in_r
     r.rc = mzb_tower16_recurrent(m, B, state_in, in_layout, in_row_stride, in_slot, slot_stride, action, o.state, o.layout,
                                  o.row_stride, o.off, want_reward ? pr : nullptr, want_pred ? pvp : nullptr, r.s);
     if (r.rc) return r.rc;
+    if (want_reward && want_pred && m->reward.mma && m->value.mma && m->policy.mma) {        // the three head mlps as one launch
+      const MmaHeadCall calls[3] = {
+          {m->reward.mma, pr, (long long)rr * hw, 0, 0, nullptr, o.reward_logits, o.reward, nullptr},
+          {m->value.mma, pvp, (long long)rvp * hw, 0, 0, nullptr, o.value_logits, o.value, nullptr},
+          {m->policy.mma, pvp, (long long)rvp * hw, m->value.r * hw, 1, nullptr, o.policy_logits, nullptr, o.priors}};
+      return r.rc = mzb_head_mma_launch_n(3, calls, B, m->S, r.s);
+    }
     head<T>(r, r.buf<T>(0), gl, m->reward, 0, nullptr, o.reward_logits, o.reward, nullptr, pr, (long long)rr * hw, 0);
     if (want_pred) {
       head<T>(r, r.buf<T>(0), gl, m->value, 0, nullptr, o.value_logits, o.value, nullptr, pvp, (long long)rvp * hw, 0);

@@ -17,6 +17,8 @@ struct mzb_resnet_model {
   float* pv_w = nullptr;           // value and policy 1x1 weights concatenated [r_value + r_policy][C] (fused projection)
   int stem_tc = 0, stem_cp1 = 0;
   std::vector<Block> ds1_tc;
+  // DownSample.conv2 (C/2 -> C, stride 2) as six 16 x 16 MMA taps on pixel-pair rows (mzb_stem16.cu): bf16 [6][C][16], or NULL
+  __nv_bfloat16* ds_conv2_mma = nullptr;
   std::vector<void*> allocs;
 };
 
@@ -34,6 +36,12 @@ bool mzb_head_mma_pack(mzb_resnet_model* m, const HeadParams& hp, const std::vec
 void mzb_head_mma_free(void* opaque);
 int mzb_head_mma_launch(void* opaque, const float* proj, long long proj_stride, int proj_off, int B, int S, int mode,
                         const uint8_t* legal, float* logits, float* scalar, float* priors, cudaStream_t stream);
+// several heads of one inference as ONE launch (grid.y = head); mode 0: support -> scalar, 1: legal-action softmax
+struct MmaHeadCall {
+  void* opaque; const float* proj; long long proj_stride; int proj_off; int mode;
+  const uint8_t* legal; float* logits; float* scalar; float* priors;
+};
+int mzb_head_mma_launch_n(int n, const MmaHeadCall* calls, int B, int S, cudaStream_t stream);
 
 // whole recurrent inference of a 16-channel network as one kernel (mzb_tower16.cu); projections feed the head kernels
 bool mzb_tower16_supported(const mzb_resnet_model* m, int in_layout, int out_layout);
@@ -43,4 +51,8 @@ int mzb_tower16_recurrent(mzb_resnet_model* m, int B, const void* state_in, int 
 
 // a stem stage's residual tower with the image resident in shared memory (mzb_stem16.cu), in place on a padded buffer
 bool mzb_stem16_supported(const std::vector<Block>& blocks, int H, int W, int C);
-int mzb_stem16_tower(const std::vector<Block>& blocks, int B, int H, int W, __nv_bfloat16* x, cudaStream_t s);
+// s2_w != NULL: the tower is the pixel-pair stage (H lines of W pair rows); its output is not written back - the stride-2
+// convolution that follows (s2_w [6][16][16] bf16, s2_shift [16]) runs on the resident image and y2 receives the
+// H/2 x W padded image of the next stage (pad rows and the trailing halo written as zeros).
+int mzb_stem16_tower(const std::vector<Block>& blocks, int B, int H, int W, __nv_bfloat16* x, cudaStream_t s,
+                     const __nv_bfloat16* s2_w = nullptr, const float* s2_shift = nullptr, __nv_bfloat16* y2 = nullptr);

@@ -41,6 +41,11 @@ struct S16Args {
   const __nv_bfloat16* w[kMaxConv];      // w_tc [16 cout][9][16 cin]
   const float* shift[kMaxConv];
   __nv_bfloat16* x;                      // padded activations [halo + B * R + halo][16], updated in place
+  // optional tail (pixel-pair stage only): DownSample.conv2, stride 2, on the resident image; then x is NOT written back
+  const __nv_bfloat16* w_s2;             // [6][16][16] (pack_s2_mma) or NULL
+  const float* shift_s2;
+  __nv_bfloat16* y2;                     // padded output [halo + B * R2 + halo][16] of H/2 x W pixels
+  int R2, T2;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,21 +125,84 @@ __device__ __forceinline__ void conv_image(uint32_t in, uint32_t out, uint32_t w
   }
 }
 
+// DownSample.conv2 (3x3, stride 2, padding 1, 8 -> 16 channels) from the pixel-pair image `in` to the H/2 x W image `out`
+// (same pitch and halo): output row r2 = (yy, xx) reads, for ky = 0..2, the pair rows (2 (yy - 1) + ky, xx - 1) and
+// (.., xx) - a per-lane gather, which ldmatrix takes as it is.  No batch-norm, no ReLU (models.py:236-255).
+__device__ __forceinline__ void conv_s2_image(uint32_t in, uint32_t out, uint32_t w_u32, const float* sh, const uint8_t* ok, int T2, int R2,
+                                              int W, int pitch, int halo, int gwarp, int gw, int lane) {
+  uint32_t af[6][4];
+  {
+    const uint32_t a_off = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * kRowB + (lane >> 4) * 16);
+#pragma unroll
+    for (int tap = 0; tap < 6; ++tap) ldsm_x4(w_u32 + (uint32_t)tap * kTapB + a_off, af[tap]);
+  }
+  const float sh_lo = sh[lane >> 2], sh_hi = sh[(lane >> 2) + 8];
+  const uint32_t half = (uint32_t)(((lane >> 3) & 1) * 16);
+  const uint32_t l_off = (uint32_t)((8 * (lane >> 4) + (lane & 7)) * kRowB) + half;
+  const int q2 = (lane & 3) * 2;
+  for (int t = gwarp; t < T2; t += gw) {
+    const int r2 = 16 * t + 8 * (lane >> 4) + (lane & 7), yy = r2 / pitch, xx = r2 - yy * pitch;
+    // rows that are not pixels gather from the zero halo (their sums are discarded by the mask)
+    const int src = (r2 < R2 && geo_is_pixel(yy, xx, W)) ? 2 * (yy - 1) * pitch + xx - 1 : -halo;
+    const uint32_t base = in + (uint32_t)(src * kRowB) + half;
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
+#pragma unroll
+    for (int tap = 0; tap < 6; ++tap) {
+      uint32_t bf[4];
+      ldsm_x4(base + (uint32_t)(((tap >> 1) * pitch + (tap & 1)) * kRowB), bf);
+      mma16816(acc[0], af[tap], bf[0], bf[1]);
+      mma16816(acc[1], af[tap], bf[2], bf[3]);
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint16_t m2 = *reinterpret_cast<const uint16_t*>(ok + t * 16 + 8 * j + q2);
+      const bool k0 = (m2 & 0xFF) != 0, k1 = (m2 >> 8) != 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float v0 = k0 ? acc[j][2 * h] + (h ? sh_hi : sh_lo) : 0.0f, v1 = k1 ? acc[j][2 * h + 1] + (h ? sh_hi : sh_lo) : 0.0f;
+        const __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+        pk[2 * j + h] = *reinterpret_cast<const uint32_t*>(&p);
+      }
+    }
+    stsm_x4_t(out + (uint32_t)(t * 16 * kRowB) + l_off, pk);
+  }
+}
+
 __global__ void __launch_bounds__(kWarps * 32, 1) k_stem_tower16(const S16Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_conv = 2 * a.n_blocks, pitch = geo_pitch(a.W), halo = geo_halo(a.W);
-  uint8_t* s_w = smem;                                                   // [n_conv][9][16][kRowB]
-  float* s_sh = reinterpret_cast<float*>(s_w + (size_t)n_conv * kConvB);  // [n_conv][16]
-  uint8_t* s_ok = reinterpret_cast<uint8_t*>(s_sh + n_conv * 16);         // [16 T]: 1 = a pixel row, 0 = pad / beyond the image
-  uint8_t* s_act = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_ok + 16 * a.T) + 127) & ~(uintptr_t)127);
+  const bool tail = a.w_s2 != nullptr;
+  const int n_w = n_conv + (tail ? 1 : 0);                               // weight slots (the tail's six taps fit one)
+  uint8_t* s_w = smem;                                                   // [n_w][9][16][kRowB]
+  float* s_sh = reinterpret_cast<float*>(s_w + (size_t)n_w * kConvB);     // [n_w][16]
+  uint8_t* s_ok = reinterpret_cast<uint8_t*>(s_sh + n_w * 16);            // [16 T]: 1 = a pixel row, 0 = pad / beyond the image
+  uint8_t* s_ok2 = s_ok + 16 * a.T;                                      // [16 T2]: the same for the tail's output geometry
+  uint8_t* s_act = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_ok2 + 16 * a.T2) + 127) & ~(uintptr_t)127);
   for (int i = threadIdx.x; i < n_conv * 9 * 16 * 2; i += blockDim.x) {
     const int half = i & 1, n = (i >> 1) & 15, tap = (i >> 5) % 9, ci = i / (9 * 32);
     const uint4 v = *reinterpret_cast<const uint4*>(a.w[ci] + (size_t)n * 144 + tap * 16 + half * 8);
     *reinterpret_cast<uint4*>(s_w + (size_t)ci * kConvB + tap * kTapB + n * kRowB + half * 16) = v;
   }
   for (int i = threadIdx.x; i < n_conv * 16; i += blockDim.x) s_sh[i] = a.shift[i >> 4][i & 15];
+  if (tail) {
+    for (int i = threadIdx.x; i < 6 * 16 * 2; i += blockDim.x) {
+      const int hf = i & 1, n = (i >> 1) & 15, tap = i >> 5;
+      *reinterpret_cast<uint4*>(s_w + (size_t)n_conv * kConvB + tap * kTapB + n * kRowB + hf * 16) =
+          *reinterpret_cast<const uint4*>(a.w_s2 + (size_t)(tap * 16 + n) * 16 + hf * 8);
+    }
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) s_sh[n_conv * 16 + i] = a.shift_s2[i];
+    for (int i = threadIdx.x; i < 16 * a.T2; i += blockDim.x) {
+      const int yy = i / pitch, xx = i - yy * pitch;
+      s_ok2[i] = (i < a.R2 && geo_is_pixel(yy, xx, a.W)) ? 1 : 0;
+    }
+  }
   for (int i = threadIdx.x; i < 16 * a.T; i += blockDim.x) {
     const int yy = i / pitch, xx = i - yy * pitch;
     s_ok[i] = (i < a.R && geo_is_pixel(yy, xx, a.W)) ? 1 : 0;
@@ -173,7 +241,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_stem_tower16(const S16Args a
       conv_image<true>(Tm, X, w_u32 + (uint32_t)(2 * k + 1) * kConvB, s_sh + (2 * k + 1) * 16, s_ok, a.T, pitch, gwarp, a.gw, lane);
       group_barrier(bar, gthreads);
     }
-    {
+    if (tail) {
+      conv_s2_image(X, Tm, w_u32 + (uint32_t)n_conv * kConvB, s_sh + n_conv * 16, s_ok2, a.T2, a.R2, a.W, pitch, halo, gwarp, a.gw, lane);
+      group_barrier(bar, gthreads);
+      uint4* dst = reinterpret_cast<uint4*>(a.y2 + ((long long)halo + b * a.R2) * 16);
+      const uint8_t* src = gbuf + (size_t)tb * a.buf_bytes + (size_t)halo * kRowB;
+      for (int i = gtid; i < 2 * a.R2; i += gthreads) dst[i] = *reinterpret_cast<const uint4*>(src + (i >> 1) * kRowB + (i & 1) * 16);
+      if (b == a.B - 1)                                                   // the trailing halo of the new geometry
+        for (int i = gtid; i < 2 * halo; i += gthreads) dst[2 * a.R2 + i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
       uint4* dst = reinterpret_cast<uint4*>(a.x + ((long long)halo + b * a.R) * 16);
       const uint8_t* src = gbuf + (size_t)cur * a.buf_bytes + (size_t)halo * kRowB;
       for (int i = gtid; i < chunks; i += gthreads) dst[i] = *reinterpret_cast<const uint4*>(src + (i >> 1) * kRowB + (i & 1) * 16);
@@ -185,12 +261,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_stem_tower16(const S16Args a
   }
 }
 
-struct Plan { int gw, G, nbuf, buf_bytes, T; size_t smem; };
+struct Plan { int gw, G, nbuf, buf_bytes, T, T2; size_t smem; };
 
-bool make_plan(int H, int W, int n_conv, Plan* p) {
+// n_w: weight slots (convolutions of the blocks + 1 for the stride-2 tail)
+bool make_plan(int H, int W, int n_w, bool tail, Plan* p) {
   const int R = geo_rows_per_image(H, W), T = (R + 15) / 16, halo = geo_halo(W);
+  const int T2 = tail ? (geo_rows_per_image(H / 2, W) + 15) / 16 : 0;
   const int buf_bytes = (int)mzb_align_up((size_t)(2 * halo + 16 * T) * kRowB, 128);
-  const size_t fixed = 128 + (size_t)n_conv * kConvB + sizeof(float) * n_conv * 16 + (size_t)16 * T + 128;
+  const size_t fixed = 128 + (size_t)n_w * kConvB + sizeof(float) * n_w * 16 + (size_t)16 * (T + T2) + 128;
   int gw = 2;                                                              // <= 8 groups: one named barrier each
   while (gw < kWarps && gw * 2 * 4 <= T) gw *= 2;                          // >= 4 tiles per warp and layer
   if (const char* e = getenv("MZB_STEM16_GW")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8 || v == 16) gw = v; }
@@ -201,7 +279,7 @@ bool make_plan(int H, int W, int n_conv, Plan* p) {
     for (int nbuf = 3; nbuf >= 2; --nbuf) {
       if (force_nbuf && nbuf != force_nbuf) continue;
       const size_t smem = fixed + (size_t)G * nbuf * buf_bytes;
-      if (smem <= 227 * 1024) { *p = Plan{gw, G, nbuf, buf_bytes, T, smem}; return true; }
+      if (smem <= 227 * 1024) { *p = Plan{gw, G, nbuf, buf_bytes, T, T2, smem}; return true; }
     }
   }
   return false;
@@ -218,13 +296,16 @@ bool mzb_stem16_supported(const std::vector<Block>& blocks, int H, int W, int C)
     for (const ConvParams* c : {&b.c1, &b.c2})
       if (!c->w_tc || c->cin != 16 || c->cout != 16 || c->extra_plane || c->stride != 1) return false;
   Plan p;
-  return make_plan(H, W, 2 * (int)blocks.size(), &p);
+  return make_plan(H, W, 2 * (int)blocks.size() + 1, H % 2 == 0, &p);       // with room for the stride-2 tail
 }
 
 // In place: x holds the padded input of the tower on entry and its output on return (pad rows re-written as zeros).
-int mzb_stem16_tower(const std::vector<Block>& blocks, int B, int H, int W, __nv_bfloat16* x, cudaStream_t s) {
+int mzb_stem16_tower(const std::vector<Block>& blocks, int B, int H, int W, __nv_bfloat16* x, cudaStream_t s,
+                     const __nv_bfloat16* s2_w, const float* s2_shift, __nv_bfloat16* y2) {
   Plan p;
-  if (!make_plan(H, W, 2 * (int)blocks.size(), &p)) { mzb_set_error("stem16: image %d x %d does not fit shared memory", H, W); return MZB_EUNSUPPORTED; }
+  const bool tail = s2_w != nullptr;
+  if (tail && (!s2_shift || !y2 || H % 2 != 0)) { mzb_set_error("stem16: stride-2 tail needs shift, output and an even height"); return MZB_EINVAL; }
+  if (!make_plan(H, W, 2 * (int)blocks.size() + (tail ? 1 : 0), tail, &p)) { mzb_set_error("stem16: image %d x %d does not fit shared memory", H, W); return MZB_EUNSUPPORTED; }
   S16Args a{};
   a.B = B; a.H = H; a.W = W; a.n_blocks = (int)blocks.size();
   a.R = geo_rows_per_image(H, W); a.T = p.T; a.gw = p.gw; a.G = p.G; a.nbuf = p.nbuf; a.buf_bytes = p.buf_bytes;
@@ -234,6 +315,8 @@ int mzb_stem16_tower(const std::vector<Block>& blocks, int B, int H, int W, __nv
     a.w[k] = b.c2.w_tc; a.shift[k++] = b.c2.shift;
   }
   a.x = x;
+  a.w_s2 = s2_w; a.shift_s2 = s2_shift; a.y2 = y2;
+  a.R2 = tail ? geo_rows_per_image(H / 2, W) : 0; a.T2 = p.T2;
   static bool configured = false;
   if (!configured) {
     MZB_CUDA(cudaFuncSetAttribute(k_stem_tower16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
