@@ -133,20 +133,37 @@ __device__ __forceinline__ void conv16(uint32_t in_u32, uint32_t out_u32, uint32
   __syncwarp();
 }
 
-// 1x1 projection of the warp's image (bf16 activations in `buf`) onto r rows: out[r][p] = sum_c x[p][c] * w[r][c]
-__device__ __forceinline__ void project(const uint8_t* buf, const float* w, int r, float* out, int HW, const int* s_row, int lane) {
-  for (int p = lane; p < HW; p += 32) {
-    const int row = s_row[p];
-    const uint4 lo = *reinterpret_cast<const uint4*>(buf + row * kRowB), hi = *reinterpret_cast<const uint4*>(buf + row * kRowB + 16);
-    const uint32_t x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    for (int k = 0; k < r; ++k) {
-      float s = 0.0f;
+// 1x1 projection of the warp's image onto r <= 16 rows, out[k][pos] = sum_c x[pos][c] * w[k][c], as one more MMA tap: the
+// fp32 weights are split into two bf16 terms (w = hi + lo exactly to 2^-17 relative), the activations are bf16 already, so
+// two MMAs per n-tile give the fp32 FMA chain's result to rounding level for 60 instructions instead of the 450 of a
+// lane-per-position loop (which was a fifth of the kernel's issue slots and 9 % of its shared-memory wavefronts).
+// s_pw: [hi | lo][16][kRowB] bf16 rows; s_pos: [48] position of padded row `rel` of the span, -1 for zero-column rows.
+__device__ __forceinline__ void project(uint32_t buf_u32, uint32_t pw_u32, int r, float* out, int HW, const int* s_pos, const Lane& L,
+                                        int lane, int HP) {
+  uint32_t ah[4], al[4];
+  ldsm_x4(pw_u32 + L.a_off, ah);
+  ldsm_x4(pw_u32 + kTapB + L.a_off, al);
+  const int c_lo = lane >> 2, q2 = (lane & 3) * 2;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s = fmaf(bf_lo(x[i]), w[k * 16 + 2 * i], s);
-        s = fmaf(bf_hi(x[i]), w[k * 16 + 2 * i + 1], s);
+  for (int p = 0; p < NP; ++p) {
+    if (16 * p >= HP) continue;
+    uint32_t bf[4];
+    ldsm_x4(buf_u32 + L.b_off[p], bf);
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      if (16 * p + 8 * jj >= HP) continue;
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      mma16816(acc, al, bf[2 * jj], bf[2 * jj + 1]);
+      mma16816(acc, ah, bf[2 * jj], bf[2 * jj + 1]);
+      const int2 pos = *reinterpret_cast<const int2*>(s_pos + 16 * p + 8 * jj + q2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = c_lo + 8 * h;
+        if (k < r) {
+          if (pos.x >= 0) out[(long long)k * HW + pos.x] = acc[2 * h];
+          if (pos.y >= 0) out[(long long)k * HW + pos.y] = acc[2 * h + 1];
+        }
       }
-      out[(long long)k * HW + p] = s;
     }
   }
 }
@@ -160,10 +177,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
   uint8_t* s_w = smem;                                              // [n_conv][9][16][kRowB]
   float* s_sc = reinterpret_cast<float*>(s_w + (size_t)a.n_conv * kConvB);       // [n_conv][32]: scale | shift
   float* s_ptab = s_sc + a.n_conv * 32;                             // [16][kTabP]: action-plane table, channel-major
-  float* s_wr = s_ptab + 16 * kTabP;                                // [r_r][16]
-  float* s_wvp = s_wr + a.r_r * 16;                                 // [r_vp][16]
-  int* s_row = reinterpret_cast<int*>(s_wvp + a.r_vp * 16);          // [HW]: padded row of position p (no divisions in the loops)
-  uint8_t* s_act = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_row + HW) + 127) & ~(uintptr_t)127);
+  int* s_row = reinterpret_cast<int*>(s_ptab + 16 * kTabP);           // [HW]: padded row of position p (no divisions in the loops)
+  int* s_pos = s_row + ((HW + 1) & ~1);                               // [16 NP]: position of row `rel` of the span, -1 for a pad row
+  uint8_t* s_pw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_pos + 16 * NP) + 15) & ~(uintptr_t)15);
+                                                                    // [reward | value+policy][hi | lo][16][kRowB]: projection weights
+  uint8_t* s_act = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_pw + 4 * kTapB) + 127) & ~(uintptr_t)127);
   const int HP = H * pitch;                                           // padded rows from the first pixel to the end of the last line
   const size_t buf_bytes = (size_t)rows * kRowB;
   // ---- stage the weights: w_tc (scale folded in) [16 cout][9 taps][16 cin] -> [tap][cout] rows of kRowB bytes
@@ -180,9 +198,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     const int c = i / kTabP, rel = i - c * kTabP, y = rel / pitch, x = rel - y * pitch;       // indexed by the row of the span
     s_ptab[i] = (rel < HP && x < W) ? a.plane_table[(y * W + x) * 16 + c] * a.conv[0].scale[c] : 0.0f;
   }
-  for (int i = threadIdx.x; i < a.r_r * 16; i += blockDim.x) s_wr[i] = a.w_r[i];
-  for (int i = threadIdx.x; i < a.r_vp * 16; i += blockDim.x) s_wvp[i] = a.w_vp[i];
+  for (int i = threadIdx.x; i < 2 * 16 * 16; i += blockDim.x) {       // w = hi + lo, two bf16 terms; rows >= r are zero
+    const int which = i >> 8, k = (i >> 4) & 15, c = i & 15;
+    const int r = which ? a.r_vp : a.r_r;
+    const float w = k < r ? (which ? a.w_vp : a.w_r)[k * 16 + c] : 0.0f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w), lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    uint8_t* base = s_pw + (size_t)which * 2 * kTapB + k * kRowB + c * 2;
+    *reinterpret_cast<__nv_bfloat16*>(base) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(base + kTapB) = lo;
+  }
   for (int p = threadIdx.x; p < HW; p += blockDim.x) s_row[p] = halo + (p / W + 1) * pitch + p % W;
+  for (int i = threadIdx.x; i < 16 * NP; i += blockDim.x) {
+    const int y = i / pitch, x = i - y * pitch;
+    s_pos[i] = (i < H * pitch && x < W) ? y * W + x : -1;
+  }
   for (size_t i = threadIdx.x; i < kWarps * 3 * buf_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0u, 0u, 0u, 0u);       // pad rows stay zero for the whole kernel
   __syncthreads();
@@ -239,7 +268,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
       cur = o;
     }
     // ---- reward head projection on the UN-normalised next state (:388-391)
-    if (a.proj_r) project(buf(cur), s_wr, a.r_r, a.proj_r + (long long)b * a.r_r * HW, HW, s_row, lane);
+    if (a.proj_r) project(smem_u32(buf(cur)), smem_u32(s_pw), a.r_r, a.proj_r + (long long)b * a.r_r * HW, HW, s_pos, L, lane, HP);
     // ---- per-channel min-max scaling (:571-586) -> next buffer + the caller's hidden-state slot
     const int nx = (cur + 1) % 3;
     {
@@ -288,7 +317,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
                             s_sc + (ci + 1) * 32 + 16, 0.0f, nullptr, L, pitch, lane, HP);
         cur = o;
       }
-      project(buf(cur), s_wvp, a.r_vp, a.proj_vp + (long long)b * a.r_vp * HW, HW, s_row, lane);
+      project(smem_u32(buf(cur)), smem_u32(s_pw) + 2 * kTapB, a.r_vp, a.proj_vp + (long long)b * a.r_vp * HW, HW, s_pos, L, lane, HP);
     }
     __syncwarp();
   }
@@ -297,7 +326,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
 size_t tower16_smem(const mzb_resnet_model* m) {
   const int n_conv = 1 + 2 * (int)m->dyn_blocks.size() + 2 * (int)m->pred_blocks.size();
   const int HW = m->Hl * m->Wl, rows = 2 * geo_halo(m->Wl) + geo_rows_per_image(m->Hl, m->Wl);
-  return 128 + (size_t)n_conv * kConvB + sizeof(float) * ((size_t)n_conv * 32 + (size_t)16 * kTabP + HW + (size_t)(m->reward.r + m->value.r + m->policy.r) * 16) +
+  return 128 + (size_t)n_conv * kConvB + sizeof(float) * ((size_t)n_conv * 32 + (size_t)16 * kTabP + HW + 1 + 16 * NP) + 16 + 4 * kTapB +
          128 + (size_t)kWarps * 3 * rows * kRowB;
 }
 
@@ -311,6 +340,7 @@ bool mzb_tower16_supported(const mzb_resnet_model* m, int in_layout, int out_lay
   if (m->dyn_blocks.size() > kMaxBlocks || m->pred_blocks.size() > kMaxBlocks) return false;
   if ((in_layout != 0 && in_layout != 2) || (out_layout != 0 && out_layout != 2)) return false;
   if (!m->dyn_conv.w_bf16 || !m->dyn_conv.plane_table || m->dyn_conv.cin != 16 || !m->pv_w) return false;
+  if (m->reward.r > 16 || m->value.r + m->policy.r > 16) return false;      // the projections are one 16-row MMA tap each
   for (const auto* blocks : {&m->dyn_blocks, &m->pred_blocks})
     for (const Block& b : *blocks)
       if (!b.c1.w_bf16 || !b.c2.w_bf16 || b.c1.cin != 16 || b.c2.cin != 16) return false;
