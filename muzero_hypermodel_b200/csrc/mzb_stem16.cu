@@ -65,6 +65,13 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma1688(float (&d)[4], const uint32_t (&a)[2], uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -78,15 +85,29 @@ __device__ __forceinline__ void group_barrier(int id, int threads) {
 
 // One 3x3 convolution of the group's image: `in` -> `out` (shared-memory byte addresses of row 0 of the image region).
 // RES: out also holds the block's input, which is added before the ReLU (read and written by the same lanes).
-template <bool RES>
+// PAIR: the pixel-pair stage (pack_conv_pair).  Its left / right taps are three-quarters zero: the left pair row feeds only its
+// SECOND pixel (input channels 8-15) to the outputs' FIRST pixel, the right pair row only its first pixel (channels 0-7) to the
+// outputs' second pixel - so those six taps are K = 8 MMAs on one 16-byte half of the rows (ldmatrix.x2: 2 wavefronts instead
+// of 4 per tile and tap; 24 instead of 36 operand wavefronts per tile and layer).
+template <bool RES, bool PAIR>
 __device__ __forceinline__ void conv_image(uint32_t in, uint32_t out, uint32_t w_u32, const float* sh, const uint8_t* ok, int T,
                                            int pitch, int gwarp, int gw, int lane) {
-  uint32_t af[9][4];
+  uint32_t af[9][4];                     // PAIR: taps 0 / 2 of a kernel line use af[tap][0..1] only
   {
-    const uint32_t a_off = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * kRowB + (lane >> 4) * 16);
+    const uint32_t a_row = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * kRowB);
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) ldsm_x4(w_u32 + (uint32_t)tap * kTapB + a_off, af[tap]);
+    for (int tap = 0; tap < 9; ++tap) {
+      if (PAIR && tap % 3 != 1) {
+        uint32_t h2[2];
+        ldsm_x2(w_u32 + (uint32_t)tap * kTapB + a_row + (tap % 3 == 0 ? 16u : 0u), h2);
+        af[tap][0] = h2[0]; af[tap][1] = h2[1]; af[tap][2] = 0u; af[tap][3] = 0u;
+      } else {
+        ldsm_x4(w_u32 + (uint32_t)tap * kTapB + a_row + (uint32_t)((lane >> 4) * 16), af[tap]);
+      }
+    }
   }
+  // rows of an ldmatrix.x2 (lanes 0-15; the other lanes pass valid, unused addresses): n-tile (lane >> 3) & 1, row lane & 7
+  const uint32_t l2_off = (uint32_t)((8 * ((lane >> 3) & 1) + (lane & 7)) * kRowB);
   const float sh_lo = sh[lane >> 2], sh_hi = sh[(lane >> 2) + 8];
   const uint32_t l_off = (uint32_t)((8 * (lane >> 4) + (lane & 7)) * kRowB + ((lane >> 3) & 1) * 16);
   const int q2 = (lane & 3) * 2;
@@ -100,10 +121,18 @@ __device__ __forceinline__ void conv_image(uint32_t in, uint32_t out, uint32_t w
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int shift = (tap / 3 - 1) * pitch + (tap % 3 - 1);
-      uint32_t bf[4];
-      ldsm_x4(in + tile + (uint32_t)(shift * kRowB), bf);
-      mma16816(acc[0], af[tap], bf[0], bf[1]);
-      mma16816(acc[1], af[tap], bf[2], bf[3]);
+      if (PAIR && tap % 3 != 1) {
+        uint32_t b2[2];
+        const uint32_t a2[2] = {af[tap][0], af[tap][1]};
+        ldsm_x2(in + (uint32_t)(t * 16 * kRowB) + l2_off + (uint32_t)(shift * kRowB) + (tap % 3 == 0 ? 16u : 0u), b2);
+        mma1688(acc[0], a2, b2[0]);
+        mma1688(acc[1], a2, b2[1]);
+      } else {
+        uint32_t bf[4];
+        ldsm_x4(in + tile + (uint32_t)(shift * kRowB), bf);
+        mma16816(acc[0], af[tap], bf[0], bf[1]);
+        mma16816(acc[1], af[tap], bf[2], bf[3]);
+      }
     }
     uint32_t rs[4] = {0u, 0u, 0u, 0u};
     if (RES) ldsm_x4_t(out + tile, rs);
@@ -236,9 +265,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_stem_tower16(const S16Args a
     const int tb = a.nbuf == 3 ? (cur + 1) % 3 : 1 - cur;
     const uint32_t X = img0 + (uint32_t)cur * (uint32_t)a.buf_bytes, Tm = img0 + (uint32_t)tb * (uint32_t)a.buf_bytes;
     for (int k = 0; k < a.n_blocks; ++k) {
-      conv_image<false>(X, Tm, w_u32 + (uint32_t)(2 * k) * kConvB, s_sh + 2 * k * 16, s_ok, a.T, pitch, gwarp, a.gw, lane);
+      if (tail) conv_image<false, true>(X, Tm, w_u32 + (uint32_t)(2 * k) * kConvB, s_sh + 2 * k * 16, s_ok, a.T, pitch, gwarp, a.gw, lane);
+      else conv_image<false, false>(X, Tm, w_u32 + (uint32_t)(2 * k) * kConvB, s_sh + 2 * k * 16, s_ok, a.T, pitch, gwarp, a.gw, lane);
       group_barrier(bar, gthreads);
-      conv_image<true>(Tm, X, w_u32 + (uint32_t)(2 * k + 1) * kConvB, s_sh + (2 * k + 1) * 16, s_ok, a.T, pitch, gwarp, a.gw, lane);
+      if (tail) conv_image<true, true>(Tm, X, w_u32 + (uint32_t)(2 * k + 1) * kConvB, s_sh + (2 * k + 1) * 16, s_ok, a.T, pitch, gwarp, a.gw, lane);
+      else conv_image<true, false>(Tm, X, w_u32 + (uint32_t)(2 * k + 1) * kConvB, s_sh + (2 * k + 1) * 16, s_ok, a.T, pitch, gwarp, a.gw, lane);
       group_barrier(bar, gthreads);
     }
     if (tail) {
