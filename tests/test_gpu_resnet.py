@@ -195,6 +195,71 @@ def test_stem_towers_in_shared_memory_equal_layer_by_layer():
     np.testing.assert_array_equal(one[0], outs[1]["s0"][200])
 
 
+@pytest.mark.parametrize("hw", [(84, 84), (64, 96), (96, 48), (90, 84)])
+def test_stem_towers_other_frame_sizes(hw):
+    """The shared-memory stem kernels at other geometries than Breakout's 96 x 96 (Atari's 84 x 84: odd pitches, 21 x 21 and
+    11 x 11 stages; non-square frames; 90 x 84: an odd half height, so the stride-2 tail is not taken and k_conv_s2 runs):
+    seeded random weights, shared-memory form against layer by layer (same tolerance as the 96 x 96 test) and against the fp32
+    path of the same network within the bf16 band; run-to-run bit-equality."""
+    import copy
+    from muzero_hypermodel_b200 import _lib, models
+    cfg = copy.deepcopy(product_config("breakout"))
+    cfg.observation_shape = (3, hw[0], hw[1])
+    torch.manual_seed(7)
+    net = models.MuZeroNetwork(cfg)
+    with torch.no_grad():
+        for name, buf in net.named_buffers():                        # non-trivial eval-mode batch-norm statistics
+            if name.endswith("running_mean"):
+                buf.copy_(0.1 * torch.randn_like(buf))
+            elif name.endswith("running_var"):
+                buf.copy_(0.5 + torch.rand_like(buf))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net.set_weights(sd)
+    net = net.to(DEV).eval()
+    rs = np.random.RandomState(hw[0])
+    obs = torch.tensor(rs.rand(171, 3, hw[0], hw[1]).astype(np.float32), device=DEV)
+    net.set_precision("fp32")
+    ref = net.initial_inference(obs)[3].float().cpu().numpy()
+    net.set_precision("bf16")
+    outs = {}
+    for mode in (1, 0, 1):
+        _lib.lib.mzb_stem16_enable(mode)
+        try:
+            got = net.initial_inference(obs)[3].float().cpu().numpy()
+        finally:
+            _lib.lib.mzb_stem16_enable(1)
+        if mode in outs:
+            np.testing.assert_array_equal(got, outs[mode])
+        outs[mode] = got
+    a, b = outs[1], outs[0]
+    d = np.abs(a - b)
+    assert a.shape == b.shape == ref.shape
+    assert np.mean(d <= 1e-2 * np.abs(b) + 1e-2) > 0.93 and np.median(d) < 4e-3, (float(d.max()), float(np.mean(d <= 1e-2 * np.abs(b) + 1e-2)))
+    e = np.abs(a - ref)
+    e0 = np.abs(b - ref)
+    # the new kernels are as close to the fp32 network as the layered bf16 path is
+    assert np.median(e) < 2e-2 and np.median(e) <= 1.5 * np.median(e0) + 1e-3, (float(np.median(e)), float(np.median(e0)))
+    # the one-kernel recurrent inference at this latent size (6 x 6, 4 x 6, 6 x 3 ...) against layer by layer
+    s0 = net.initial_inference(obs)[3]
+    act = torch.tensor(rs.randint(4, size=(obs.shape[0], 1)), device=DEV)
+    rec = {}
+    for mode in (1, 0, 1):
+        _lib.lib.mzb_tower16_enable(mode)
+        try:
+            v1, r1, p1, s1 = net.recurrent_inference(s0, act)
+            got = [t.float().cpu().numpy() for t in (v1, r1, p1, s1)]
+        finally:
+            _lib.lib.mzb_tower16_enable(1)
+        if mode in rec:
+            for x, y in zip(got, rec[mode]):
+                np.testing.assert_array_equal(x, y)
+        rec[mode] = got
+    for x, y in zip(rec[1][:3], rec[0][:3]):
+        np.testing.assert_allclose(x, y, rtol=3e-2, atol=3e-2)
+    d = np.abs(rec[1][3] - rec[0][3])
+    assert np.mean(d <= 1e-2 * np.abs(rec[0][3]) + 1e-2) > 0.93 and np.median(d) < 4e-3, float(d.max())
+
+
 def test_cta_pair_convolution_equals_single_cta_form():
     """The cta_group::2 form of the tensor-core convolution (clusters of two CTAs sharing every MMA, each holding half of
     the weight rows; csrc/mzb_conv_tc.cu, PAIR) against the single-CTA form on a batch large enough to take it
