@@ -302,9 +302,10 @@ bool make_plan(int H, int W, int n_w, bool tail, Plan* p) {
   const size_t fixed = 128 + (size_t)n_w * kConvB + sizeof(float) * n_w * 16 + (size_t)16 * (T + T2) + 128;
   int gw = 2;                                                              // <= 8 groups: one named barrier each
   while (gw < kWarps && gw * 2 * 4 <= T) gw *= 2;                          // >= 4 tiles per warp and layer
-  if (const char* e = getenv("MZB_STEM16_GW")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8 || v == 16) gw = v; }
-  int force_nbuf = 0;
-  if (const char* e = getenv("MZB_STEM16_NBUF")) force_nbuf = atoi(e);
+  // tuning knobs (tests/profile_stem16.py), read once
+  static const int env_gw = [] { const char* e = getenv("MZB_STEM16_GW"); return e ? atoi(e) : 0; }();
+  static const int force_nbuf = [] { const char* e = getenv("MZB_STEM16_NBUF"); return e ? atoi(e) : 0; }();
+  if (env_gw == 2 || env_gw == 4 || env_gw == 8 || env_gw == 16) gw = env_gw;
   for (; gw <= kWarps; gw *= 2) {
     const int G = kWarps / gw;
     for (int nbuf = 3; nbuf >= 2; --nbuf) {
