@@ -50,8 +50,11 @@ constexpr int kMaxJobs = 3;
 struct HeadJobs { HeadJob j[kMaxJobs]; };
 
 // MAXN: widest layer output (64 or 128): bounds the accumulator / fragment register arrays
-template <int MAXN>
-__global__ void __launch_bounds__(256) k_head_mma(const __grid_constant__ HeadJobs jobs, int B, int S) {
+// MINB = 3 (<= 85 registers, 8 bytes of spills): three resident CTAs per SM.  The three heads of 16,384 images are 384 CTAs, which
+// at two per SM (96 registers) ran as 1.3 waves - the merged launch took as long as two of the separate ones (ncu:
+// launch__waves_per_multiprocessor 1.30).  Launches that fit one wave at two CTAs per SM keep the 96-register form.
+template <int MAXN, int MINB = 0>
+__global__ void __launch_bounds__(256, MINB) k_head_mma(const __grid_constant__ HeadJobs jobs, int B, int S) {
   extern __shared__ __align__(16) uint8_t smem[];
   const HeadJob& job = jobs.j[blockIdx.y];
   const MmaHead& hp = job.hp;
@@ -253,13 +256,15 @@ int mzb_head_mma_launch_n(int n, const MmaHeadCall* calls, int B, int S, cudaStr
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_head_mma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_head_mma<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_head_mma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
   int gx = (B + 8 * 16 - 1) / (8 * 16);
   if (gx > 148 * 2) gx = 148 * 2;
   const dim3 grid(gx, n);
-  if (maxn <= 64) k_head_mma<64><<<grid, 256, smem, stream>>>(jobs, B, S);
+  if (maxn <= 64 && gx * n > 148 * 2 && smem * 3 <= 200 * 1024) k_head_mma<64, 3><<<grid, 256, smem, stream>>>(jobs, B, S);
+  else if (maxn <= 64) k_head_mma<64><<<grid, 256, smem, stream>>>(jobs, B, S);
   else k_head_mma<128><<<grid, 256, smem, stream>>>(jobs, B, S);
   MZB_LAUNCH_CHECK();
   return MZB_OK;
