@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     if (a.in_layout == 2) {
       // the hidden-state pool streams through L2 (read once per child, 38 MB per simulation in and out): evict_first keeps it
       // from displacing the tree records, whose dependent loads pace k_select / k_expand_backup (L2 hit rate 26 % / 36 %);
-      // measured: k_expand_backup 6.2 -> 5.2 us, k_select unchanged (19 us: its misses are the first touch of a record per move)
+      // measured: k_expand_backup 6.2 -> 5.2 us, k_select unchanged (19 us: one partial wave whose length is the deepest walk)
       const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.state_in) + in_off);
       for (int i = lane; i < 2 * HW; i += 32) {
         const int p = i >> 1;
