@@ -819,7 +819,8 @@ int mzb_resnet_create(mzb_resnet_model** out, const mzb_resnet_config* c) {
        init_head(m, m->value, C, c->reduced_channels_value, hw, c->fc_value, c->n_fc_value, m->full) &&
        init_head(m, m->policy, C, c->reduced_channels_policy, hw, c->fc_policy, c->n_fc_policy, m->A);
   m->pv_w = (float*)dev_alloc(m, sizeof(float) * (size_t)(m->value.r + m->policy.r) * C);
-  ok = ok && m->pv_w;
+  m->t16_counters = (int*)dev_alloc(m, 256);              // work / exit counters of k_recurrent16 (zero between launches)
+  ok = ok && m->pv_w && m->t16_counters;
   if (!ok) {
     mzb_resnet_destroy(m);
     mzb_set_error("resnet create: allocation failed or head mlp wider than 128");

@@ -15,6 +15,7 @@ struct mzb_resnet_model {
   HeadParams reward, value, policy;
   // bf16 DownSample stem on the tensor cores: resblocks1 with channels zero-padded C/2 -> stem_cp1 (multiple of 16)
   float* pv_w = nullptr;           // value and policy 1x1 weights concatenated [r_value + r_policy][C] (fused projection)
+  int* t16_counters = nullptr;     // k_recurrent16: [0] next image, [1] warps that left; reset by the last warp of a launch
   int stem_tc = 0, stem_cp1 = 0;
   std::vector<Block> ds1_tc;
   // DownSample.conv2 (C/2 -> C, stride 2) as six 16 x 16 MMA taps on pixel-pair rows (mzb_stem16.cu): bf16 [6][C][16], or NULL

@@ -30,7 +30,7 @@ constexpr int kRowB = 48;              // bytes per shared-memory row: 16 bf16 +
 constexpr int kTapB = 16 * kRowB;      // one tap of one convolution: 16 output channels x 16 input channels
 constexpr int kConvB = 9 * kTapB;
 constexpr int kMaxBlocks = 4;
-constexpr int kWarps = 16;
+constexpr int kWarps = 20;
 constexpr int NP = 3;                  // pairs of n-tiles: up to 48 positions
 constexpr int kTabP = 72;              // row length of the transposed action-plane table: 72 / 2 = 4 (mod 16) -> the 8-byte
                                        // loads of a half-warp (4 channels x 4 position pairs) hit 16 distinct bank pairs
@@ -46,6 +46,7 @@ struct T16Args {
   const int* action;
   void* state_out; int out_layout; long long out_row_stride, out_off;
   float* proj_r; float* proj_vp;               // [B][r * H*W] fp32, bias added by the head kernels
+  int* counters;                               // [0] next image, [1] warps that have left (both zero between launches)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,9 +84,6 @@ struct Lane {
 template <bool PLANE, bool RES>
 __device__ __forceinline__ void conv16(uint32_t in_u32, uint32_t out_u32, uint32_t res_u32, uint32_t w_u32, const float* sh, float pl,
                                        const float* ptab, const Lane& L, int pitch, int lane, int HP) {
-  uint32_t af[9][4];
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) ldsm_x4(w_u32 + (uint32_t)tap * kTapB + L.a_off, af[tap]);
   float acc[2 * NP][4];
 #pragma unroll
   for (int j = 0; j < 2 * NP; ++j)
@@ -94,13 +92,15 @@ __device__ __forceinline__ void conv16(uint32_t in_u32, uint32_t out_u32, uint32
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const uint32_t shift = (uint32_t)(((tap / 3 - 1) * pitch + (tap % 3 - 1)) * kRowB);
+    uint32_t af[4];                                    // a tap's weights are used by this warp's 6 n-tiles and not again: no reason to
+    ldsm_x4(w_u32 + (uint32_t)tap * kTapB + L.a_off, af);   // hold all nine taps (36 registers) - that is what limits the warps per SM
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       if (16 * p >= HP) continue;                      // warp-uniform: HP = H * pitch rows from the first to the last pixel
       uint32_t bf[4];
       ldsm_x4(in_u32 + L.b_off[p] + shift, bf);
-      mma16816(acc[2 * p], af[tap], bf[0], bf[1]);
-      if (16 * p + 8 < HP) mma16816(acc[2 * p + 1], af[tap], bf[2], bf[3]);
+      mma16816(acc[2 * p], af, bf[0], bf[1]);
+      if (16 * p + 8 < HP) mma16816(acc[2 * p + 1], af, bf[2], bf[3]);
     }
   }
   const int c_lo = lane >> 2, q2 = (lane & 3) * 2;
@@ -212,12 +212,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     const int y = i / pitch, x = i - y * pitch;
     s_pos[i] = (i < H * pitch && x < W) ? y * W + x : -1;
   }
-  for (size_t i = threadIdx.x; i < kWarps * 3 * buf_bytes / 16; i += blockDim.x)
+  for (size_t i = threadIdx.x; i < kWarps * 2 * buf_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(s_act)[i] = make_uint4(0u, 0u, 0u, 0u);       // pad rows stay zero for the whole kernel
   __syncthreads();
 
-  // the warp's three rotating buffers: buf(i) by arithmetic (an indexed pointer array would live in local memory)
-  uint8_t* const buf0 = s_act + (size_t)(warp * 3) * buf_bytes;
+  // the warp's two buffers: buf(i) by arithmetic (an indexed pointer array would live in local memory)
+  uint8_t* const buf0 = s_act + (size_t)(warp * 2) * buf_bytes;
   auto buf = [&](int i) -> uint8_t* { return buf0 + (size_t)i * buf_bytes; };
   Lane L;
   {
@@ -238,7 +238,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
   uint64_t pol_stream;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
 
-  for (int b = blockIdx.x * kWarps + warp; b < a.B; b += gridDim.x * kWarps) {
+  // Images are handed out by a counter, not by a fixed stride: 16,384 images over 148 x 20 warps are 5.5 rounds, and with a fixed
+  // assignment the launch lasts 6.  Which warp computes an image does not change its result.
+  while (true) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(a.counters, 1);
+    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+    if (b >= a.B) break;
     // ---- hidden state of the parent node -> buffer 0
     const long long in_off = (long long)b * a.in_row_stride + (a.in_slot ? (long long)a.in_slot[b] * a.slot_stride : 0);
     if (a.in_layout == 2) {
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     ci = 1;
     int cur = 1;
     for (int k = 0; k < a.n_dyn; ++k, ci += 2) {
-      const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+      const int t = 1 - cur, o = cur;                             // the block's second convolution writes over its input
       conv16<false, false>(smem_u32(buf(cur)), smem_u32(buf(t)), 0u, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32 + 16, 0.0f,
                            nullptr, L, pitch, lane, HP);
       conv16<false, true>(smem_u32(buf(t)), smem_u32(buf(o)), smem_u32(buf(cur)), w_u32 + (uint32_t)(ci + 1) * kConvB,
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     // ---- reward head projection on the UN-normalised next state (:388-391)
     if (a.proj_r) project(smem_u32(buf(cur)), smem_u32(s_pw), a.r_r, a.proj_r + (long long)b * a.r_r * HW, HW, s_pos, L, lane, HP);
     // ---- per-channel min-max scaling (:571-586) -> next buffer + the caller's hidden-state slot
-    const int nx = (cur + 1) % 3;
+    const int nx = cur;                                             // in place: a lane re-writes the elements it read
     {
       const int cp = lane & 7, pg = lane >> 3;                      // channel pair, position group (p = 4 i + pg)
       float lo0 = CUDART_INF_F, hi0 = -CUDART_INF_F, lo1 = CUDART_INF_F, hi1 = -CUDART_INF_F;
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     cur = nx;
     if (a.proj_vp) {
       for (int k = 0; k < a.n_pred; ++k, ci += 2) {
-        const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+        const int t = 1 - cur, o = cur;                             // the block's second convolution writes over its input
         conv16<false, false>(smem_u32(buf(cur)), smem_u32(buf(t)), 0u, w_u32 + (uint32_t)ci * kConvB, s_sc + ci * 32 + 16,
                              0.0f, nullptr, L, pitch, lane, HP);
         conv16<false, true>(smem_u32(buf(t)), smem_u32(buf(o)), smem_u32(buf(cur)), w_u32 + (uint32_t)(ci + 1) * kConvB,
@@ -330,13 +336,23 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_recurrent16(const T16Args a)
     }
     __syncwarp();
   }
+  // a warp leaves after its failed fetch; the last one to leave (every fetch of the launch is behind it) zeroes both counters for
+  // the next launch - no memset node per simulation in the captured search graph
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(a.counters + 1, 1) == (int)(gridDim.x * kWarps) - 1) {
+      a.counters[0] = 0;
+      a.counters[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 size_t tower16_smem(const mzb_resnet_model* m) {
   const int n_conv = 1 + 2 * (int)m->dyn_blocks.size() + 2 * (int)m->pred_blocks.size();
   const int HW = m->Hl * m->Wl, rows = 2 * geo_halo(m->Wl) + geo_rows_per_image(m->Hl, m->Wl);
   return 128 + (size_t)n_conv * kConvB + sizeof(float) * ((size_t)n_conv * 32 + (size_t)16 * kTabP + HW + 1 + 16 * NP) + 16 + 4 * kTapB +
-         128 + (size_t)kWarps * 3 * rows * kRowB;
+         128 + (size_t)kWarps * 2 * rows * kRowB;
 }
 
 }  // namespace
@@ -375,6 +391,7 @@ int mzb_tower16_recurrent(mzb_resnet_model* m, int B, const void* state_in, int 
   a.action = action;
   a.state_out = state_out; a.out_layout = out_layout; a.out_row_stride = out_row_stride; a.out_off = out_off;
   a.proj_r = proj_r; a.proj_vp = proj_vp;
+  a.counters = m->t16_counters;
   const size_t smem = tower16_smem(m);
   static bool configured = false;
   if (!configured) {
