@@ -9,7 +9,7 @@
 // activation set of an image is 1.1 KB.  Here a WARP owns an image: its activations live in shared memory in the padded
 // layout of mzb_resnet.cuh (so a tap is a row shift), all layers' weights are resident in shared memory (9 x 4.6 KB),
 // and each convolution is 9 taps x ceil(HW / 8) n-tiles of mma.sync.m16n8k16 (bf16 operands, fp32 accumulate) with the roles
-// of mzb_stem16.cu: A = a tap's weights [cout][cin], the nine A fragments of a layer held in registers; B = 8 positions x 16
+// of mzb_stem16.cu: A = a tap's weights [cout][cin] (one ldmatrix.x4 per tap, used by the image's 6 n-tiles); B = 8 positions x 16
 // input channels, one ldmatrix.x4 feeds two n-tiles; D = [cout][position], stored through stmatrix.trans, the residual read
 // through ldmatrix.trans.  An n-tile is 8 CONSECUTIVE PADDED ROWS starting at the first pixel line (6 n-tiles span the 42
 // rows of a 6 x 6 image; the zero-column rows inside are computed and stored as zeros): with 48-byte rows any 8 consecutive
