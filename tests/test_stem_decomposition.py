@@ -83,3 +83,31 @@ def test_swapped_mma_roles_give_the_same_product():
         a += xs @ w[tap].T
         d += w[tap] @ xs.T
     np.testing.assert_allclose(d.T, a, rtol=1e-12, atol=1e-12)
+
+
+def test_shared_memory_layout_properties():
+    """The bank arithmetic the kernels' layouts rely on: a shared-memory wavefront serves 128 bytes = eight
+    16-byte lanes; an ldmatrix 8 x 8 matrix is conflict-free iff its eight row addresses fall into eight different lanes."""
+    lane = lambda byte: (byte // 16) % 8
+    # 48-byte rows: any 8 CONSECUTIVE rows are conflict-free (both 16-byte halves)
+    for r0 in range(64):
+        for half in (0, 16):
+            assert len({lane(48 * (r0 + i) + half) for i in range(8)}) == 8
+    # ... but 8 consecutive POSITIONS of a 6-wide image (pitch 7: one zero-column row per line) are 8 of 9 consecutive rows and
+    # always contain rows r and r + 8, which share a lane: the position-mapped form paid 2 wavefronts per matrix
+    W, pitch = 6, 7
+    row = lambda p: (p // W + 1) * pitch + p % W
+    for p0 in range(0, 32, 8):
+        rows = [row(p0 + i) for i in range(8)]
+        assert rows[-1] - rows[0] == 8 and len({lane(48 * r) for r in rows}) == 7
+    # 32-byte rows without padding conflict two-way; swapping the halves in every second group of four rows repairs it
+    assert len({lane(32 * i) for i in range(8)}) == 4
+    swz = lambda r, h: 32 * r + 16 * (h ^ ((r >> 2) & 1))
+    for r0 in range(64):
+        for h in (0, 1):
+            assert len({lane(swz(r0 + i, h)) for i in range(8)}) == 8
+    # transposed action-plane table of k_recurrent16: row length 72 floats; a half-warp's 8-byte loads (4 channels x 4 position
+    # pairs) must hit 16 different 8-byte bank pairs
+    kTabP = 72
+    for base in range(0, 48, 8):
+        assert len({((c * kTabP + base + 2 * q) // 2) % 16 for c in range(4) for q in range(4)}) == 16
