@@ -48,7 +48,7 @@ WORKLOADS = {
 NESTED = ("tictactoe", "connect4", "gomoku", "breakout")
 # committed `ncu --set full` captures of the dominant kernel at the bench shape (profiles/): DRAM bytes per launch
 NCU_CAPTURE = {"cartpole": "r03_ncu_k_search_fc_cartpole.csv", "connect4": "r03_ncu_k_conv_tc_connect4.csv",
-               "gomoku": "r03_ncu_k_conv_tc_gomoku.csv", "breakout": "r02_ncu_breakout.csv"}
+               "gomoku": "r03_ncu_k_conv_tc_gomoku.csv", "breakout": "r04_ncu_k_recurrent16.csv"}
 # column of the capture that holds the probed layer (a plain tower layer, no residual input): the connect4 capture is of
 # four consecutive launches (residual, plain, residual, plain)
 NCU_COLUMN = {"connect4": 1}
@@ -584,8 +584,8 @@ def run_workload(args, workload, steps, warmup, cpu_seconds, want_cpu, want_coll
             narrow = {"kernel": "k_recurrent16 (whole recurrent inference of the 16-channel network, warp per image, mma.sync on "
                                 "shared-memory activations) + 3 x k_head_mma", "us": rec_ms * 1e3, "achieved": rec_tf, "peak": tpeak,
                       "unit": "TFLOP/s", "frac": rec_tf / tpeak, "flop_per_launch": flops[1] * G,
-                      "limiter": "shared-memory pipe 82 % busy (profiles/r02_ncu_breakout.csv): the implicit GEMM re-reads each "
-                                 "activation row once per tap; tensor pipe 27 %",
+                      "limiter": "shared-memory pipe 70 % busy (profiles/r04_ncu_k_recurrent16.csv): the implicit GEMM re-reads each "
+                                 "activation row once per tap; HMMA pipe 38 %",
                       "traffic": ncu_traffic(workload), "traffic_source": "profiles/" + NCU_CAPTURE[workload]}
         in_ms = ms / n_moves                              # a whole move inside the timed region
         tflops_in = (flops[1] * S + flops[0]) * G / (in_ms * 1e-3) / 1e12
